@@ -1,0 +1,454 @@
+// C ABI (include/gcz.h): device contexts, the per-block build driver and thin wrappers over the query side.
+#include "query.cuh"
+#include "suffix_sort.cuh"
+#include "wavelet_build.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+
+namespace gcz {
+
+// ---- errors ---------------------------------------------------------------------------------------------
+static thread_local char t_error[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_error, sizeof(t_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+void clear_error() { t_error[0] = 0; }
+
+// ---- arena -------------------------------------------------------------------------------------------------
+int Arena::reserve(size_t bytes) {
+    if (bytes <= capacity) return GCZ_OK;
+    if (base) { cudaFree(base); base = nullptr; capacity = 0; }
+    const size_t want = (bytes + ((size_t)1 << 26)) & ~(((size_t)1 << 20) - 1);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&base), want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        base = nullptr;
+        return fail(GCZ_E_NOMEM, "device workspace of %zu bytes: %s", want, cudaGetErrorString(e));
+    }
+    capacity = want;
+    top = 0;
+    return GCZ_OK;
+}
+void Arena::destroy() {
+    if (base) cudaFree(base);
+    base = nullptr; capacity = 0; top = 0;
+}
+
+// ---- device contexts ----------------------------------------------------------------------------------------
+static std::mutex g_ctx_mu;
+static std::map<int, std::unique_ptr<DeviceCtx>> g_ctx;
+static thread_local std::map<int, cudaStream_t> t_stream_override;
+
+int get_ctx(int device, DeviceCtx** out) {
+    std::lock_guard<std::mutex> lock(g_ctx_mu);
+    auto it = g_ctx.find(device);
+    if (it != g_ctx.end()) { *out = it->second.get(); return GCZ_OK; }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        return fail(GCZ_E_NODEVICE, "no CUDA device is visible; this library has no CPU path");
+    }
+    if (device < 0 || device >= count) return fail(GCZ_E_ARG, "device %d out of range (%d visible)", device, count);
+    GCZ_CUDA(cudaSetDevice(device));
+    std::unique_ptr<DeviceCtx> ctx(new DeviceCtx());
+    ctx->device = device;
+    cudaDeviceProp prop;
+    GCZ_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    GCZ_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    *out = ctx.get();
+    g_ctx[device] = std::move(ctx);
+    return GCZ_OK;
+}
+
+cudaStream_t stream_of(DeviceCtx* ctx) {
+    auto it = t_stream_override.find(ctx->device);
+    return it != t_stream_override.end() ? it->second : ctx->own_stream;
+}
+
+void destroy_all_ctx() {
+    std::lock_guard<std::mutex> lock(g_ctx_mu);
+    for (auto& kv : g_ctx) {
+        cudaSetDevice(kv.first);
+        kv.second->arena.destroy();
+        if (kv.second->own_stream) cudaStreamDestroy(kv.second->own_stream);
+    }
+    g_ctx.clear();
+}
+
+static thread_local gcz_build_timing t_timing;
+
+// ---- histogram -------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(512)
+symbol_histogram_kernel(const uint8_t* __restrict__ text, int64_t n, unsigned long long* __restrict__ counts) {
+    __shared__ unsigned s_cnt[8][256];          // one copy per pair of warps to spread same-symbol atomics
+    for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) (&s_cnt[0][0])[i] = 0;
+    __syncthreads();
+    unsigned* mine = s_cnt[(threadIdx.x >> 6) & 7];
+    const int64_t n16 = n >> 4;
+    const uint4* t16 = reinterpret_cast<const uint4*>(text);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        const uint4 q = t16[i];
+        const uint32_t w[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            atomicAdd(&mine[w[k] & 255], 1u);
+            atomicAdd(&mine[(w[k] >> 8) & 255], 1u);
+            atomicAdd(&mine[(w[k] >> 16) & 255], 1u);
+            atomicAdd(&mine[w[k] >> 24], 1u);
+        }
+    }
+    if (blockIdx.x == 0) {
+        for (int64_t i = (n16 << 4) + threadIdx.x; i < n; i += blockDim.x) atomicAdd(&mine[text[i]], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        unsigned long long v = 0;
+        for (int k = 0; k < 8; k++) v += s_cnt[k][i];
+        if (v) atomicAdd(&counts[i], v);
+    }
+}
+}  // namespace
+
+static int histogram_device(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t n, unsigned long long* d_counts) {
+    GCZ_CUDA(cudaMemsetAsync(d_counts, 0, 256 * 8, st));
+    if ((reinterpret_cast<uintptr_t>(d_text) & 15) != 0) return fail(GCZ_E_ARG, "device text must be 16-byte aligned");
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n / 16 + 511) / 512, (int64_t)ctx->sm_count * 4));
+    GCZ_LAUNCH(ctx, symbol_histogram_kernel, grid, 512, 0, st, d_text, n, d_counts);
+    return GCZ_OK;
+}
+
+static int count_symbols(int device, const uint8_t* text, int64_t n, int64_t counts[256]) {
+    if (!text || !counts || n <= 0) return fail(GCZ_E_ARG, "count_symbols arguments");
+    DeviceCtx* ctx = nullptr;
+    GCZ_TRY(get_ctx(device, &ctx));
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    GCZ_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream_of(ctx);
+    ctx->arena.reset();
+    const bool on_dev = is_device_ptr(text);
+    const size_t need = (on_dev ? 0 : (size_t)n) + (1 << 20);
+    if (ctx->arena.capacity < need) GCZ_TRY(ctx->arena.reserve(need));
+    const uint8_t* d_text = text;
+    if (!on_dev) {
+        uint8_t* d = ctx->arena.get<uint8_t>((size_t)n + 64);
+        if (!d) return fail(GCZ_E_NOMEM, "text staging");
+        GCZ_CUDA(cudaMemcpyAsync(d, text, (size_t)n, cudaMemcpyHostToDevice, st));
+        d_text = d;
+    }
+    unsigned long long* d_counts = ctx->arena.get<unsigned long long>(256);
+    if (!d_counts) return fail(GCZ_E_NOMEM, "histogram scratch");
+    GCZ_TRY(histogram_device(ctx, st, d_text, n, d_counts));
+    GCZ_CUDA(cudaMemcpyAsync(counts, d_counts, 256 * 8, cudaMemcpyDeviceToHost, st));
+    GCZ_CUDA(cudaStreamSynchronize(st));
+    return GCZ_OK;
+}
+
+// ---- one block -------------------------------------------------------------------------------------------------
+static int build_block(int device, const uint8_t* text, int64_t n, int32_t sampling_rate, const gcz_shape* shape,
+                       uint8_t* gcz_body, int64_t gcz_body_len, uint8_t* gcx_body, int64_t gcx_body_len,
+                       int32_t* sa_out, uint8_t* bwt_out) {
+    if (!text || !shape || !gcz_body || !gcx_body) return fail(GCZ_E_ARG, "build_block: null buffer");
+    if (n <= 0 || n > 0x7FFFFFFFll) return fail(GCZ_E_RANGE, "block of %lld symbols (1 .. 2^31-1 supported)", (long long)n);
+    if (sampling_rate <= 0 || (sampling_rate & (sampling_rate - 1)) != 0) return fail(GCZ_E_ARG, "sampling rate must be a power of two");
+    const int sf = 31 - __builtin_clz((unsigned)sampling_rate);
+    if (shape->length != n) return fail(GCZ_E_ARG, "shape was built for %lld symbols, text has %lld", (long long)shape->length, (long long)n);
+    if (gcz_body_len != shape->size) return fail(GCZ_E_ARG, "gcz body must be %lld bytes", (long long)shape->size);
+    if (gcx_body_len != index_size(n, sf)) return fail(GCZ_E_ARG, "gcx body must be %lld bytes", (long long)index_size(n, sf));
+
+    DeviceCtx* ctx = nullptr;
+    GCZ_TRY(get_ctx(device, &ctx));
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    GCZ_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream_of(ctx);
+    const int64_t launches0 = ctx->launches;
+    std::memset(&t_timing, 0, sizeof(t_timing));
+
+    const bool text_dev = is_device_ptr(text), gcz_dev = is_device_ptr(gcz_body), gcx_dev = is_device_ptr(gcx_body);
+    const bool sa_dev = sa_out && is_device_ptr(sa_out), bwt_dev = bwt_out && is_device_ptr(bwt_out);
+
+    const size_t fixed = (text_dev ? 0 : (size_t)n + 256) + (size_t)n * 4 + (size_t)n + 256 +
+                         (gcz_dev ? 0 : (size_t)gcz_body_len + 256) + (gcx_dev ? 0 : (size_t)gcx_body_len + 256) + 4096;
+    const size_t need = fixed + std::max(suffix_sort_workspace_bytes(n), wavelet_workspace_bytes(n, sf)) + ((size_t)8 << 20);
+    ctx->arena.reset();
+    if (ctx->arena.capacity < need) GCZ_TRY(ctx->arena.reserve(need));
+    Arena& arena = ctx->arena;
+
+    cudaEvent_t ev[4];
+    for (auto& e : ev) GCZ_CUDA(cudaEventCreate(&e));
+    GCZ_CUDA(cudaEventRecord(ev[0], st));
+
+    const uint8_t* d_text = text;
+    if (!text_dev) {
+        uint8_t* d = arena.get<uint8_t>((size_t)n + 64);
+        if (!d) return fail(GCZ_E_NOMEM, "text staging");
+        GCZ_CUDA(cudaMemcpyAsync(d, text, (size_t)n, cudaMemcpyHostToDevice, st));
+        d_text = d;
+    }
+    uint32_t* d_sa = (sa_dev) ? reinterpret_cast<uint32_t*>(sa_out) : arena.get<uint32_t>((size_t)n);
+    uint8_t* d_bwt = (bwt_dev) ? bwt_out : arena.get<uint8_t>((size_t)n + 64);
+    uint8_t* d_gcz = gcz_dev ? gcz_body : arena.get<uint8_t>((size_t)gcz_body_len + 64);
+    uint8_t* d_gcx = gcx_dev ? gcx_body : arena.get<uint8_t>((size_t)gcx_body_len + 64);
+    unsigned long long* d_counts = arena.get<unsigned long long>(256);
+    if (!d_sa || !d_bwt || !d_gcz || !d_gcx || !d_counts) return fail(GCZ_E_NOMEM, "block buffers for n=%lld", (long long)n);
+    GCZ_CUDA(cudaEventRecord(ev[1], st));
+
+    // the histogram is recomputed on the device: it both drives the key packer and guards against a shape
+    // that belongs to another text (the reference trusts its caller; a mismatch there corrupts the file)
+    GCZ_TRY(histogram_device(ctx, st, d_text, n, d_counts));
+    int64_t counts[256];
+    GCZ_CUDA(cudaMemcpyAsync(counts, d_counts, sizeof(counts), cudaMemcpyDeviceToHost, st));
+    GCZ_CUDA(cudaStreamSynchronize(st));
+    for (int c = 0; c < 256; c++) {
+        if ((counts[c] > 0) != (shape->bit_lengths[c] > 0)) return fail(GCZ_E_ARG, "shape does not match the text (symbol %d)", c);
+    }
+
+    SuffixSortStats ss;
+    GCZ_TRY(suffix_sort(ctx, st, d_text, n, counts, d_sa, arena, &ss));
+    WaveletStats ws;
+    GCZ_TRY(build_wavelet_structures(ctx, st, d_text, d_sa, n, shape, sf, d_bwt, d_gcz, d_gcx, arena, &ws));
+    GCZ_CUDA(cudaEventRecord(ev[2], st));
+
+    if (!gcz_dev) GCZ_CUDA(cudaMemcpyAsync(gcz_body, d_gcz, (size_t)gcz_body_len, cudaMemcpyDeviceToHost, st));
+    if (!gcx_dev) GCZ_CUDA(cudaMemcpyAsync(gcx_body, d_gcx, (size_t)gcx_body_len, cudaMemcpyDeviceToHost, st));
+    if (sa_out && !sa_dev) GCZ_CUDA(cudaMemcpyAsync(sa_out, d_sa, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (bwt_out && !bwt_dev) GCZ_CUDA(cudaMemcpyAsync(bwt_out, d_bwt, (size_t)n, cudaMemcpyDeviceToHost, st));
+    GCZ_CUDA(cudaEventRecord(ev[3], st));
+    GCZ_CUDA(cudaEventSynchronize(ev[3]));
+
+    cudaEventElapsedTime(&t_timing.h2d_ms, ev[0], ev[1]);
+    cudaEventElapsedTime(&t_timing.d2h_ms, ev[2], ev[3]);
+    cudaEventElapsedTime(&t_timing.total_ms, ev[0], ev[3]);
+    t_timing.sort_initial_ms = ss.initial_ms;
+    t_timing.sort_refine_ms = ss.refine_ms;
+    t_timing.bwt_hswt_ms = ws.bwt_hswt_ms;
+    t_timing.ssa_ms = ws.ssa_ms;
+    t_timing.refine_rounds = ss.rounds;
+    t_timing.radix_launches = ss.radix_passes;
+    t_timing.radix_elements = ss.radix_elements;
+    t_timing.kernel_launches = ctx->launches - launches0;
+    for (auto& e : ev) cudaEventDestroy(e);
+    return GCZ_OK;
+}
+
+}  // namespace gcz
+
+// =====================================================================================================================
+using namespace gcz;
+
+extern "C" {
+
+int gcz_init(int n_devices, const int* device_ids) {
+    clear_error();
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        return fail(GCZ_E_NODEVICE, "no CUDA device is visible; this library has no CPU path");
+    }
+    if (n_devices <= 0) n_devices = count;
+    for (int i = 0; i < n_devices; i++) {
+        DeviceCtx* ctx = nullptr;
+        GCZ_TRY(get_ctx(device_ids ? device_ids[i] : i, &ctx));
+    }
+    return GCZ_OK;
+}
+
+void gcz_shutdown(void) { destroy_all_ctx(); }
+const char* gcz_last_error(void) { return t_error; }
+const char* gcz_version(void) { return "gecoz_b200 0.1 (sm_100a)"; }
+
+int gcz_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return count;
+}
+
+int gcz_set_stream(int device, void* cuda_stream) {
+    clear_error();
+    DeviceCtx* ctx = nullptr;
+    GCZ_TRY(get_ctx(device, &ctx));
+    if (cuda_stream) t_stream_override[device] = static_cast<cudaStream_t>(cuda_stream);
+    else t_stream_override.erase(device);
+    return GCZ_OK;
+}
+
+int gcz_shape_from_counts(const int64_t counts[256], gcz_shape* out) {
+    clear_error();
+    if (!counts || !out) return fail(GCZ_E_ARG, "null argument");
+    return shape_from_counts(counts, out);
+}
+int64_t gcz_shape_write(const gcz_shape* shape, uint8_t* out, int64_t cap) {
+    clear_error();
+    if (!shape || !out) return fail(GCZ_E_ARG, "null argument");
+    return shape_write(shape, out, cap);
+}
+int gcz_shape_read(const uint8_t* body, int64_t body_len, gcz_shape* out) {
+    clear_error();
+    if (!body || !out || body_len <= 0) return fail(GCZ_E_ARG, "null argument");
+    return shape_read(body, body_len, out);
+}
+int64_t gcz_ranked_bytes(int64_t len_bits) { return ranked_bytes(len_bits); }
+int64_t gcz_index_size(int64_t n, int32_t sampling_factor) { return index_size(n, sampling_factor); }
+
+int gcz_count_symbols(int device, const uint8_t* text, int64_t n, int64_t counts[256]) {
+    clear_error();
+    return count_symbols(device, text, n, counts);
+}
+
+int gcz_build_block(int device, const uint8_t* text, int64_t n, int32_t sampling_rate, const gcz_shape* shape,
+                    uint8_t* gcz_body, int64_t gcz_body_len, uint8_t* gcx_body, int64_t gcx_body_len,
+                    int32_t* sa_out, uint8_t* bwt_out) {
+    clear_error();
+    return build_block(device, text, n, sampling_rate, shape, gcz_body, gcz_body_len, gcx_body, gcx_body_len, sa_out, bwt_out);
+}
+
+int gcz_last_build_timing(gcz_build_timing* out) {
+    if (!out) return fail(GCZ_E_ARG, "null argument");
+    *out = t_timing;
+    return GCZ_OK;
+}
+
+int gcz_open_block(int device, const uint8_t* gcz_body, int64_t body_len, int64_t text_len,
+                   const uint8_t* gcx_body, int64_t gcx_len, gcz_index** out) {
+    clear_error();
+    DeviceCtx* ctx = nullptr;
+    GCZ_TRY(get_ctx(device, &ctx));
+    return open_block(ctx, gcz_body, body_len, text_len, gcx_body, gcx_len, out);
+}
+void gcz_close_block(gcz_index* idx) { close_block(idx); }
+
+int gcz_text_length(const gcz_index* idx, int64_t* out) { if (!idx || !out) return fail(GCZ_E_ARG, "null argument"); *out = idx->n; return GCZ_OK; }
+int gcz_sampling_factor(const gcz_index* idx, int32_t* out) { if (!idx || !out) return fail(GCZ_E_ARG, "null argument"); *out = idx->sampling_factor; return GCZ_OK; }
+int gcz_num_strings(const gcz_index* idx, int32_t* out) { if (!idx || !out) return fail(GCZ_E_ARG, "null argument"); *out = (int32_t)idx->e.size(); return GCZ_OK; }
+int gcz_string_ends(const gcz_index* idx, int64_t* e) {
+    if (!idx || !e) return fail(GCZ_E_ARG, "null argument");
+    std::memcpy(e, idx->e.data(), idx->e.size() * sizeof(int64_t));
+    return GCZ_OK;
+}
+int gcz_c_array(const gcz_index* idx, int64_t c[256]) {
+    if (!idx || !c) return fail(GCZ_E_ARG, "null argument");
+    std::memcpy(c, idx->c, sizeof(idx->c));
+    return GCZ_OK;
+}
+
+int gcz_count_batch(gcz_index* idx, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats, int64_t* sp, int64_t* ep) {
+    clear_error();
+    return count_batch(idx, pats, pat_off, n_pats, sp, ep);
+}
+int gcz_locate_rows(gcz_index* idx, const int64_t* rows, int64_t n_rows, int64_t* positions) {
+    clear_error();
+    return locate_rows(idx, rows, n_rows, positions);
+}
+int gcz_find_batch(gcz_index* idx, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats,
+                   int64_t* per_string_counts, int64_t** positions, int64_t** pos_off) {
+    clear_error();
+    return find_batch(idx, pats, pat_off, n_pats, per_string_counts, positions, pos_off);
+}
+void gcz_free(void* p) { std::free(p); }
+
+// ---- stage hooks ---------------------------------------------------------------------------------------------------
+int gcz_dbg_sort_pairs(int device, uint64_t* keys, uint32_t* vals, int64_t n, int32_t begin_bit, int32_t end_bit) {
+    clear_error();
+    DeviceCtx* ctx = nullptr;
+    GCZ_TRY(get_ctx(device, &ctx));
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    GCZ_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream_of(ctx);
+    ctx->arena.reset();
+    const size_t need = (size_t)n * 24 + radix_sort_temp_bytes(n) + (1 << 20);
+    if (ctx->arena.capacity < need) GCZ_TRY(ctx->arena.reserve(need));
+    RadixBuffers b;
+    b.keys[0] = ctx->arena.get<uint64_t>((size_t)n); b.keys[1] = ctx->arena.get<uint64_t>((size_t)n);
+    if (vals) { b.vals[0] = ctx->arena.get<uint32_t>((size_t)n); b.vals[1] = ctx->arena.get<uint32_t>((size_t)n); }
+    void* tmp = ctx->arena.raw(radix_sort_temp_bytes(n));
+    if (!b.keys[0] || !b.keys[1] || (vals && (!b.vals[0] || !b.vals[1])) || !tmp) return fail(GCZ_E_NOMEM, "sort workspace");
+    GCZ_CUDA(cudaMemcpyAsync(b.keys[0], keys, (size_t)n * 8, cudaMemcpyDefault, st));
+    if (vals) GCZ_CUDA(cudaMemcpyAsync(b.vals[0], vals, (size_t)n * 4, cudaMemcpyDefault, st));
+    GCZ_TRY(radix_sort_pairs(ctx, st, b, n, begin_bit, end_bit, tmp, nullptr));
+    GCZ_CUDA(cudaMemcpyAsync(keys, b.keys[b.cur], (size_t)n * 8, cudaMemcpyDefault, st));
+    if (vals) GCZ_CUDA(cudaMemcpyAsync(vals, b.vals[b.cur], (size_t)n * 4, cudaMemcpyDefault, st));
+    GCZ_CUDA(cudaStreamSynchronize(st));
+    return GCZ_OK;
+}
+
+int gcz_dbg_suffix_array(int device, const uint8_t* text, int64_t n, int32_t* sa) {
+    clear_error();
+    if (!text || !sa || n <= 0) return fail(GCZ_E_ARG, "null argument");
+    int64_t counts[256];
+    GCZ_TRY(count_symbols(device, text, n, counts));
+    DeviceCtx* ctx = nullptr;
+    GCZ_TRY(get_ctx(device, &ctx));
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    GCZ_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream_of(ctx);
+    ctx->arena.reset();
+    const size_t need = (size_t)n * 5 + suffix_sort_workspace_bytes(n) + (1 << 20);
+    if (ctx->arena.capacity < need) GCZ_TRY(ctx->arena.reserve(need));
+    uint8_t* d_text = ctx->arena.get<uint8_t>((size_t)n + 64);
+    uint32_t* d_sa = ctx->arena.get<uint32_t>((size_t)n);
+    if (!d_text || !d_sa) return fail(GCZ_E_NOMEM, "suffix array workspace");
+    GCZ_CUDA(cudaMemcpyAsync(d_text, text, (size_t)n, cudaMemcpyDefault, st));
+    GCZ_TRY(suffix_sort(ctx, st, d_text, n, counts, d_sa, ctx->arena, nullptr));
+    GCZ_CUDA(cudaMemcpyAsync(sa, d_sa, (size_t)n * 4, cudaMemcpyDefault, st));
+    GCZ_CUDA(cudaStreamSynchronize(st));
+    return GCZ_OK;
+}
+
+int gcz_dbg_ranked_vector(int device, const uint8_t* bits, int64_t len, uint8_t* out) {
+    clear_error();
+    if (!bits || !out || len <= 0) return fail(GCZ_E_ARG, "null argument");
+    DeviceCtx* ctx = nullptr;
+    GCZ_TRY(get_ctx(device, &ctx));
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    GCZ_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream_of(ctx);
+    ctx->arena.reset();
+    const size_t need = (size_t)len * 2 + ((size_t)len / 65536 + 2) * 8200 + (1 << 20);
+    if (ctx->arena.capacity < need) GCZ_TRY(ctx->arena.reserve(need));
+    const int64_t nb = ranked_bytes(len);
+    uint8_t* d_bits = ctx->arena.get<uint8_t>((size_t)len + 64);
+    uint8_t* d_out = ctx->arena.get<uint8_t>((size_t)nb + 64);
+    if (!d_bits || !d_out) return fail(GCZ_E_NOMEM, "ranked vector workspace");
+    GCZ_CUDA(cudaMemcpyAsync(d_bits, bits, (size_t)len, cudaMemcpyDefault, st));
+    GCZ_TRY(ranked_vector_from_bits(ctx, st, d_bits, len, d_out, ctx->arena));
+    GCZ_CUDA(cudaMemcpyAsync(out, d_out, (size_t)nb, cudaMemcpyDefault, st));
+    GCZ_CUDA(cudaStreamSynchronize(st));
+    return GCZ_OK;
+}
+
+int gcz_dbg_index_wavelet_tree(int device, const int32_t* vals, int64_t m, uint8_t* out) {
+    clear_error();
+    if (!vals || !out || m <= 0) return fail(GCZ_E_ARG, "null argument");
+    DeviceCtx* ctx = nullptr;
+    GCZ_TRY(get_ctx(device, &ctx));
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    GCZ_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream_of(ctx);
+    ctx->arena.reset();
+    const int levels = 64 - __builtin_clzll((uint64_t)m);
+    const int64_t nb = ranked_bytes(m) * levels;
+    const size_t need = (size_t)m * 16 + (size_t)nb + ((size_t)m / 65536 + 2) * 8200 * levels + (1 << 20);
+    if (ctx->arena.capacity < need) GCZ_TRY(ctx->arena.reserve(need));
+    uint32_t* d_vals = ctx->arena.get<uint32_t>((size_t)m);
+    uint8_t* d_out = ctx->arena.get<uint8_t>((size_t)nb + 64);
+    if (!d_vals || !d_out) return fail(GCZ_E_NOMEM, "IWT workspace");
+    GCZ_CUDA(cudaMemcpyAsync(d_vals, vals, (size_t)m * 4, cudaMemcpyDefault, st));
+    GCZ_TRY(index_wavelet_tree_from_values(ctx, st, d_vals, m, d_out, ctx->arena));
+    GCZ_CUDA(cudaMemcpyAsync(out, d_out, (size_t)nb, cudaMemcpyDefault, st));
+    GCZ_CUDA(cudaStreamSynchronize(st));
+    return GCZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,103 @@
+// Device context, workspace arena and small device helpers shared by the CUDA translation units.
+#pragma once
+
+#include "gcz_host.h"
+
+#include <cuda_runtime.h>
+
+#include <mutex>
+
+namespace gcz {
+
+#define GCZ_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            return ::gcz::fail(e__ == cudaErrorMemoryAllocation ? GCZ_E_NOMEM : GCZ_E_CUDA,         \
+                               "%s -> %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+        }                                                                                           \
+    } while (0)
+
+#define GCZ_TRY(expr)                       \
+    do {                                    \
+        int rc__ = (expr);                  \
+        if (rc__ != GCZ_OK) return rc__;    \
+    } while (0)
+
+// Grow-only device arena: one cudaMalloc per device, bump-allocated per call.  A build of n symbols
+// needs tens of n bytes; asking the driver for that on every block would cost more than the sort.
+struct Arena {
+    char*  base = nullptr;
+    size_t capacity = 0;
+    size_t top = 0;
+    int reserve(size_t bytes);                 // ensures capacity >= bytes (frees + reallocates; contents lost)
+    void reset() { top = 0; }
+    size_t mark() const { return top; }
+    void release(size_t m) { top = m; }
+    void* raw(size_t bytes) {
+        const size_t aligned = (top + 255) & ~size_t(255);
+        if (aligned + bytes > capacity) return nullptr;
+        top = aligned + bytes;
+        return base + aligned;
+    }
+    template <class T> T* get(size_t count) { return static_cast<T*>(raw(count * sizeof(T))); }
+    void destroy();
+};
+
+struct DeviceCtx {
+    int          device = -1;
+    int          sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    std::mutex   mu;                          // one build / query batch at a time per device (shared arena)
+    Arena        arena;
+    void*        pinned = nullptr;            // small pinned scratch for read-backs
+    size_t       pinned_bytes = 0;
+    int64_t      launches = 0;                // kernels launched by this library on this device
+    bool         sort_attr[2] = { false, false };   // dynamic-smem opt-in done for the onesweep kernels
+};
+
+int          get_ctx(int device, DeviceCtx** out);   // creates on first use; fails with GCZ_E_NODEVICE
+cudaStream_t stream_of(DeviceCtx* ctx);              // thread-local override from gcz_set_stream, else own
+void         destroy_all_ctx();
+
+inline bool is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+#define GCZ_LAUNCH(ctx, kernel, grid, block, smem, stream, ...)                                    \
+    do {                                                                                            \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                 \
+        (ctx)->launches++;                                                                          \
+        GCZ_CUDA(cudaPeekAtLastError());                                                            \
+    } while (0)
+
+// ---- device helpers -----------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// warp inclusive scans
+__device__ __forceinline__ unsigned warp_incl_sum(unsigned v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, v, o); if (lane_id() >= (unsigned)o) v += t; }
+    return v;
+}
+__device__ __forceinline__ long long warp_incl_max(long long v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(0xffffffffu, v, o); if (lane_id() >= (unsigned)o && t > v) v = t; }
+    return v;
+}
+#endif
+
+}  // namespace gcz

@@ -1,0 +1,22 @@
+// GPU suffix array construction (see suffix_sort.cu).
+#pragma once
+
+#include "radix_sort.cuh"
+
+namespace gcz {
+
+struct SuffixSortStats {
+    float   initial_ms = 0, refine_ms = 0;
+    int     rounds = 0;
+    int     symbols_per_key = 0;
+    int64_t radix_passes = 0, radix_elements = 0;
+};
+
+size_t suffix_sort_workspace_bytes(int64_t n);
+
+// d_text: n bytes on the device; counts: byte histogram of the text (host); d_sa: n x u32 on the device (output).
+// Scratch comes from `arena` (released before returning).
+int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t n, const int64_t counts[256],
+                uint32_t* d_sa, Arena& arena, SuffixSortStats* stats);
+
+}  // namespace gcz

@@ -1,0 +1,599 @@
+// BWT, Huffman-shaped wavelet tree, sampled-SA index and the ranked bit-vector layout, built on the GPU.
+//
+// Replaces, per block (fmt/GecozFileWriter.java:256-284):
+//   BWTDataSource.get                    fmt/GecozFileWriter.java:301-303   -> bwt_count_kernel
+//   HuffmanShapedWaveletTree.fill        algo/tree/HuffmanShapedWaveletTree.java:127-146 -> hswt_emit_kernel
+//   RankedWTNode.putLong (counters)      algo/tree/RankedWTNode.java:228-245 -> ranked_layout_kernel
+//   GSSAIndex write ctor                 algo/ssa/GSSAIndex.java:129-150    -> marker bits + sample_kernel
+//   IndexWaveletTree build ctor          algo/tree/IndexWaveletTree.java:83-112 -> iwt_* kernels
+// The reference streams one symbol at a time into bit writers; here every structure is produced by
+// prefix sums over warp tiles (a bit's position in a node = number of earlier symbols routed to that node).
+#include "wavelet_build.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+namespace gcz {
+
+namespace {
+
+constexpr int kWarpTile = 1024;             // BWT positions per warp
+constexpr int kWtThreads = 256;             // 8 warps
+constexpr int kWtBlockTile = kWarpTile * (kWtThreads / 32);
+constexpr int kNoNode = 0xFFFF;
+
+// symbol tables of one block, resident in global memory for the duration of the build
+struct SymbolTables {
+    uint8_t  dense[256];        // byte -> dense symbol index, 0xFF when absent
+    uint16_t code[256];         // dense -> code bits (bit d = branch at depth d)
+    uint8_t  len[256];          // dense -> code length
+    uint8_t  node_of[256][16];  // dense, depth -> node (file order) on the symbol's path
+    uint16_t node_prefix[256];  // node -> path bits
+    uint8_t  node_depth[256];   // node -> depth
+    int32_t  sigma;             // symbols present
+    int32_t  n_nodes;
+    int32_t  max_len;
+};
+
+// ---- BWT gather + per-tile symbol counts + marker bits -----------------------------------------------
+__global__ void __launch_bounds__(kWtThreads)
+bwt_count_kernel(const uint8_t* __restrict__ text, const uint32_t* __restrict__ sa, int64_t n,
+                 const SymbolTables* __restrict__ tab, uint32_t sample_mask,
+                 uint8_t* __restrict__ bwt, uint32_t* __restrict__ marker_raw,
+                 uint32_t* __restrict__ tile_counts /* [(sigma + 1)][tiles] */, int64_t tiles) {
+    __shared__ uint32_t s_cnt[kWtThreads / 32][260];
+    __shared__ uint8_t s_dense[256];
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    s_dense[threadIdx.x] = tab->dense[threadIdx.x];
+    const int sigma = tab->sigma;
+    for (int i = lane; i <= sigma; i += 32) s_cnt[warp][i] = 0;
+    __syncthreads();
+    const int64_t tile = (int64_t)blockIdx.x * (kWtThreads / 32) + warp;
+    if (tile >= tiles) return;
+    const int64_t base = tile * kWarpTile;
+    uint32_t* cnt = s_cnt[warp];
+    unsigned marks = 0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < kWarpTile / 32; c0 += 4) {
+        uint32_t s[4];
+        int sym[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int64_t j = base + (c0 + u) * 32 + lane;
+            s[u] = j < n ? sa[j] : 1u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int64_t j = base + (c0 + u) * 32 + lane;
+            sym[u] = j < n ? (int)text[s[u] ? (int64_t)s[u] - 1 : n - 1] : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int64_t j = base + (c0 + u) * 32 + lane;
+            const bool valid = j < n;
+            if (valid) bwt[j] = (uint8_t)sym[u];
+            const unsigned mk = __ballot_sync(0xffffffffu, valid && (s[u] & sample_mask) == 0);
+            if (lane == 0 && base + (c0 + u) * 32 < n) marker_raw[(base >> 5) + c0 + u] = mk;
+            marks += (lane == 0) ? __popc(mk) : 0;
+            // count every distinct symbol of this chunk once
+            const int d = valid ? (int)s_dense[sym[u]] : -1;
+            unsigned todo = __ballot_sync(0xffffffffu, valid);
+            while (todo) {
+                const int leader = __ffs(todo) - 1;
+                const int v = __shfl_sync(0xffffffffu, d, leader);
+                const unsigned same = __ballot_sync(0xffffffffu, d == v);
+                if ((int)lane == leader) cnt[v] += __popc(same);
+                todo &= ~same;
+            }
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    if (lane == 0) cnt[sigma] = marks;
+    __syncwarp();
+    for (int i = lane; i <= sigma; i += 32) tile_counts[(size_t)i * tiles + tile] = cnt[i];
+}
+
+// one CTA per row: exclusive scan of `len` u32 values in place; row total -> totals[row]
+__global__ void __launch_bounds__(1024)
+row_scan_kernel(uint32_t* __restrict__ rows, int64_t len, uint32_t* __restrict__ totals) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    uint32_t* row = rows + (size_t)blockIdx.x * len;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < len; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        const uint32_t v = i < len ? row[i] : 0;
+        const uint32_t incl = warp_incl_sum(v);
+        if (lane_id() == 31) s_warp[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        uint32_t b = s_carry;
+        for (unsigned w = 0; w < (threadIdx.x >> 5); w++) b += s_warp[w];
+        if (i < len) row[i] = b + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = b + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && totals) totals[blockIdx.x] = s_carry;
+}
+
+// ---- node bit emission ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWtThreads)
+hswt_emit_kernel(const uint8_t* __restrict__ bwt, int64_t n, const SymbolTables* __restrict__ tab,
+                 const uint32_t* __restrict__ tile_prefix /* [sigma][tiles], exclusive */, int64_t tiles,
+                 const uint64_t* __restrict__ node_raw_word /* node -> first u32 word of its raw vector */,
+                 uint32_t* __restrict__ raw) {
+    __shared__ SymbolTables s_tab;
+    __shared__ unsigned long long s_acc[kWtThreads / 32][256];
+    __shared__ uint32_t s_word[kWtThreads / 32][256];
+    __shared__ uint8_t s_fill[kWtThreads / 32][256];
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(tab);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
+        for (int i = threadIdx.x; i < (int)(sizeof(SymbolTables) / 4); i += kWtThreads) dst[i] = src[i];
+    }
+    __syncthreads();
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    const unsigned lt = lanemask_lt();
+    const int64_t tile = (int64_t)blockIdx.x * (kWtThreads / 32) + warp;
+    if (tile >= tiles) return;
+    const int sigma = s_tab.sigma, n_nodes = s_tab.n_nodes, max_len = s_tab.max_len;
+
+    // where this tile's bits start in every node: symbols routed through the node, summed over earlier tiles
+    for (int v = lane; v < n_nodes; v += 32) {
+        const int depth = s_tab.node_depth[v];
+        const unsigned prefix = s_tab.node_prefix[v], pmask = (1u << depth) - 1;
+        unsigned long long bit0 = 0;
+        for (int s = 0; s < sigma; s++) {
+            if (s_tab.len[s] > depth && (s_tab.code[s] & pmask) == prefix) bit0 += tile_prefix[(size_t)s * tiles + tile];
+        }
+        bit0 += node_raw_word[v] * 32ull;
+        s_acc[warp][v] = 0;
+        s_word[warp][v] = (uint32_t)(bit0 >> 5);     // raw areas are far below 2^32 words
+        s_fill[warp][v] = (uint8_t)(bit0 & 31);
+    }
+    __syncwarp();
+
+    const int64_t base = tile * kWarpTile;
+#pragma unroll 1
+    for (int c = 0; c < kWarpTile / 32; c++) {
+        const int64_t j = base + c * 32 + lane;
+        if (base + c * 32 >= n) break;
+        const int d = j < n ? (int)s_tab.dense[bwt[j]] : 255;
+        const int len = j < n ? (int)s_tab.len[d] : 0;
+        const unsigned code = j < n ? s_tab.code[d] : 0;
+        for (int depth = 0; depth < max_len; depth++) {
+            const int nid = depth < len ? (int)s_tab.node_of[d][depth] : kNoNode;
+            const unsigned bit = (code >> depth) & 1u;
+            unsigned todo = __ballot_sync(0xffffffffu, nid != kNoNode);
+            while (todo) {
+                const int leader = __ffs(todo) - 1;
+                const int v = __shfl_sync(0xffffffffu, nid, leader);
+                const bool member = nid == v;
+                const unsigned members = __ballot_sync(0xffffffffu, member);
+                const unsigned packed = __reduce_or_sync(0xffffffffu, member ? (bit << __popc(members & lt)) : 0u);
+                if ((int)lane == leader) {
+                    unsigned long long acc = s_acc[warp][v] | ((unsigned long long)packed << s_fill[warp][v]);
+                    unsigned fill = s_fill[warp][v] + __popc(members);
+                    if (fill >= 32) {
+                        atomicOr(&raw[s_word[warp][v]], (uint32_t)acc);
+                        s_word[warp][v]++;
+                        acc >>= 32;
+                        fill -= 32;
+                    }
+                    s_acc[warp][v] = acc;
+                    s_fill[warp][v] = (uint8_t)fill;
+                }
+                todo &= ~members;
+                __syncwarp();
+            }
+        }
+    }
+    __syncwarp();
+    for (int v = lane; v < n_nodes; v += 32) {
+        if (s_fill[warp][v] > 0 && (uint32_t)s_acc[warp][v] != 0) atomicOr(&raw[s_word[warp][v]], (uint32_t)s_acc[warp][v]);
+    }
+}
+
+// ---- sampled suffix array values in SA order -----------------------------------------------------------
+__global__ void __launch_bounds__(kWtThreads)
+sample_kernel(const uint32_t* __restrict__ sa, int64_t n, uint32_t sample_mask, int sample_shift,
+              const uint32_t* __restrict__ marker_prefix /* [tiles] exclusive */, int64_t tiles,
+              uint32_t* __restrict__ ssa) {
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    const int64_t tile = (int64_t)blockIdx.x * (kWtThreads / 32) + warp;
+    if (tile >= tiles) return;
+    const int64_t base = tile * kWarpTile;
+    uint32_t out = marker_prefix[tile];
+#pragma unroll 4
+    for (int c = 0; c < kWarpTile / 32; c++) {
+        const int64_t j = base + c * 32 + lane;
+        const uint32_t s = j < n ? sa[j] : 1u;
+        const bool mk = j < n && (s & sample_mask) == 0;
+        const unsigned m = __ballot_sync(0xffffffffu, mk);
+        if (mk) ssa[out + __popc(m & lanemask_lt())] = s >> sample_shift;
+        out += __popc(m);
+    }
+}
+
+// ---- IndexWaveletTree levels ---------------------------------------------------------------------------
+// level h, current order = values grouped (stably) by v >> (h + 1), group g at slot g << (h + 1)
+__global__ void iwt_bits_kernel(const uint32_t* __restrict__ vals, int64_t m, int h, uint32_t* __restrict__ raw,
+                                uint32_t* __restrict__ zeros /* per word */) {
+    const int64_t words = (m + 31) >> 5;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = gw; w < words; w += nwarps) {
+        const int64_t p = w * 32 + lane_id();
+        const bool valid = p < m;
+        const unsigned bit = valid ? (vals[p] >> h) & 1u : 0u;
+        const unsigned word = __ballot_sync(0xffffffffu, bit);
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        if (lane_id() == 0) { raw[w] = word; zeros[w] = __popc(~word & vmask); }
+    }
+}
+
+__device__ __forceinline__ uint32_t zeros_before(const uint32_t* __restrict__ raw, const uint32_t* __restrict__ zexcl, int64_t p) {
+    const unsigned r = (unsigned)(p & 31);
+    return zexcl[p >> 5] + (r ? __popc(~raw[p >> 5] & ((1u << r) - 1u)) : 0);
+}
+
+__global__ void iwt_scatter_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int64_t m, int h,
+                                   const uint32_t* __restrict__ raw, const uint32_t* __restrict__ zexcl) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < m; p += stride) {
+        const uint32_t v = in[p];
+        const int64_t bs = (int64_t)(v >> (h + 1)) << (h + 1);
+        const int64_t zp = zeros_before(raw, zexcl, p);
+        const int64_t zb = bs < m ? zeros_before(raw, zexcl, bs) : 0;
+        int64_t np;
+        if (((v >> h) & 1u) == 0) {
+            np = bs + (zp - zb);
+        } else {
+            const int64_t zeros_in_block = min((int64_t)1 << h, m - bs);
+            np = bs + zeros_in_block + ((p - zp) - (bs - zb));
+        }
+        out[np] = v;
+    }
+}
+
+// ---- ranked layout: raw bits -> RankedWTNode bytes -------------------------------------------------------
+struct VectorDesc {
+    uint64_t raw_word;      // first u32 word of the raw (contiguous) bits; padded with zeros to whole superblocks
+    int64_t  len;           // bits
+    uint8_t* out;           // where the ranked bytes go (device)
+    int64_t  sb_first;      // first entry of this vector in the global superblock arrays
+    int64_t  sb_count;
+};
+
+// ones per 65536-bit superblock (one warp each)
+__global__ void superblock_popcount_kernel(const uint32_t* __restrict__ raw, const VectorDesc* __restrict__ vecs, int nvec,
+                                           int64_t total_sb, uint32_t* __restrict__ sb_ones) {
+    const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= total_sb) return;
+    int v = 0;
+    while (v + 1 < nvec && vecs[v + 1].sb_first <= g) v++;
+    const uint4* p = reinterpret_cast<const uint4*>(raw + vecs[v].raw_word + (uint64_t)(g - vecs[v].sb_first) * 2048u);
+    unsigned ones = 0;
+#pragma unroll 4
+    for (int i = lane_id(); i < 512; i += 32) {
+        const uint4 q = p[i];
+        ones += __popc(q.x) + __popc(q.y) + __popc(q.z) + __popc(q.w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ones += __shfl_xor_sync(0xffffffffu, ones, o);
+    if (lane_id() == 0) sb_ones[g] = ones;
+}
+
+// exclusive scan of the superblock counts of every vector separately (one CTA per vector)
+__global__ void __launch_bounds__(1024)
+superblock_scan_kernel(uint32_t* __restrict__ sb_ones, const VectorDesc* __restrict__ vecs) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int64_t first = vecs[blockIdx.x].sb_first, len = vecs[blockIdx.x].sb_count;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < len; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        const uint32_t v = i < len ? sb_ones[first + i] : 0;
+        const uint32_t incl = warp_incl_sum(v);
+        if (lane_id() == 31) s_warp[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        uint32_t b = s_carry;
+        for (unsigned w = 0; w < (threadIdx.x >> 5); w++) b += s_warp[w];
+        if (i < len) sb_ones[first + i] = b + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = b + incl;
+        __syncthreads();
+    }
+}
+
+// One CTA per superblock, one thread per 512-bit chunk: 64 data bytes, then a uint16 running count inside the
+// superblock, or a uint64 absolute count after the 128th chunk — only when more data follows
+// (algo/tree/RankedWTNode.java:228-245, layout in SURVEY.md A.3).
+__global__ void __launch_bounds__(128)
+ranked_layout_kernel(const uint32_t* __restrict__ raw, const VectorDesc* __restrict__ vecs, int nvec,
+                     const uint32_t* __restrict__ sb_excl) {
+    __shared__ __align__(16) uint16_t s_out[4232];
+    __shared__ uint32_t s_warp[4];
+    const int64_t g = blockIdx.x;
+    int v = 0;
+    while (v + 1 < nvec && vecs[v + 1].sb_first <= g) v++;
+    const VectorDesc vd = vecs[v];
+    const int64_t sb = g - vd.sb_first;
+    const int c = threadIdx.x;
+    const uint4* p = reinterpret_cast<const uint4*>(raw + vd.raw_word + (uint64_t)sb * 2048u + (uint64_t)c * 16u);
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint4 q = p[i];
+        w[4 * i] = q.x; w[4 * i + 1] = q.y; w[4 * i + 2] = q.z; w[4 * i + 3] = q.w;
+    }
+    unsigned ones = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) ones += __popc(w[i]);
+    const unsigned incl_w = warp_incl_sum(ones);
+    if (lane_id() == 31) s_warp[c >> 5] = incl_w;
+    __syncthreads();
+    unsigned incl = incl_w;
+    for (int k = 0; k < (c >> 5); k++) incl += s_warp[k];
+
+    uint16_t* o = s_out + c * 33;
+#pragma unroll
+    for (int i = 0; i < 16; i++) { o[2 * i] = (uint16_t)w[i]; o[2 * i + 1] = (uint16_t)(w[i] >> 16); }
+    const int64_t chunk = sb * 128 + c;                       // chunk index inside the vector
+    const bool counter_follows = (chunk + 1) * 512 < vd.len;
+    if (counter_follows) {
+        if (c < 127) {
+            o[32] = (uint16_t)incl;
+        } else {
+            const unsigned long long abs_ones = (unsigned long long)sb_excl[g] + incl;
+            o[32] = (uint16_t)abs_ones; o[33] = (uint16_t)(abs_ones >> 16);
+            o[34] = (uint16_t)(abs_ones >> 32); o[35] = (uint16_t)(abs_ones >> 48);
+        }
+    }
+    __syncthreads();
+    const int64_t total = (int64_t)(((uint64_t)(vd.len - 1) >> 16) * 6 + ((uint64_t)(vd.len - 1) >> 9) * 2 + ((uint64_t)(vd.len + 7) >> 3));
+    const int64_t start = sb * 8454;
+    const int nbytes = (int)min((int64_t)8454, total - start);
+    const uint8_t* sbytes = reinterpret_cast<const uint8_t*>(s_out);
+    uint8_t* dst = vd.out + start;
+    for (int i = threadIdx.x; i < nbytes; i += 128) dst[i] = sbytes[i];
+}
+
+inline int64_t superblocks(int64_t len) { return (len + 65535) >> 16; }
+
+}  // namespace
+
+size_t wavelet_workspace_bytes(int64_t n, int sampling_factor) {
+    const int64_t m = (n + ((int64_t)1 << sampling_factor) - 1) >> sampling_factor;
+    const int levels = 64 - __builtin_clzll((uint64_t)std::max<int64_t>(m, 1));
+    const size_t tiles = (size_t)((n + kWarpTile - 1) / kWarpTile);
+    size_t raw_words = (size_t)superblocks(n) * 2048 * 15 + 256 * 2048;   // nodes: <= 15 levels of n bits + padding
+    raw_words += (size_t)superblocks(n) * 2048;                   // marker
+    raw_words += (size_t)superblocks(m) * 2048 * levels;          // IWT levels
+    return raw_words * 4 + tiles * 4 * 258 + (size_t)m * 8 + (size_t)((m + 31) / 32) * 4 + (4 << 20);
+}
+
+int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, const uint32_t* d_sa, int64_t n,
+                             const gcz_shape* shape, int sampling_factor, uint8_t* d_bwt,
+                             uint8_t* d_gcz_body, uint8_t* d_gcx_body, Arena& arena, WaveletStats* stats) {
+    const size_t mark0 = arena.mark();
+    // ---- host tables -------------------------------------------------------------------------------
+    SymbolTables h_tab;
+    std::memset(&h_tab, 0, sizeof(h_tab));
+    std::memset(h_tab.dense, 0xFF, sizeof(h_tab.dense));
+    int sigma = 0, max_len = 0;
+    int dense_to_byte[256];
+    for (int c = 0; c < 256; c++) {
+        if (shape->bit_lengths[c] > 0) {
+            h_tab.dense[c] = (uint8_t)sigma;
+            h_tab.code[sigma] = (uint16_t)shape->codes[c];
+            h_tab.len[sigma] = (uint8_t)shape->bit_lengths[c];
+            max_len = std::max(max_len, (int)shape->bit_lengths[c]);
+            dense_to_byte[sigma++] = c;
+        }
+    }
+    (void)dense_to_byte;
+    const int n_nodes = shape->n_nodes;
+    if (n_nodes <= 0 || n_nodes > 255 || max_len > 15) return fail(GCZ_E_RANGE, "unsupported tree shape");
+    for (int v = 0; v < n_nodes; v++) {
+        h_tab.node_prefix[v] = (uint16_t)shape->node_prefix[v];
+        h_tab.node_depth[v] = (uint8_t)shape->node_depth[v];
+    }
+    for (int s = 0; s < sigma; s++) {
+        for (int d = 0; d < h_tab.len[s]; d++) {
+            int found = -1;
+            for (int v = 0; v < n_nodes; v++) {
+                if (h_tab.node_depth[v] == d && h_tab.node_prefix[v] == (h_tab.code[s] & ((1u << d) - 1))) { found = v; break; }
+            }
+            if (found < 0) return fail(GCZ_E_INTERNAL, "symbol path leaves the tree");
+            h_tab.node_of[s][d] = (uint8_t)found;
+        }
+    }
+    h_tab.sigma = sigma; h_tab.n_nodes = n_nodes; h_tab.max_len = max_len;
+
+    // ---- vectors: HSWT nodes, marker, IWT levels ------------------------------------------------------
+    const int64_t m = (n + ((int64_t)1 << sampling_factor) - 1) >> sampling_factor;
+    const int levels = 64 - __builtin_clzll((uint64_t)m);
+    std::vector<VectorDesc> vecs;
+    uint64_t raw_words = 0;
+    int64_t total_sb = 0;
+    auto add_vec = [&](int64_t len, uint8_t* out) {
+        VectorDesc d;
+        d.raw_word = raw_words; d.len = len; d.out = out; d.sb_first = total_sb; d.sb_count = superblocks(len);
+        raw_words += (uint64_t)d.sb_count * 2048u;
+        total_sb += d.sb_count;
+        vecs.push_back(d);
+    };
+    std::vector<uint64_t> h_node_raw(n_nodes);
+    for (int v = 0; v < n_nodes; v++) {
+        if (shape->node_bits[v] <= 0) return fail(GCZ_E_ARG, "shape has an empty node (was it built from counts?)");
+        h_node_raw[v] = raw_words;
+        add_vec(shape->node_bits[v], d_gcz_body + shape->node_offset[v]);
+    }
+    const int marker_vec = (int)vecs.size();
+    add_vec(n, d_gcx_body);
+    const int64_t rank_bytes = ranked_bytes(n), level_bytes = ranked_bytes(m);
+    const int level_vec0 = (int)vecs.size();
+    for (int l = 0; l < levels; l++) add_vec(m, d_gcx_body + rank_bytes + (int64_t)l * level_bytes);   // highest bit first
+    if (raw_words >= (1ull << 32)) return fail(GCZ_E_RANGE, "raw bit area above 2^32 words");
+
+    const int64_t tiles = (n + kWarpTile - 1) / kWarpTile;
+    SymbolTables* d_tab = arena.get<SymbolTables>(1);
+    uint32_t* d_raw = arena.get<uint32_t>((size_t)raw_words + 16);
+    uint32_t* d_tile_counts = arena.get<uint32_t>((size_t)tiles * (sigma + 1));
+    uint64_t* d_node_raw = arena.get<uint64_t>((size_t)n_nodes);
+    VectorDesc* d_vecs = arena.get<VectorDesc>(vecs.size());
+    uint32_t* d_sb = arena.get<uint32_t>((size_t)total_sb + 1);
+    uint32_t* d_ssa[2] = { arena.get<uint32_t>((size_t)m), arena.get<uint32_t>((size_t)m) };
+    uint32_t* d_zeros = arena.get<uint32_t>((size_t)((m + 31) >> 5) + 1);
+    if (!d_tab || !d_raw || !d_tile_counts || !d_node_raw || !d_vecs || !d_sb || !d_ssa[0] || !d_ssa[1] || !d_zeros)
+        return fail(GCZ_E_NOMEM, "wavelet workspace for n=%lld", (long long)n);
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    if (stats) {
+        GCZ_CUDA(cudaEventCreate(&ev0)); GCZ_CUDA(cudaEventCreate(&ev1)); GCZ_CUDA(cudaEventCreate(&ev2));
+        GCZ_CUDA(cudaEventRecord(ev0, st));
+    }
+    GCZ_CUDA(cudaMemcpyAsync(d_tab, &h_tab, sizeof(h_tab), cudaMemcpyHostToDevice, st));
+    GCZ_CUDA(cudaMemcpyAsync(d_node_raw, h_node_raw.data(), sizeof(uint64_t) * n_nodes, cudaMemcpyHostToDevice, st));
+    GCZ_CUDA(cudaMemcpyAsync(d_vecs, vecs.data(), sizeof(VectorDesc) * vecs.size(), cudaMemcpyHostToDevice, st));
+    GCZ_CUDA(cudaMemsetAsync(d_raw, 0, ((size_t)raw_words + 16) * 4, st));
+
+    // shape table at the head of the body
+    {
+        std::vector<uint8_t> tbl((size_t)shape->table_bytes + 8);
+        const int64_t w = shape_write(shape, tbl.data(), (int64_t)tbl.size());
+        if (w != shape->table_bytes) return w < 0 ? (int)w : fail(GCZ_E_INTERNAL, "shape table size changed");
+        GCZ_CUDA(cudaMemcpyAsync(d_gcz_body, tbl.data(), (size_t)w, cudaMemcpyHostToDevice, st));
+        GCZ_CUDA(cudaStreamSynchronize(st));             // tbl and the other host staging vectors go out of scope
+    }
+
+    // ---- BWT, counts, marker bits ------------------------------------------------------------------------
+    const unsigned wt_grid = (unsigned)((tiles + kWtThreads / 32 - 1) / (kWtThreads / 32));
+    const uint32_t sample_mask = (1u << sampling_factor) - 1u;
+    uint32_t* d_marker_raw = d_raw + vecs[marker_vec].raw_word;
+    GCZ_LAUNCH(ctx, bwt_count_kernel, wt_grid, kWtThreads, 0, st, d_text, d_sa, n, d_tab, sample_mask, d_bwt, d_marker_raw,
+               d_tile_counts, tiles);
+    GCZ_LAUNCH(ctx, row_scan_kernel, (unsigned)(sigma + 1), 1024, 0, st, d_tile_counts, tiles, (uint32_t*)nullptr);
+    GCZ_LAUNCH(ctx, hswt_emit_kernel, wt_grid, kWtThreads, 0, st, d_bwt, n, d_tab, d_tile_counts, tiles, d_node_raw, d_raw);
+    if (stats) GCZ_CUDA(cudaEventRecord(ev1, st));
+
+    // ---- sampled SA + IndexWaveletTree ---------------------------------------------------------------------
+    GCZ_LAUNCH(ctx, sample_kernel, wt_grid, kWtThreads, 0, st, d_sa, n, sample_mask, sampling_factor,
+               d_tile_counts + (size_t)sigma * tiles, tiles, d_ssa[0]);
+    const int64_t mwords = (m + 31) >> 5;
+    const int lvl_grid = (int)std::min<int64_t>((m + 255) / 256, (int64_t)ctx->sm_count * 8);
+    int cur = 0;
+    for (int l = 0; l < levels; l++) {
+        const int h = levels - 1 - l;
+        uint32_t* lraw = d_raw + vecs[level_vec0 + l].raw_word;
+        GCZ_LAUNCH(ctx, iwt_bits_kernel, lvl_grid, 256, 0, st, d_ssa[cur], m, h, lraw, d_zeros);
+        if (h > 0) {
+            GCZ_LAUNCH(ctx, row_scan_kernel, 1, 1024, 0, st, d_zeros, mwords, (uint32_t*)nullptr);
+            GCZ_LAUNCH(ctx, iwt_scatter_kernel, lvl_grid, 256, 0, st, d_ssa[cur], d_ssa[cur ^ 1], m, h, lraw, d_zeros);
+            cur ^= 1;
+        }
+    }
+
+    // ---- counters + final byte layout of every vector ---------------------------------------------------------
+    GCZ_LAUNCH(ctx, superblock_popcount_kernel, (unsigned)((total_sb * 32 + 255) / 256), 256, 0, st, d_raw, d_vecs,
+               (int)vecs.size(), total_sb, d_sb);
+    GCZ_LAUNCH(ctx, superblock_scan_kernel, (unsigned)vecs.size(), 1024, 0, st, d_sb, d_vecs);
+    GCZ_LAUNCH(ctx, ranked_layout_kernel, (unsigned)total_sb, 128, 0, st, d_raw, d_vecs, (int)vecs.size(), d_sb);
+
+    if (stats) {
+        GCZ_CUDA(cudaEventRecord(ev2, st));
+        GCZ_CUDA(cudaEventSynchronize(ev2));
+        cudaEventElapsedTime(&stats->bwt_hswt_ms, ev0, ev1);
+        cudaEventElapsedTime(&stats->ssa_ms, ev1, ev2);
+        cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
+    } else {
+        GCZ_CUDA(cudaStreamSynchronize(st));
+    }
+    arena.release(mark0);
+    return GCZ_OK;
+}
+
+// Stage hooks for the parity tests ---------------------------------------------------------------------------
+
+namespace {
+__global__ void pack_bits_kernel(const uint8_t* __restrict__ bits, int64_t len, uint32_t* __restrict__ raw) {
+    const int64_t words = (len + 31) >> 5;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = gw; w < words; w += nwarps) {
+        const int64_t p = w * 32 + lane_id();
+        const unsigned word = __ballot_sync(0xffffffffu, p < len && (bits[p] & 1));
+        if (lane_id() == 0) raw[w] = word;
+    }
+}
+}  // namespace
+
+int ranked_vector_from_bits(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_bits, int64_t len, uint8_t* d_out, Arena& arena) {
+    const size_t mark0 = arena.mark();
+    VectorDesc d;
+    d.raw_word = 0; d.len = len; d.out = d_out; d.sb_first = 0; d.sb_count = superblocks(len);
+    uint32_t* d_raw = arena.get<uint32_t>((size_t)d.sb_count * 2048 + 16);
+    VectorDesc* d_vec = arena.get<VectorDesc>(1);
+    uint32_t* d_sb = arena.get<uint32_t>((size_t)d.sb_count + 1);
+    if (!d_raw || !d_vec || !d_sb) return fail(GCZ_E_NOMEM, "ranked vector workspace");
+    GCZ_CUDA(cudaMemsetAsync(d_raw, 0, ((size_t)d.sb_count * 2048 + 16) * 4, st));
+    GCZ_CUDA(cudaMemcpyAsync(d_vec, &d, sizeof(d), cudaMemcpyHostToDevice, st));
+    GCZ_CUDA(cudaStreamSynchronize(st));
+    GCZ_LAUNCH(ctx, pack_bits_kernel, ctx->sm_count * 4, 256, 0, st, d_bits, len, d_raw);
+    GCZ_LAUNCH(ctx, superblock_popcount_kernel, (unsigned)((d.sb_count * 32 + 255) / 256), 256, 0, st, d_raw, d_vec, 1, d.sb_count, d_sb);
+    GCZ_LAUNCH(ctx, superblock_scan_kernel, 1, 1024, 0, st, d_sb, d_vec);
+    GCZ_LAUNCH(ctx, ranked_layout_kernel, (unsigned)d.sb_count, 128, 0, st, d_raw, d_vec, 1, d_sb);
+    GCZ_CUDA(cudaStreamSynchronize(st));
+    arena.release(mark0);
+    return GCZ_OK;
+}
+
+int index_wavelet_tree_from_values(DeviceCtx* ctx, cudaStream_t st, const uint32_t* d_vals, int64_t m, uint8_t* d_out, Arena& arena) {
+    const size_t mark0 = arena.mark();
+    const int levels = 64 - __builtin_clzll((uint64_t)m);
+    const int64_t level_bytes = ranked_bytes(m);
+    std::vector<VectorDesc> vecs;
+    uint64_t raw_words = 0; int64_t total_sb = 0;
+    for (int l = 0; l < levels; l++) {
+        VectorDesc d;
+        d.raw_word = raw_words; d.len = m; d.out = d_out + (int64_t)l * level_bytes; d.sb_first = total_sb; d.sb_count = superblocks(m);
+        raw_words += (uint64_t)d.sb_count * 2048u; total_sb += d.sb_count;
+        vecs.push_back(d);
+    }
+    uint32_t* d_raw = arena.get<uint32_t>((size_t)raw_words + 16);
+    VectorDesc* d_vecs = arena.get<VectorDesc>(vecs.size());
+    uint32_t* d_sb = arena.get<uint32_t>((size_t)total_sb + 1);
+    uint32_t* d_ssa[2] = { arena.get<uint32_t>((size_t)m), arena.get<uint32_t>((size_t)m) };
+    uint32_t* d_zeros = arena.get<uint32_t>((size_t)((m + 31) >> 5) + 1);
+    if (!d_raw || !d_vecs || !d_sb || !d_ssa[0] || !d_ssa[1] || !d_zeros) return fail(GCZ_E_NOMEM, "IWT workspace");
+    GCZ_CUDA(cudaMemsetAsync(d_raw, 0, ((size_t)raw_words + 16) * 4, st));
+    GCZ_CUDA(cudaMemcpyAsync(d_vecs, vecs.data(), sizeof(VectorDesc) * vecs.size(), cudaMemcpyHostToDevice, st));
+    GCZ_CUDA(cudaMemcpyAsync(d_ssa[0], d_vals, (size_t)m * 4, cudaMemcpyDeviceToDevice, st));
+    GCZ_CUDA(cudaStreamSynchronize(st));
+    const int64_t mwords = (m + 31) >> 5;
+    const int lvl_grid = (int)std::min<int64_t>((m + 255) / 256, (int64_t)ctx->sm_count * 8);
+    int cur = 0;
+    for (int l = 0; l < levels; l++) {
+        const int h = levels - 1 - l;
+        uint32_t* lraw = d_raw + vecs[l].raw_word;
+        GCZ_LAUNCH(ctx, iwt_bits_kernel, lvl_grid, 256, 0, st, d_ssa[cur], m, h, lraw, d_zeros);
+        if (h > 0) {
+            GCZ_LAUNCH(ctx, row_scan_kernel, 1, 1024, 0, st, d_zeros, mwords, (uint32_t*)nullptr);
+            GCZ_LAUNCH(ctx, iwt_scatter_kernel, lvl_grid, 256, 0, st, d_ssa[cur], d_ssa[cur ^ 1], m, h, lraw, d_zeros);
+            cur ^= 1;
+        }
+    }
+    GCZ_LAUNCH(ctx, superblock_popcount_kernel, (unsigned)((total_sb * 32 + 255) / 256), 256, 0, st, d_raw, d_vecs, (int)vecs.size(), total_sb, d_sb);
+    GCZ_LAUNCH(ctx, superblock_scan_kernel, (unsigned)vecs.size(), 1024, 0, st, d_sb, d_vecs);
+    GCZ_LAUNCH(ctx, ranked_layout_kernel, (unsigned)total_sb, 128, 0, st, d_raw, d_vecs, (int)vecs.size(), d_sb);
+    GCZ_CUDA(cudaStreamSynchronize(st));
+    arena.release(mark0);
+    return GCZ_OK;
+}
+
+}  // namespace gcz

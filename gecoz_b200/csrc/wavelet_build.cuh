@@ -1,0 +1,25 @@
+// BWT / HSWT / sampled-SA index builders (see wavelet_build.cu).
+#pragma once
+
+#include "device.cuh"
+
+namespace gcz {
+
+struct WaveletStats {
+    float bwt_hswt_ms = 0, ssa_ms = 0;
+};
+
+size_t wavelet_workspace_bytes(int64_t n, int sampling_factor);
+
+// Inputs on the device: text (n bytes), suffix array (n x u32).  Outputs on the device: d_bwt (n bytes),
+// d_gcz_body (shape->size bytes: shape table + ranked HSWT nodes), d_gcx_body (index_size bytes: ranked marker
+// vector + IndexWaveletTree levels).  `shape` must come from shape_from_counts on this text's histogram.
+int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, const uint32_t* d_sa, int64_t n,
+                             const gcz_shape* shape, int sampling_factor, uint8_t* d_bwt,
+                             uint8_t* d_gcz_body, uint8_t* d_gcx_body, Arena& arena, WaveletStats* stats);
+
+// stage hooks (parity tests)
+int ranked_vector_from_bits(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_bits, int64_t len, uint8_t* d_out, Arena& arena);
+int index_wavelet_tree_from_values(DeviceCtx* ctx, cudaStream_t st, const uint32_t* d_vals, int64_t m, uint8_t* d_out, Arena& arena);
+
+}  // namespace gcz

@@ -1,0 +1,146 @@
+/*
+ * gcz.h — C ABI of the B200-native FM-index engine that replaces gecoz's nova-algo hot path.
+ *
+ * The reference (redmitry/gecoz) is pure Java and has no FFI today; the seam is nova-algo's public
+ * Java API as used by nova-formats / nova-gecoz.  Every entry point below names the reference
+ * interface it replaces (paths relative to /root/reference/java, see INTEGRATION.md for the JNI /
+ * Panama-FFM stubs a maintainer would add on the Java side):
+ *   algo/  = nova-algo/src/main/java/es/elixir/bsc/ngs/nova/algo/
+ *   fmt/   = nova-formats/src/main/java/es/elixir/bsc/ngs/nova/gecoz/
+ *
+ * Conventions: plain pointers and sizes only; no exceptions cross the boundary; every function
+ * returns 0 on success or a negative gcz_status; gcz_last_error() gives a thread-local message.
+ * Buffers are caller-owned unless stated.  `text`, `gcz_body`, `gcx_body`, pattern and result
+ * buffers may be host pointers (pageable, pinned, or mmap'd file slices) or device pointers of
+ * the selected device; the library detects which.  There is NO CPU fallback: without a CUDA
+ * device every compute entry point fails with GCZ_E_NODEVICE.
+ */
+#ifndef GCZ_H
+#define GCZ_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum gcz_status {
+    GCZ_OK          =  0,
+    GCZ_E_ARG       = -1,   /* bad argument (null, size mismatch, n out of range)                      */
+    GCZ_E_NOMEM     = -2,   /* device/host memory exhausted: the caller may re-queue the block, like
+                               WriterPoolExecutor.afterExecute  fmt/GecozFileWriter.java:203-226          */
+    GCZ_E_CUDA      = -3,   /* CUDA runtime error (message in gcz_last_error)                            */
+    GCZ_E_FORMAT    = -4,   /* malformed .gcz/.gcx bytes: DataFormatException("invalid index file")
+                               fmt/GecozFileReader.java:165-172                                          */
+    GCZ_E_NODEVICE  = -5,   /* no CUDA device / library built without one: there is no CPU path          */
+    GCZ_E_RANGE     = -6,   /* code length > 15, block > 2^31-1 symbols, pattern byte >= 0x80 ...        */
+    GCZ_E_INTERNAL  = -7
+} gcz_status;
+
+/* ---- library --------------------------------------------------------------------------------- */
+int         gcz_init(int n_devices, const int* device_ids);   /* NULL ids = devices 0..n-1; 0 = all visible */
+void        gcz_shutdown(void);                                /* releases cached device workspaces        */
+const char* gcz_last_error(void);                              /* thread-local                             */
+const char* gcz_version(void);
+int         gcz_device_count(void);
+/* Run every launch of the calling thread on `cuda_stream` (a cudaStream_t; NULL = the library's own
+ * per-device stream).  Lets a harness time the kernels with events on its own stream. */
+int         gcz_set_stream(int device, void* cuda_stream);
+
+/* ---- shape: HSWTShape(long[] counts)   algo/tree/HSWTShape.java:55-87 ------------------------- */
+typedef struct gcz_shape {
+    int8_t   bit_lengths[256];  /* DeflateEncodeTable.bit_lengths   algo/deflate/DeflateEncodeTable.java:52-56 */
+    int16_t  codes[256];        /* DeflateEncodeTable.table: bit j = branch taken at depth j (:150-173)        */
+    int32_t  n_nodes;           /* internal nodes of the Huffman tree                                            */
+    int32_t  node_name[256];    /* file (pre-)order -> name = left-most leaf of the 1-subtree
+                                   algo/tree/HuffmanShapedWaveletTree.java:106-108,165-182                       */
+    int32_t  node_depth[256];   /* file order -> depth of the node                                               */
+    int32_t  node_prefix[256];  /* file order -> path bits (LSB = root branch)                                   */
+    int64_t  node_bits[256];    /* file order -> length of the node's bit vector                                 */
+    int64_t  node_offset[256];  /* file order -> byte offset inside the block body (after the shape table)       */
+    int64_t  table_bytes;       /* serialized RFC1951-style length table  algo/deflate/DeflateLengthsTable.java:136-171 */
+    int64_t  length;            /* HSWTShape.length = sum(counts)                                                */
+    int64_t  size;              /* HSWTShape.size   = table_bytes + sum RankedWTNode.bytes(node_bits)            */
+} gcz_shape;
+
+int     gcz_shape_from_counts(const int64_t counts[256], gcz_shape* out);
+/* HSWTShape.write(ByteBuffer)  :111-115; writes table_bytes bytes, returns them (or <0) */
+int64_t gcz_shape_write(const gcz_shape* shape, uint8_t* out, int64_t cap);
+/* HSWTShape.read(ByteBuffer, long)  :89-109; fills bit_lengths/codes/table_bytes/tree, node_bits = 0 */
+int     gcz_shape_read(const uint8_t* body, int64_t body_len, gcz_shape* out);
+
+int64_t gcz_ranked_bytes(int64_t len_bits);                    /* RankedWTNode.bytes  algo/tree/RankedWTNode.java:60-67 */
+int64_t gcz_index_size(int64_t n, int32_t sampling_factor);    /* GSSAIndex.getIndexSize  algo/ssa/GSSAIndex.java:200-205 */
+
+/* ---- build ------------------------------------------------------------------------------------ */
+/* The counting loop of GecozFileWriter.write  fmt/GecozFileWriter.java:127-130 (GPU histogram). */
+int gcz_count_symbols(int device, const uint8_t* text, int64_t n, int64_t counts[256]);
+
+/* One call == BlockWriter.run  fmt/GecozFileWriter.java:256-284:
+ *   SAIS.suffix(in, sa) :262, shape.write(out) :267, HuffmanShapedWaveletTree.write(shape, BWT, out) :268,
+ *   GSSAIndex.write(sa, rate, idx) :274.
+ * gcz_body (shape->size bytes) and gcx_body (gcz_index_size(n, log2 rate) bytes) are the mapped file slices
+ * positioned just after their headers; every byte of both is written.  sa_out (n int32) and bwt_out
+ * (n bytes) are optional parity artefacts.  Thread-safe for different blocks; blocks on the same device
+ * serialize on that device's workspace. */
+int gcz_build_block(int device, const uint8_t* text, int64_t n, int32_t sampling_rate,
+                    const gcz_shape* shape,
+                    uint8_t* gcz_body, int64_t gcz_body_len,
+                    uint8_t* gcx_body, int64_t gcx_body_len,
+                    int32_t* sa_out, uint8_t* bwt_out);
+
+/* Device-time breakdown (milliseconds, CUDA events) of the calling thread's last gcz_build_block. */
+typedef struct gcz_build_timing {
+    float h2d_ms, sort_initial_ms, sort_refine_ms, bwt_hswt_ms, ssa_ms, d2h_ms, total_ms;
+    int32_t refine_rounds;
+    int64_t radix_launches, radix_elements;     /* onesweep passes launched, elements they moved     */
+    float   radix_ms;                            /* device time inside those passes                   */
+    int64_t kernel_launches;                     /* all kernels of this library launched by the call  */
+} gcz_build_timing;
+int gcz_last_build_timing(gcz_build_timing* out);
+
+/* ---- query: handle == GSSA  algo/ssa/GSSA.java ------------------------------------------------- */
+typedef struct gcz_index gcz_index;
+
+/* GecozFileReader.read(header)  fmt/GecozFileReader.java:115-177: gcz_body starts at the shape table
+ * (just after the block header), gcx_body just after the 25-byte GecozSSA header.  The sampling factor is
+ * recovered from gcx_len like GSSAIndex(ByteBuffer,long)  algo/ssa/GSSAIndex.java:57-71.  The .gcx is
+ * mandatory (the reference cannot locate without it): NULL fails fast with GCZ_E_ARG. */
+int  gcz_open_block(int device, const uint8_t* gcz_body, int64_t body_len, int64_t text_len,
+                    const uint8_t* gcx_body, int64_t gcx_len, gcz_index** out);
+void gcz_close_block(gcz_index* idx);
+
+int  gcz_text_length(const gcz_index* idx, int64_t* out);          /* GSSA.getLength()        :67-69   */
+int  gcz_sampling_factor(const gcz_index* idx, int32_t* out);
+int  gcz_num_strings(const gcz_index* idx, int32_t* out);          /* e.length, GSSA.index    :232-238 */
+int  gcz_string_ends(const gcz_index* idx, int64_t* e);            /* sorted '\0' positions            */
+int  gcz_c_array(const gcz_index* idx, int64_t c[256]);            /* GSSA.index              :215-226 */
+
+/* Backward search, the interval part of GSSA.search  :187-197 with HSWT.occ  algo/tree/
+ * HuffmanShapedWaveletTree.java:247-267.  Pattern i is pats[pat_off[i] .. pat_off[i+1]).  sp/ep are the
+ * values the Java loop holds when it exits (ep < sp  <=>  not found). */
+int  gcz_count_batch(gcz_index* idx, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats,
+                     int64_t* sp, int64_t* ep);
+
+/* GSSA.locate  :241-251 for explicit SA rows (LF-walk to a marked row + IndexWaveletTree.get). */
+int  gcz_locate_rows(gcz_index* idx, const int64_t* rows, int64_t n_rows, int64_t* positions);
+
+/* GSSA.find  :160-185 for a batch.  per_string_counts is n_pats x n_strings (row-major) = GSSA.count :136-148.
+ * *positions receives, pattern after pattern and string after string, the ascending 0-based positions
+ * relative to the string start; (*pos_off)[i] .. (*pos_off)[i+1] delimits pattern i.  Both arrays are
+ * callee-allocated host memory, released with gcz_free. */
+int  gcz_find_batch(gcz_index* idx, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats,
+                    int64_t* per_string_counts, int64_t** positions, int64_t** pos_off);
+void gcz_free(void* p);
+
+/* ---- stage-level hooks used by the parity tests (each one is a stage of gcz_build_block) ------- */
+int gcz_dbg_sort_pairs(int device, uint64_t* keys, uint32_t* vals, int64_t n, int32_t begin_bit, int32_t end_bit);
+int gcz_dbg_suffix_array(int device, const uint8_t* text, int64_t n, int32_t* sa);
+int gcz_dbg_ranked_vector(int device, const uint8_t* bits, int64_t len, uint8_t* out);   /* one bit per byte in */
+int gcz_dbg_index_wavelet_tree(int device, const int32_t* vals, int64_t m, uint8_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCZ_H */

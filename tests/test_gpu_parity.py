@@ -1,0 +1,319 @@
+"""GPU parity tests: every stage of the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bit-exact everywhere (integer / byte / index work).  Sizes are what the oracle finishes in seconds; the
+BASELINE.json full sizes are covered by size-independent properties in test_gpu_fullsize.py.
+"""
+import ctypes as C
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = Path(__file__).parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gecoz_b200 as g
+    g.lib()                      # fails loudly when libgcz_b200.so is missing
+    return g
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import gcz_oracle as o
+    o.lib()
+    return o
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ---- radix sort -------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,bits", [(1, 64), (7, 64), (6143, 64), (6144, 64), (6145, 64), (100_000, 64),
+                                    (1_000_003, 64), (300_000, 41), (250_000, 8), (3_000_000, 63)])
+def test_sort_pairs(G, n, bits):
+    rng = np.random.default_rng(n + bits)
+    keys = rng.integers(0, 2 ** 63, n, dtype=np.uint64)
+    if bits < 64:
+        keys &= np.uint64((1 << bits) - 1)
+    if n > 1000:
+        keys[: n // 3] = keys[n // 3: 2 * (n // 3)]       # plenty of duplicates: stability matters
+    vals = np.arange(n, dtype=np.uint32)
+    k2, v2 = keys.copy(), vals.copy()
+    G._native.check(G.lib().gcz_dbg_sort_pairs(0, _p(k2), _p(v2), n, 0, bits))
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(k2, keys[order])
+    assert np.array_equal(v2, vals[order])
+
+
+def test_sort_skewed_digits(G):
+    n = 500_000
+    keys = np.zeros(n, dtype=np.uint64)
+    keys[::7] = 1 << 40
+    keys[::1001] = (1 << 62) + 5
+    vals = np.arange(n, dtype=np.uint32)
+    k2, v2 = keys.copy(), vals.copy()
+    G._native.check(G.lib().gcz_dbg_sort_pairs(0, _p(k2), _p(v2), n, 0, 64))
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(k2, keys[order]) and np.array_equal(v2, vals[order])
+
+
+# ---- ranked bit vector layout ---------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 7, 64, 511, 512, 513, 65535, 65536, 65537, 70001, 131072, 1_000_001])
+def test_ranked_vector(G, O, n):
+    rng = np.random.default_rng(n)
+    bits = (rng.random(n) < 0.4).astype(np.uint8)
+    out = np.zeros(O.ranked_bytes(n) + 16, np.uint8)
+    out[-16:] = 0xEE
+    G._native.check(G.lib().gcz_dbg_ranked_vector(0, _p(bits), n, _p(out)))
+    exp = O.ranked_write(bits)
+    assert len(exp) == G.lib().gcz_ranked_bytes(n)
+    assert np.array_equal(out[:len(exp)], exp)
+    assert (out[-16:] == 0xEE).all()
+
+
+# ---- IndexWaveletTree ---------------------------------------------------------------------------------
+def test_iwt_pdf_table3(G):
+    k = json.loads((GOLD / "reference_kats.json").read_text())["iwt_table3"]
+    vals = np.array(k["values"], dtype=np.int32)
+    out = np.zeros(15, np.uint8)
+    G._native.check(G.lib().gcz_dbg_index_wavelet_tree(0, _p(vals), len(vals), _p(out)))
+    assert out.tobytes().hex() == k["serialized_hex"]
+
+
+@pytest.mark.parametrize("m", [1, 2, 3, 31, 32, 33, 1000, 65536, 65537, 500_001])
+def test_iwt_random(G, O, m):
+    vals = np.random.default_rng(m).permutation(m).astype(np.int32)
+    exp = O.iwt_write(vals)
+    out = np.zeros(len(exp), np.uint8)
+    G._native.check(G.lib().gcz_dbg_index_wavelet_tree(0, _p(vals), m, _p(out)))
+    assert np.array_equal(out, exp)
+
+
+# ---- suffix array ----------------------------------------------------------------------------------------
+def _texts():
+    from gecoz_b200 import synth
+    rng = np.random.default_rng(11)
+    yield "tiny", np.frombuffer(b"GATTACA\0", np.uint8).copy()
+    yield "one", np.frombuffer(b"\0", np.uint8).copy()
+    yield "two_strings", np.frombuffer(b"ACGTN\0ACG\0", np.uint8).copy()
+    yield "iid_100k", synth.cfg1_text(100_000)
+    yield "chr_shaped_2M", synth.cfg2_text(2_000_000)                    # long N runs: deep prefix doubling
+    yield "all_same", synth.block_of([np.full(50_000, ord("A"), np.uint8)])
+    yield "tandem", synth.block_of([np.frombuffer(b"ACACACACGT" * 30_000, np.uint8)])
+    yield "multi", synth.block_of([synth.iid_acgtn(30_000, 5), synth.iid_acgtn(20_000, 6), synth.iid_acgtn(7, 7),
+                                   np.zeros(0, np.uint8), synth.iid_acgtn(20_000, 6)])   # empty + duplicate sequences
+    yield "bytes", np.concatenate([rng.integers(1, 255, 80_000, dtype=np.uint8), np.zeros(1, np.uint8)])
+    yield "lower_iupac", synth.block_of([np.frombuffer(b"ACGTNacgtnRYKM", np.uint8)[rng.integers(0, 14, 150_000)]])
+
+
+@pytest.mark.parametrize("name,text", list(_texts()), ids=[t[0] for t in _texts()])
+def test_suffix_array(G, O, name, text):
+    sa = np.zeros(len(text), np.int32)
+    G._native.check(G.lib().gcz_dbg_suffix_array(0, _p(text), len(text), _p(sa)))
+    assert np.array_equal(sa, O.suffix_array(text))
+
+
+# ---- whole block: SA, BWT, .gcz body, .gcx body ------------------------------------------------------------
+def _build(G, text, rate=32, want=True):
+    counts = G.symbol_counts(text)
+    assert np.array_equal(counts, np.bincount(text, minlength=256))
+    shape = G.shape_from_counts(counts)
+    gcz = np.zeros(shape.size + 32, np.uint8)
+    gcx = np.zeros(G.index_size(len(text), rate.bit_length() - 1) + 32, np.uint8)
+    gcz[-32:] = 0xEE
+    gcx[-32:] = 0xEE
+    sa = np.zeros(len(text), np.int32) if want else None
+    bwt = np.zeros(len(text), np.uint8) if want else None
+    t = G.build_block(0, text, len(text), rate, shape, gcz, gcx, sa, bwt)
+    assert (gcz[-32:] == 0xEE).all() and (gcx[-32:] == 0xEE).all()        # nothing written past the slices
+    return shape, gcz[:-32], gcx[:-32], sa, bwt, t
+
+
+@pytest.mark.parametrize("name,text", list(_texts()), ids=[t[0] for t in _texts()])
+@pytest.mark.parametrize("rate", [32, 4])
+def test_build_block(G, O, name, text, rate):
+    if name == "bytes":
+        pytest.skip("alphabets whose length table needs a >7-bit code-length code are refused like the reference")
+    shape, gcz, gcx, sa, bwt, t = _build(G, text, rate)
+    ref = O.build_block(text, rate, want_sa=True, want_bwt=True)
+    assert np.array_equal(sa, ref["sa"])
+    assert np.array_equal(bwt, ref["bwt"])
+    assert len(gcz) == len(ref["gcz_body"]) and np.array_equal(gcz, ref["gcz_body"])
+    assert len(gcx) == len(ref["gcx_body"]) and np.array_equal(gcx, ref["gcx_body"])
+    assert t["kernel_launches"] > 0
+
+
+def test_provisional_golden_blocks(G):
+    prov = json.loads((GOLD / "provisional_blocks.json").read_text())
+    for name, p in prov.items():
+        if name.startswith("_"):
+            continue
+        text = np.frombuffer(b"".join(s.encode() + b"\0" for s in p["sequences"]), np.uint8).copy()
+        shape, gcz, gcx, sa, bwt, _ = _build(G, text, p["sampling_rate"])
+        hdr = G.GecozRefBlockHeader(p["headers"], G.GecozRefBlockHeader.block_header_length(p["headers"]) + shape.size, len(text))
+        assert (hdr.to_bytes() + gcz.tobytes()).hex() == p["gcz_hex"]
+        assert (G.GecozSSABlockHeader(p["headers"], len(gcx)).to_bytes() + gcx.tobytes()).hex() == p["gcx_hex"]
+        assert sa.tolist() == p["sa"] and bwt.tobytes().hex() == p["bwt_hex"]
+
+
+# ---- queries ---------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def block_1m(G, O):
+    from gecoz_b200 import synth
+    text = synth.cfg2_text(1_000_000, seed=21)
+    ref = O.build_block(text, 32, want_sa=True)
+    return text, ref
+
+
+def test_open_and_tables(G, O, block_1m):
+    text, ref = block_1m
+    og = O.GSSA(ref["gcz_body"], len(text), ref["gcx_body"])
+    g = G.GSSA.open(0, ref["gcz_body"], len(text), ref["gcx_body"])
+    assert g.length == len(text) and g.sampling_factor == og.sampling_factor == 5
+    assert np.array_equal(g.c, og.c_array())
+    assert g.e.tolist() == og.string_ends().tolist() == [len(text) - 1]
+    g.close()
+
+
+def test_count_batch(G, O, block_1m):
+    from gecoz_b200 import synth
+    text, ref = block_1m
+    og = O.GSSA(ref["gcz_body"], len(text), ref["gcx_body"])
+    g = G.GSSA.open(0, ref["gcz_body"], len(text), ref["gcx_body"])
+    data, off = synth.patterns(text, 20_000, 1, 60, seed=2)
+    # edge cases appended: poly-N (huge interval), absent symbol, separator, byte >= 0x80
+    extra = [b"N" * 30, b"NNNNA", b"Z", b"AC\0", b"\0", bytes([200, 65]), b"A"]
+    data = np.concatenate([data, np.frombuffer(b"".join(extra), np.uint8)])
+    off = np.concatenate([off, off[-1] + np.cumsum([len(x) for x in extra])]).astype(np.int64)
+    sp, ep = g.count_batch(packed=(data, off))
+    esp, eep, calls = og.search_batch(data, off)
+    assert np.array_equal(sp, esp) and np.array_equal(ep, eep)
+    assert calls > 0 and int((ep >= sp).sum()) > 9_000
+    g.close()
+
+
+def test_locate_rows(G, O, block_1m):
+    text, ref = block_1m
+    g = G.GSSA.open(0, ref["gcz_body"], len(text), ref["gcx_body"])
+    rows = np.random.default_rng(3).integers(0, len(text), 50_000)
+    assert np.array_equal(g.locate_rows(rows), ref["sa"][rows].astype(np.int64))
+    g.close()
+
+
+def _as_lists(res):
+    return None if res is None else [None if x is None else np.asarray(x).tolist() for x in res]
+
+
+def test_find_batch_single_string(G, O, block_1m):
+    from gecoz_b200 import synth
+    text, ref = block_1m
+    og = O.GSSA(ref["gcz_body"], len(text), ref["gcx_body"])
+    g = G.GSSA.open(0, ref["gcz_body"], len(text), ref["gcx_body"])
+    data, off = synth.patterns(text, 300, 4, 14, seed=8)
+    pats = [data[off[i]:off[i + 1]].tobytes() for i in range(300)] + [b"NNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNN", b"ZZ"]
+    got = g.find_batch(pats)
+    for p, r in zip(pats, got):
+        assert _as_lists(r) == _as_lists(og.find(p)), p
+    assert g.count(pats[0]) == [len(got[0][0])] if got[0] is not None else g.count(pats[0]) is None
+    g.close()
+
+
+def test_find_batch_merged_block_with_reference_quirk(G, O):
+    """Merged block whose later strings sort BEFORE the first one: LF across a separator
+    lands one row low in the reference; the GPU path must reproduce exactly what the oracle's literal
+    LF-walk reports, whatever that is."""
+    from gecoz_b200 import synth
+    seqs = [synth.iid_acgtn(5000, 31), synth.iid_acgtn(3000, 32), synth.iid_acgtn(2987, 33), synth.iid_acgtn(19, 34)]
+    seqs[0][:4] = np.frombuffer(b"TTTT", np.uint8)            # s1 is the largest: every other start sorts before it
+    text = synth.block_of(seqs)
+    ref = O.build_block(text, 32)
+    og = O.GSSA(ref["gcz_body"], len(text), ref["gcx_body"])
+    g = G.GSSA.open(0, ref["gcz_body"], len(text), ref["gcx_body"])
+    assert g.n_strings == og.n_strings == 4
+    assert g.e.tolist() == og.string_ends().tolist()
+    rng = np.random.default_rng(4)
+    pats = []
+    for s in seqs:
+        for _ in range(60):
+            ln = int(rng.integers(2, 9))
+            a = int(rng.integers(0, max(1, len(s) - ln)))
+            pats.append(s[a:a + ln].tobytes())
+        pats.append(s[:5].tobytes())                          # occurrences at the very start of a string
+        pats.append(s[:2].tobytes())
+    got = g.find_batch(pats)
+    for p, r in zip(pats, got):
+        assert _as_lists(r) == _as_lists(og.find(p)), p
+    g.close()
+
+
+# ---- files ---------------------------------------------------------------------------------------------------------
+def test_files_match_oracle_and_roundtrip(G, O, tmp_path):
+    from gecoz_b200 import synth
+    recs = [(f"seq{i} some description", synth.iid_acgtn(int(ln), 40 + i)) for i, ln in
+            enumerate([90_000, 61_000, 30_500, 30_000, 9_000, 500, 20, 20])]
+    fa = tmp_path / "x.fa"
+    with open(fa, "wb") as f:
+        for h, s in recs:
+            f.write(b">" + h.encode() + b"\n")
+            for i in range(0, len(s), 60):
+                f.write(s[i:i + 60].tobytes() + b"\r\n")
+    info = G.index(fa, tmp_path / "x.gcz")
+    gcz, gcx, blocks = O.write_files([(h, s.tobytes()) for h, s in recs])
+    assert (tmp_path / "x.gcz").read_bytes() == gcz
+    assert (tmp_path / "x.gcx").read_bytes() == gcx
+    assert info["blocks"] == [[recs[i][0] for i in b] for b in blocks]
+    assert len(blocks) < len(recs)                           # some sequences were merged
+    with G.GecozFileReader(tmp_path / "x.gcz") as reader:
+        assert G.GecozFileReader.checkFormat(tmp_path / "x.gcz")
+        hdr = reader.findBlockHeader("seq3 some description")
+        assert hdr is not None and reader.findBlockHeader("seq3") is None     # full header line, exact match
+        ssa = reader.read(hdr)
+        nstr = hdr.findHeader("seq3 some description")
+        pat = recs[3][1][1000:1012].tobytes()
+        res = ssa.find(pat)
+        assert res is not None and 1000 in res[nstr].tolist()
+        assert ssa.getLength(nstr) == 30_000
+        ssa.close()
+
+
+def test_missing_gcx_fails_fast(G, O, tmp_path):
+    from gecoz_b200 import synth
+    G.index_records([("a", synth.iid_acgtn(5000, 1))], tmp_path / "a.gcz")
+    (tmp_path / "a.gcx").unlink()
+    with G.GecozFileReader(tmp_path / "a.gcz") as reader:
+        with pytest.raises(G.GczError):
+            reader.read(reader.getBlockHeaders()[0])
+
+
+def test_corrupt_index_is_rejected(G, O, tmp_path):
+    from gecoz_b200 import synth
+    G.index_records([("a", synth.iid_acgtn(5000, 1))], tmp_path / "a.gcz")
+    raw = bytearray((tmp_path / "a.gcx").read_bytes())
+    raw[20] ^= 0xFF                                           # header hash
+    (tmp_path / "a.gcx").write_bytes(raw)
+    with G.GecozFileReader(tmp_path / "a.gcz") as reader:
+        with pytest.raises(G.GczFormatError):
+            reader.read(reader.getBlockHeaders()[0])
+
+
+def test_argument_errors(G):
+    text = np.frombuffer(b"ACGT\0", np.uint8).copy()
+    shape = G.shape_from_counts(np.bincount(text, minlength=256))
+    gcz = np.zeros(shape.size, np.uint8)
+    gcx = np.zeros(G.index_size(len(text), 5), np.uint8)
+    with pytest.raises(G.GczError):                          # wrong body size
+        G._native.check(G.lib().gcz_build_block(0, _p(text), len(text), 32, C.byref(shape), _p(gcz), shape.size - 1,
+                                                _p(gcx), len(gcx), None, None))
+    with pytest.raises(G.GczError):                          # sampling rate not a power of two
+        G._native.check(G.lib().gcz_build_block(0, _p(text), len(text), 24, C.byref(shape), _p(gcz), shape.size,
+                                                _p(gcx), len(gcx), None, None))
+    other = np.frombuffer(b"AAAA\0", np.uint8).copy()
+    with pytest.raises(G.GczError):                          # shape of another text
+        G._native.check(G.lib().gcz_build_block(0, _p(other), len(other), 32, C.byref(shape), _p(gcz), shape.size,
+                                                _p(gcx), len(gcx), None, None))
