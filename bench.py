@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py — FM-index build Mbp/s (headline) and count queries/s on synthetic ACGTN data.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1]
+
+A "step" is one pass of the hot path over one block: gcz_build_block == BlockWriter.run of the reference
+(suffix array, BWT, Huffman-shaped wavelet tree, sampled-SA index).  At N=1 the workload is BASELINE.json
+configs[1]: a synthetic chr1-shaped block of 248 956 422 bp (+ terminator).  With N>1 (torchrun, one process
+per GPU) every rank builds its own chr1-shaped block (seed 3 + rank): blocks are independent, there is no
+data-path collective, scaling is weak.
+
+  value  : whole-job Mbp/s with the text and both outputs resident in HBM (device pointers through the C ABI)
+  e2e    : same metric through the same C-ABI call with pinned HOST buffers: H2D of the text and D2H of the
+           .gcz/.gcx bodies are inside the timed region
+  count  : backward-search count queries/s against the index just built (secondary metric of BASELINE.json)
+  roofline / cpu_baseline : see DESIGN.md
+`--impl reference` times the CPU restatement of the Java path (oracle/, no JVM exists on the box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+CFG = {
+    "cfg2": dict(length=248_956_422, name="cfg2: synthetic chr1-shaped 248956422 bp single block, SA+BWT+HSWT+SSA"),
+    "cfg1": dict(length=16_000_000, name="cfg1: synthetic 16 Mbp single sequence"),
+}
+
+
+def make_text(workload: str, rank: int, length: int | None = None) -> np.ndarray:
+    from gecoz_b200 import synth
+    ln = length or CFG[workload]["length"]
+    if workload == "cfg1":
+        return synth.block_of([synth.iid_acgtn(ln, seed=1 + rank)])
+    return synth.cfg2_text(ln, seed=3 + rank)
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.rows = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_reference(args, rank: int) -> None:
+    """CPU arm: the oracle's restatement of BlockWriter.run (SA-IS, then HSWT on a side thread while the
+    sampled-SA index is written, as fmt/GecozFileWriter.java:264-277) on a bounded sample."""
+    if rank != 0:
+        return
+    from oracle import gcz_oracle as O
+    O.build()
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    budget_s = 150.0 / (steps + warm)
+    sample = int(min(64_000_000, max(2_000_000, budget_s * 4.0e6)))
+    text = make_text(args.workload, 0, sample)
+    bases = len(text) - 1
+    times = []
+    for i in range(warm + steps):
+        t0 = time.perf_counter()
+        O.build_block(text, 32, threads=2)
+        if i >= warm:
+            times.append(time.perf_counter() - t0)
+    sec = float(np.mean(times))
+    value = bases / 1e6 / sec
+    line = {
+        "impl": "reference", "metric": "FM-index build throughput (SA+BWT+HSWT+SSA per block)", "value": value, "unit": "Mbp/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
+        "config": {"workload": CFG[args.workload]["name"], "sample": f"{sample} bp block of the same generator (scaled N runs)"},
+        "cpu_baseline": {"value": value, "unit": "Mbp/s", "cores": 2, "kind": "port",
+                         "sample": f"{sample} bp chr1-shaped block; C restatement of the Java path (no JVM on this box), "
+                                   f"SA-IS single-threaded then HSWT || SSA on 2 threads like BlockWriter.run; host has {os.cpu_count()} cores, "
+                                   f"one block can use 2"},
+        "e2e": {"value": value, "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=list(CFG))
+    ap.add_argument("--length", type=int, default=None, help="override the block length (debugging)")
+    ap.add_argument("--patterns", type=int, default=4_000_000, help="count-leg patterns (length 15..100)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import gecoz_b200 as G
+    from gecoz_b200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: gecoz_b200 has no CPU fallback")
+    G.lib()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    steps, warm = max(1, args.steps), max(3, args.warmup)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- workload -------------------------------------------------------------------------------------------
+    text = make_text(args.workload, rank, args.length)
+    n = len(text)
+    bases = n - 1
+    # a dedicated (non-default) stream: the library launches on it, and the timing events are recorded on it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    G._native.check(G.lib().gcz_set_stream(local_rank, stream.cuda_stream))
+    h_text = torch.from_numpy(text).pin_memory()
+    d_text = h_text.to(dev, non_blocking=True)
+    shape = G.shape_from_counts(G.symbol_counts(d_text, local_rank))
+    gcx_len = G.index_size(n, 5)
+    d_gcz = torch.empty(int(shape.size), dtype=torch.uint8, device=dev)
+    d_gcx = torch.empty(gcx_len, dtype=torch.uint8, device=dev)
+    h_gcz = torch.empty(int(shape.size), dtype=torch.uint8).pin_memory()
+    h_gcx = torch.empty(gcx_len, dtype=torch.uint8).pin_memory()
+
+    def timed(fn, k: int) -> tuple[float, list[dict]]:
+        """k steps bracketed by barrier + synchronize, device time from CUDA events on the launching stream."""
+        infos = []
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(k):
+            infos.append(fn())
+        e1.record(stream)
+        barrier()
+        return e0.elapsed_time(e1), infos
+
+    dev_step = lambda: G.build_block(local_rank, d_text, n, 32, shape, d_gcz, d_gcx)
+    e2e_step = lambda: G.build_block(local_rank, h_text, n, 32, shape, h_gcz, h_gcx)
+
+    timed(dev_step, warm)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms_total, infos = timed(dev_step, steps)
+    clk = clocks.stop() if rank == 0 else None
+    ms_step = max_over_ranks(ms_total / steps)
+    total_bases = sum_over_ranks(float(bases))
+    value = total_bases / 1e6 / (ms_step / 1e3)
+
+    timed(e2e_step, 1)
+    ms_e2e_total, _ = timed(e2e_step, steps)
+    ms_e2e = max_over_ranks(ms_e2e_total / steps)
+    assert torch.equal(h_gcz, d_gcz.cpu()) and torch.equal(h_gcx, d_gcx.cpu()), "device and host arms disagree"
+    e2e_value = total_bases / 1e6 / (ms_e2e / 1e3)
+
+    # ---- roofline of the dominant kernel (onesweep digit pass) ------------------------------------------------------
+    peak, peak_src = measured_peaks()
+    radix_ms = float(np.mean([i["radix_ms"] for i in infos]))
+    radix_launches = float(np.mean([i["radix_launches"] for i in infos]))
+    radix_elems = float(np.mean([i["radix_elements"] for i in infos]))
+    alg_bytes_per_launch = 24.0 * radix_elems / max(radix_launches, 1)          # read 12 B + write 12 B per pair
+    achieved = 24.0 * radix_elems / (radix_ms / 1e3) / 1e9 if radix_ms > 0 else 0.0
+    step_alg_bytes = 11.0 * n + int(shape.size) + gcx_len                          # SURVEY.md §8(d) B_build(n)
+    roofline = {
+        "bound": "hbm", "kernel": "onesweep_kernel<384,16,pairs> (LSD radix digit pass of the suffix sorter)",
+        "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": None,
+        "algorithmic_bytes_per_launch": alg_bytes_per_launch, "launches_per_step": radix_launches,
+        "avg_launch_ms": radix_ms / max(radix_launches, 1), "kernel_share_of_step": radix_ms / (ms_total / steps),
+        "whole_step": {"algorithmic_bytes": step_alg_bytes, "achieved": step_alg_bytes / (ms_total / steps / 1e3) / 1e9,
+                       "frac": step_alg_bytes / (ms_total / steps / 1e3) / 1e9 / peak},
+    }
+    tr = ROOT / "profiles" / "traffic_r01.json"
+    if tr.exists():
+        try:
+            roofline["traffic"] = json.loads(tr.read_text()).get("onesweep_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- count leg: queries against the index that was just built ------------------------------------------------------
+    count = None
+    try:
+        g = G.GSSA.open(local_rank, d_gcz, n, d_gcx)
+        npat = max(1000, args.patterns)
+        pdata, poff = synth.patterns(text, npat, 15, 100, seed=5 + rank)
+        hp, ho = torch.from_numpy(pdata).pin_memory(), torch.from_numpy(poff).pin_memory()
+        dp, do = hp.to(dev), ho.to(dev)
+        dsp, dep = torch.empty(npat, dtype=torch.int64, device=dev), torch.empty(npat, dtype=torch.int64, device=dev)
+        hsp, hep = torch.empty(npat, dtype=torch.int64).pin_memory(), torch.empty(npat, dtype=torch.int64).pin_memory()
+        cdev = lambda: g.count_batch(packed=(dp, do), out=(dsp, dep)) and None
+        chost = lambda: g.count_batch(packed=(hp, ho), out=(hsp, hep)) and None
+        timed(cdev, 3)
+        cms, _ = timed(cdev, 5)
+        cms = max_over_ranks(cms / 5)
+        timed(chost, 1)
+        cms_e2e, _ = timed(chost, 5)
+        cms_e2e = max_over_ranks(cms_e2e / 5)
+        assert torch.equal(hsp, dsp.cpu()) and torch.equal(hep, dep.cpu())
+        total_pat = sum_over_ranks(float(npat))
+        found = int((dep >= dsp).sum().item())
+        count = {"metric": "count queries/s (backward-search intervals)", "value": total_pat / (cms / 1e3), "unit": "queries/s",
+                 "patterns": int(total_pat), "pattern_length": "uniform 15..100, 50% text-sampled / 50% random", "found": found,
+                 "ms_per_batch": cms,
+                 "e2e": {"value": total_pat / (cms_e2e / 1e3), "unit": "queries/s", "h2d_bytes_per_step": int(pdata.nbytes + poff.nbytes),
+                         "d2h_bytes_per_step": int(npat * 16)}}
+        g.close()
+    except Exception as ex:                                  # the headline metric must still be reported
+        count = {"error": repr(ex)}
+
+    # ---- CPU baseline (rank 0, N=1 only) --------------------------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import gcz_oracle as O
+        sample = min(64_000_000, bases)
+        stext = make_text(args.workload, 0, sample) if sample < bases else text
+        t0 = time.perf_counter()
+        O.build_block(stext, 32, threads=2)
+        sec = time.perf_counter() - t0
+        cpu = {"value": (len(stext) - 1) / 1e6 / sec, "unit": "Mbp/s", "cores": 2, "kind": "port",
+               "sample": f"{len(stext) - 1} bp chr1-shaped block from the same generator, one run ({sec:.1f} s); C restatement of the "
+                         f"Java path (no JVM on the box); one block can use 2 threads (SA-IS, then HSWT || SSA); host has {os.cpu_count()} cores"}
+
+    if rank == 0:
+        line = {
+            "metric": "FM-index build throughput (SA+BWT+HSWT+SSA per block)", "value": value, "unit": "Mbp/s",
+            "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 (64-bit packed keys)", "data": "synthetic",
+            "config": {"workload": CFG[args.workload]["name"] + (f" (length overridden to {args.length})" if args.length else ""),
+                       "symbols_per_block": n, "blocks": world, "sampling_rate": 32,
+                       "l2": "inputs larger than L2 (249 MB text, ~3 GB sort working set per pass vs 126 MB L2)",
+                       "parallelism": f"{world} independent block(s), one per GPU, no collective"},
+            "e2e": {"value": e2e_value, "unit": "Mbp/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(n),
+                    "d2h_bytes_per_step": int(shape.size) + gcx_len},
+            "gpu_launches": int(sum(i["kernel_launches"] for i in infos)),
+            "clocks": clk,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "count": count,
+            "phases_ms": {k: float(np.mean([i[k] for i in infos])) for k in
+                          ("sort_initial_ms", "sort_refine_ms", "bwt_hswt_ms", "ssa_ms", "total_ms")},
+            "refine_rounds": int(infos[-1]["refine_rounds"]),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -238,6 +238,7 @@ static int build_block(int device, const uint8_t* text, int64_t n, int32_t sampl
     t_timing.refine_rounds = ss.rounds;
     t_timing.radix_launches = ss.radix_passes;
     t_timing.radix_elements = ss.radix_elements;
+    t_timing.radix_ms = ss.radix_ms;
     t_timing.kernel_launches = ctx->launches - launches0;
     for (auto& e : ev) cudaEventDestroy(e);
     return GCZ_OK;

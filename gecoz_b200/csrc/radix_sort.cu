@@ -238,6 +238,11 @@ int radix_sort_pairs(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n
         GCZ_CUDA(cudaMemsetAsync(status, 0, (size_t)tiles * kRadix * 8 + 64, st));
         const int in = b.cur, out = b.cur ^ 1;
         const int shift = begin_bit + 8 * p;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (stats) {
+            GCZ_CUDA(cudaEventCreate(&e0)); GCZ_CUDA(cudaEventCreate(&e1));
+            GCZ_CUDA(cudaEventRecord(e0, st));
+        }
         if (has_vals) {
             GCZ_LAUNCH(ctx, (onesweep_kernel<kSortThreads, kSortItems, true>), (unsigned)tiles, kSortThreads,
                        onesweep_smem<true>(), st, b.keys[in], b.keys[out], b.vals[in], b.vals[out], n, shift,
@@ -248,9 +253,22 @@ int radix_sort_pairs(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n
                        hist + p * kRadix, status, ticket);
         }
         b.cur = out;
-        if (stats) { stats->passes++; stats->elements += n; }
+        if (stats) {
+            GCZ_CUDA(cudaEventRecord(e1, st));
+            stats->events.push_back(e0); stats->events.push_back(e1);
+            stats->passes++; stats->elements += n;
+        }
     }
     return GCZ_OK;
+}
+
+void SortStats::resolve() {
+    for (size_t i = 0; i + 1 < events.size(); i += 2) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, events[i], events[i + 1]) == cudaSuccess) ms += t;
+        cudaEventDestroy(events[i]); cudaEventDestroy(events[i + 1]);
+    }
+    events.clear();
 }
 
 }  // namespace gcz

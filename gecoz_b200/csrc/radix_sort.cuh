@@ -3,6 +3,8 @@
 
 #include "device.cuh"
 
+#include <vector>
+
 namespace gcz {
 
 struct RadixBuffers {
@@ -14,6 +16,9 @@ struct RadixBuffers {
 struct SortStats {
     int64_t passes = 0;
     int64_t elements = 0;
+    float   ms = 0;                       // device time inside the digit passes (after resolve())
+    std::vector<cudaEvent_t> events;      // start/stop pairs, one per digit pass
+    void resolve();                       // call after the stream has been synchronised
 };
 
 size_t radix_sort_temp_bytes(int64_t n);

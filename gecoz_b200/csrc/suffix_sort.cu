@@ -277,7 +277,8 @@ int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t 
     const int pack_grid = (int)((n + kPackTile - 1) / kPackTile);
     GCZ_LAUNCH(ctx, pack_keys_kernel, pack_grid, kPackThreads, 0, st, d_text, n, d_code, bits, k, b.keys[b.cur], b.vals[b.cur]);
     SortStats ss;
-    GCZ_TRY(radix_sort_pairs(ctx, st, b, n, 0, key_bits, d_temp, &ss));
+    SortStats* ssp = stats ? &ss : nullptr;
+    GCZ_TRY(radix_sort_pairs(ctx, st, b, n, 0, key_bits, d_temp, ssp));
     if (b.cur != 0) return fail(GCZ_E_INTERNAL, "initial sort landed in the wrong buffer");
 
     // groups of equal keys
@@ -314,7 +315,7 @@ int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t 
         GCZ_LAUNCH(ctx, refine_keys_kernel, grid, 256, 0, st, list_suf[cur], list_gid[cur], m, d_rank, n, h, low_bits,
                    rb.keys[0], rb.vals[0]);
         const int gid_bits = bits_for((uint64_t)std::max<int64_t>(groups - 1, 0));
-        GCZ_TRY(radix_sort_pairs(ctx, st, rb, m, 0, low_bits + gid_bits, d_temp, &ss));
+        GCZ_TRY(radix_sort_pairs(ctx, st, rb, m, 0, low_bits + gid_bits, d_temp, ssp));
         const int64_t tiles_m = (m + kGrpTile - 1) / kGrpTile;
         GCZ_LAUNCH(ctx, group_aggregate_kernel, (unsigned)tiles_m, kGrpThreads, 0, st, rb.keys[rb.cur], m, agg_last, agg_keep, agg_groups);
         GCZ_LAUNCH(ctx, group_scan_kernel, 1, 1024, 0, st, agg_last, agg_keep, agg_groups, tiles_m, d_totals);
@@ -334,8 +335,10 @@ int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t 
         cudaEventElapsedTime(&stats->initial_ms, ev0, ev1);
         cudaEventElapsedTime(&stats->refine_ms, ev1, ev2);
         stats->rounds = rounds;
+        ss.resolve();
         stats->radix_passes = ss.passes;
         stats->radix_elements = ss.elements;
+        stats->radix_ms = ss.ms;
         stats->symbols_per_key = k;
         cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
     }

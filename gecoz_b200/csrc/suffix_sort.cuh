@@ -10,6 +10,7 @@ struct SuffixSortStats {
     int     rounds = 0;
     int     symbols_per_key = 0;
     int64_t radix_passes = 0, radix_elements = 0;
+    float   radix_ms = 0;
 };
 
 size_t suffix_sort_workspace_bytes(int64_t n);
