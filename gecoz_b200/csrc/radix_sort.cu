@@ -13,6 +13,7 @@
 #include "radix_sort.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace gcz {
 
@@ -20,6 +21,7 @@ namespace {
 
 constexpr int kRadix = 256;
 constexpr int kHistThreads = 512;
+constexpr int kLookWindow = 8;
 
 constexpr unsigned long long kFlagAgg = 1ull << 62;
 constexpr unsigned long long kFlagPrefix = 2ull << 62;
@@ -66,8 +68,18 @@ __global__ void radix_scan_kernel(unsigned long long* hist, int npass) {
 }
 
 // ---- one digit pass --------------------------------------------------------------------------------
-template <int THREADS, int ITEMS, bool HAS_VALS>
-__global__ void __launch_bounds__(THREADS, 2)
+// Phases of one CTA (tile of THREADS x ITEMS pairs):
+//   1 load keys (warp-striped)
+//   2 rank keys inside each warp: peers with the same digit (8 ballots, or one match.any) get consecutive
+//     ranks in element order; per-warp digit counters live in shared memory
+//   3 values are requested from global memory only now (they are not live during the ranking)
+//   4 threads 0..255: per-warp counts -> exclusive warp offsets and the tile histogram; publish the tile
+//     aggregate for the look-back; scan -> digit starts inside the tile
+//   5 reorder keys and values in shared memory
+//   6 threads 0..255: decoupled look-back over windows of predecessor tiles
+//   7 write digit runs out, coalesced
+template <int THREADS, int ITEMS, bool HAS_VALS, int MIN_BLOCKS, bool USE_MATCH>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
                 const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
                 int64_t n, int shift, const unsigned long long* __restrict__ digit_base,
@@ -94,24 +106,33 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned lt = lanemask_lt();
 
-    // warp-striped load: item i of lane l in warp w is element w*ITEMS*32 + i*32 + l of the tile
+    // 1. warp-striped load: item i of lane l in warp w is element w*ITEMS*32 + i*32 + l of the tile
     uint64_t key[ITEMS];
-    uint32_t val[ITEMS];
     const int warp_base = warp * ITEMS * 32;
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
         const int e = warp_base + i * 32 + lane;
         key[i] = e < count ? keys_in[tile_base + e] : ~0ull;
-        if (HAS_VALS) val[i] = e < count ? vals_in[tile_base + e] : 0u;
     }
 
-    // rank inside the warp: peers with the same digit get consecutive ranks in element order
+    // 2. rank inside the warp
     unsigned short rank[ITEMS];
     unsigned* my_hist = s_warp_hist + warp * kRadix;
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
         const unsigned d = (unsigned)(key[i] >> shift) & 255u;
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        unsigned peers;
+        if (USE_MATCH) {
+            peers = __match_any_sync(0xffffffffu, d);
+        } else {
+            peers = 0xffffffffu;
+#pragma unroll
+            for (int bit = 0; bit < 8; bit++) {
+                const bool set = (d >> bit) & 1u;
+                const unsigned vote = __ballot_sync(0xffffffffu, set);
+                peers &= set ? vote : ~vote;
+            }
+        }
         const unsigned below = __popc(peers & lt);
         unsigned base = 0;
         if (below == 0) {
@@ -122,9 +143,19 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
         rank[i] = (unsigned short)(base + below);
         __syncwarp();
     }
+
+    // 3. values
+    uint32_t val[ITEMS];
+    if (HAS_VALS) {
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            const int e = warp_base + i * 32 + lane;
+            val[i] = e < count ? vals_in[tile_base + e] : 0u;
+        }
+    }
     __syncthreads();
 
-    // digit d (thread d): turn per-warp counts into exclusive warp offsets, get the tile total
+    // 4. per-warp counts -> exclusive warp offsets, tile histogram, aggregate, digit starts
     unsigned total = 0;
     if (threadIdx.x < kRadix) {
 #pragma unroll
@@ -134,12 +165,8 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
             total += c;
         }
         if (threadIdx.x == kRadix - 1) total -= (unsigned)(TILE - count);     // padding keys are all digit 255
-        // publish the aggregate as early as possible
         st_relaxed_u64(&status[(size_t)tile * kRadix + threadIdx.x],
                        (unsigned long long)total | (tile == 0 ? kFlagPrefix : kFlagAgg));
-    }
-    // exclusive scan of the 256 totals -> start of every digit inside the tile
-    if (threadIdx.x < kRadix) {
         const unsigned incl = warp_incl_sum(total);
         if (lane == 31) s_scan[warp] = incl;
         s_digit_start[threadIdx.x] = incl - total;
@@ -148,27 +175,11 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
     if (threadIdx.x < kRadix) {
         unsigned base = 0;
         for (unsigned w = 0; w < warp; w++) base += s_scan[w];
-        const unsigned start = s_digit_start[threadIdx.x] + base;
-        s_digit_start[threadIdx.x] = start;
-        // decoupled look-back: sum aggregates of predecessor tiles until an inclusive prefix shows up
-        unsigned long long excl = 0;
-        if (tile > 0) {
-            long long t = (long long)tile - 1;
-            while (true) {
-                const unsigned long long v = ld_relaxed_u64(&status[(size_t)t * kRadix + threadIdx.x]);
-                const unsigned long long flag = v & ~kValueMask;
-                if (flag == 0) continue;
-                excl += v & kValueMask;
-                if (flag == kFlagPrefix) break;
-                t--;
-            }
-            st_relaxed_u64(&status[(size_t)tile * kRadix + threadIdx.x], (excl + total) | kFlagPrefix);
-        }
-        s_gofs[threadIdx.x] = (long long)(digit_base[threadIdx.x] + excl) - (long long)start;
+        s_digit_start[threadIdx.x] += base;
     }
     __syncthreads();
 
-    // reorder the tile in shared memory
+    // 5. reorder the tile in shared memory (padding keys are digit 255 and rank last: they land at >= count)
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
         const unsigned d = (unsigned)(key[i] >> shift) & 255u;
@@ -176,9 +187,37 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
         s_keys[pos] = key[i];
         if (HAS_VALS) s_vals[pos] = val[i];
     }
+
+    // 6. decoupled look-back, kLookWindow predecessors per step: their status words are loaded together so the
+    //    walk back to the nearest inclusive prefix costs one memory latency per window, not one per tile
+    if (threadIdx.x < kRadix) {
+        unsigned long long excl = 0;
+        long long t = (long long)tile - 1;
+        bool done = tile == 0;
+        while (!done) {
+            unsigned long long v[kLookWindow];
+#pragma unroll
+            for (int j = 0; j < kLookWindow; j++) {
+                v[j] = t - j >= 0 ? ld_relaxed_u64(&status[(size_t)(t - j) * kRadix + threadIdx.x]) : kFlagPrefix;
+            }
+            int used = 0;
+#pragma unroll
+            for (int j = 0; j < kLookWindow; j++) {
+                const unsigned long long flag = v[j] & ~kValueMask;
+                if (!done && used == j && flag != 0) {
+                    excl += v[j] & kValueMask;
+                    used = j + 1;
+                    done = flag == kFlagPrefix;
+                }
+            }
+            t -= used;                                   // a status word that was not ready yet is polled again
+        }
+        if (tile > 0) st_relaxed_u64(&status[(size_t)tile * kRadix + threadIdx.x], (excl + total) | kFlagPrefix);
+        s_gofs[threadIdx.x] = (long long)(digit_base[threadIdx.x] + excl) - (long long)s_digit_start[threadIdx.x];
+    }
     __syncthreads();
 
-    // digit runs are contiguous both in shared memory and at their destination
+    // 7. digit runs are contiguous both in shared memory and at their destination
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
         const int j = i * THREADS + threadIdx.x;
@@ -191,20 +230,55 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
     }
 }
 
-constexpr int kSortThreads = 384;
-constexpr int kSortItems = 16;
-constexpr int kSortTile = kSortThreads * kSortItems;
+typedef void (*OnesweepFn)(const uint64_t*, uint64_t*, const uint32_t*, uint32_t*, int64_t, int, const unsigned long long*,
+                           unsigned long long*, unsigned*);
 
-template <bool HAS_VALS>
-constexpr size_t onesweep_smem() {
-    return (size_t)kSortTile * 8 + (HAS_VALS ? (size_t)kSortTile * 4 : 0) + (size_t)(kSortThreads / 32) * kRadix * 4 +
-           kRadix * 8 + kRadix * 4 + 64;
+struct OnesweepConfig {
+    int threads, items;
+    OnesweepFn pairs, keys_only;
+    size_t smem_pairs, smem_keys;
+    int tile() const { return threads * items; }
+};
+
+template <int THREADS, int ITEMS, int MIN_BLOCKS, bool USE_MATCH>
+OnesweepConfig make_config() {
+    const size_t fixed = (size_t)(THREADS / 32) * kRadix * 4 + kRadix * 8 + kRadix * 4 + 64;
+    OnesweepConfig c;
+    c.threads = THREADS; c.items = ITEMS;
+    c.pairs = onesweep_kernel<THREADS, ITEMS, true, MIN_BLOCKS, USE_MATCH>;
+    c.keys_only = onesweep_kernel<THREADS, ITEMS, false, MIN_BLOCKS, USE_MATCH>;
+    c.smem_pairs = (size_t)THREADS * ITEMS * 12 + fixed;
+    c.smem_keys = (size_t)THREADS * ITEMS * 8 + fixed;
+    return c;
 }
+
+// GCZ_SORT_VARIANT selects the tile shape / ranking primitive (tuning knob; 0 is what the benchmarks use).
+// profiles/sort_variants_r01.md holds the sweep these were picked from.
+const OnesweepConfig& config() {
+    static const OnesweepConfig table[] = {
+        make_config<512, 12, 2, false>(),     // 0: 6144 pairs, 2 CTAs/SM (32 warps), ballots   <- measured best on B200
+        make_config<512, 12, 2, true>(),      // 1: same, match.any
+        make_config<384, 16, 2, false>(),     // 2: 6144 pairs, 24 warps/SM
+        make_config<256, 16, 3, false>(),     // 3: 4096 pairs, 3 CTAs/SM
+        make_config<384, 12, 3, false>(),     // 4: 4608 pairs, 3 CTAs/SM
+        make_config<512, 8, 3, false>(),      // 5: 4096 pairs, 3 CTAs/SM (48 warps, 40 regs)
+        make_config<1024, 6, 1, false>(),     // 6: 6144 pairs, 1 CTA/SM
+        make_config<512, 16, 1, false>(),     // 7: 8192 pairs, 1 CTA/SM
+    };
+    static const int pick = [] {
+        const char* e = getenv("GCZ_SORT_VARIANT");
+        const int v = e ? atoi(e) : 0;
+        return (v >= 0 && v < (int)(sizeof(table) / sizeof(table[0]))) ? v : 0;
+    }();
+    return table[pick];
+}
+
+constexpr int kMinTile = 4096;          // smallest tile of any variant: sizes the status array
 
 }  // namespace
 
 size_t radix_sort_temp_bytes(int64_t n) {
-    const int64_t tiles = (n + kSortTile - 1) / kSortTile;
+    const int64_t tiles = (n + kMinTile - 1) / kMinTile;
     // [8][256] histogram + per-pass (status[tiles][256] + ticket)
     return 8 * kRadix * 8 + 256 + ((size_t)tiles * kRadix * 8 + 256);
 }
@@ -215,18 +289,15 @@ int radix_sort_pairs(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n
     if (end_bit - begin_bit > 64 || begin_bit < 0) return fail(GCZ_E_ARG, "radix sort bit range");
     const int npass = (end_bit - begin_bit + 7) / 8;
     const bool has_vals = b.vals[0] != nullptr;
+    const OnesweepConfig& cfg = config();
     if (!ctx->sort_attr[has_vals ? 1 : 0]) {
-        if (has_vals)
-            GCZ_CUDA(cudaFuncSetAttribute(onesweep_kernel<kSortThreads, kSortItems, true>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)onesweep_smem<true>()));
-        else
-            GCZ_CUDA(cudaFuncSetAttribute(onesweep_kernel<kSortThreads, kSortItems, false>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)onesweep_smem<false>()));
+        GCZ_CUDA(cudaFuncSetAttribute(has_vals ? cfg.pairs : cfg.keys_only, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(has_vals ? cfg.smem_pairs : cfg.smem_keys)));
         ctx->sort_attr[has_vals ? 1 : 0] = true;
     }
     auto* hist = static_cast<unsigned long long*>(temp);
     auto* status = hist + 8 * kRadix + 32;
-    const int64_t tiles = (n + kSortTile - 1) / kSortTile;
+    const int64_t tiles = (n + cfg.tile() - 1) / cfg.tile();
     auto* ticket = reinterpret_cast<unsigned*>(status + (size_t)tiles * kRadix);
 
     GCZ_CUDA(cudaMemsetAsync(hist, 0, 8 * kRadix * 8, st));
@@ -244,14 +315,14 @@ int radix_sort_pairs(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n
             GCZ_CUDA(cudaEventRecord(e0, st));
         }
         if (has_vals) {
-            GCZ_LAUNCH(ctx, (onesweep_kernel<kSortThreads, kSortItems, true>), (unsigned)tiles, kSortThreads,
-                       onesweep_smem<true>(), st, b.keys[in], b.keys[out], b.vals[in], b.vals[out], n, shift,
-                       hist + p * kRadix, status, ticket);
+            cfg.pairs<<<(unsigned)tiles, cfg.threads, cfg.smem_pairs, st>>>(b.keys[in], b.keys[out], b.vals[in], b.vals[out], n, shift,
+                                                                            hist + p * kRadix, status, ticket);
         } else {
-            GCZ_LAUNCH(ctx, (onesweep_kernel<kSortThreads, kSortItems, false>), (unsigned)tiles, kSortThreads,
-                       onesweep_smem<false>(), st, b.keys[in], b.keys[out], nullptr, nullptr, n, shift,
-                       hist + p * kRadix, status, ticket);
+            cfg.keys_only<<<(unsigned)tiles, cfg.threads, cfg.smem_keys, st>>>(b.keys[in], b.keys[out], nullptr, nullptr, n, shift,
+                                                                               hist + p * kRadix, status, ticket);
         }
+        ctx->launches++;
+        GCZ_CUDA(cudaPeekAtLastError());
         b.cur = out;
         if (stats) {
             GCZ_CUDA(cudaEventRecord(e1, st));
