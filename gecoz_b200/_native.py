@@ -60,6 +60,8 @@ class BuildTiming(C.Structure):
         ("radix_launches", C.c_int64), ("radix_elements", C.c_int64),
         ("radix_ms", C.c_float),
         ("kernel_launches", C.c_int64),
+        ("symbols_per_key", C.c_int32), ("long_runs", C.c_int32),
+        ("unresolved_after_first_sort", C.c_int64),
     ]
 
     def as_dict(self):

@@ -240,6 +240,9 @@ static int build_block(int device, const uint8_t* text, int64_t n, int32_t sampl
     t_timing.radix_elements = ss.radix_elements;
     t_timing.radix_ms = ss.radix_ms;
     t_timing.kernel_launches = ctx->launches - launches0;
+    t_timing.symbols_per_key = ss.symbols_per_key;
+    t_timing.long_runs = ss.long_runs;
+    t_timing.unresolved_after_first_sort = ss.unresolved_after_first_sort;
     for (auto& e : ev) cudaEventDestroy(e);
     return GCZ_OK;
 }

@@ -11,6 +11,8 @@ struct SuffixSortStats {
     int     symbols_per_key = 0;
     int64_t radix_passes = 0, radix_elements = 0;
     float   radix_ms = 0;
+    int64_t unresolved_after_first_sort = 0;
+    int     long_runs = 0;
 };
 
 size_t suffix_sort_workspace_bytes(int64_t n);

@@ -219,41 +219,58 @@ sample_kernel(const uint32_t* __restrict__ sa, int64_t n, uint32_t sample_mask, 
 }
 
 // ---- IndexWaveletTree levels ---------------------------------------------------------------------------
-// level h, current order = values grouped (stably) by v >> (h + 1), group g at slot g << (h + 1)
-__global__ void iwt_bits_kernel(const uint32_t* __restrict__ vals, int64_t m, int h, uint32_t* __restrict__ raw,
-                                uint32_t* __restrict__ zeros /* per word */) {
+// level h, current order = values grouped (stably) by v >> (h + 1), group g at slot g << (h + 1).
+// One warp per 1024 positions: bit h of the values -> 32 raw words, zeros before each word inside the block,
+// zeros of the block.  A short scan over the block totals completes the two-level zero count.
+__global__ void __launch_bounds__(256)
+iwt_bits_kernel(const uint32_t* __restrict__ vals, int64_t m, int h, uint32_t* __restrict__ raw,
+                uint32_t* __restrict__ zeros_in_block /* per word, exclusive inside its 32-word block */,
+                uint32_t* __restrict__ block_zeros /* per block */) {
+    const int64_t blocks = (m + 1023) >> 10;
     const int64_t words = (m + 31) >> 5;
     const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t w = gw; w < words; w += nwarps) {
-        const int64_t p = w * 32 + lane_id();
-        const bool valid = p < m;
-        const unsigned bit = valid ? (vals[p] >> h) & 1u : 0u;
-        const unsigned word = __ballot_sync(0xffffffffu, bit);
-        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-        if (lane_id() == 0) { raw[w] = word; zeros[w] = __popc(~word & vmask); }
+    const unsigned lane = lane_id();
+    for (int64_t blk = gw; blk < blocks; blk += nwarps) {
+        unsigned my_word = 0, my_valid = 0;
+#pragma unroll 8
+        for (int w = 0; w < 32; w++) {
+            const int64_t p = (blk << 10) + w * 32 + lane;
+            const bool valid = p < m;
+            const unsigned bit = valid ? (vals[p] >> h) & 1u : 0u;
+            const unsigned word = __ballot_sync(0xffffffffu, bit);
+            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+            if ((int)lane == w) { my_word = word; my_valid = vmask; }
+        }
+        const unsigned z = __popc(~my_word & my_valid);
+        const unsigned incl = warp_incl_sum(z);
+        const int64_t wi = (blk << 5) + lane;
+        if (wi < words) { raw[wi] = my_word; zeros_in_block[wi] = incl - z; }
+        if (lane == 31) block_zeros[blk] = incl;
     }
 }
 
-__device__ __forceinline__ uint32_t zeros_before(const uint32_t* __restrict__ raw, const uint32_t* __restrict__ zexcl, int64_t p) {
+__device__ __forceinline__ uint32_t zeros_before(const uint32_t* __restrict__ raw, const uint32_t* __restrict__ zeros_in_block,
+                                                 const uint32_t* __restrict__ block_excl, int64_t p) {
     const unsigned r = (unsigned)(p & 31);
-    return zexcl[p >> 5] + (r ? __popc(~raw[p >> 5] & ((1u << r) - 1u)) : 0);
+    return block_excl[p >> 10] + zeros_in_block[p >> 5] + (r ? __popc(~raw[p >> 5] & ((1u << r) - 1u)) : 0);
 }
 
 __global__ void iwt_scatter_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int64_t m, int h,
-                                   const uint32_t* __restrict__ raw, const uint32_t* __restrict__ zexcl) {
+                                   const uint32_t* __restrict__ raw, const uint32_t* __restrict__ zeros_in_block,
+                                   const uint32_t* __restrict__ block_excl) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < m; p += stride) {
         const uint32_t v = in[p];
         const int64_t bs = (int64_t)(v >> (h + 1)) << (h + 1);
-        const int64_t zp = zeros_before(raw, zexcl, p);
-        const int64_t zb = bs < m ? zeros_before(raw, zexcl, bs) : 0;
+        const int64_t zp = zeros_before(raw, zeros_in_block, block_excl, p);
+        const int64_t zb = bs < m ? zeros_before(raw, zeros_in_block, block_excl, bs) : 0;
         int64_t np;
         if (((v >> h) & 1u) == 0) {
             np = bs + (zp - zb);
         } else {
-            const int64_t zeros_in_block = min((int64_t)1 << h, m - bs);
-            np = bs + zeros_in_block + ((p - zp) - (bs - zb));
+            const int64_t zeros_in_group = min((int64_t)1 << h, m - bs);
+            np = bs + zeros_in_group + ((p - zp) - (bs - zb));
         }
         out[np] = v;
     }
@@ -450,6 +467,8 @@ int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_t
     uint32_t* d_sb = arena.get<uint32_t>((size_t)total_sb + 1);
     uint32_t* d_ssa[2] = { arena.get<uint32_t>((size_t)m), arena.get<uint32_t>((size_t)m) };
     uint32_t* d_zeros = arena.get<uint32_t>((size_t)((m + 31) >> 5) + 1);
+    uint32_t* d_block_zeros = arena.get<uint32_t>((size_t)((m + 1023) >> 10) + 1);
+    if (!d_block_zeros) return fail(GCZ_E_NOMEM, "wavelet workspace for n=%lld", (long long)n);
     if (!d_tab || !d_raw || !d_tile_counts || !d_node_raw || !d_vecs || !d_sb || !d_ssa[0] || !d_ssa[1] || !d_zeros)
         return fail(GCZ_E_NOMEM, "wavelet workspace for n=%lld", (long long)n);
 
@@ -485,16 +504,17 @@ int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_t
     // ---- sampled SA + IndexWaveletTree ---------------------------------------------------------------------
     GCZ_LAUNCH(ctx, sample_kernel, wt_grid, kWtThreads, 0, st, d_sa, n, sample_mask, sampling_factor,
                d_tile_counts + (size_t)sigma * tiles, tiles, d_ssa[0]);
-    const int64_t mwords = (m + 31) >> 5;
+    const int64_t mblocks = (m + 1023) >> 10;
     const int lvl_grid = (int)std::min<int64_t>((m + 255) / 256, (int64_t)ctx->sm_count * 8);
+    const int bits_grid = (int)std::min<int64_t>((mblocks + 7) / 8, (int64_t)ctx->sm_count * 8);
     int cur = 0;
     for (int l = 0; l < levels; l++) {
         const int h = levels - 1 - l;
         uint32_t* lraw = d_raw + vecs[level_vec0 + l].raw_word;
-        GCZ_LAUNCH(ctx, iwt_bits_kernel, lvl_grid, 256, 0, st, d_ssa[cur], m, h, lraw, d_zeros);
+        GCZ_LAUNCH(ctx, iwt_bits_kernel, bits_grid, 256, 0, st, d_ssa[cur], m, h, lraw, d_zeros, d_block_zeros);
         if (h > 0) {
-            GCZ_LAUNCH(ctx, row_scan_kernel, 1, 1024, 0, st, d_zeros, mwords, (uint32_t*)nullptr);
-            GCZ_LAUNCH(ctx, iwt_scatter_kernel, lvl_grid, 256, 0, st, d_ssa[cur], d_ssa[cur ^ 1], m, h, lraw, d_zeros);
+            GCZ_LAUNCH(ctx, row_scan_kernel, 1, 1024, 0, st, d_block_zeros, mblocks, (uint32_t*)nullptr);
+            GCZ_LAUNCH(ctx, iwt_scatter_kernel, lvl_grid, 256, 0, st, d_ssa[cur], d_ssa[cur ^ 1], m, h, lraw, d_zeros, d_block_zeros);
             cur ^= 1;
         }
     }
@@ -570,21 +590,23 @@ int index_wavelet_tree_from_values(DeviceCtx* ctx, cudaStream_t st, const uint32
     uint32_t* d_sb = arena.get<uint32_t>((size_t)total_sb + 1);
     uint32_t* d_ssa[2] = { arena.get<uint32_t>((size_t)m), arena.get<uint32_t>((size_t)m) };
     uint32_t* d_zeros = arena.get<uint32_t>((size_t)((m + 31) >> 5) + 1);
-    if (!d_raw || !d_vecs || !d_sb || !d_ssa[0] || !d_ssa[1] || !d_zeros) return fail(GCZ_E_NOMEM, "IWT workspace");
+    uint32_t* d_block_zeros = arena.get<uint32_t>((size_t)((m + 1023) >> 10) + 1);
+    if (!d_raw || !d_vecs || !d_sb || !d_ssa[0] || !d_ssa[1] || !d_zeros || !d_block_zeros) return fail(GCZ_E_NOMEM, "IWT workspace");
     GCZ_CUDA(cudaMemsetAsync(d_raw, 0, ((size_t)raw_words + 16) * 4, st));
     GCZ_CUDA(cudaMemcpyAsync(d_vecs, vecs.data(), sizeof(VectorDesc) * vecs.size(), cudaMemcpyHostToDevice, st));
     GCZ_CUDA(cudaMemcpyAsync(d_ssa[0], d_vals, (size_t)m * 4, cudaMemcpyDeviceToDevice, st));
     GCZ_CUDA(cudaStreamSynchronize(st));
-    const int64_t mwords = (m + 31) >> 5;
+    const int64_t mblocks = (m + 1023) >> 10;
     const int lvl_grid = (int)std::min<int64_t>((m + 255) / 256, (int64_t)ctx->sm_count * 8);
+    const int bits_grid = (int)std::min<int64_t>((mblocks + 7) / 8, (int64_t)ctx->sm_count * 8);
     int cur = 0;
     for (int l = 0; l < levels; l++) {
         const int h = levels - 1 - l;
         uint32_t* lraw = d_raw + vecs[l].raw_word;
-        GCZ_LAUNCH(ctx, iwt_bits_kernel, lvl_grid, 256, 0, st, d_ssa[cur], m, h, lraw, d_zeros);
+        GCZ_LAUNCH(ctx, iwt_bits_kernel, bits_grid, 256, 0, st, d_ssa[cur], m, h, lraw, d_zeros, d_block_zeros);
         if (h > 0) {
-            GCZ_LAUNCH(ctx, row_scan_kernel, 1, 1024, 0, st, d_zeros, mwords, (uint32_t*)nullptr);
-            GCZ_LAUNCH(ctx, iwt_scatter_kernel, lvl_grid, 256, 0, st, d_ssa[cur], d_ssa[cur ^ 1], m, h, lraw, d_zeros);
+            GCZ_LAUNCH(ctx, row_scan_kernel, 1, 1024, 0, st, d_block_zeros, mblocks, (uint32_t*)nullptr);
+            GCZ_LAUNCH(ctx, iwt_scatter_kernel, lvl_grid, 256, 0, st, d_ssa[cur], d_ssa[cur ^ 1], m, h, lraw, d_zeros, d_block_zeros);
             cur ^= 1;
         }
     }

@@ -97,6 +97,9 @@ typedef struct gcz_build_timing {
     int64_t radix_launches, radix_elements;     /* onesweep passes launched, elements they moved     */
     float   radix_ms;                            /* device time inside those passes                   */
     int64_t kernel_launches;                     /* all kernels of this library launched by the call  */
+    int32_t symbols_per_key;                     /* k: symbols packed into the first sort key         */
+    int32_t long_runs;                           /* runs of >= k equal symbols (ordered in closed form) */
+    int64_t unresolved_after_first_sort;         /* suffixes not unique in their first k symbols      */
 } gcz_build_timing;
 int gcz_last_build_timing(gcz_build_timing* out);
 

@@ -110,6 +110,20 @@ def _texts():
                                    np.zeros(0, np.uint8), synth.iid_acgtn(20_000, 6)])   # empty + duplicate sequences
     yield "bytes", np.concatenate([rng.integers(1, 255, 80_000, dtype=np.uint8), np.zeros(1, np.uint8)])
     yield "lower_iupac", synth.block_of([np.frombuffer(b"ACGTNacgtnRYKM", np.uint8)[rng.integers(0, 14, 150_000)]])
+    # long runs of one symbol take the closed-form path of the sorter (suffix_sort.cu, point 5)
+    acgtn = np.frombuffer(b"ACGTN", np.uint8)
+    lens = rng.integers(1, 200, 4000)
+    yield "runs_mixed", synth.block_of([np.repeat(acgtn[rng.integers(0, 5, len(lens))], lens)])
+    parts = []
+    for i in range(600):                               # equal-length N runs: ties on the run length, both sides
+        parts += [np.full(60 + (i % 3), ord("N"), np.uint8), acgtn[rng.integers(0, 4, 1 + i % 7)]]
+    yield "runs_equal", synth.block_of([np.concatenate(parts), np.full(64, ord("T"), np.uint8), np.full(64, ord("A"), np.uint8)])
+    yield "runs_at_ends", synth.block_of([np.concatenate([np.full(5000, ord("N"), np.uint8), synth.iid_acgtn(20_000, 3),
+                                                          np.full(7000, ord("N"), np.uint8)])])
+    yield "separator_runs", synth.block_of([np.zeros(0, np.uint8)] * 40 + [synth.iid_acgtn(3000, 8)] + [np.zeros(0, np.uint8)] * 50)
+    lens = rng.integers(3, 6, 30_000)                  # more long runs than the mark buffer holds: plain doubling
+    yield "runs_bytes_overflow", np.concatenate([np.repeat(rng.integers(1, 255, len(lens), dtype=np.uint8), lens), np.zeros(1, np.uint8)])
+    yield "periodic", synth.block_of([np.frombuffer(b"ACGT" * 40_000, np.uint8)])
 
 
 @pytest.mark.parametrize("name,text", list(_texts()), ids=[t[0] for t in _texts()])
