@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -216,9 +217,12 @@ static int build_block(int device, const uint8_t* text, int64_t n, int32_t sampl
     }
 
     SuffixSortStats ss;
-    GCZ_TRY(suffix_sort(ctx, st, d_text, n, counts, d_sa, arena, &ss));
+    // SA entries may carry their BWT symbol (no text gather afterwards); GCZ_BWT_GATHER=1 forces the gather path
+    // that blocks too large for the carry take (tests)
+    int carry_shift = std::getenv("GCZ_BWT_GATHER") ? 0 : 1;
+    GCZ_TRY(suffix_sort(ctx, st, d_text, n, counts, d_sa, arena, &ss, &carry_shift));
     WaveletStats ws;
-    GCZ_TRY(build_wavelet_structures(ctx, st, d_text, d_sa, n, shape, sf, d_bwt, d_gcz, d_gcx, arena, &ws));
+    GCZ_TRY(build_wavelet_structures(ctx, st, d_text, d_sa, carry_shift, sa_out != nullptr, n, shape, sf, d_bwt, d_gcz, d_gcx, arena, &ws));
     GCZ_CUDA(cudaEventRecord(ev[2], st));
 
     if (!gcz_dev) GCZ_CUDA(cudaMemcpyAsync(gcz_body, d_gcz, (size_t)gcz_body_len, cudaMemcpyDeviceToHost, st));

@@ -48,7 +48,7 @@ constexpr int kPackTile = kPackThreads * kPackItems;
 
 __global__ void __launch_bounds__(kPackThreads)
 pack_keys_kernel(const uint8_t* __restrict__ text, int64_t n, const uint8_t* __restrict__ code_of, KeyCoder kc,
-                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int carry_shift,
                  uint64_t* __restrict__ run_marks, unsigned* __restrict__ run_mark_count, unsigned run_mark_cap) {
     __shared__ uint8_t s_code_of[256];
     __shared__ uint8_t s_codes[kPackTile + 2 * kMaxK + 8];      // [left halo kMaxK | tile | right halo]
@@ -92,9 +92,16 @@ pack_keys_kernel(const uint8_t* __restrict__ text, int64_t n, const uint8_t* __r
         }
     }
     __syncthreads();
+    // value = position, with the code of the PRECEDING symbol (the suffix's BWT symbol) above it when both fit
+    // 32 bits: the BWT then needs no gather from the text (carry_shift = 0: not carried)
     for (int i = threadIdx.x; i < kPackTile; i += kPackThreads) {
         const int64_t p = base + i;
-        if (p < n) { keys[p] = s_keys[i]; vals[p] = (uint32_t)p; }
+        if (p < n) {
+            uint32_t v = (uint32_t)p;
+            if (carry_shift) v |= (uint32_t)(p > 0 ? s_codes[kMaxK + i - 1] : s_code_of[text[n - 1]]) << carry_shift;
+            keys[p] = s_keys[i];
+            vals[p] = v;
+        }
     }
 }
 
@@ -287,6 +294,7 @@ struct ApplyArgs {
     uint32_t*       suf_out;
     uint32_t*       gid_out;
     uint32_t        gid_base;
+    uint32_t        pos_mask;      // suffix = value & pos_mask (the bits above carry the BWT symbol)
     // initial only: the long-run suffixes leave through a separate list, already keyed for their one sort
     const uint64_t* allc;
     int             sigma;
@@ -347,10 +355,10 @@ group_apply_kernel(ApplyArgs a) {
         if ((f.boundary >> i) & 1) last = t;
         if ((f.single >> i) & 1) {
             // final.  Initial: already in place, and its rank is left unset (found by key search when needed)
-            if (!INITIAL) { const uint32_t s = a.suf[t]; a.rank[s] = a.pos[last]; a.sa[a.pos[t]] = s; }
+            if (!INITIAL) { const uint32_t v = a.suf[t]; a.rank[v & a.pos_mask] = a.pos[last]; a.sa[a.pos[t]] = v; }
             continue;
         }
-        const uint32_t s = a.suf[t];
+        const uint32_t sv = a.suf[t], s = sv & a.pos_mask;
         a.rank[s] = INITIAL ? (uint32_t)last : a.pos[last];
         if (INITIAL && ((f.run >> i) & 1)) {
             const int c = allc_symbol(a.keys[t], s_allc, a.sigma);
@@ -360,12 +368,12 @@ group_apply_kernel(ApplyArgs a) {
             const uint32_t order = larger ? (0x80000000u | (0x7FFFFFFFu - r)) : r;
             a.run_pos_out[keep_run] = (uint32_t)t;
             a.run_key_out[keep_run] = ((uint64_t)c << 32) | order;
-            a.run_suf_out[keep_run] = s;
+            a.run_suf_out[keep_run] = sv;
             keep_run++;
         } else {
             if ((f.boundary >> i) & 1) groups++;
             a.pos_out[keep] = INITIAL ? (uint32_t)t : a.pos[t];
-            a.suf_out[keep] = s;
+            a.suf_out[keep] = sv;
             a.gid_out[keep] = a.gid_base + (uint32_t)(groups - 1);
             keep++;
         }
@@ -387,7 +395,7 @@ __device__ __forceinline__ uint64_t key_at(const uint8_t* __restrict__ text, int
 // A suffix inside a long run of r >= k symbols looks r - k symbols further than the others (header, point 5).
 __global__ void __launch_bounds__(256)
 refine_keys_kernel(const uint32_t* __restrict__ suf, const uint32_t* __restrict__ gid, int64_t m,
-                   uint32_t* __restrict__ rank, int64_t n, int64_t h, int low_bits,
+                   uint32_t* __restrict__ rank, int64_t n, int64_t h, int low_bits, uint32_t pos_mask,
                    const Run* __restrict__ runs, int n_runs, const uint8_t* __restrict__ text,
                    const uint8_t* __restrict__ code_of, KeyCoder kc, const uint64_t* __restrict__ sorted_keys,
                    uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
@@ -396,7 +404,7 @@ refine_keys_kernel(const uint32_t* __restrict__ suf, const uint32_t* __restrict_
     __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < m; u += stride) {
-        const uint32_t s = suf[u];
+        const uint32_t sv = suf[u], s = sv & pos_mask;
         int64_t q = (int64_t)s + h;
         if (n_runs > 0) {
             bool larger;
@@ -420,7 +428,7 @@ refine_keys_kernel(const uint32_t* __restrict__ suf, const uint32_t* __restrict_
             low = (uint64_t)rk + 1;
         }
         keys[u] = ((uint64_t)gid[u] << low_bits) | low;
-        vals[u] = s;
+        vals[u] = sv;
     }
 }
 
@@ -461,7 +469,7 @@ size_t suffix_sort_workspace_bytes(int64_t n) {
 }
 
 int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t n, const int64_t counts[256],
-                uint32_t* d_sa, Arena& arena, SuffixSortStats* stats) {
+                uint32_t* d_sa, Arena& arena, SuffixSortStats* stats, int* carry_shift) {
     if (n <= 0 || n > 0x7FFFFFFFll) return fail(GCZ_E_RANGE, "block of %lld symbols", (long long)n);
 
     // dense symbol codes: 1..sigma in byte order, 0 reserved for "past the end"
@@ -479,6 +487,11 @@ int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t 
         for (int c = 1; c <= sigma; c++) h_allc[c - 1] = unit * (uint64_t)c;
     }
     const int key_bits = bits_for(h_allc[sigma - 1]);
+    // the BWT symbol rides above the position when both fit 32 bits (any block up to 2^28 symbols of DNA)
+    const int pos_bits = bits_for((uint64_t)n - 1);
+    const int carry = (carry_shift && *carry_shift && pos_bits + bits_for((uint64_t)sigma) <= 32) ? pos_bits : 0;
+    const uint32_t pos_mask = carry ? (1u << carry) - 1u : 0xFFFFFFFFu;
+    if (carry_shift) *carry_shift = carry;
 
     const size_t mark0 = arena.mark();
     const unsigned mark_cap = (unsigned)std::min<int64_t>(n / 8 + 1024, 0x7FFFFFF0ll);
@@ -519,7 +532,7 @@ int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t 
     b.vals[0] = d_sa;    b.vals[1] = d_vals1;
     b.cur = npass & 1;
     const int pack_grid = (int)((n + kPackTile - 1) / kPackTile);
-    GCZ_LAUNCH(ctx, pack_keys_kernel, pack_grid, kPackThreads, 0, st, d_text, n, d_code, kc, b.keys[b.cur], b.vals[b.cur],
+    GCZ_LAUNCH(ctx, pack_keys_kernel, pack_grid, kPackThreads, 0, st, d_text, n, d_code, kc, b.keys[b.cur], b.vals[b.cur], carry,
                d_marks[0], d_mark_count, mark_cap);
     SortStats ss;
     SortStats* ssp = stats ? &ss : nullptr;
@@ -571,7 +584,7 @@ int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t 
 
     ApplyArgs aa;
     aa.keys = d_keys0; aa.suf = d_sa; aa.pos = nullptr; aa.m = n; aa.pre = agg; aa.rank = d_rank; aa.sa = d_sa;
-    aa.pos_out = list_pos[0]; aa.suf_out = list_suf[0]; aa.gid_out = list_gid[0]; aa.gid_base = 0;
+    aa.pos_out = list_pos[0]; aa.suf_out = list_suf[0]; aa.gid_out = list_gid[0]; aa.gid_base = 0; aa.pos_mask = pos_mask;
     aa.allc = d_allc; aa.sigma = sigma_runs; aa.runs = d_runs; aa.n_runs = n_runs; aa.k = k;
     aa.run_pos_out = run_pos; aa.run_key_out = r_keys0; aa.run_suf_out = r_vals0;
     GCZ_LAUNCH(ctx, group_apply_kernel<true>, (unsigned)tiles_n, kGrpThreads, 0, st, aa);
@@ -608,7 +621,7 @@ int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t 
         rb.vals[0] = r_vals0; rb.vals[1] = r_vals1;
         rb.cur = 0;
         const int grid = (int)std::min<int64_t>((m + 255) / 256, (int64_t)ctx->sm_count * 16);
-        GCZ_LAUNCH(ctx, refine_keys_kernel, grid, 256, 0, st, list_suf[cur], list_gid[cur], m, d_rank, n, h, low_bits,
+        GCZ_LAUNCH(ctx, refine_keys_kernel, grid, 256, 0, st, list_suf[cur], list_gid[cur], m, d_rank, n, h, low_bits, pos_mask,
                    d_runs, n_runs, d_text, d_code, kc, d_keys0, rb.keys[0], rb.vals[0]);
         const int gid_bits = bits_for((uint64_t)std::max<int64_t>(groups - 1, 0));
         GCZ_TRY(radix_sort_pairs(ctx, st, rb, m, 0, low_bits + gid_bits, d_temp, ssp));

@@ -19,7 +19,9 @@ size_t suffix_sort_workspace_bytes(int64_t n);
 
 // d_text: n bytes on the device; counts: byte histogram of the text (host); d_sa: n x u32 on the device (output).
 // Scratch comes from `arena` (released before returning).
+// carry_shift (optional): in, nonzero = the caller accepts SA entries that carry the dense code (1..sigma) of the
+// preceding text symbol above the position; out, the bit the code starts at, or 0 when the entries are plain.
 int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t n, const int64_t counts[256],
-                uint32_t* d_sa, Arena& arena, SuffixSortStats* stats);
+                uint32_t* d_sa, Arena& arena, SuffixSortStats* stats, int* carry_shift = nullptr);
 
 }  // namespace gcz

@@ -26,6 +26,7 @@ constexpr int kNoNode = 0xFFFF;
 // symbol tables of one block, resident in global memory for the duration of the build
 struct SymbolTables {
     uint8_t  dense[256];        // byte -> dense symbol index, 0xFF when absent
+    uint8_t  byte_of[256];      // dense symbol index -> byte
     uint16_t code[256];         // dense -> code bits (bit d = branch at depth d)
     uint8_t  len[256];          // dense -> code length
     uint8_t  node_of[256][16];  // dense, depth -> node (file order) on the symbol's path
@@ -37,27 +38,31 @@ struct SymbolTables {
 };
 
 // ---- BWT gather + per-tile symbol counts + marker bits -----------------------------------------------
+// carry_shift != 0: SA entries hold the dense code (1..sigma) of the preceding text symbol above bit carry_shift
+// (suffix_sort.cuh) — the BWT is read off the entries and, when sa_clean is set, plain positions are written back.
 __global__ void __launch_bounds__(kWtThreads)
 bwt_count_kernel(const uint8_t* __restrict__ text, const uint32_t* __restrict__ sa, int64_t n,
-                 const SymbolTables* __restrict__ tab, uint32_t sample_mask,
+                 const SymbolTables* __restrict__ tab, uint32_t sample_mask, int carry_shift, uint32_t* __restrict__ sa_clean,
                  uint8_t* __restrict__ bwt, uint32_t* __restrict__ marker_raw,
                  uint32_t* __restrict__ tile_counts /* [(sigma + 1)][tiles] */, int64_t tiles) {
     __shared__ uint32_t s_cnt[kWtThreads / 32][260];
-    __shared__ uint8_t s_dense[256];
+    __shared__ uint8_t s_dense[256], s_byte_of[256];
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     s_dense[threadIdx.x] = tab->dense[threadIdx.x];
+    s_byte_of[threadIdx.x] = tab->byte_of[threadIdx.x];
     const int sigma = tab->sigma;
     for (int i = lane; i <= sigma; i += 32) s_cnt[warp][i] = 0;
     __syncthreads();
     const int64_t tile = (int64_t)blockIdx.x * (kWtThreads / 32) + warp;
     if (tile >= tiles) return;
     const int64_t base = tile * kWarpTile;
+    const uint32_t pos_mask = carry_shift ? (1u << carry_shift) - 1u : 0xFFFFFFFFu;
     uint32_t* cnt = s_cnt[warp];
     unsigned marks = 0;
 #pragma unroll 1
     for (int c0 = 0; c0 < kWarpTile / 32; c0 += 4) {
         uint32_t s[4];
-        int sym[4];
+        int d[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const int64_t j = base + (c0 + u) * 32 + lane;
@@ -66,23 +71,28 @@ bwt_count_kernel(const uint8_t* __restrict__ text, const uint32_t* __restrict__ 
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const int64_t j = base + (c0 + u) * 32 + lane;
-            sym[u] = j < n ? (int)text[s[u] ? (int64_t)s[u] - 1 : n - 1] : -1;
+            if (carry_shift) {
+                d[u] = j < n ? (int)(s[u] >> carry_shift) - 1 : -1;
+                s[u] &= pos_mask;
+            } else {
+                d[u] = j < n ? (int)s_dense[text[s[u] ? (int64_t)s[u] - 1 : n - 1]] : -1;
+            }
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const int64_t j = base + (c0 + u) * 32 + lane;
             const bool valid = j < n;
-            if (valid) bwt[j] = (uint8_t)sym[u];
+            if (valid) bwt[j] = s_byte_of[d[u]];
+            if (valid && sa_clean) sa_clean[j] = s[u];
             const unsigned mk = __ballot_sync(0xffffffffu, valid && (s[u] & sample_mask) == 0);
             if (lane == 0 && base + (c0 + u) * 32 < n) marker_raw[(base >> 5) + c0 + u] = mk;
             marks += (lane == 0) ? __popc(mk) : 0;
             // count every distinct symbol of this chunk once
-            const int d = valid ? (int)s_dense[sym[u]] : -1;
             unsigned todo = __ballot_sync(0xffffffffu, valid);
             while (todo) {
                 const int leader = __ffs(todo) - 1;
-                const int v = __shfl_sync(0xffffffffu, d, leader);
-                const unsigned same = __ballot_sync(0xffffffffu, d == v);
+                const int v = __shfl_sync(0xffffffffu, d[u], leader);
+                const unsigned same = __ballot_sync(0xffffffffu, d[u] == v);
                 if ((int)lane == leader) cnt[v] += __popc(same);
                 todo &= ~same;
             }
@@ -199,7 +209,7 @@ hswt_emit_kernel(const uint8_t* __restrict__ bwt, int64_t n, const SymbolTables*
 
 // ---- sampled suffix array values in SA order -----------------------------------------------------------
 __global__ void __launch_bounds__(kWtThreads)
-sample_kernel(const uint32_t* __restrict__ sa, int64_t n, uint32_t sample_mask, int sample_shift,
+sample_kernel(const uint32_t* __restrict__ sa, int64_t n, uint32_t pos_mask, uint32_t sample_mask, int sample_shift,
               const uint32_t* __restrict__ marker_prefix /* [tiles] exclusive */, int64_t tiles,
               uint32_t* __restrict__ ssa) {
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
@@ -210,7 +220,7 @@ sample_kernel(const uint32_t* __restrict__ sa, int64_t n, uint32_t sample_mask, 
 #pragma unroll 4
     for (int c = 0; c < kWarpTile / 32; c++) {
         const int64_t j = base + c * 32 + lane;
-        const uint32_t s = j < n ? sa[j] : 1u;
+        const uint32_t s = j < n ? sa[j] & pos_mask : 1u;
         const bool mk = j < n && (s & sample_mask) == 0;
         const unsigned m = __ballot_sync(0xffffffffu, mk);
         if (mk) ssa[out + __popc(m & lanemask_lt())] = s >> sample_shift;
@@ -394,8 +404,8 @@ size_t wavelet_workspace_bytes(int64_t n, int sampling_factor) {
     return raw_words * 4 + tiles * 4 * 258 + (size_t)m * 8 + (size_t)((m + 31) / 32) * 4 + (4 << 20);
 }
 
-int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, const uint32_t* d_sa, int64_t n,
-                             const gcz_shape* shape, int sampling_factor, uint8_t* d_bwt,
+int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, uint32_t* d_sa, int carry_shift, bool clean_sa,
+                             int64_t n, const gcz_shape* shape, int sampling_factor, uint8_t* d_bwt,
                              uint8_t* d_gcz_body, uint8_t* d_gcx_body, Arena& arena, WaveletStats* stats) {
     const size_t mark0 = arena.mark();
     // ---- host tables -------------------------------------------------------------------------------
@@ -407,6 +417,7 @@ int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_t
     for (int c = 0; c < 256; c++) {
         if (shape->bit_lengths[c] > 0) {
             h_tab.dense[c] = (uint8_t)sigma;
+            h_tab.byte_of[sigma] = (uint8_t)c;
             h_tab.code[sigma] = (uint16_t)shape->codes[c];
             h_tab.len[sigma] = (uint8_t)shape->bit_lengths[c];
             max_len = std::max(max_len, (int)shape->bit_lengths[c]);
@@ -495,14 +506,15 @@ int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_t
     const unsigned wt_grid = (unsigned)((tiles + kWtThreads / 32 - 1) / (kWtThreads / 32));
     const uint32_t sample_mask = (1u << sampling_factor) - 1u;
     uint32_t* d_marker_raw = d_raw + vecs[marker_vec].raw_word;
-    GCZ_LAUNCH(ctx, bwt_count_kernel, wt_grid, kWtThreads, 0, st, d_text, d_sa, n, d_tab, sample_mask, d_bwt, d_marker_raw,
-               d_tile_counts, tiles);
+    GCZ_LAUNCH(ctx, bwt_count_kernel, wt_grid, kWtThreads, 0, st, d_text, d_sa, n, d_tab, sample_mask, carry_shift,
+               (carry_shift && clean_sa) ? d_sa : (uint32_t*)nullptr, d_bwt, d_marker_raw, d_tile_counts, tiles);
     GCZ_LAUNCH(ctx, row_scan_kernel, (unsigned)(sigma + 1), 1024, 0, st, d_tile_counts, tiles, (uint32_t*)nullptr);
     GCZ_LAUNCH(ctx, hswt_emit_kernel, wt_grid, kWtThreads, 0, st, d_bwt, n, d_tab, d_tile_counts, tiles, d_node_raw, d_raw);
     if (stats) GCZ_CUDA(cudaEventRecord(ev1, st));
 
     // ---- sampled SA + IndexWaveletTree ---------------------------------------------------------------------
-    GCZ_LAUNCH(ctx, sample_kernel, wt_grid, kWtThreads, 0, st, d_sa, n, sample_mask, sampling_factor,
+    GCZ_LAUNCH(ctx, sample_kernel, wt_grid, kWtThreads, 0, st, d_sa, n,
+               carry_shift ? (1u << carry_shift) - 1u : 0xFFFFFFFFu, sample_mask, sampling_factor,
                d_tile_counts + (size_t)sigma * tiles, tiles, d_ssa[0]);
     const int64_t mblocks = (m + 1023) >> 10;
     const int lvl_grid = (int)std::min<int64_t>((m + 255) / 256, (int64_t)ctx->sm_count * 8);

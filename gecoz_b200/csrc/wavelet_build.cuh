@@ -14,8 +14,9 @@ size_t wavelet_workspace_bytes(int64_t n, int sampling_factor);
 // Inputs on the device: text (n bytes), suffix array (n x u32).  Outputs on the device: d_bwt (n bytes),
 // d_gcz_body (shape->size bytes: shape table + ranked HSWT nodes), d_gcx_body (index_size bytes: ranked marker
 // vector + IndexWaveletTree levels).  `shape` must come from shape_from_counts on this text's histogram.
-int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, const uint32_t* d_sa, int64_t n,
-                             const gcz_shape* shape, int sampling_factor, uint8_t* d_bwt,
+// carry_shift: as returned by suffix_sort (SA entries carry their BWT symbol); clean_sa: leave plain positions in d_sa.
+int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, uint32_t* d_sa, int carry_shift, bool clean_sa,
+                             int64_t n, const gcz_shape* shape, int sampling_factor, uint8_t* d_bwt,
                              uint8_t* d_gcz_body, uint8_t* d_gcx_body, Arena& arena, WaveletStats* stats);
 
 // stage hooks (parity tests)
