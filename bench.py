@@ -138,6 +138,7 @@ def main() -> None:
     ap.add_argument("--workload", default="cfg2", choices=list(CFG))
     ap.add_argument("--length", type=int, default=None, help="override the block length (debugging)")
     ap.add_argument("--patterns", type=int, default=4_000_000, help="count-leg patterns (length 15..100)")
+    ap.add_argument("--locate-patterns", type=int, default=200_000, help="locate-leg patterns (subset of the count batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -253,35 +254,99 @@ def main() -> None:
         except Exception:
             pass
 
-    # ---- count leg: queries against the index that was just built ------------------------------------------------------
-    count = None
+    # ---- count leg: query-sharded batch against a replicated index ---------------------------------------
+    # The index of rank 0's block is replicated (NCCL broadcast of the two bodies); the global batch of
+    # world x --patterns patterns is cut into contiguous shards; every rank counts its shard and the intervals
+    # come back to rank 0 with one NCCL gather inside the timed region.
+    count = locate = None
     try:
-        g = G.GSSA.open(local_rank, d_gcz, n, d_gcx)
-        npat = max(1000, args.patterns)
-        pdata, poff = synth.patterns(text, npat, 15, 100, seed=5 + rank)
-        hp, ho = torch.from_numpy(pdata).pin_memory(), torch.from_numpy(poff).pin_memory()
+        from gecoz_b200 import sharding
+        if world > 1:
+            meta = torch.tensor([int(shape.size), gcx_len, n], dtype=torch.int64, device=dev)
+            dist.broadcast(meta, 0)
+            size0, gcx0, n0 = (int(x) for x in meta.tolist())
+            r_gcz = d_gcz if rank == 0 else torch.empty(size0, dtype=torch.uint8, device=dev)
+            r_gcx = d_gcx if rank == 0 else torch.empty(gcx0, dtype=torch.uint8, device=dev)
+            dist.broadcast(r_gcz, 0)
+            dist.broadcast(r_gcx, 0)
+        else:
+            r_gcz, r_gcx, n0 = d_gcz, d_gcx, n
+        g = G.GSSA.open(local_rank, r_gcz, n0, r_gcx)
+        npat = max(1000, args.patterns) * world
+        lo, hi = sharding.shard_bounds(npat, world)[rank]
+        width = sharding.shard_bounds(npat, world)[0][1]
+        if world > 1:                                     # every rank needs the same batch: rank 0 draws it
+            if rank == 0:
+                pdata, poff = synth.patterns(text, npat, 15, 100, seed=5)
+                tot = torch.tensor([len(pdata)], dtype=torch.int64, device=dev)
+            else:
+                tot = torch.zeros(1, dtype=torch.int64, device=dev)
+            dist.broadcast(tot, 0)
+            t_data = torch.from_numpy(pdata).to(dev) if rank == 0 else torch.empty(int(tot.item()), dtype=torch.uint8, device=dev)
+            t_off = torch.from_numpy(poff).to(dev) if rank == 0 else torch.empty(npat + 1, dtype=torch.int64, device=dev)
+            dist.broadcast(t_data, 0)
+            dist.broadcast(t_off, 0)
+            pdata, poff = t_data.cpu().numpy(), t_off.cpu().numpy()
+        else:
+            pdata, poff = synth.patterns(text, npat, 15, 100, seed=5)
+        sdata, soff = sharding._shard_patterns(pdata, poff, lo, hi)
+        hp, ho = torch.from_numpy(sdata).pin_memory(), torch.from_numpy(soff).pin_memory()
         dp, do = hp.to(dev), ho.to(dev)
-        dsp, dep = torch.empty(npat, dtype=torch.int64, device=dev), torch.empty(npat, dtype=torch.int64, device=dev)
-        hsp, hep = torch.empty(npat, dtype=torch.int64).pin_memory(), torch.empty(npat, dtype=torch.int64).pin_memory()
-        cdev = lambda: g.count_batch(packed=(dp, do), out=(dsp, dep)) and None
-        chost = lambda: g.count_batch(packed=(hp, ho), out=(hsp, hep)) and None
+        d_res = torch.full((2, width), -1, dtype=torch.int64, device=dev)        # row 0 = sp, row 1 = ep
+        h_res = torch.empty((2, width), dtype=torch.int64).pin_memory()
+        parts = [torch.empty((2, width), dtype=torch.int64, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+        h_all = torch.empty((world, 2, width), dtype=torch.int64).pin_memory() if rank == 0 else None
+
+        def cdev():
+            g.count_batch(packed=(dp, do), out=(d_res[0, :hi - lo], d_res[1, :hi - lo]))
+            if world > 1:
+                dist.gather(d_res, parts, dst=0)
+
+        def chost():
+            # host shard in, all intervals back on rank 0's host
+            g.count_batch(packed=(hp, ho), out=(h_res[0, :hi - lo], h_res[1, :hi - lo]))
+            if world > 1:
+                d_res.copy_(h_res, non_blocking=True)
+                dist.gather(d_res, parts, dst=0)
+                if rank == 0:
+                    h_all.copy_(torch.stack(parts), non_blocking=True)
+
         timed(cdev, 3)
         cms, _ = timed(cdev, 5)
         cms = max_over_ranks(cms / 5)
         timed(chost, 1)
         cms_e2e, _ = timed(chost, 5)
         cms_e2e = max_over_ranks(cms_e2e / 5)
-        assert torch.equal(hsp, dsp.cpu()) and torch.equal(hep, dep.cpu())
-        total_pat = sum_over_ranks(float(npat))
-        found = int((dep >= dsp).sum().item())
-        count = {"metric": "count queries/s (backward-search intervals)", "value": total_pat / (cms / 1e3), "unit": "queries/s",
-                 "patterns": int(total_pat), "pattern_length": "uniform 15..100, 50% text-sampled / 50% random", "found": found,
-                 "ms_per_batch": cms,
-                 "e2e": {"value": total_pat / (cms_e2e / 1e3), "unit": "queries/s", "h2d_bytes_per_step": int(pdata.nbytes + poff.nbytes),
+        torch.cuda.synchronize()
+        assert torch.equal(h_res[:, :hi - lo], d_res[:, :hi - lo].cpu())
+        if rank == 0 and world > 1:                        # gathered shards == what rank 0 computes for them itself
+            chk_sp, chk_ep = g.count_batch(packed=(pdata, poff))
+            got = torch.cat([p[:, :b - a] for p, (a, b) in zip(parts, sharding.shard_bounds(npat, world))], dim=1).cpu().numpy()
+            assert np.array_equal(got[0], chk_sp) and np.array_equal(got[1], chk_ep), "sharded count differs"
+        found = int(sum_over_ranks(float((d_res[1, :hi - lo] >= d_res[0, :hi - lo]).sum().item())))
+        count = {"metric": "count queries/s (backward-search intervals)", "value": npat / (cms / 1e3), "unit": "queries/s",
+                 "patterns": int(npat), "pattern_length": "uniform 15..100, 50% text-sampled / 50% random", "found": found,
+                 "ms_per_batch": cms, "sharding": f"{world} contiguous shard(s), replicated index" + (", one NCCL gather to rank 0" if world > 1 else ""),
+                 "e2e": {"value": npat / (cms_e2e / 1e3), "unit": "queries/s", "h2d_bytes_per_step": int(pdata.nbytes + poff.nbytes),
                          "d2h_bytes_per_step": int(npat * 16)}}
+
+        # ---- locate leg (rank 0's shard only at N>1 is not the point: every rank runs its shard, no gather timed) ----
+        nloc = max(1000, min(args.locate_patterns, hi - lo))
+        ldata, loff = sharding._shard_patterns(sdata, soff, 0, nloc)
+        t0 = time.perf_counter()
+        per, pos, pof = g.find_batch_raw(packed=(ldata, loff))
+        torch.cuda.synchronize()
+        lsec = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        per, pos, pof = g.find_batch_raw(packed=(ldata, loff))
+        lsec = min(lsec, time.perf_counter() - t0)
+        locate = {"metric": "locate (GSSA.find) through gcz_find_batch, host buffers, wall clock of the call", "patterns": int(nloc),
+                  "occurrences": int(len(pos)), "patterns_per_s": nloc / lsec, "occurrences_per_s": len(pos) / lsec, "ms": lsec * 1e3,
+                  "per_rank": True}
         g.close()
     except Exception as ex:                                  # the headline metric must still be reported
-        count = {"error": repr(ex)}
+        count = count or {"error": repr(ex)}
+        locate = locate or {"error": repr(ex)}
 
     # ---- CPU baseline (rank 0, N=1 only) --------------------------------------------------------------------------------------
     cpu = None
@@ -312,6 +377,7 @@ def main() -> None:
             "roofline": roofline,
             "cpu_baseline": cpu,
             "count": count,
+            "locate": locate,
             "phases_ms": {k: float(np.mean([i[k] for i in infos])) for k in
                           ("sort_initial_ms", "sort_refine_ms", "bwt_hswt_ms", "ssa_ms", "total_ms")},
             "refine_rounds": int(infos[-1]["refine_rounds"]),

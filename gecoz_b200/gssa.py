@@ -90,11 +90,13 @@ class GSSA:
         N.check(N.lib().gcz_locate_rows(self._h, N.ptr(rows), len(rows), N.ptr(out)))
         return out
 
-    def find_batch(self, patterns: Sequence[bytes]):
-        """GSSA.find for every pattern: list of (None | list per string of (None | int64 array))."""
-        data, off = pack_patterns(patterns)
-        n = len(patterns)
-        ns = self.n_strings
+    def find_batch_raw(self, patterns=None, packed=None):
+        """GSSA.find for a batch, as arrays: (per_string_counts [n, n_strings], positions, pos_off[n + 1]).
+        positions holds, pattern after pattern and string after string, the ascending 0-based positions
+        relative to the string start."""
+        data, off = packed if packed is not None else pack_patterns(patterns)
+        data, off = np.ascontiguousarray(data, dtype=np.uint8), np.ascontiguousarray(off, dtype=np.int64)
+        n, ns = len(off) - 1, self.n_strings
         per = np.zeros(max(n * ns, 1), dtype=np.int64)
         ppos, poff = C.c_void_p(), C.c_void_p()
         N.check(N.lib().gcz_find_batch(self._h, N.ptr(data), N.ptr(off), n, N.ptr(per), C.byref(ppos), C.byref(poff)))
@@ -106,6 +108,13 @@ class GSSA:
             N.lib().gcz_free(ppos)
             N.lib().gcz_free(poff)
         per = per[:n * ns].reshape(n, ns) if ns else per[:0].reshape(n, 0)
+        return per, pos, offs
+
+    def find_batch(self, patterns: Sequence[bytes]):
+        """GSSA.find for every pattern: list of (None | list per string of (None | int64 array))."""
+        data, off = pack_patterns(patterns)
+        n, ns = len(patterns), self.n_strings
+        per, pos, offs = self.find_batch_raw(packed=(data, off))
         sp, ep = self.count_batch(packed=(data, off))
         res = []
         for i in range(n):

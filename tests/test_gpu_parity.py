@@ -346,3 +346,49 @@ def test_argument_errors(G):
     with pytest.raises(G.GczError):                          # shape of another text
         G._native.check(G.lib().gcz_build_block(0, _p(other), len(other), 32, C.byref(shape), _p(gcz), shape.size,
                                                 _p(gcx), len(gcx), None, None))
+
+
+# ---- multi-GPU partitioning (gecoz_b200/sharding.py) with the CUDA engine ---------------------------------------------
+def test_sharded_index_one_rank(G, O, tmp_path):
+    from gecoz_b200 import sharding, synth
+    recs = [(f"s{i}", synth.iid_acgtn(int(ln), 90 + i)) for i, ln in enumerate([50_000, 33_000, 17_000, 16_000, 900, 900, 12])]
+    info = sharding.sharded_index_records(recs, tmp_path / "y.gcz", engine=sharding.GpuEngine(0))
+    gcz, gcx, blocks = O.write_files([(h, s.tobytes()) for h, s in recs])
+    assert (tmp_path / "y.gcz").read_bytes() == gcz and (tmp_path / "y.gcx").read_bytes() == gcx
+    assert info["mine"] == list(range(len(blocks)))
+
+
+def _two_gpus():
+    import torch
+    return torch.cuda.device_count() >= 2
+
+
+@pytest.mark.parametrize("mode", ["build_gpu", "query_gpu"])
+def test_sharded_two_gpus_nccl(G, O, tmp_path, mode):
+    """Two ranks, two GPUs, NCCL: one file pair written by both / one batch answered by both."""
+    if not _two_gpus():
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import subprocess
+    import sys
+    here = Path(__file__).resolve().parent
+    sys.path.insert(0, str(here))
+    import dist_worker as W
+    init = tmp_path / "rendezvous"
+    procs = [subprocess.Popen([sys.executable, str(here / "dist_worker.py"), str(r), "2", str(init), str(tmp_path), mode],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    for p in procs:
+        out, _ = p.communicate(timeout=600)
+        assert p.returncode == 0, out
+    if mode == "build_gpu":
+        recs = W.records()
+        gcz, gcx, _ = O.write_files([(h, s.tobytes()) for h, s in recs])
+        assert (tmp_path / "x.gcz").read_bytes() == gcz and (tmp_path / "x.gcx").read_bytes() == gcx
+    else:
+        got = np.load(tmp_path / "query.npz")
+        texts, data, off = W.query_inputs()
+        for b, t in enumerate(texts):
+            og = W.OracleGSSA(t)
+            sp, ep = og.count_batch((data, off))
+            assert np.array_equal(got["sp"][b], sp) and np.array_equal(got["ep"][b], ep)
+            per, pos, poff = og.find_batch_raw((data, off))
+            assert np.array_equal(got[f"per{b}"], per) and np.array_equal(got[f"pos{b}"], pos) and np.array_equal(got[f"off{b}"], poff)
