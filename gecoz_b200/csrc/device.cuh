@@ -53,7 +53,7 @@ struct DeviceCtx {
     void*        pinned = nullptr;            // small pinned scratch for read-backs
     size_t       pinned_bytes = 0;
     int64_t      launches = 0;                // kernels launched by this library on this device
-    bool         sort_attr[2] = { false, false };   // dynamic-smem opt-in done for the onesweep kernels
+    bool         sort_attr[3] = { false, false, false };   // dynamic-smem opt-in done for the onesweep kernels
 };
 
 int          get_ctx(int device, DeviceCtx** out);   // creates on first use; fails with GCZ_E_NODEVICE

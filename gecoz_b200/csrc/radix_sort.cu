@@ -47,6 +47,95 @@ radix_hist_kernel(const uint64_t* __restrict__ keys, int64_t n, int begin_bit, i
     }
 }
 
+// Same histogram, with the keys computed from the text (TextKeySource): every thread converts its own
+// kTextItems consecutive symbols (one 16-byte load) to codes and slides a k-symbol window over them.
+// A key equal to c * (radix^k - 1) / (radix - 1) is k copies of symbol c: that is how the first and last
+// positions of runs of >= k equal symbols are found without walking the text.
+constexpr int kTextThreads = 256;
+constexpr int kTextItems = 16;
+constexpr int kTextTile = kTextThreads * kTextItems;
+
+__device__ __forceinline__ uint64_t slide_key(uint64_t key, uint32_t c_out, uint32_t c_in, uint32_t radix, uint64_t top) {
+    key -= (uint64_t)c_out * top;                          // 8-bit x 64-bit and 64-bit x 9-bit products: two IMADs each
+    return key * radix + c_in;
+}
+
+__global__ void __launch_bounds__(kTextThreads)
+text_hist_kernel(TextKeySource src, int npass, unsigned long long* __restrict__ hist /* [npass][256] */, int64_t tiles) {
+    __shared__ unsigned s_hist[8 * kRadix];
+    __shared__ uint8_t s_code_of[256];
+    __shared__ __align__(16) uint8_t s_codes[16 + kTextTile + kMaxKeySymbols + 16];    // index 16 = first position of the tile
+    for (int i = threadIdx.x; i < 8 * kRadix; i += kTextThreads) s_hist[i] = 0;
+    s_code_of[threadIdx.x] = src.code_of[threadIdx.x];
+    const int k = src.coder.k;
+    const uint32_t radix = (uint32_t)src.coder.radix;
+    const uint64_t top = src.coder.top;
+    uint64_t unit = 0;                                     // k ones in base radix
+    for (int j = 0; j < k; j++) unit = unit * radix + 1;
+    const int64_t n = src.n;
+    const bool aligned = (reinterpret_cast<uintptr_t>(src.text) & 15) == 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t base = tile * kTextTile;
+        __syncthreads();
+        {
+            const int64_t p0 = base + (int64_t)threadIdx.x * kTextItems;
+            uint32_t packed[4] = { 0, 0, 0, 0 };
+            if (aligned && p0 + kTextItems <= n) {
+                const uint4 q = *reinterpret_cast<const uint4*>(src.text + p0);
+                const uint32_t w[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    packed[j] = (uint32_t)s_code_of[w[j] & 255] | (uint32_t)s_code_of[(w[j] >> 8) & 255] << 8 |
+                                (uint32_t)s_code_of[(w[j] >> 16) & 255] << 16 | (uint32_t)s_code_of[w[j] >> 24] << 24;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < kTextItems; j++) {
+                    const int64_t p = p0 + j;
+                    if (p < n) packed[j >> 2] |= (uint32_t)s_code_of[src.text[p]] << (8 * (j & 3));   // 0 = past the end
+                }
+            }
+            *reinterpret_cast<uint4*>(s_codes + 16 + threadIdx.x * kTextItems) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            if (threadIdx.x <= (unsigned)k) {                 // right halo: k + 1 symbols
+                const int64_t p = base + kTextTile + threadIdx.x;
+                s_codes[16 + kTextTile + threadIdx.x] = p < n ? s_code_of[src.text[p]] : 0;
+            }
+            if (threadIdx.x == kTextThreads - 1) s_codes[15] = base > 0 ? s_code_of[src.text[base - 1]] : 0;
+        }
+        __syncthreads();
+        const int first = 16 + threadIdx.x * kTextItems;
+        uint64_t key = 0;
+        for (int j = 0; j < k - 1; j++) key = key * radix + s_codes[first + j];
+#pragma unroll 4
+        for (int i = 0; i < kTextItems; i++) {
+            key = slide_key(key, i > 0 ? s_codes[first + i - 1] : 0u, s_codes[first + i + k - 1], radix, top);
+            const int64_t p = base + first - 16 + i;
+            if (p < n) {
+#pragma unroll
+                for (int d = 0; d < 8; d++) {
+                    if (d < npass) atomicAdd(&s_hist[d * kRadix + (int)((key >> (8 * d)) & 255)], 1u);
+                }
+                const uint32_t c = s_codes[first + i];
+                if (src.run_marks && key == (uint64_t)c * unit) {
+                    if (p == 0 || s_codes[first + i - 1] != c) {
+                        const unsigned at = atomicAdd(src.run_mark_count, 1u);
+                        if (at < src.run_mark_cap) src.run_marks[at] = 2ull * (uint64_t)p;
+                    }
+                    if (s_codes[first + i + k] != c) {
+                        const unsigned at = atomicAdd(src.run_mark_count, 1u);
+                        if (at < src.run_mark_cap) src.run_marks[at] = 2ull * (uint64_t)(p + k - 1) + 1;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < npass * kRadix; i += kTextThreads) {
+        const unsigned v = s_hist[i];
+        if (v) atomicAdd(&hist[i], (unsigned long long)v);
+    }
+}
+
 // exclusive scan of each pass's 256 bins, in place
 __global__ void radix_scan_kernel(unsigned long long* hist, int npass) {
     __shared__ unsigned long long s_warp[8];
@@ -78,15 +167,19 @@ __global__ void radix_scan_kernel(unsigned long long* hist, int npass) {
 //   5 reorder keys and values in shared memory
 //   6 threads 0..255: decoupled look-back over windows of predecessor tiles
 //   7 write digit runs out, coalesced
-template <int THREADS, int ITEMS, bool HAS_VALS, int MIN_BLOCKS, bool USE_MATCH>
+//   1' (FROM_TEXT) the tile's keys are computed from the text instead: codes to shared memory, a k-symbol window
+//      slid over ITEMS consecutive positions per thread, transposed to the warp-striped order through shared memory
+template <int THREADS, int ITEMS, bool HAS_VALS, int MIN_BLOCKS, bool USE_MATCH, bool FROM_TEXT>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
                 const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
                 int64_t n, int shift, const unsigned long long* __restrict__ digit_base,
-                unsigned long long* __restrict__ status, unsigned* __restrict__ ticket) {
+                unsigned long long* __restrict__ status, unsigned* __restrict__ ticket, TextKeySource src) {
     constexpr int TILE = THREADS * ITEMS;
     constexpr int WARPS = THREADS / 32;
     static_assert(THREADS >= kRadix, "one thread per digit is needed for the look-back");
+    static_assert(!FROM_TEXT || HAS_VALS, "text input produces (key, position) pairs");
+    static_assert(TILE * 4 >= TILE + kMaxKeySymbols + 8 + 256, "the value staging area holds the tile's symbol codes");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* s_keys = reinterpret_cast<uint64_t*>(smem_raw);                       // TILE
@@ -109,10 +202,58 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
     // 1. warp-striped load: item i of lane l in warp w is element w*ITEMS*32 + i*32 + l of the tile
     uint64_t key[ITEMS];
     const int warp_base = warp * ITEMS * 32;
+    uint8_t* s_codes = reinterpret_cast<uint8_t*>(s_vals);        // FROM_TEXT: code of position tile_base - 1 + i
+    if (FROM_TEXT) {
+        uint8_t* s_code_of = s_codes + TILE + kMaxKeySymbols + 8;
+        if (threadIdx.x < 256) s_code_of[threadIdx.x] = src.code_of[threadIdx.x];
+        __syncthreads();
+        const int k = src.coder.k;
+        const uint32_t radix = (uint32_t)src.coder.radix;
+        // codes of positions tile_base - 1 .. tile_base + TILE + k - 2 at s_codes[0 ..]; 16-byte loads where possible
+        static_assert(TILE % 16 == 0, "tile starts stay 16-byte aligned");
+        const bool aligned = (reinterpret_cast<uintptr_t>(src.text) & 15) == 0;
+        for (int v = threadIdx.x; v < TILE / 16; v += THREADS) {
+            const int64_t p0 = tile_base + (int64_t)v * 16;
+            if (aligned && p0 + 16 <= n) {
+                const uint4 q = *reinterpret_cast<const uint4*>(src.text + p0);
+                const uint32_t w[4] = { q.x, q.y, q.z, q.w };
 #pragma unroll
-    for (int i = 0; i < ITEMS; i++) {
-        const int e = warp_base + i * 32 + lane;
-        key[i] = e < count ? keys_in[tile_base + e] : ~0ull;
+                for (int j = 0; j < 4; j++) {
+                    s_codes[1 + v * 16 + 4 * j] = s_code_of[w[j] & 255];
+                    s_codes[2 + v * 16 + 4 * j] = s_code_of[(w[j] >> 8) & 255];
+                    s_codes[3 + v * 16 + 4 * j] = s_code_of[(w[j] >> 16) & 255];
+                    s_codes[4 + v * 16 + 4 * j] = s_code_of[w[j] >> 24];
+                }
+            } else {
+                for (int j = 0; j < 16; j++) s_codes[1 + v * 16 + j] = p0 + j < n ? s_code_of[src.text[p0 + j]] : 0;
+            }
+        }
+        if (threadIdx.x < (unsigned)k) {
+            const int64_t p = tile_base + TILE + threadIdx.x;
+            s_codes[1 + TILE + threadIdx.x] = p < n ? s_code_of[src.text[p]] : 0;
+        }
+        if (threadIdx.x == THREADS - 1) s_codes[0] = s_code_of[src.text[tile_base > 0 ? tile_base - 1 : n - 1]];   // BWT symbol of the first suffix
+        __syncthreads();
+        const int first = 1 + threadIdx.x * ITEMS;
+        uint64_t w = 0;
+        for (int j = 0; j < k - 1; j++) w = w * radix + s_codes[first + j];
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            w = slide_key(w, i > 0 ? s_codes[first + i - 1] : 0u, s_codes[first + i + k - 1], radix, src.coder.top);
+            s_keys[threadIdx.x * ITEMS + i] = w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            const int e = warp_base + i * 32 + lane;
+            key[i] = e < count ? s_keys[e] : ~0ull;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            const int e = warp_base + i * 32 + lane;
+            key[i] = e < count ? keys_in[tile_base + e] : ~0ull;
+        }
     }
 
     // 2. rank inside the warp
@@ -146,7 +287,13 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
 
     // 3. values
     uint32_t val[ITEMS];
-    if (HAS_VALS) {
+    if (FROM_TEXT) {
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            const int e = warp_base + i * 32 + lane;
+            val[i] = (uint32_t)(tile_base + e) | (src.carry_shift ? (uint32_t)s_codes[e] << src.carry_shift : 0u);
+        }
+    } else if (HAS_VALS) {
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
             const int e = warp_base + i * 32 + lane;
@@ -231,11 +378,11 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
 }
 
 typedef void (*OnesweepFn)(const uint64_t*, uint64_t*, const uint32_t*, uint32_t*, int64_t, int, const unsigned long long*,
-                           unsigned long long*, unsigned*);
+                           unsigned long long*, unsigned*, TextKeySource);
 
 struct OnesweepConfig {
     int threads, items;
-    OnesweepFn pairs, keys_only;
+    OnesweepFn pairs, keys_only, from_text;
     size_t smem_pairs, smem_keys;
     int tile() const { return threads * items; }
 };
@@ -245,8 +392,9 @@ OnesweepConfig make_config() {
     const size_t fixed = (size_t)(THREADS / 32) * kRadix * 4 + kRadix * 8 + kRadix * 4 + 64;
     OnesweepConfig c;
     c.threads = THREADS; c.items = ITEMS;
-    c.pairs = onesweep_kernel<THREADS, ITEMS, true, MIN_BLOCKS, USE_MATCH>;
-    c.keys_only = onesweep_kernel<THREADS, ITEMS, false, MIN_BLOCKS, USE_MATCH>;
+    c.pairs = onesweep_kernel<THREADS, ITEMS, true, MIN_BLOCKS, USE_MATCH, false>;
+    c.keys_only = onesweep_kernel<THREADS, ITEMS, false, MIN_BLOCKS, USE_MATCH, false>;
+    c.from_text = onesweep_kernel<THREADS, ITEMS, true, MIN_BLOCKS, USE_MATCH, true>;
     c.smem_pairs = (size_t)THREADS * ITEMS * 12 + fixed;
     c.smem_keys = (size_t)THREADS * ITEMS * 8 + fixed;
     return c;
@@ -284,25 +432,37 @@ size_t radix_sort_temp_bytes(int64_t n) {
 }
 
 int radix_sort_pairs(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n, int begin_bit, int end_bit,
-                     void* temp, SortStats* stats) {
+                     void* temp, SortStats* stats, const TextKeySource* src) {
     if (n <= 0 || end_bit <= begin_bit) return GCZ_OK;
     if (end_bit - begin_bit > 64 || begin_bit < 0) return fail(GCZ_E_ARG, "radix sort bit range");
     const int npass = (end_bit - begin_bit + 7) / 8;
     const bool has_vals = b.vals[0] != nullptr;
+    if (src && (!has_vals || begin_bit != 0 || src->n != n)) return fail(GCZ_E_ARG, "radix sort from text: arguments");
     const OnesweepConfig& cfg = config();
     if (!ctx->sort_attr[has_vals ? 1 : 0]) {
         GCZ_CUDA(cudaFuncSetAttribute(has_vals ? cfg.pairs : cfg.keys_only, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(has_vals ? cfg.smem_pairs : cfg.smem_keys)));
         ctx->sort_attr[has_vals ? 1 : 0] = true;
     }
+    if (src && !ctx->sort_attr[2]) {
+        GCZ_CUDA(cudaFuncSetAttribute(cfg.from_text, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_pairs));
+        ctx->sort_attr[2] = true;
+    }
     auto* hist = static_cast<unsigned long long*>(temp);
     auto* status = hist + 8 * kRadix + 32;
     const int64_t tiles = (n + cfg.tile() - 1) / cfg.tile();
     auto* ticket = reinterpret_cast<unsigned*>(status + (size_t)tiles * kRadix);
+    const TextKeySource none;
 
     GCZ_CUDA(cudaMemsetAsync(hist, 0, 8 * kRadix * 8, st));
-    const int hist_grid = (int)std::min<int64_t>((n + kHistThreads * 8 - 1) / (kHistThreads * 8), (int64_t)ctx->sm_count * 4);
-    GCZ_LAUNCH(ctx, radix_hist_kernel, hist_grid, kHistThreads, 0, st, b.keys[b.cur], n, begin_bit, npass, hist);
+    if (src) {
+        const int64_t ttiles = (n + kTextTile - 1) / kTextTile;
+        const int grid = (int)std::min<int64_t>(ttiles, (int64_t)ctx->sm_count * 8);
+        GCZ_LAUNCH(ctx, text_hist_kernel, grid, kTextThreads, 0, st, *src, npass, hist, ttiles);
+    } else {
+        const int hist_grid = (int)std::min<int64_t>((n + kHistThreads * 8 - 1) / (kHistThreads * 8), (int64_t)ctx->sm_count * 4);
+        GCZ_LAUNCH(ctx, radix_hist_kernel, hist_grid, kHistThreads, 0, st, b.keys[b.cur], n, begin_bit, npass, hist);
+    }
     GCZ_LAUNCH(ctx, radix_scan_kernel, 1, kRadix, 0, st, hist, npass);
 
     for (int p = 0; p < npass; p++) {
@@ -314,12 +474,15 @@ int radix_sort_pairs(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n
             GCZ_CUDA(cudaEventCreate(&e0)); GCZ_CUDA(cudaEventCreate(&e1));
             GCZ_CUDA(cudaEventRecord(e0, st));
         }
-        if (has_vals) {
+        if (src && p == 0) {
+            cfg.from_text<<<(unsigned)tiles, cfg.threads, cfg.smem_pairs, st>>>(nullptr, b.keys[out], nullptr, b.vals[out], n, shift,
+                                                                                hist + p * kRadix, status, ticket, *src);
+        } else if (has_vals) {
             cfg.pairs<<<(unsigned)tiles, cfg.threads, cfg.smem_pairs, st>>>(b.keys[in], b.keys[out], b.vals[in], b.vals[out], n, shift,
-                                                                            hist + p * kRadix, status, ticket);
+                                                                            hist + p * kRadix, status, ticket, none);
         } else {
             cfg.keys_only<<<(unsigned)tiles, cfg.threads, cfg.smem_keys, st>>>(b.keys[in], b.keys[out], nullptr, nullptr, n, shift,
-                                                                               hist + p * kRadix, status, ticket);
+                                                                               hist + p * kRadix, status, ticket, none);
         }
         ctx->launches++;
         GCZ_CUDA(cudaPeekAtLastError());

@@ -30,81 +30,10 @@ namespace gcz {
 namespace {
 
 constexpr uint32_t kNoRank = 0xFFFFFFFFu;
-constexpr int kMaxK = 64;                       // radix 2 (one symbol + end marker) in 64 bits
-
-struct KeyCoder {                               // key(i) = sum_j code[i + j] * radix^(k - 1 - j), j < k
-    uint64_t radix;
-    uint64_t top;                               // radix^(k - 1)
-    int      k;
-};
-
 // Maximal runs of one symbol that are at least k long, sorted by position.
 struct Run { uint32_t start, end_side; };       // end (exclusive) in bits 0..30; bit 31: the run is followed by a LARGER symbol
 
-// ---- 1. key packing + long-run detection ------------------------------------------------------------
-constexpr int kPackThreads = 256;
-constexpr int kPackItems = 8;
-constexpr int kPackTile = kPackThreads * kPackItems;
-
-__global__ void __launch_bounds__(kPackThreads)
-pack_keys_kernel(const uint8_t* __restrict__ text, int64_t n, const uint8_t* __restrict__ code_of, KeyCoder kc,
-                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int carry_shift,
-                 uint64_t* __restrict__ run_marks, unsigned* __restrict__ run_mark_count, unsigned run_mark_cap) {
-    __shared__ uint8_t s_code_of[256];
-    __shared__ uint8_t s_codes[kPackTile + 2 * kMaxK + 8];      // [left halo kMaxK | tile | right halo]
-    __shared__ uint64_t s_keys[kPackTile];
-    const int64_t base = (int64_t)blockIdx.x * kPackTile;
-    const int k = kc.k;
-    s_code_of[threadIdx.x] = code_of[threadIdx.x];
-    __syncthreads();
-    for (int i = threadIdx.x; i < kPackTile + 2 * kMaxK; i += kPackThreads) {
-        const int64_t p = base - kMaxK + i;
-        s_codes[i] = (p >= 0 && p < n) ? s_code_of[text[p]] : 0;          // 0 = past the end, below every symbol
-    }
-    __syncthreads();
-    // every thread slides a k-symbol window over kPackItems consecutive positions
-    const int first = kMaxK + threadIdx.x * kPackItems;
-    uint64_t key = 0;
-    for (int j = 0; j < k - 1; j++) key = key * kc.radix + s_codes[first + j];
-#pragma unroll
-    for (int i = 0; i < kPackItems; i++) {
-        if (i > 0) key -= (uint64_t)s_codes[first + i - 1] * kc.top;
-        key = key * kc.radix + s_codes[first + i + k - 1];
-        s_keys[first - kMaxK + i] = key;
-    }
-    // starts and ends of runs of >= k equal symbols: mark = 2 * position (+ 1 for the last position of a run)
-    if (run_marks) {
-#pragma unroll 1
-        for (int i = 0; i < kPackItems; i++) {
-            const int64_t p = base + first - kMaxK + i;
-            if (p >= n) break;
-            const int li = first + i;
-            const uint8_t c = s_codes[li];
-            bool is_start = p == 0 || s_codes[li - 1] != c;
-            bool is_end = s_codes[li + 1] != c;
-            if (is_start) { for (int j = 1; j < k && is_start; j++) is_start = s_codes[li + j] == c; }
-            if (is_end) {
-                is_end = p >= k - 1;
-                for (int j = 1; j < k && is_end; j++) is_end = s_codes[li - j] == c;
-            }
-            if (is_start) { const unsigned at = atomicAdd(run_mark_count, 1u); if (at < run_mark_cap) run_marks[at] = 2ull * (uint64_t)p; }
-            if (is_end)   { const unsigned at = atomicAdd(run_mark_count, 1u); if (at < run_mark_cap) run_marks[at] = 2ull * (uint64_t)p + 1; }
-        }
-    }
-    __syncthreads();
-    // value = position, with the code of the PRECEDING symbol (the suffix's BWT symbol) above it when both fit
-    // 32 bits: the BWT then needs no gather from the text (carry_shift = 0: not carried)
-    for (int i = threadIdx.x; i < kPackTile; i += kPackThreads) {
-        const int64_t p = base + i;
-        if (p < n) {
-            uint32_t v = (uint32_t)p;
-            if (carry_shift) v |= (uint32_t)(p > 0 ? s_codes[kMaxK + i - 1] : s_code_of[text[n - 1]]) << carry_shift;
-            keys[p] = s_keys[i];
-            vals[p] = v;
-        }
-    }
-}
-
+// ---- 1. long runs (the marks come from the histogram pass of the first sort, radix_sort.cu) ------------------
 // sorted marks (start, end, start, end, ...) -> runs
 __global__ void pair_runs_kernel(const uint64_t* __restrict__ marks, int64_t n_runs, const uint8_t* __restrict__ text,
                                  int64_t n, Run* __restrict__ runs) {
@@ -137,7 +66,7 @@ __device__ __forceinline__ uint32_t run_remaining(const Run* __restrict__ runs, 
 
 // ---- 3. group bookkeeping ---------------------------------------------------------------------------
 constexpr int kGrpThreads = 256;
-constexpr int kGrpItems = 8;
+constexpr int kGrpItems = 16;
 constexpr int kGrpTile = kGrpThreads * kGrpItems;
 constexpr int kAggs = 5;                        // last boundary, kept slots, kept groups, kept run slots, kept run groups
 
@@ -155,99 +84,109 @@ __device__ __forceinline__ int allc_symbol(uint64_t key, const uint64_t* __restr
     return (lo < sigma && tab[lo] == key) ? lo + 1 : 0;
 }
 
-// boundary[t] = first slot of a key group; single[t] = the group has exactly one member;
-// run[t] (INITIAL only) = unresolved and the key is k copies of one symbol
-template <bool INITIAL>
-__device__ __forceinline__ SlotFlags slot_flags(const uint64_t* __restrict__ keys, int64_t m, int64_t t0,
-                                                const uint64_t* __restrict__ s_allc, int sigma) {
-    uint64_t k[kGrpItems + 2];
-#pragma unroll
-    for (int i = 0; i < kGrpItems + 2; i++) {
-        const int64_t t = t0 - 1 + i;
-        k[i] = (t >= 0 && t < m) ? keys[t] : 0;
-    }
-    unsigned bnd = 0;                       // bits 0..kGrpItems (one extra slot to the right)
-#pragma unroll
-    for (int i = 0; i <= kGrpItems; i++) {
-        const int64_t t = t0 + i;
-        const bool b = t == 0 || t >= m || k[i + 1] != k[i];
-        bnd |= (unsigned)b << i;
-    }
-    SlotFlags f;
-    f.valid = 0;
-#pragma unroll
-    for (int i = 0; i < kGrpItems; i++) f.valid |= (unsigned)(t0 + i < m) << i;
-    f.boundary = bnd & f.valid;
-    f.single = bnd & (bnd >> 1) & f.valid;
-    f.run = 0;
-    if (INITIAL && sigma > 0) {
-        const unsigned open = f.valid & ~f.single;
-#pragma unroll
-        for (int i = 0; i < kGrpItems; i++) {
-            if ((open >> i) & 1) f.run |= (unsigned)(allc_symbol(k[i + 1], s_allc, sigma) != 0) << i;
-        }
-    }
-    return f;
-}
+// Grouping of a sorted key sequence, three launches and no serial chain between tiles:
+//   flags   every key is read once, coalesced: bit arrays "slot starts a key group" / "unresolved long-run suffix",
+//           and per-tile aggregates (last group start, kept slots / groups of the general and of the long-run kind);
+//   scan    exclusive scan of the tile aggregates (one CTA);
+//   apply   works from the bit arrays only: ranks, finished suffixes and the next list.
+struct GroupArgs {
+    const uint64_t* keys;          // sorted keys of the m slots / list entries
+    const uint32_t* suf;           // suffix of every entry
+    const uint32_t* pos;           // refine: SA slot of every list entry (ascending); initial: null (slot = index)
+    int64_t         m;
+    unsigned*       bnd_bits;      // [m / 32 + 2] bit t: slot t starts a key group
+    unsigned*       run_bits;      // [m / 32 + 2] bit t: slot t is an unresolved long-run suffix (initial only)
+    unsigned*       agg;           // [kAggs][tiles] tile aggregates, then their exclusive scans
+    long long*      totals;        // [4]: kept slots, kept groups, kept long-run slots, kept long-run groups
+    uint32_t*       rank;
+    uint32_t*       sa;
+    uint32_t*       pos_out;       // next list
+    uint32_t*       suf_out;
+    uint32_t*       gid_out;
+    uint32_t        gid_base;
+    uint32_t        pos_mask;      // suffix = value & pos_mask (the bits above carry the BWT symbol)
+    // initial only: the long-run suffixes leave through a separate list (switched off when the run marks overflowed)
+    const uint64_t* allc;
+    int             sigma;
+    const unsigned* run_mark_count;
+    unsigned        run_mark_cap;
+    uint32_t*       run_pos_out;
+    uint32_t*       run_suf_out;
+};
 
-struct GroupAggs { long long* a[kAggs]; };       // per-tile aggregates / their exclusive scans
-
-// pass A: per-tile aggregates
 template <bool INITIAL>
 __global__ void __launch_bounds__(kGrpThreads)
-group_aggregate_kernel(const uint64_t* __restrict__ keys, int64_t m, const uint64_t* __restrict__ allc, int sigma, GroupAggs agg) {
-    __shared__ long long s_last[kGrpThreads / 32];
-    __shared__ unsigned s_cnt[4][kGrpThreads / 32];
+group_flags_kernel(GroupArgs a) {
+    __shared__ uint64_t s_keys[kGrpTile + 2];          // [0] = slot before the tile, [1 ..] the tile, then the slot after
     __shared__ uint64_t s_allc[256];
-    if (INITIAL && sigma > 0) {
-        if ((int)threadIdx.x < sigma) s_allc[threadIdx.x] = allc[threadIdx.x];
-        __syncthreads();
+    __shared__ unsigned s_agg[kAggs][kGrpThreads / 32];
+    int sigma = 0;
+    if (INITIAL) {
+        sigma = (a.sigma > 0 && *a.run_mark_count <= a.run_mark_cap) ? a.sigma : 0;
+        if ((int)threadIdx.x < sigma) s_allc[threadIdx.x] = a.allc[threadIdx.x];
     }
-    const int64_t t0 = (int64_t)blockIdx.x * kGrpTile + (int64_t)threadIdx.x * kGrpItems;
-    const SlotFlags f = slot_flags<INITIAL>(keys, m, t0, s_allc, sigma);
-    long long last = f.boundary ? t0 + (31 - __clz(f.boundary)) : -1;
-    unsigned c[4] = { (unsigned)__popc(f.valid & ~f.single & ~f.run), (unsigned)__popc(f.boundary & ~f.single & ~f.run),
-                      (unsigned)__popc(f.run), (unsigned)__popc(f.boundary & f.run) };
+    const int64_t tile_base = (int64_t)blockIdx.x * kGrpTile;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+    for (int i = 0; i < kGrpItems; i++) {
+        const int e = i * kGrpThreads + threadIdx.x;
+        const int64_t t = tile_base + e;
+        s_keys[1 + e] = t < a.m ? a.keys[t] : 0;
+    }
+    if (threadIdx.x == 0) s_keys[0] = tile_base > 0 ? a.keys[tile_base - 1] : 0;
+    if (threadIdx.x == 32) s_keys[kGrpTile + 1] = tile_base + kGrpTile < a.m ? a.keys[tile_base + kGrpTile] : 0;
+    __syncthreads();
+    unsigned last1 = 0, keep = 0, groups = 0, keep_run = 0, groups_run = 0;     // last1 = in-tile slot of the last boundary + 1
 #pragma unroll
-        for (int q = 0; q < 4; q++) c[q] += __shfl_xor_sync(0xffffffffu, c[q], o);
+    for (int i = 0; i < kGrpItems; i++) {
+        const int e = i * kGrpThreads + threadIdx.x;
+        const int64_t t = tile_base + e;
+        const uint64_t key = s_keys[1 + e];
+        const bool valid = t < a.m;
+        const bool b = valid && (t == 0 || key != s_keys[e]);
+        const bool open = valid && !(b && (t + 1 >= a.m || s_keys[2 + e] != key));   // shares its key with a neighbour
+        bool run = false;
+        if (INITIAL && sigma > 0 && open) run = allc_symbol(key, s_allc, sigma) != 0;
+        const unsigned wb = __ballot_sync(0xffffffffu, b), wr = __ballot_sync(0xffffffffu, run);
+        const unsigned wo = __ballot_sync(0xffffffffu, open);
+        if (lane_id() == 0 && tile_base + (e & ~31) < a.m) {
+            a.bnd_bits[t >> 5] = wb;
+            if (INITIAL) a.run_bits[t >> 5] = wr;
+            if (wb) last1 = (e & ~31) + 32 - __clz(wb);                           // items ascend: the latest word wins
+            keep += __popc(wo & ~wr); groups += __popc(wb & wo & ~wr);
+            keep_run += __popc(wr);   groups_run += __popc(wb & wr);
+        }
     }
     if (lane_id() == 0) {
-        s_last[threadIdx.x >> 5] = last;
-        for (int q = 0; q < 4; q++) s_cnt[q][threadIdx.x >> 5] = c[q];
+        const int w = threadIdx.x >> 5;
+        s_agg[0][w] = last1; s_agg[1][w] = keep; s_agg[2][w] = groups; s_agg[3][w] = keep_run; s_agg[4][w] = groups_run;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        long long l = -1, t[4] = { 0, 0, 0, 0 };
-        for (int w = 0; w < kGrpThreads / 32; w++) {
-            l = max(l, s_last[w]);
-            for (int q = 0; q < 4; q++) t[q] += s_cnt[q][w];
-        }
-        agg.a[0][blockIdx.x] = l;
-        for (int q = 0; q < 4; q++) agg.a[1 + q][blockIdx.x] = t[q];
+    if (threadIdx.x < kAggs) {
+        unsigned v = 0;
+        for (int w = 0; w < kGrpThreads / 32; w++) v = threadIdx.x == 0 ? max(v, s_agg[0][w]) : v + s_agg[threadIdx.x][w];
+        // aggregate 0 travels as a global slot + 1 (0 = no boundary in the tile)
+        if (threadIdx.x == 0 && v) v += (unsigned)tile_base;
+        a.agg[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = v;
     }
 }
 
-// single-CTA exclusive scans over the tile aggregates (max for `last`, sum for the others), in place;
-// totals[q] = sum of aggregate 1 + q
+// single-CTA exclusive scans over the tile aggregates (max for the last boundary, sum for the others), in place
 __global__ void __launch_bounds__(1024)
-group_scan_kernel(GroupAggs agg, int64_t tiles, long long* __restrict__ totals) {
-    __shared__ long long s_w[kAggs][32];
-    __shared__ long long s_carry[kAggs];
-    if (threadIdx.x < kAggs) s_carry[threadIdx.x] = threadIdx.x == 0 ? -1 : 0;
+group_scan_kernel(unsigned* __restrict__ agg, int64_t tiles, long long* __restrict__ totals) {
+    __shared__ unsigned s_w[kAggs][32];
+    __shared__ unsigned s_carry[kAggs];
+    if (threadIdx.x < kAggs) s_carry[threadIdx.x] = 0;
     __syncthreads();
     for (int64_t base = 0; base < tiles; base += 1024) {
         const int64_t i = base + threadIdx.x;
-        long long v[kAggs], inc[kAggs];
+        unsigned v[kAggs], inc[kAggs];
 #pragma unroll
-        for (int q = 0; q < kAggs; q++) { v[q] = i < tiles ? agg.a[q][i] : (q == 0 ? -1 : 0); inc[q] = v[q]; }
+        for (int q = 0; q < kAggs; q++) { v[q] = i < tiles ? agg[(size_t)q * tiles + i] : 0; inc[q] = v[q]; }
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
 #pragma unroll
             for (int q = 0; q < kAggs; q++) {
-                const long long t = __shfl_up_sync(0xffffffffu, inc[q], o);
+                const unsigned t = __shfl_up_sync(0xffffffffu, inc[q], o);
                 if (lane_id() >= (unsigned)o) inc[q] = q == 0 ? max(inc[q], t) : inc[q] + t;
             }
         }
@@ -256,7 +195,7 @@ group_scan_kernel(GroupAggs agg, int64_t tiles, long long* __restrict__ totals) 
             for (int q = 0; q < kAggs; q++) s_w[q][threadIdx.x >> 5] = inc[q];
         }
         __syncthreads();
-        long long b[kAggs];
+        unsigned b[kAggs];
 #pragma unroll
         for (int q = 0; q < kAggs; q++) b[q] = s_carry[q];
         for (unsigned w = 0; w < (threadIdx.x >> 5); w++) {
@@ -264,12 +203,11 @@ group_scan_kernel(GroupAggs agg, int64_t tiles, long long* __restrict__ totals) 
 #pragma unroll
             for (int q = 1; q < kAggs; q++) b[q] += s_w[q][w];
         }
-        // exclusive results
-        const long long prev_l = __shfl_up_sync(0xffffffffu, inc[0], 1);
+        const unsigned prev0 = __shfl_up_sync(0xffffffffu, inc[0], 1);
         if (i < tiles) {
-            agg.a[0][i] = lane_id() == 0 ? b[0] : max(b[0], prev_l);
+            agg[i] = lane_id() == 0 ? b[0] : max(b[0], prev0);
 #pragma unroll
-            for (int q = 1; q < kAggs; q++) agg.a[q][i] = b[q] + inc[q] - v[q];
+            for (int q = 1; q < kAggs; q++) agg[(size_t)q * tiles + i] = b[q] + inc[q] - v[q];
         }
         __syncthreads();
         if (threadIdx.x == 1023) {
@@ -279,108 +217,122 @@ group_scan_kernel(GroupAggs agg, int64_t tiles, long long* __restrict__ totals) 
         }
         __syncthreads();
     }
-    if (threadIdx.x < kAggs - 1) totals[threadIdx.x] = s_carry[1 + threadIdx.x];
+    if (threadIdx.x >= 1 && threadIdx.x < kAggs) totals[threadIdx.x - 1] = s_carry[threadIdx.x];
 }
 
-struct ApplyArgs {
-    const uint64_t* keys;          // sorted keys of the m slots / list entries
-    const uint32_t* suf;           // suffix of every entry
-    const uint32_t* pos;           // refine: SA slot of every list entry (ascending); initial: null (slot = index)
-    int64_t         m;
-    GroupAggs       pre;           // exclusive scans of the tile aggregates
-    uint32_t*       rank;
-    uint32_t*       sa;
-    uint32_t*       pos_out;       // next list
-    uint32_t*       suf_out;
-    uint32_t*       gid_out;
-    uint32_t        gid_base;
-    uint32_t        pos_mask;      // suffix = value & pos_mask (the bits above carry the BWT symbol)
-    // initial only: the long-run suffixes leave through a separate list, already keyed for their one sort
-    const uint64_t* allc;
-    int             sigma;
-    const Run*      runs;
-    int             n_runs;
-    int             k;
-    uint32_t*       run_pos_out;
-    uint64_t*       run_key_out;
-    uint32_t*       run_suf_out;
-};
-
-// pass B: ranks, finished suffixes, next list
 template <bool INITIAL>
 __global__ void __launch_bounds__(kGrpThreads)
-group_apply_kernel(ApplyArgs a) {
-    __shared__ long long s_last[kGrpThreads / 32];
-    __shared__ unsigned s_cnt[4][kGrpThreads / 32];
-    __shared__ uint64_t s_allc[256];
-    if (INITIAL && a.sigma > 0) {
-        if ((int)threadIdx.x < a.sigma) s_allc[threadIdx.x] = a.allc[threadIdx.x];
-        __syncthreads();
+group_apply_kernel(GroupArgs a) {
+    __shared__ unsigned s_w[kAggs][kGrpThreads / 32];
+    const int64_t tile_base = (int64_t)blockIdx.x * kGrpTile;
+    const int64_t t0 = tile_base + (int64_t)threadIdx.x * kGrpItems;
+    // flags of my kGrpItems consecutive slots (+ the boundary bit of the slot after them)
+    unsigned valid = 0, boundary = 0, single = 0, run = 0;
+    if (t0 < a.m) {
+        const int64_t w = t0 >> 5;
+        const int sh = (int)(t0 & 31);
+        const int cnt = (int)min((int64_t)kGrpItems, a.m - t0);
+        valid = (1u << cnt) - 1u;
+        const int64_t words = (a.m + 31) >> 5;
+        const unsigned long long two = (unsigned long long)a.bnd_bits[w] | (w + 1 < words ? (unsigned long long)a.bnd_bits[w + 1] << 32 : 0ull);
+        unsigned bnd = (unsigned)(two >> sh) & ((2u << kGrpItems) - 1u);          // kGrpItems + 1 bits
+        if (t0 + cnt >= a.m) bnd |= 1u << cnt;                                     // the end closes the last group
+        boundary = bnd & valid;
+        single = bnd & (bnd >> 1) & valid;
+        if (INITIAL) {
+            const unsigned long long rtwo = (unsigned long long)a.run_bits[w] | (w + 1 < words ? (unsigned long long)a.run_bits[w + 1] << 32 : 0ull);
+            run = (unsigned)(rtwo >> sh) & valid & ~single;
+        }
     }
-    const int64_t t0 = (int64_t)blockIdx.x * kGrpTile + (int64_t)threadIdx.x * kGrpItems;
-    const SlotFlags f = slot_flags<INITIAL>(a.keys, a.m, t0, s_allc, a.sigma);
-    const long long my_last = f.boundary ? t0 + (31 - __clz(f.boundary)) : -1;
-    const unsigned mine[4] = { (unsigned)__popc(f.valid & ~f.single & ~f.run), (unsigned)__popc(f.boundary & ~f.single & ~f.run),
-                               (unsigned)__popc(f.run), (unsigned)__popc(f.boundary & f.run) };
+    const unsigned my_last1 = boundary ? (unsigned)t0 + 32 - __clz(boundary) : 0u;      // global slot + 1
+    const unsigned mine[4] = { (unsigned)__popc(valid & ~single & ~run), (unsigned)__popc(boundary & ~single & ~run),
+                               (unsigned)__popc(run), (unsigned)__popc(boundary & run) };
     // block-wide exclusive scans of the per-thread aggregates
-    const long long il = warp_incl_max(my_last);
+    unsigned il = my_last1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, il, o); if (lane_id() >= (unsigned)o) il = max(il, t); }
     unsigned inc[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) inc[q] = warp_incl_sum(mine[q]);
     if (lane_id() == 31) {
-        s_last[threadIdx.x >> 5] = il;
+        s_w[0][threadIdx.x >> 5] = il;
 #pragma unroll
-        for (int q = 0; q < 4; q++) s_cnt[q][threadIdx.x >> 5] = inc[q];
+        for (int q = 0; q < 4; q++) s_w[1 + q][threadIdx.x >> 5] = inc[q];
     }
     __syncthreads();
-    long long last = a.pre.a[0][blockIdx.x];
-    long long cnt[4];
+    unsigned last1 = a.agg[blockIdx.x];
+    unsigned cnt[4];
 #pragma unroll
-    for (int q = 0; q < 4; q++) cnt[q] = a.pre.a[1 + q][blockIdx.x];
+    for (int q = 0; q < 4; q++) cnt[q] = a.agg[(size_t)(1 + q) * gridDim.x + blockIdx.x];
     for (unsigned w = 0; w < (threadIdx.x >> 5); w++) {
-        last = max(last, s_last[w]);
+        last1 = max(last1, s_w[0][w]);
 #pragma unroll
-        for (int q = 0; q < 4; q++) cnt[q] += s_cnt[q][w];
+        for (int q = 0; q < 4; q++) cnt[q] += s_w[1 + q][w];
     }
-    const long long prev_l = __shfl_up_sync(0xffffffffu, il, 1);
-    if (lane_id() > 0) last = max(last, prev_l);
+    const unsigned prev_l = __shfl_up_sync(0xffffffffu, il, 1);
+    if (lane_id() > 0) last1 = max(last1, prev_l);
 #pragma unroll
     for (int q = 0; q < 4; q++) cnt[q] += inc[q] - mine[q];
-    long long keep = cnt[0], groups = cnt[1], keep_run = cnt[2];
+    if ((valid & ~single) == 0) return;                                                // nothing unresolved here
+    unsigned keep = cnt[0], groups = cnt[1], keep_run = cnt[2];
+    unsigned last = last1 - 1;                                                         // group start of the slot before mine
 
 #pragma unroll
     for (int i = 0; i < kGrpItems; i++) {
-        if (!((f.valid >> i) & 1)) break;
-        const int64_t t = t0 + i;
-        if ((f.boundary >> i) & 1) last = t;
-        if ((f.single >> i) & 1) {
-            // final.  Initial: already in place, and its rank is left unset (found by key search when needed)
-            if (!INITIAL) { const uint32_t v = a.suf[t]; a.rank[v & a.pos_mask] = a.pos[last]; a.sa[a.pos[t]] = v; }
-            continue;
-        }
-        const uint32_t sv = a.suf[t], s = sv & a.pos_mask;
-        a.rank[s] = INITIAL ? (uint32_t)last : a.pos[last];
-        if (INITIAL && ((f.run >> i) & 1)) {
-            const int c = allc_symbol(a.keys[t], s_allc, a.sigma);
-            bool larger = false;
-            const uint32_t r = run_remaining(a.runs, a.n_runs, s, a.k, &larger);
-            // symbol, then the side the run ends on, then run length left: ascending below, descending above
-            const uint32_t order = larger ? (0x80000000u | (0x7FFFFFFFu - r)) : r;
-            a.run_pos_out[keep_run] = (uint32_t)t;
-            a.run_key_out[keep_run] = ((uint64_t)c << 32) | order;
+        if (!((valid >> i) & 1)) break;
+        const uint32_t t = (uint32_t)t0 + i;
+        if ((boundary >> i) & 1) last = t;
+        if ((single >> i) & 1) continue;
+        const uint32_t sv = a.suf[t];
+        a.rank[sv & a.pos_mask] = INITIAL ? last : a.pos[last];
+        if (INITIAL && ((run >> i) & 1)) {
+            a.run_pos_out[keep_run] = t;
             a.run_suf_out[keep_run] = sv;
             keep_run++;
         } else {
-            if ((f.boundary >> i) & 1) groups++;
-            a.pos_out[keep] = INITIAL ? (uint32_t)t : a.pos[t];
+            if ((boundary >> i) & 1) groups++;
+            a.pos_out[keep] = INITIAL ? t : a.pos[t];
             a.suf_out[keep] = sv;
-            a.gid_out[keep] = a.gid_base + (uint32_t)(groups - 1);
+            a.gid_out[keep] = a.gid_base + groups - 1;
             keep++;
         }
     }
 }
 
-// key of the suffix at q, straight from the text (what pack_keys_kernel stored for it)
+// refine rounds: a suffix alone in its group is final (the first grouping leaves those where the sort put them)
+__global__ void __launch_bounds__(256)
+group_finish_kernel(GroupArgs a) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t words = (a.m + 31) >> 5;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < a.m; t += stride) {
+        const bool b = (a.bnd_bits[t >> 5] >> (t & 31)) & 1u;
+        const int64_t t1 = t + 1;
+        const bool b_next = t1 >= a.m || ((a.bnd_bits[t1 >> 5] >> (t1 & 31)) & 1u);
+        (void)words;
+        if (b && b_next) {
+            const uint32_t v = a.suf[t], slot = a.pos[t];
+            a.rank[v & a.pos_mask] = slot;
+            a.sa[slot] = v;
+        }
+    }
+}
+
+// sort key of a long-run suffix: symbol, then the side the run ends on, then the run length left —
+// ascending when the run ends below its symbol, descending when it ends above (header, point 5)
+__global__ void run_keys_kernel(const uint32_t* __restrict__ run_suf, int64_t m_run, uint32_t pos_mask, const Run* __restrict__ runs,
+                                int n_runs, int k, const uint8_t* __restrict__ text, const uint8_t* __restrict__ code_of,
+                                uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= m_run) return;
+    const uint32_t sv = run_suf[u], s = sv & pos_mask;
+    bool larger = false;
+    const uint32_t r = run_remaining(runs, n_runs, s, k, &larger);
+    const uint32_t order = larger ? (0x80000000u | (0x7FFFFFFFu - r)) : r;
+    keys[u] = ((uint64_t)code_of[text[s]] << 32) | order;
+    vals[u] = sv;
+}
+
+// key of the suffix at q, straight from the text (what the first sort computed for it)
 __device__ __forceinline__ uint64_t key_at(const uint8_t* __restrict__ text, int64_t n, const uint8_t* __restrict__ code_of,
                                            const KeyCoder& kc, int64_t q) {
     uint64_t key = 0;
@@ -445,13 +397,13 @@ KeyCoder choose_key(const int64_t counts[256], int64_t n, int sigma) {
     double sum_p2 = 0;
     for (int c = 0; c < 256; c++) { const double p = (double)counts[c] / (double)n; sum_p2 += p * p; }
     const double h2 = std::max(1e-3, -std::log2(std::min(1.0, sum_p2)));
-    const int k_min = (int)std::min<double>(kMaxK, std::ceil((std::log2((double)n + 1) + 6.0) / h2));
+    const int k_min = (int)std::min<double>(kMaxKeySymbols, std::ceil((std::log2((double)n + 1) + 6.0) / h2));
     KeyCoder kc;
     kc.radix = radix;
     for (int passes = 1; passes <= 8; passes++) {
         int k = 0;
         unsigned __int128 pw = 1;                            // radix^k
-        while (k < kMaxK && pw * radix <= (one << (8 * passes))) { pw *= radix; k++; }
+        while (k < kMaxKeySymbols && pw * radix <= (one << (8 * passes))) { pw *= radix; k++; }
         kc.k = std::max(k, 1);
         if (k >= k_min) break;
     }
@@ -463,9 +415,9 @@ KeyCoder choose_key(const int64_t counts[256], int64_t n, int sigma) {
 }  // namespace
 
 size_t suffix_sort_workspace_bytes(int64_t n) {
-    // rank 4n + keys 16n + vals(other) 4n + refinement worst case (lists 24n, sort 12n, run list 4n) + run marks + sort temp
+    // rank 4n + keys 16n + vals(other) 4n + refinement worst case (lists 24n, sort 12n, run list 8n) + run marks + sort temp
     const size_t tiles = (size_t)(n / kGrpTile + 2);
-    return (size_t)n * (4 + 16 + 4 + 40 + 2) + radix_sort_temp_bytes(n) + tiles * kAggs * 8 + (1 << 20);
+    return (size_t)n * (4 + 16 + 4 + 44 + 2) + radix_sort_temp_bytes(n) + tiles * kAggs * 8 + (size_t)n / 4 + (1 << 20);
 }
 
 int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t n, const int64_t counts[256],
@@ -503,15 +455,18 @@ int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t 
     uint32_t* d_vals1 = arena.get<uint32_t>((size_t)n);
     void* d_temp = arena.raw(radix_sort_temp_bytes(n));
     const int64_t tiles_n = (n + kGrpTile - 1) / kGrpTile;
-    long long* d_agg = arena.get<long long>((size_t)tiles_n * kAggs + 8);
+    unsigned* d_agg = arena.get<unsigned>((size_t)tiles_n * kAggs + 8);
+    unsigned* d_bits = arena.get<unsigned>((size_t)(n / 32 + 2) * 2);
     long long* d_totals = arena.get<long long>(8);                 // [0..3] group totals, [4] run marks (as unsigned)
     uint64_t* d_marks[2] = { arena.get<uint64_t>(mark_cap), arena.get<uint64_t>(mark_cap) };
     Run* d_runs = arena.get<Run>(mark_cap / 2 + 1);
-    if (!d_code || !d_allc || !d_rank || !d_keys0 || !d_keys1 || !d_vals1 || !d_temp || !d_agg || !d_totals ||
-        !d_marks[0] || !d_marks[1] || !d_runs)
+    // first list and the long-run list: how many suffixes stay unresolved is only known after the grouping pass
+    uint32_t* list0[3] = { arena.get<uint32_t>((size_t)n), arena.get<uint32_t>((size_t)n), arena.get<uint32_t>((size_t)n) };
+    uint32_t* run_pos = arena.get<uint32_t>((size_t)n);
+    uint32_t* run_suf = arena.get<uint32_t>((size_t)n);
+    if (!d_code || !d_allc || !d_rank || !d_keys0 || !d_keys1 || !d_vals1 || !d_temp || !d_agg || !d_bits || !d_totals ||
+        !d_marks[0] || !d_marks[1] || !d_runs || !list0[0] || !list0[1] || !list0[2] || !run_pos || !run_suf)
         return fail(GCZ_E_NOMEM, "suffix sort workspace for n=%lld", (long long)n);
-    GroupAggs agg;
-    for (int q = 0; q < kAggs; q++) agg.a[q] = d_agg + (size_t)q * tiles_n;
     unsigned* d_mark_count = reinterpret_cast<unsigned*>(d_totals + 4);
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -531,86 +486,86 @@ int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t 
     b.keys[0] = d_keys0; b.keys[1] = d_keys1;
     b.vals[0] = d_sa;    b.vals[1] = d_vals1;
     b.cur = npass & 1;
-    const int pack_grid = (int)((n + kPackTile - 1) / kPackTile);
-    GCZ_LAUNCH(ctx, pack_keys_kernel, pack_grid, kPackThreads, 0, st, d_text, n, d_code, kc, b.keys[b.cur], b.vals[b.cur], carry,
-               d_marks[0], d_mark_count, mark_cap);
+    // keys and values are never written out unsorted: the first digit pass reads the text (TextKeySource)
+    TextKeySource src;
+    src.text = d_text; src.n = n; src.code_of = d_code; src.coder = kc; src.carry_shift = carry;
+    src.run_marks = d_marks[0]; src.run_mark_count = d_mark_count; src.run_mark_cap = mark_cap;
     SortStats ss;
     SortStats* ssp = stats ? &ss : nullptr;
-    GCZ_TRY(radix_sort_pairs(ctx, st, b, n, 0, key_bits, d_temp, ssp));
+    GCZ_TRY(radix_sort_pairs(ctx, st, b, n, 0, key_bits, d_temp, ssp, &src));
     if (b.cur != 0) return fail(GCZ_E_INTERNAL, "initial sort landed in the wrong buffer");
 
-    // groups of equal keys
-    int sigma_runs = sigma;                 // 0 switches the long-run path off
-    GCZ_LAUNCH(ctx, group_aggregate_kernel<true>, (unsigned)tiles_n, kGrpThreads, 0, st, d_keys0, n, d_allc, sigma_runs, agg);
-    GCZ_LAUNCH(ctx, group_scan_kernel, 1, 1024, 0, st, agg, tiles_n, d_totals);
+    // groups of equal keys -> ranks, first list, long-run list.  More long runs than the mark buffer holds (a
+    // text made of medium runs) switches the long-run path off on the device: plain doubling, where a "run"
+    // suffix is an ordinary member of its key group.
+    auto launch_group = [&](bool initial, GroupArgs& ga) -> int {
+        const int64_t tiles = (ga.m + kGrpTile - 1) / kGrpTile;
+        ga.bnd_bits = d_bits; ga.run_bits = d_bits + (n / 32 + 2); ga.agg = d_agg; ga.totals = d_totals;
+        if (initial) {
+            GCZ_LAUNCH(ctx, group_flags_kernel<true>, (unsigned)tiles, kGrpThreads, 0, st, ga);
+            GCZ_LAUNCH(ctx, group_scan_kernel, 1, 1024, 0, st, d_agg, tiles, d_totals);
+            GCZ_LAUNCH(ctx, group_apply_kernel<true>, (unsigned)tiles, kGrpThreads, 0, st, ga);
+        } else {
+            GCZ_LAUNCH(ctx, group_flags_kernel<false>, (unsigned)tiles, kGrpThreads, 0, st, ga);
+            GCZ_LAUNCH(ctx, group_scan_kernel, 1, 1024, 0, st, d_agg, tiles, d_totals);
+            GCZ_LAUNCH(ctx, group_apply_kernel<false>, (unsigned)tiles, kGrpThreads, 0, st, ga);
+            const int grid = (int)std::min<int64_t>((ga.m + 255) / 256, (int64_t)ctx->sm_count * 16);
+            GCZ_LAUNCH(ctx, group_finish_kernel, grid, 256, 0, st, ga);
+        }
+        return GCZ_OK;
+    };
+    GroupArgs ga;
+    ga.keys = d_keys0; ga.suf = d_sa; ga.pos = nullptr; ga.m = n; ga.rank = d_rank; ga.sa = d_sa;
+    ga.pos_out = list0[0]; ga.suf_out = list0[1]; ga.gid_out = list0[2]; ga.gid_base = 0; ga.pos_mask = pos_mask;
+    ga.allc = d_allc; ga.sigma = sigma; ga.run_mark_count = d_mark_count; ga.run_mark_cap = mark_cap;
+    ga.run_pos_out = run_pos; ga.run_suf_out = run_suf;
+    GCZ_TRY(launch_group(true, ga));
     long long h_totals[5] = { 0, 0, 0, 0, 0 };
     GCZ_CUDA(cudaMemcpyAsync(h_totals, d_totals, sizeof(h_totals), cudaMemcpyDeviceToHost, st));
     GCZ_CUDA(cudaStreamSynchronize(st));
     int64_t m = h_totals[0], groups = h_totals[1];
-    int64_t m_run = h_totals[2];
+    const int64_t m_run = h_totals[2];
     const int64_t n_marks = (int64_t)(uint32_t)h_totals[4];
-    int n_runs = 0;
-    if (m_run > 0 && (n_marks > (int64_t)mark_cap || (n_marks & 1))) {
-        // more long runs than the mark buffer holds (a text made of medium runs): plain doubling, where a
-        // "run" suffix is an ordinary member of its key group — regroup without the run classification
-        sigma_runs = 0;
-        GCZ_LAUNCH(ctx, group_aggregate_kernel<true>, (unsigned)tiles_n, kGrpThreads, 0, st, d_keys0, n, d_allc, 0, agg);
-        GCZ_LAUNCH(ctx, group_scan_kernel, 1, 1024, 0, st, agg, tiles_n, d_totals);
-        GCZ_CUDA(cudaMemcpyAsync(h_totals, d_totals, 4 * sizeof(long long), cudaMemcpyDeviceToHost, st));
-        GCZ_CUDA(cudaStreamSynchronize(st));
-        m = h_totals[0]; groups = h_totals[1]; m_run = h_totals[2];
-    }
-    if (m_run > 0) {
-        n_runs = (int)(n_marks / 2);
-        RadixBuffers rb;
-        rb.keys[0] = d_marks[0]; rb.keys[1] = d_marks[1];
-        GCZ_TRY(radix_sort_pairs(ctx, st, rb, n_marks, 0, bits_for(2ull * (uint64_t)n + 1), d_temp, nullptr));
-        GCZ_LAUNCH(ctx, pair_runs_kernel, (unsigned)((n_runs + 255) / 256), 256, 0, st, rb.keys[rb.cur], (int64_t)n_runs, d_text, n, d_runs);
-    }
+    if (m_run > 0 && (n_marks > (int64_t)mark_cap || (n_marks & 1))) return fail(GCZ_E_INTERNAL, "long-run bookkeeping");
+    const int n_runs = m_run > 0 ? (int)(n_marks / 2) : 0;
+    if (stats) GCZ_CUDA(cudaEventRecord(ev1, st));
 
     // refinement buffers: the initial sort's second key/value arrays are dead, its sorted keys stay (point 4)
     const int64_t m0 = m + m_run;
     const size_t cap = (size_t)std::max<int64_t>(m0, 1);
-    uint32_t* list_pos[2] = { arena.get<uint32_t>(cap), arena.get<uint32_t>(cap) };
-    uint32_t* list_suf[2] = { arena.get<uint32_t>(cap), arena.get<uint32_t>(cap) };
-    uint32_t* list_gid[2] = { arena.get<uint32_t>(cap), arena.get<uint32_t>(cap) };
+    uint32_t* list_pos[2] = { list0[0], arena.get<uint32_t>(cap) };
+    uint32_t* list_suf[2] = { list0[1], arena.get<uint32_t>(cap) };
+    uint32_t* list_gid[2] = { list0[2], arena.get<uint32_t>(cap) };
     uint64_t* r_keys1 = arena.get<uint64_t>(cap);
     uint32_t* r_vals1 = arena.get<uint32_t>(cap);
-    uint32_t* run_pos = arena.get<uint32_t>((size_t)std::max<int64_t>(m_run, 1));
-    if (!list_pos[0] || !list_pos[1] || !list_suf[0] || !list_suf[1] || !list_gid[0] || !list_gid[1] || !r_keys1 || !r_vals1 || !run_pos)
+    if (!list_pos[1] || !list_suf[1] || !list_gid[1] || !r_keys1 || !r_vals1)
         return fail(GCZ_E_NOMEM, "suffix sort refinement lists for %lld unresolved suffixes", (long long)m0);
     uint64_t* r_keys0 = d_keys1;
     uint32_t* r_vals0 = d_vals1;
 
-    ApplyArgs aa;
-    aa.keys = d_keys0; aa.suf = d_sa; aa.pos = nullptr; aa.m = n; aa.pre = agg; aa.rank = d_rank; aa.sa = d_sa;
-    aa.pos_out = list_pos[0]; aa.suf_out = list_suf[0]; aa.gid_out = list_gid[0]; aa.gid_base = 0; aa.pos_mask = pos_mask;
-    aa.allc = d_allc; aa.sigma = sigma_runs; aa.runs = d_runs; aa.n_runs = n_runs; aa.k = k;
-    aa.run_pos_out = run_pos; aa.run_key_out = r_keys0; aa.run_suf_out = r_vals0;
-    GCZ_LAUNCH(ctx, group_apply_kernel<true>, (unsigned)tiles_n, kGrpThreads, 0, st, aa);
-    if (stats) GCZ_CUDA(cudaEventRecord(ev1, st));
-
     int rounds = 0;
     if (m_run > 0) {
         // the long-run suffixes: one sort by (symbol, side, run length left); what stays tied joins the list
+        RadixBuffers mb;
+        mb.keys[0] = d_marks[0]; mb.keys[1] = d_marks[1];
+        GCZ_TRY(radix_sort_pairs(ctx, st, mb, n_marks, 0, bits_for(2ull * (uint64_t)n + 1), d_temp, nullptr));
+        GCZ_LAUNCH(ctx, pair_runs_kernel, (unsigned)((n_runs + 255) / 256), 256, 0, st, mb.keys[mb.cur], (int64_t)n_runs, d_text, n, d_runs);
         RadixBuffers rb;
         rb.keys[0] = r_keys0; rb.keys[1] = r_keys1;
         rb.vals[0] = r_vals0; rb.vals[1] = r_vals1;
         rb.cur = 0;
+        GCZ_LAUNCH(ctx, run_keys_kernel, (unsigned)((m_run + 255) / 256), 256, 0, st, run_suf, m_run, pos_mask, d_runs, n_runs, k,
+                   d_text, d_code, rb.keys[0], rb.vals[0]);
         GCZ_TRY(radix_sort_pairs(ctx, st, rb, m_run, 0, 32 + bits_for((uint64_t)sigma), d_temp, ssp));
-        const int64_t tiles_r = (m_run + kGrpTile - 1) / kGrpTile;
-        GCZ_LAUNCH(ctx, group_aggregate_kernel<false>, (unsigned)tiles_r, kGrpThreads, 0, st, rb.keys[rb.cur], m_run, nullptr, 0, agg);
-        GCZ_LAUNCH(ctx, group_scan_kernel, 1, 1024, 0, st, agg, tiles_r, d_totals);
-        ApplyArgs ar = aa;
-        ar.keys = rb.keys[rb.cur]; ar.suf = rb.vals[rb.cur]; ar.pos = run_pos; ar.m = m_run; ar.sigma = 0;
-        ar.pos_out = list_pos[0] + m; ar.suf_out = list_suf[0] + m; ar.gid_out = list_gid[0] + m; ar.gid_base = (uint32_t)groups;
-        GCZ_LAUNCH(ctx, group_apply_kernel<false>, (unsigned)tiles_r, kGrpThreads, 0, st, ar);
+        GroupArgs gr = ga;
+        gr.keys = rb.keys[rb.cur]; gr.suf = rb.vals[rb.cur]; gr.pos = run_pos; gr.m = m_run;
+        gr.pos_out = list_pos[0] + m; gr.suf_out = list_suf[0] + m; gr.gid_out = list_gid[0] + m; gr.gid_base = (uint32_t)groups;
+        GCZ_TRY(launch_group(false, gr));
         GCZ_CUDA(cudaMemcpyAsync(h_totals, d_totals, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
         GCZ_CUDA(cudaStreamSynchronize(st));
         m += h_totals[0]; groups += h_totals[1];
         rounds++;
     }
-
     const int low_bits = bits_for((uint64_t)n);        // rank + 1 <= n
     int cur = 0;
     int64_t h = k;
@@ -625,13 +580,10 @@ int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t 
                    d_runs, n_runs, d_text, d_code, kc, d_keys0, rb.keys[0], rb.vals[0]);
         const int gid_bits = bits_for((uint64_t)std::max<int64_t>(groups - 1, 0));
         GCZ_TRY(radix_sort_pairs(ctx, st, rb, m, 0, low_bits + gid_bits, d_temp, ssp));
-        const int64_t tiles_m = (m + kGrpTile - 1) / kGrpTile;
-        GCZ_LAUNCH(ctx, group_aggregate_kernel<false>, (unsigned)tiles_m, kGrpThreads, 0, st, rb.keys[rb.cur], m, nullptr, 0, agg);
-        GCZ_LAUNCH(ctx, group_scan_kernel, 1, 1024, 0, st, agg, tiles_m, d_totals);
-        ApplyArgs ar = aa;
-        ar.keys = rb.keys[rb.cur]; ar.suf = rb.vals[rb.cur]; ar.pos = list_pos[cur]; ar.m = m; ar.sigma = 0;
-        ar.pos_out = list_pos[cur ^ 1]; ar.suf_out = list_suf[cur ^ 1]; ar.gid_out = list_gid[cur ^ 1]; ar.gid_base = 0;
-        GCZ_LAUNCH(ctx, group_apply_kernel<false>, (unsigned)tiles_m, kGrpThreads, 0, st, ar);
+        GroupArgs gr = ga;
+        gr.keys = rb.keys[rb.cur]; gr.suf = rb.vals[rb.cur]; gr.pos = list_pos[cur]; gr.m = m;
+        gr.pos_out = list_pos[cur ^ 1]; gr.suf_out = list_suf[cur ^ 1]; gr.gid_out = list_gid[cur ^ 1]; gr.gid_base = 0;
+        GCZ_TRY(launch_group(false, gr));
         GCZ_CUDA(cudaMemcpyAsync(h_totals, d_totals, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
         GCZ_CUDA(cudaStreamSynchronize(st));
         m = h_totals[0]; groups = h_totals[1];
