@@ -156,6 +156,28 @@ __global__ void radix_scan_kernel(unsigned long long* hist, int npass) {
     }
 }
 
+// Lanes of the warp whose 8-bit digit equals mine: one ballot per bit, each folded in with two logic ops
+// (written in PTX: the compiler's own expansion of the C form spends six instructions per bit).
+__device__ __forceinline__ unsigned peers_with_same_digit(unsigned d) {
+    unsigned acc;
+    asm(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b32 t, v, m;\n"
+        "mov.b32 %0, 0xffffffff;\n"
+        "and.b32 t, %1, 1;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; selp.b32 m, 0, 0xffffffff, p; lop3.b32 %0, %0, v, m, 0x60;\n"
+        "and.b32 t, %1, 2;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; selp.b32 m, 0, 0xffffffff, p; lop3.b32 %0, %0, v, m, 0x60;\n"
+        "and.b32 t, %1, 4;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; selp.b32 m, 0, 0xffffffff, p; lop3.b32 %0, %0, v, m, 0x60;\n"
+        "and.b32 t, %1, 8;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; selp.b32 m, 0, 0xffffffff, p; lop3.b32 %0, %0, v, m, 0x60;\n"
+        "and.b32 t, %1, 16;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; selp.b32 m, 0, 0xffffffff, p; lop3.b32 %0, %0, v, m, 0x60;\n"
+        "and.b32 t, %1, 32;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; selp.b32 m, 0, 0xffffffff, p; lop3.b32 %0, %0, v, m, 0x60;\n"
+        "and.b32 t, %1, 64;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; selp.b32 m, 0, 0xffffffff, p; lop3.b32 %0, %0, v, m, 0x60;\n"
+        "and.b32 t, %1, 128; setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; selp.b32 m, 0, 0xffffffff, p; lop3.b32 %0, %0, v, m, 0x60;\n"
+        "}\n"
+        : "=&r"(acc) : "r"(d));
+    return acc;
+}
+
 // ---- one digit pass --------------------------------------------------------------------------------
 // Phases of one CTA (tile of THREADS x ITEMS pairs):
 //   1 load keys (warp-striped)
@@ -248,6 +270,10 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
             const int e = warp_base + i * 32 + lane;
             key[i] = e < count ? s_keys[e] : ~0ull;
         }
+    } else if (count == TILE) {               // all tiles but the last: no bounds predicates in the way of the loads
+        const uint64_t* src_keys = keys_in + tile_base + warp_base + lane;
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) key[i] = src_keys[i * 32];
     } else {
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
@@ -256,8 +282,14 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
         }
     }
 
+    // every key is requested before the first one is used (the ranking below is short enough that the scheduler
+    // would otherwise sink each load next to its use and wait for it there)
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) asm volatile("" : "+l"(key[i]));
+
     // 2. rank inside the warp
-    unsigned short rank[ITEMS];
+    static_assert(ITEMS % 2 == 0, "ranks are kept two to a register");
+    unsigned rank2[ITEMS / 2];                  // ranks of items 2j (low half) and 2j + 1 (high half)
     unsigned* my_hist = s_warp_hist + warp * kRadix;
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
@@ -266,13 +298,7 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
         if (USE_MATCH) {
             peers = __match_any_sync(0xffffffffu, d);
         } else {
-            peers = 0xffffffffu;
-#pragma unroll
-            for (int bit = 0; bit < 8; bit++) {
-                const bool set = (d >> bit) & 1u;
-                const unsigned vote = __ballot_sync(0xffffffffu, set);
-                peers &= set ? vote : ~vote;
-            }
+            peers = peers_with_same_digit(d);
         }
         const unsigned below = __popc(peers & lt);
         unsigned base = 0;
@@ -281,7 +307,7 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
             my_hist[d] = base + __popc(peers);
         }
         base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
-        rank[i] = (unsigned short)(base + below);
+        if (i & 1) rank2[i >> 1] |= (base + below) << 16; else rank2[i >> 1] = base + below;
         __syncwarp();
     }
 
@@ -294,10 +320,16 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
             val[i] = (uint32_t)(tile_base + e) | (src.carry_shift ? (uint32_t)s_codes[e] << src.carry_shift : 0u);
         }
     } else if (HAS_VALS) {
+        if (count == TILE) {
+            const uint32_t* src_vals = vals_in + tile_base + warp_base + lane;
 #pragma unroll
-        for (int i = 0; i < ITEMS; i++) {
-            const int e = warp_base + i * 32 + lane;
-            val[i] = e < count ? vals_in[tile_base + e] : 0u;
+            for (int i = 0; i < ITEMS; i++) val[i] = src_vals[i * 32];
+        } else {
+#pragma unroll
+            for (int i = 0; i < ITEMS; i++) {
+                const int e = warp_base + i * 32 + lane;
+                val[i] = e < count ? vals_in[tile_base + e] : 0u;
+            }
         }
     }
     __syncthreads();
@@ -330,7 +362,7 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
         const unsigned d = (unsigned)(key[i] >> shift) & 255u;
-        const unsigned pos = s_digit_start[d] + my_hist[d] + rank[i];
+        const unsigned pos = s_digit_start[d] + my_hist[d] + ((i & 1) ? rank2[i >> 1] >> 16 : rank2[i >> 1] & 0xffffu);
         s_keys[pos] = key[i];
         if (HAS_VALS) s_vals[pos] = val[i];
     }
