@@ -55,8 +55,10 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks/throttle reasons sampled every 50 ms from before the warm-up on; stop(t0, t1) keeps the
+    samples taken inside the timed region [t0, t1] (wall clock), or the nearest ones when the region is shorter
+    than a sampling period."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
@@ -64,7 +66,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -72,15 +74,21 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
-    def stop(self) -> dict:
+    def stop(self, t0: float, t1: float) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        time.sleep(0.15)
         self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.06]
+        how = "inside the timed region"
+        if not rows and self.rows:
+            mid = 0.5 * (t0 + t1)
+            rows = [r for _, r in sorted(self.rows, key=lambda tr: abs(tr[0] - mid))[:3]]
+            how = "nearest to the timed region (region shorter than the sampling period)"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except Exception:
@@ -88,9 +96,8 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        busy = [s for s in sm if s > 0]
-        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "sampled": how}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -214,12 +221,13 @@ def main() -> None:
     dev_step = lambda: G.build_block(local_rank, d_text, n, 32, shape, d_gcz, d_gcx)
     e2e_step = lambda: G.build_block(local_rank, h_text, n, 32, shape, h_gcz, h_gcx)
 
-    timed(dev_step, warm)
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+    timed(dev_step, warm)
+    w0 = time.time()
     ms_total, infos = timed(dev_step, steps)
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop(w0, time.time()) if rank == 0 else None
     ms_step = max_over_ranks(ms_total / steps)
     total_bases = sum_over_ranks(float(bases))
     value = total_bases / 1e6 / (ms_step / 1e3)
@@ -230,20 +238,27 @@ def main() -> None:
     assert torch.equal(h_gcz, d_gcz.cpu()) and torch.equal(h_gcx, d_gcx.cpu()), "device and host arms disagree"
     e2e_value = total_bases / 1e6 / (ms_e2e / 1e3)
 
-    # ---- roofline of the dominant kernel (onesweep digit pass) ------------------------------------------------------
+    # ---- roofline of the dominant kernel: an onesweep digit pass over all n (key, value) pairs ---------------------------
+    # achieved = algorithmic bytes of one such launch (24 B per pair: 12 read + 12 written) / its average device time,
+    # measured live with CUDA events around every launch inside the library (on the stream it launches on).
     peak, peak_src = measured_peaks()
-    radix_ms = float(np.mean([i["radix_ms"] for i in infos]))
-    radix_launches = float(np.mean([i["radix_launches"] for i in infos]))
-    radix_elems = float(np.mean([i["radix_elements"] for i in infos]))
-    alg_bytes_per_launch = 24.0 * radix_elems / max(radix_launches, 1)          # read 12 B + write 12 B per pair
-    achieved = 24.0 * radix_elems / (radix_ms / 1e3) / 1e9 if radix_ms > 0 else 0.0
+    full_ms = float(np.mean([i["radix_full_ms"] for i in infos]))
+    full_launches = float(np.mean([i["radix_full_launches"] for i in infos]))
+    all_ms = float(np.mean([i["radix_ms"] for i in infos]))
+    all_launches = float(np.mean([i["radix_launches"] for i in infos]))
+    text_ms = float(np.mean([i["radix_text_ms"] for i in infos]))
+    alg_bytes_per_launch = 24.0 * n
+    avg_launch_ms = full_ms / max(full_launches, 1)
+    achieved = alg_bytes_per_launch / (avg_launch_ms / 1e3) / 1e9 if avg_launch_ms > 0 else 0.0
     step_alg_bytes = 11.0 * n + int(shape.size) + gcx_len                          # SURVEY.md §8(d) B_build(n)
     roofline = {
-        "bound": "hbm", "kernel": "onesweep_kernel<384,16,pairs> (LSD radix digit pass of the suffix sorter)",
+        "bound": "hbm", "kernel": "onesweep_kernel<512,12,pairs>: one 8-bit digit pass of the suffix sorter over all n (key, position) pairs",
         "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
         "traffic": None,
-        "algorithmic_bytes_per_launch": alg_bytes_per_launch, "launches_per_step": radix_launches,
-        "avg_launch_ms": radix_ms / max(radix_launches, 1), "kernel_share_of_step": radix_ms / (ms_total / steps),
+        "algorithmic_bytes_per_launch": alg_bytes_per_launch, "launches_per_step": full_launches,
+        "avg_launch_ms": avg_launch_ms, "kernel_share_of_step": full_ms / (ms_total / steps),
+        "all_digit_passes": {"launches_per_step": all_launches, "ms_per_step": all_ms, "share_of_step": all_ms / (ms_total / steps),
+                             "first_pass_from_text_ms": text_ms},
         "whole_step": {"algorithmic_bytes": step_alg_bytes, "achieved": step_alg_bytes / (ms_total / steps / 1e3) / 1e9,
                        "frac": step_alg_bytes / (ms_total / steps / 1e3) / 1e9 / peak},
     }
@@ -381,6 +396,8 @@ def main() -> None:
             "phases_ms": {k: float(np.mean([i[k] for i in infos])) for k in
                           ("sort_initial_ms", "sort_refine_ms", "bwt_hswt_ms", "ssa_ms", "total_ms")},
             "refine_rounds": int(infos[-1]["refine_rounds"]),
+            "sorter": {"symbols_per_key": int(infos[-1]["symbols_per_key"]), "long_runs": int(infos[-1]["long_runs"]),
+                       "unresolved_after_first_sort": int(infos[-1]["unresolved_after_first_sort"])},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -62,6 +62,7 @@ class BuildTiming(C.Structure):
         ("kernel_launches", C.c_int64),
         ("symbols_per_key", C.c_int32), ("long_runs", C.c_int32),
         ("unresolved_after_first_sort", C.c_int64),
+        ("radix_full_launches", C.c_int64), ("radix_full_ms", C.c_float), ("radix_text_ms", C.c_float),
     ]
 
     def as_dict(self):

@@ -247,6 +247,9 @@ static int build_block(int device, const uint8_t* text, int64_t n, int32_t sampl
     t_timing.symbols_per_key = ss.symbols_per_key;
     t_timing.long_runs = ss.long_runs;
     t_timing.unresolved_after_first_sort = ss.unresolved_after_first_sort;
+    t_timing.radix_full_launches = ss.radix_full_passes;
+    t_timing.radix_full_ms = ss.radix_full_ms;
+    t_timing.radix_text_ms = ss.radix_text_ms;
     for (auto& e : ev) cudaEventDestroy(e);
     return GCZ_OK;
 }

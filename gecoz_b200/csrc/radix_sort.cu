@@ -523,6 +523,7 @@ int radix_sort_pairs(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n
             GCZ_CUDA(cudaEventRecord(e1, st));
             stats->events.push_back(e0); stats->events.push_back(e1);
             stats->passes++; stats->elements += n;
+            stats->pass_elements.push_back((src && p == 0) ? -n : n);
         }
     }
     return GCZ_OK;
@@ -532,6 +533,7 @@ void SortStats::resolve() {
     for (size_t i = 0; i + 1 < events.size(); i += 2) {
         float t = 0;
         if (cudaEventElapsedTime(&t, events[i], events[i + 1]) == cudaSuccess) ms += t;
+        pass_ms.push_back(t);
         cudaEventDestroy(events[i]); cudaEventDestroy(events[i + 1]);
     }
     events.clear();

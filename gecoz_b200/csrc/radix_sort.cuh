@@ -41,6 +41,8 @@ struct SortStats {
     int64_t elements = 0;
     float   ms = 0;                       // device time inside the digit passes (after resolve())
     std::vector<cudaEvent_t> events;      // start/stop pairs, one per digit pass
+    std::vector<int64_t> pass_elements;   // per digit pass: pairs moved (negative: the pass read the text, not arrays)
+    std::vector<float>   pass_ms;         // per digit pass: device time (after resolve())
     void resolve();                       // call after the stream has been synchronised
 };
 

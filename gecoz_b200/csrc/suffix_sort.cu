@@ -68,6 +68,8 @@ __device__ __forceinline__ uint32_t run_remaining(const Run* __restrict__ runs, 
 constexpr int kGrpThreads = 256;
 constexpr int kGrpItems = 16;
 constexpr int kGrpTile = kGrpThreads * kGrpItems;
+constexpr int kSampleShift = 6;                 // every 64th sorted key is kept as an index for rank lookups (key_slot)
+constexpr int kSampleStep = 1 << kSampleShift;
 constexpr int kAggs = 5;                        // last boundary, kept slots, kept groups, kept run slots, kept run groups
 
 struct SlotFlags {
@@ -97,6 +99,7 @@ struct GroupArgs {
     unsigned*       bnd_bits;      // [m / 32 + 2] bit t: slot t starts a key group
     unsigned*       run_bits;      // [m / 32 + 2] bit t: slot t is an unresolved long-run suffix (initial only)
     unsigned*       agg;           // [kAggs][tiles] tile aggregates, then their exclusive scans
+    uint64_t*       sample;        // initial only: every kSampleStep-th key (see key_slot)
     long long*      totals;        // [4]: kept slots, kept groups, kept long-run slots, kept long-run groups
     uint32_t*       rank;
     uint32_t*       sa;
@@ -142,6 +145,7 @@ group_flags_kernel(GroupArgs a) {
         const int64_t t = tile_base + e;
         const uint64_t key = s_keys[1 + e];
         const bool valid = t < a.m;
+        if (INITIAL && valid && (t & (kSampleStep - 1)) == 0) a.sample[t >> kSampleShift] = key;
         const bool b = valid && (t == 0 || key != s_keys[e]);
         const bool open = valid && !(b && (t + 1 >= a.m || s_keys[2 + e] != key));   // shares its key with a neighbour
         bool run = false;
@@ -343,6 +347,25 @@ __device__ __forceinline__ uint64_t key_at(const uint8_t* __restrict__ text, int
     return key;
 }
 
+// First slot whose key is >= want.  `sample` holds every kSampleStep-th sorted key (written by the grouping pass):
+// small enough to stay in L2 across the lookups of a round, it pins the answer to kSampleStep consecutive keys,
+// so that a lookup costs a few DRAM sectors instead of one per level of a search over all n keys.
+__device__ __forceinline__ uint32_t key_slot(const uint64_t* __restrict__ sorted_keys, int64_t n, const uint64_t* __restrict__ sample,
+                                             uint64_t want) {
+    int64_t lo = 0, hi = (n + kSampleStep - 1) >> kSampleShift;            // first sample >= want
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(&sample[mid]) < want) lo = mid + 1; else hi = mid;
+    }
+    hi = min(lo << kSampleShift, n);                                       // sorted_keys[hi] >= want (or hi == n)
+    lo = lo > 0 ? ((lo - 1) << kSampleShift) + 1 : 0;                      // sorted_keys[lo - 1] < want
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(&sorted_keys[mid]) < want) lo = mid + 1; else hi = mid;
+    }
+    return (uint32_t)lo;
+}
+
 // refinement key: (group ordinal, rank of the suffix `h` symbols further, 0 when that is past the end).
 // A suffix inside a long run of r >= k symbols looks r - k symbols further than the others (header, point 5).
 __global__ void __launch_bounds__(256)
@@ -350,6 +373,7 @@ refine_keys_kernel(const uint32_t* __restrict__ suf, const uint32_t* __restrict_
                    uint32_t* __restrict__ rank, int64_t n, int64_t h, int low_bits, uint32_t pos_mask,
                    const Run* __restrict__ runs, int n_runs, const uint8_t* __restrict__ text,
                    const uint8_t* __restrict__ code_of, KeyCoder kc, const uint64_t* __restrict__ sorted_keys,
+                   const uint64_t* __restrict__ sample,
                    uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     __shared__ uint8_t s_code_of[256];
     s_code_of[threadIdx.x] = code_of[threadIdx.x];
@@ -368,13 +392,7 @@ refine_keys_kernel(const uint32_t* __restrict__ suf, const uint32_t* __restrict_
             uint32_t rk = rank[q];
             if (rk == kNoRank) {
                 // final since the first sort: its key is unique, its slot is where the key sits
-                const uint64_t want = key_at(text, n, s_code_of, kc, q);
-                int64_t lo = 0, hi = n;
-                while (lo < hi) {
-                    const int64_t mid = (lo + hi) >> 1;
-                    if (__ldg(&sorted_keys[mid]) < want) lo = mid + 1; else hi = mid;
-                }
-                rk = (uint32_t)lo;
+                rk = key_slot(sorted_keys, n, sample, key_at(text, n, s_code_of, kc, q));
                 rank[q] = rk;                               // every writer stores the same value
             }
             low = (uint64_t)rk + 1;
@@ -417,7 +435,7 @@ KeyCoder choose_key(const int64_t counts[256], int64_t n, int sigma) {
 size_t suffix_sort_workspace_bytes(int64_t n) {
     // rank 4n + keys 16n + vals(other) 4n + refinement worst case (lists 24n, sort 12n, run list 8n) + run marks + sort temp
     const size_t tiles = (size_t)(n / kGrpTile + 2);
-    return (size_t)n * (4 + 16 + 4 + 44 + 2) + radix_sort_temp_bytes(n) + tiles * kAggs * 8 + (size_t)n / 4 + (1 << 20);
+    return (size_t)n * (4 + 16 + 4 + 44 + 2) + radix_sort_temp_bytes(n) + tiles * kAggs * 8 + (size_t)n / 4 + (size_t)n / 8 + (8 << 20);
 }
 
 int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t n, const int64_t counts[256],
@@ -457,6 +475,7 @@ int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t 
     const int64_t tiles_n = (n + kGrpTile - 1) / kGrpTile;
     unsigned* d_agg = arena.get<unsigned>((size_t)tiles_n * kAggs + 8);
     unsigned* d_bits = arena.get<unsigned>((size_t)(n / 32 + 2) * 2);
+    uint64_t* d_sample = arena.get<uint64_t>((size_t)(n >> kSampleShift) + 2);
     long long* d_totals = arena.get<long long>(8);                 // [0..3] group totals, [4] run marks (as unsigned)
     uint64_t* d_marks[2] = { arena.get<uint64_t>(mark_cap), arena.get<uint64_t>(mark_cap) };
     Run* d_runs = arena.get<Run>(mark_cap / 2 + 1);
@@ -464,7 +483,7 @@ int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t 
     uint32_t* list0[3] = { arena.get<uint32_t>((size_t)n), arena.get<uint32_t>((size_t)n), arena.get<uint32_t>((size_t)n) };
     uint32_t* run_pos = arena.get<uint32_t>((size_t)n);
     uint32_t* run_suf = arena.get<uint32_t>((size_t)n);
-    if (!d_code || !d_allc || !d_rank || !d_keys0 || !d_keys1 || !d_vals1 || !d_temp || !d_agg || !d_bits || !d_totals ||
+    if (!d_code || !d_allc || !d_rank || !d_keys0 || !d_keys1 || !d_vals1 || !d_temp || !d_agg || !d_bits || !d_sample || !d_totals ||
         !d_marks[0] || !d_marks[1] || !d_runs || !list0[0] || !list0[1] || !list0[2] || !run_pos || !run_suf)
         return fail(GCZ_E_NOMEM, "suffix sort workspace for n=%lld", (long long)n);
     unsigned* d_mark_count = reinterpret_cast<unsigned*>(d_totals + 4);
@@ -518,7 +537,7 @@ int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t 
     ga.keys = d_keys0; ga.suf = d_sa; ga.pos = nullptr; ga.m = n; ga.rank = d_rank; ga.sa = d_sa;
     ga.pos_out = list0[0]; ga.suf_out = list0[1]; ga.gid_out = list0[2]; ga.gid_base = 0; ga.pos_mask = pos_mask;
     ga.allc = d_allc; ga.sigma = sigma; ga.run_mark_count = d_mark_count; ga.run_mark_cap = mark_cap;
-    ga.run_pos_out = run_pos; ga.run_suf_out = run_suf;
+    ga.run_pos_out = run_pos; ga.run_suf_out = run_suf; ga.sample = d_sample;
     GCZ_TRY(launch_group(true, ga));
     long long h_totals[5] = { 0, 0, 0, 0, 0 };
     GCZ_CUDA(cudaMemcpyAsync(h_totals, d_totals, sizeof(h_totals), cudaMemcpyDeviceToHost, st));
@@ -577,7 +596,7 @@ int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t 
         rb.cur = 0;
         const int grid = (int)std::min<int64_t>((m + 255) / 256, (int64_t)ctx->sm_count * 16);
         GCZ_LAUNCH(ctx, refine_keys_kernel, grid, 256, 0, st, list_suf[cur], list_gid[cur], m, d_rank, n, h, low_bits, pos_mask,
-                   d_runs, n_runs, d_text, d_code, kc, d_keys0, rb.keys[0], rb.vals[0]);
+                   d_runs, n_runs, d_text, d_code, kc, d_keys0, d_sample, rb.keys[0], rb.vals[0]);
         const int gid_bits = bits_for((uint64_t)std::max<int64_t>(groups - 1, 0));
         GCZ_TRY(radix_sort_pairs(ctx, st, rb, m, 0, low_bits + gid_bits, d_temp, ssp));
         GroupArgs gr = ga;
@@ -602,6 +621,10 @@ int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t 
         stats->radix_passes = ss.passes;
         stats->radix_elements = ss.elements;
         stats->radix_ms = ss.ms;
+        for (size_t i = 0; i < ss.pass_ms.size() && i < ss.pass_elements.size(); i++) {
+            if (ss.pass_elements[i] == n) { stats->radix_full_passes++; stats->radix_full_ms += ss.pass_ms[i]; }
+            else if (ss.pass_elements[i] == -n) stats->radix_text_ms += ss.pass_ms[i];
+        }
         stats->symbols_per_key = k;
         stats->unresolved_after_first_sort = m0;
         stats->long_runs = n_runs;

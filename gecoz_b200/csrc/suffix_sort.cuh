@@ -11,6 +11,9 @@ struct SuffixSortStats {
     int     symbols_per_key = 0;
     int64_t radix_passes = 0, radix_elements = 0;
     float   radix_ms = 0;
+    int64_t radix_full_passes = 0;     // digit passes over all n pairs with array input: the roofline kernel
+    float   radix_full_ms = 0;
+    float   radix_text_ms = 0;         // the first digit pass (reads the text)
     int64_t unresolved_after_first_sort = 0;
     int     long_runs = 0;
 };

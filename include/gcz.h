@@ -100,6 +100,9 @@ typedef struct gcz_build_timing {
     int32_t symbols_per_key;                     /* k: symbols packed into the first sort key         */
     int32_t long_runs;                           /* runs of >= k equal symbols (ordered in closed form) */
     int64_t unresolved_after_first_sort;         /* suffixes not unique in their first k symbols      */
+    int64_t radix_full_launches;                 /* onesweep passes over all n pairs, array input     */
+    float   radix_full_ms;                       /* device time inside those                          */
+    float   radix_text_ms;                       /* device time of the first pass (reads the text)    */
 } gcz_build_timing;
 int gcz_last_build_timing(gcz_build_timing* out);
 
