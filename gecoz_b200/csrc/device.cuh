@@ -53,6 +53,7 @@ struct DeviceCtx {
     void*        pinned = nullptr;            // small pinned scratch for read-backs
     size_t       pinned_bytes = 0;
     int64_t      launches = 0;                // kernels launched by this library on this device
+    bool         iwt_attr = false;             // dynamic-smem opt-in done for iwt_low_levels_kernel
     bool         sort_attr[3] = { false, false, false };   // dynamic-smem opt-in done for the onesweep kernels
 };
 

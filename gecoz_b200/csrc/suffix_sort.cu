@@ -324,15 +324,16 @@ group_finish_kernel(GroupArgs a) {
 // sort key of a long-run suffix: symbol, then the side the run ends on, then the run length left —
 // ascending when the run ends below its symbol, descending when it ends above (header, point 5)
 __global__ void run_keys_kernel(const uint32_t* __restrict__ run_suf, int64_t m_run, uint32_t pos_mask, const Run* __restrict__ runs,
-                                int n_runs, int k, const uint8_t* __restrict__ text, const uint8_t* __restrict__ code_of,
+                                int n_runs, int k, int len_bits, const uint8_t* __restrict__ text, const uint8_t* __restrict__ code_of,
                                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= m_run) return;
     const uint32_t sv = run_suf[u], s = sv & pos_mask;
     bool larger = false;
     const uint32_t r = run_remaining(runs, n_runs, s, k, &larger);
-    const uint32_t order = larger ? (0x80000000u | (0x7FFFFFFFu - r)) : r;
-    keys[u] = ((uint64_t)code_of[text[s]] << 32) | order;
+    const uint64_t len_mask = (1ull << len_bits) - 1;                    // r <= n < 2^len_bits
+    const uint64_t order = larger ? ((1ull << len_bits) | (len_mask - r)) : (uint64_t)r;
+    keys[u] = ((uint64_t)code_of[text[s]] << (len_bits + 1)) | order;
     vals[u] = sv;
 }
 
@@ -573,9 +574,10 @@ int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t 
         rb.keys[0] = r_keys0; rb.keys[1] = r_keys1;
         rb.vals[0] = r_vals0; rb.vals[1] = r_vals1;
         rb.cur = 0;
+        const int len_bits = bits_for((uint64_t)n);
         GCZ_LAUNCH(ctx, run_keys_kernel, (unsigned)((m_run + 255) / 256), 256, 0, st, run_suf, m_run, pos_mask, d_runs, n_runs, k,
-                   d_text, d_code, rb.keys[0], rb.vals[0]);
-        GCZ_TRY(radix_sort_pairs(ctx, st, rb, m_run, 0, 32 + bits_for((uint64_t)sigma), d_temp, ssp));
+                   len_bits, d_text, d_code, rb.keys[0], rb.vals[0]);
+        GCZ_TRY(radix_sort_pairs(ctx, st, rb, m_run, 0, len_bits + 1 + bits_for((uint64_t)sigma), d_temp, ssp));
         GroupArgs gr = ga;
         gr.keys = rb.keys[rb.cur]; gr.suf = rb.vals[rb.cur]; gr.pos = run_pos; gr.m = m_run;
         gr.pos_out = list_pos[0] + m; gr.suf_out = list_suf[0] + m; gr.gid_out = list_gid[0] + m; gr.gid_base = (uint32_t)groups;

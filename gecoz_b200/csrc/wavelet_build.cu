@@ -30,6 +30,8 @@ struct SymbolTables {
     uint16_t code[256];         // dense -> code bits (bit d = branch at depth d)
     uint8_t  len[256];          // dense -> code length
     uint8_t  node_of[256][16];  // dense, depth -> node (file order) on the symbol's path
+    uint32_t path_mask[256];    // dense -> nodes on the symbol's path, one bit per node (trees of <= 32 nodes)
+    uint32_t bit_mask[256];     // dense -> those of them where the symbol branches to the 1-child
     uint16_t node_prefix[256];  // node -> path bits
     uint8_t  node_depth[256];   // node -> depth
     int32_t  sigma;             // symbols present
@@ -207,6 +209,65 @@ hswt_emit_kernel(const uint8_t* __restrict__ bwt, int64_t n, const SymbolTables*
     }
 }
 
+// Trees of at most 32 internal nodes (any DNA/IUPAC text): lane v of the warp owns node v and keeps its bit
+// accumulator in registers.  Per 32 BWT symbols and node: the lanes routed through the node (one ballot), their
+// branch bits compacted to the low end (`pext` spelled as shift + warp OR-reduction), appended by the owning lane.
+__global__ void __launch_bounds__(kWtThreads)
+hswt_emit_small_kernel(const uint8_t* __restrict__ bwt, int64_t n, const SymbolTables* __restrict__ tab,
+                       const uint32_t* __restrict__ tile_prefix /* [sigma][tiles], exclusive */, int64_t tiles,
+                       const uint64_t* __restrict__ node_raw_word /* node -> first u32 word of its raw vector */,
+                       uint32_t* __restrict__ raw) {
+    __shared__ uint32_t s_path[256], s_bit[256];
+    __shared__ uint8_t s_dense[256];
+    s_path[threadIdx.x] = tab->path_mask[threadIdx.x];
+    s_bit[threadIdx.x] = tab->bit_mask[threadIdx.x];
+    s_dense[threadIdx.x] = tab->dense[threadIdx.x];
+    __syncthreads();
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    const unsigned lt = lanemask_lt();
+    const int64_t tile = (int64_t)blockIdx.x * (kWtThreads / 32) + warp;
+    if (tile >= tiles) return;
+    const int sigma = tab->sigma, n_nodes = tab->n_nodes;
+
+    // where this tile's bits start in "my" node: symbols routed through it, summed over earlier tiles
+    unsigned long long acc = 0;
+    uint32_t word = 0;
+    unsigned fill = 0;
+    if ((int)lane < n_nodes) {
+        unsigned long long bit0 = node_raw_word[lane] * 32ull;
+        for (int s = 0; s < sigma; s++) {
+            if ((s_path[s] >> lane) & 1u) bit0 += tile_prefix[(size_t)s * tiles + tile];
+        }
+        word = (uint32_t)(bit0 >> 5);                    // raw areas are far below 2^32 words
+        fill = (unsigned)(bit0 & 31);
+    }
+    const int64_t base = tile * kWarpTile;
+#pragma unroll 1
+    for (int c = 0; c < kWarpTile / 32; c++) {
+        if (base + c * 32 >= n) break;
+        const int64_t j = base + c * 32 + lane;
+        const int d = j < n ? (int)s_dense[bwt[j]] : -1;
+        const uint32_t pm = d >= 0 ? s_path[d] : 0u;
+        const uint32_t bm = d >= 0 ? (s_bit[d] & pm) : 0u;
+        unsigned my_packed = 0, my_count = 0;
+        for (int v = 0; v < n_nodes; v++) {
+            const unsigned members = __ballot_sync(0xffffffffu, (pm >> v) & 1u);
+            if (members == 0) continue;
+            const unsigned packed = __reduce_or_sync(0xffffffffu, ((bm >> v) & 1u) << __popc(members & lt));
+            if ((int)lane == v) { my_packed = packed; my_count = __popc(members); }
+        }
+        acc |= (unsigned long long)my_packed << fill;
+        fill += my_count;
+        if (fill >= 32) {
+            atomicOr(&raw[word], (uint32_t)acc);
+            word++;
+            acc >>= 32;
+            fill -= 32;
+        }
+    }
+    if (fill > 0 && (uint32_t)acc != 0) atomicOr(&raw[word], (uint32_t)acc);
+}
+
 // ---- sampled suffix array values in SA order -----------------------------------------------------------
 __global__ void __launch_bounds__(kWtThreads)
 sample_kernel(const uint32_t* __restrict__ sa, int64_t n, uint32_t pos_mask, uint32_t sample_mask, int sample_shift,
@@ -285,6 +346,69 @@ __global__ void iwt_scatter_kernel(const uint32_t* __restrict__ in, uint32_t* __
         out[np] = v;
     }
 }
+
+// The low levels: once a group (values sharing v >> (h + 1)) is no longer than kIwtBlock, one CTA keeps its
+// block of values in shared memory and runs every remaining level there — bit h of the values to the level's raw
+// vector, then the stable split inside each group — instead of three launches per level over global memory.
+constexpr int kIwtLowBits = 13;
+constexpr int kIwtBlock = 1 << kIwtLowBits;              // values per CTA
+constexpr int kIwtThreads = 1024;
+constexpr int kIwtPer = kIwtBlock / kIwtThreads;         // consecutive values per thread
+static_assert(kIwtPer == 8, "one byte of level bits per thread");
+
+__global__ void __launch_bounds__(kIwtThreads)
+iwt_low_levels_kernel(const uint32_t* __restrict__ vals, int64_t m, int top_h, int levels, uint32_t* __restrict__ raw,
+                      const uint64_t* __restrict__ level_raw_word /* level vector (highest bit first) -> first raw word */) {
+    extern __shared__ __align__(16) uint32_t s_iwt[];
+    uint32_t* cur = s_iwt;
+    uint32_t* nxt = s_iwt + kIwtBlock;
+    uint32_t* s_zc = s_iwt + 2 * kIwtBlock;              // zeros before each thread's first value
+    uint32_t* s_wsum = s_zc + kIwtThreads;
+    const int64_t block_start = (int64_t)blockIdx.x * kIwtBlock;
+    const int cnt = (int)min((int64_t)kIwtBlock, m - block_start);
+    const int t = threadIdx.x;
+    for (int i = 0; i < kIwtPer; i++) {
+        const int e = i * kIwtThreads + t;
+        cur[e] = e < cnt ? vals[block_start + e] : 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    for (int h = top_h; h >= 0; h--) {
+        const uint4 q0 = reinterpret_cast<const uint4*>(cur)[2 * t], q1 = reinterpret_cast<const uint4*>(cur)[2 * t + 1];
+        const uint32_t v[kIwtPer] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w };
+        const int e0 = t * kIwtPer;
+        const unsigned valid = e0 >= cnt ? 0u : (e0 + kIwtPer <= cnt ? 0xFFu : (1u << (cnt - e0)) - 1u);
+        unsigned bits = 0;
+#pragma unroll
+        for (int i = 0; i < kIwtPer; i++) bits |= ((v[i] >> h) & 1u) << i;
+        bits &= valid;
+        const unsigned zmask = ~bits & valid;
+        if (valid) reinterpret_cast<uint8_t*>(raw + level_raw_word[levels - 1 - h])[(block_start >> 3) + t] = (uint8_t)bits;
+        if (h == 0) break;
+        const unsigned z = __popc(zmask);
+        const unsigned incl = warp_incl_sum(z);
+        if (lane_id() == 31) s_wsum[t >> 5] = incl;
+        __syncthreads();
+        const unsigned wincl = warp_incl_sum(s_wsum[lane_id()]);                         // every warp scans the warp totals
+        const unsigned wbase = __shfl_sync(0xffffffffu, wincl - s_wsum[lane_id()], t >> 5);
+        const unsigned zexcl = wbase + incl - z;
+        s_zc[t] = zexcl;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kIwtPer; i++) {
+            if (!((valid >> i) & 1u)) break;
+            const int e = e0 + i;
+            const int bs = (e >> (h + 1)) << (h + 1);
+            const unsigned zp = zexcl + __popc(zmask & ((1u << i) - 1u));
+            const unsigned zb = (h + 1 >= 3) ? s_zc[bs >> 3] : zexcl + __popc(zmask & ((1u << (bs - e0)) - 1u));
+            const int zeros_in_group = min(1 << h, cnt - bs);
+            const int np = ((bits >> i) & 1u) ? bs + zeros_in_group + ((e - (int)zp) - (bs - (int)zb)) : bs + (int)(zp - zb);
+            nxt[np] = v[i];
+        }
+        __syncthreads();
+        uint32_t* tmp = cur; cur = nxt; nxt = tmp;
+    }
+}
+constexpr size_t kIwtLowSmem = (size_t)(2 * kIwtBlock + kIwtThreads + 32) * 4;
 
 // ---- ranked layout: raw bits -> RankedWTNode bytes -------------------------------------------------------
 struct VectorDesc {
@@ -392,6 +516,37 @@ ranked_layout_kernel(const uint32_t* __restrict__ raw, const VectorDesc* __restr
 
 inline int64_t superblocks(int64_t len) { return (len + 65535) >> 16; }
 
+// All levels of an IndexWaveletTree over the m values in d_ssa[0] (d_ssa[1]: scratch of the same size): the high
+// levels with three launches each over global memory, the low ones in one launch (iwt_low_levels_kernel).
+int iwt_levels(DeviceCtx* ctx, cudaStream_t st, uint32_t* const d_ssa[2], int64_t m, int levels, uint32_t* d_raw,
+               const std::vector<VectorDesc>& vecs, int level_vec0, uint32_t* d_zeros, uint32_t* d_block_zeros,
+               uint64_t* d_level_raw) {
+    std::vector<uint64_t> h_level_raw((size_t)levels);
+    for (int l = 0; l < levels; l++) h_level_raw[(size_t)l] = vecs[(size_t)(level_vec0 + l)].raw_word;
+    GCZ_CUDA(cudaMemcpyAsync(d_level_raw, h_level_raw.data(), sizeof(uint64_t) * levels, cudaMemcpyHostToDevice, st));
+    GCZ_CUDA(cudaStreamSynchronize(st));                 // h_level_raw goes out of scope
+    const int64_t mblocks = (m + 1023) >> 10;
+    const int lvl_grid = (int)std::min<int64_t>((m + 255) / 256, (int64_t)ctx->sm_count * 8);
+    const int bits_grid = (int)std::min<int64_t>((mblocks + 7) / 8, (int64_t)ctx->sm_count * 8);
+    int cur = 0;
+    int l = 0;
+    for (; l < levels && levels - 1 - l >= kIwtLowBits; l++) {
+        const int h = levels - 1 - l;
+        uint32_t* lraw = d_raw + vecs[(size_t)(level_vec0 + l)].raw_word;
+        GCZ_LAUNCH(ctx, iwt_bits_kernel, bits_grid, 256, 0, st, d_ssa[cur], m, h, lraw, d_zeros, d_block_zeros);
+        GCZ_LAUNCH(ctx, row_scan_kernel, 1, 1024, 0, st, d_block_zeros, mblocks, (uint32_t*)nullptr);
+        GCZ_LAUNCH(ctx, iwt_scatter_kernel, lvl_grid, 256, 0, st, d_ssa[cur], d_ssa[cur ^ 1], m, h, lraw, d_zeros, d_block_zeros);
+        cur ^= 1;
+    }
+    if (!ctx->iwt_attr) {
+        GCZ_CUDA(cudaFuncSetAttribute(iwt_low_levels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kIwtLowSmem));
+        ctx->iwt_attr = true;
+    }
+    GCZ_LAUNCH(ctx, iwt_low_levels_kernel, (unsigned)((m + kIwtBlock - 1) / kIwtBlock), kIwtThreads, kIwtLowSmem, st, d_ssa[cur], m,
+               levels - 1 - l, levels, d_raw, d_level_raw);
+    return GCZ_OK;
+}
+
 }  // namespace
 
 size_t wavelet_workspace_bytes(int64_t n, int sampling_factor) {
@@ -439,6 +594,10 @@ int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_t
             }
             if (found < 0) return fail(GCZ_E_INTERNAL, "symbol path leaves the tree");
             h_tab.node_of[s][d] = (uint8_t)found;
+            if (found < 32) {
+                h_tab.path_mask[s] |= 1u << found;
+                if ((h_tab.code[s] >> d) & 1u) h_tab.bit_mask[s] |= 1u << found;
+            }
         }
     }
     h_tab.sigma = sigma; h_tab.n_nodes = n_nodes; h_tab.max_len = max_len;
@@ -479,7 +638,8 @@ int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_t
     uint32_t* d_ssa[2] = { arena.get<uint32_t>((size_t)m), arena.get<uint32_t>((size_t)m) };
     uint32_t* d_zeros = arena.get<uint32_t>((size_t)((m + 31) >> 5) + 1);
     uint32_t* d_block_zeros = arena.get<uint32_t>((size_t)((m + 1023) >> 10) + 1);
-    if (!d_block_zeros) return fail(GCZ_E_NOMEM, "wavelet workspace for n=%lld", (long long)n);
+    uint64_t* d_level_raw = arena.get<uint64_t>(64);
+    if (!d_block_zeros || !d_level_raw) return fail(GCZ_E_NOMEM, "wavelet workspace for n=%lld", (long long)n);
     if (!d_tab || !d_raw || !d_tile_counts || !d_node_raw || !d_vecs || !d_sb || !d_ssa[0] || !d_ssa[1] || !d_zeros)
         return fail(GCZ_E_NOMEM, "wavelet workspace for n=%lld", (long long)n);
 
@@ -509,27 +669,18 @@ int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_t
     GCZ_LAUNCH(ctx, bwt_count_kernel, wt_grid, kWtThreads, 0, st, d_text, d_sa, n, d_tab, sample_mask, carry_shift,
                (carry_shift && clean_sa) ? d_sa : (uint32_t*)nullptr, d_bwt, d_marker_raw, d_tile_counts, tiles);
     GCZ_LAUNCH(ctx, row_scan_kernel, (unsigned)(sigma + 1), 1024, 0, st, d_tile_counts, tiles, (uint32_t*)nullptr);
-    GCZ_LAUNCH(ctx, hswt_emit_kernel, wt_grid, kWtThreads, 0, st, d_bwt, n, d_tab, d_tile_counts, tiles, d_node_raw, d_raw);
+    if (n_nodes <= 32) {
+        GCZ_LAUNCH(ctx, hswt_emit_small_kernel, wt_grid, kWtThreads, 0, st, d_bwt, n, d_tab, d_tile_counts, tiles, d_node_raw, d_raw);
+    } else {
+        GCZ_LAUNCH(ctx, hswt_emit_kernel, wt_grid, kWtThreads, 0, st, d_bwt, n, d_tab, d_tile_counts, tiles, d_node_raw, d_raw);
+    }
     if (stats) GCZ_CUDA(cudaEventRecord(ev1, st));
 
     // ---- sampled SA + IndexWaveletTree ---------------------------------------------------------------------
     GCZ_LAUNCH(ctx, sample_kernel, wt_grid, kWtThreads, 0, st, d_sa, n,
                carry_shift ? (1u << carry_shift) - 1u : 0xFFFFFFFFu, sample_mask, sampling_factor,
                d_tile_counts + (size_t)sigma * tiles, tiles, d_ssa[0]);
-    const int64_t mblocks = (m + 1023) >> 10;
-    const int lvl_grid = (int)std::min<int64_t>((m + 255) / 256, (int64_t)ctx->sm_count * 8);
-    const int bits_grid = (int)std::min<int64_t>((mblocks + 7) / 8, (int64_t)ctx->sm_count * 8);
-    int cur = 0;
-    for (int l = 0; l < levels; l++) {
-        const int h = levels - 1 - l;
-        uint32_t* lraw = d_raw + vecs[level_vec0 + l].raw_word;
-        GCZ_LAUNCH(ctx, iwt_bits_kernel, bits_grid, 256, 0, st, d_ssa[cur], m, h, lraw, d_zeros, d_block_zeros);
-        if (h > 0) {
-            GCZ_LAUNCH(ctx, row_scan_kernel, 1, 1024, 0, st, d_block_zeros, mblocks, (uint32_t*)nullptr);
-            GCZ_LAUNCH(ctx, iwt_scatter_kernel, lvl_grid, 256, 0, st, d_ssa[cur], d_ssa[cur ^ 1], m, h, lraw, d_zeros, d_block_zeros);
-            cur ^= 1;
-        }
-    }
+    GCZ_TRY(iwt_levels(ctx, st, d_ssa, m, levels, d_raw, vecs, level_vec0, d_zeros, d_block_zeros, d_level_raw));
 
     // ---- counters + final byte layout of every vector ---------------------------------------------------------
     GCZ_LAUNCH(ctx, superblock_popcount_kernel, (unsigned)((total_sb * 32 + 255) / 256), 256, 0, st, d_raw, d_vecs,
@@ -603,25 +754,13 @@ int index_wavelet_tree_from_values(DeviceCtx* ctx, cudaStream_t st, const uint32
     uint32_t* d_ssa[2] = { arena.get<uint32_t>((size_t)m), arena.get<uint32_t>((size_t)m) };
     uint32_t* d_zeros = arena.get<uint32_t>((size_t)((m + 31) >> 5) + 1);
     uint32_t* d_block_zeros = arena.get<uint32_t>((size_t)((m + 1023) >> 10) + 1);
-    if (!d_raw || !d_vecs || !d_sb || !d_ssa[0] || !d_ssa[1] || !d_zeros || !d_block_zeros) return fail(GCZ_E_NOMEM, "IWT workspace");
+    uint64_t* d_level_raw = arena.get<uint64_t>(64);
+    if (!d_raw || !d_vecs || !d_sb || !d_ssa[0] || !d_ssa[1] || !d_zeros || !d_block_zeros || !d_level_raw) return fail(GCZ_E_NOMEM, "IWT workspace");
     GCZ_CUDA(cudaMemsetAsync(d_raw, 0, ((size_t)raw_words + 16) * 4, st));
     GCZ_CUDA(cudaMemcpyAsync(d_vecs, vecs.data(), sizeof(VectorDesc) * vecs.size(), cudaMemcpyHostToDevice, st));
     GCZ_CUDA(cudaMemcpyAsync(d_ssa[0], d_vals, (size_t)m * 4, cudaMemcpyDeviceToDevice, st));
     GCZ_CUDA(cudaStreamSynchronize(st));
-    const int64_t mblocks = (m + 1023) >> 10;
-    const int lvl_grid = (int)std::min<int64_t>((m + 255) / 256, (int64_t)ctx->sm_count * 8);
-    const int bits_grid = (int)std::min<int64_t>((mblocks + 7) / 8, (int64_t)ctx->sm_count * 8);
-    int cur = 0;
-    for (int l = 0; l < levels; l++) {
-        const int h = levels - 1 - l;
-        uint32_t* lraw = d_raw + vecs[l].raw_word;
-        GCZ_LAUNCH(ctx, iwt_bits_kernel, bits_grid, 256, 0, st, d_ssa[cur], m, h, lraw, d_zeros, d_block_zeros);
-        if (h > 0) {
-            GCZ_LAUNCH(ctx, row_scan_kernel, 1, 1024, 0, st, d_block_zeros, mblocks, (uint32_t*)nullptr);
-            GCZ_LAUNCH(ctx, iwt_scatter_kernel, lvl_grid, 256, 0, st, d_ssa[cur], d_ssa[cur ^ 1], m, h, lraw, d_zeros, d_block_zeros);
-            cur ^= 1;
-        }
-    }
+    GCZ_TRY(iwt_levels(ctx, st, d_ssa, m, levels, d_raw, vecs, 0, d_zeros, d_block_zeros, d_level_raw));
     GCZ_LAUNCH(ctx, superblock_popcount_kernel, (unsigned)((total_sb * 32 + 255) / 256), 256, 0, st, d_raw, d_vecs, (int)vecs.size(), total_sb, d_sb);
     GCZ_LAUNCH(ctx, superblock_scan_kernel, (unsigned)vecs.size(), 1024, 0, st, d_sb, d_vecs);
     GCZ_LAUNCH(ctx, ranked_layout_kernel, (unsigned)total_sb, 128, 0, st, d_raw, d_vecs, (int)vecs.size(), d_sb);

@@ -124,6 +124,9 @@ def _texts():
     lens = rng.integers(3, 6, 30_000)                  # more long runs than the mark buffer holds: plain doubling
     yield "runs_bytes_overflow", np.concatenate([np.repeat(rng.integers(1, 255, len(lens), dtype=np.uint8), lens), np.zeros(1, np.uint8)])
     yield "periodic", synth.block_of([np.frombuffer(b"ACGT" * 40_000, np.uint8)])
+    # > 32 internal tree nodes: the general node-bit emitter
+    sym = np.arange(48, 48 + 44, dtype=np.uint8)
+    yield "ascii44", synth.block_of([sym[np.minimum(rng.geometric(0.12, 120_000) - 1, 43)]])
 
 
 @pytest.mark.parametrize("name,text", list(_texts()), ids=[t[0] for t in _texts()])
