@@ -10,8 +10,9 @@ per GPU) every rank builds its own chr1-shaped block (seed 3 + rank): blocks are
 data-path collective, scaling is weak.
 
   value  : whole-job Mbp/s with the text and both outputs resident in HBM (device pointers through the C ABI)
-  e2e    : same metric through the same C-ABI call with pinned HOST buffers: H2D of the text and D2H of the
-           .gcz/.gcx bodies are inside the timed region
+  e2e    : same metric through the C-ABI calls of one GecozFileWriter.write (gcz_count_symbols, gcz_shape_from_counts,
+           gcz_build_block) with pinned HOST buffers: the H2D of the text and the D2H of the .gcz/.gcx bodies are
+           inside the timed region
   count  : backward-search count queries/s against the index just built (secondary metric of BASELINE.json)
   roofline / cpu_baseline : see DESIGN.md
 `--impl reference` times the CPU restatement of the Java path (oracle/, no JVM exists on the box).
@@ -219,7 +220,12 @@ def main() -> None:
         return e0.elapsed_time(e1), infos
 
     dev_step = lambda: G.build_block(local_rank, d_text, n, 32, shape, d_gcz, d_gcx)
-    e2e_step = lambda: G.build_block(local_rank, h_text, n, 32, shape, h_gcz, h_gcx)
+
+    def e2e_step():
+        # what GecozFileWriter.write does per block, from host memory: count (the upload), shape, build, bodies back
+        shp = G.shape_from_counts(G.symbol_counts(h_text, local_rank))
+        return G.build_block(local_rank, h_text, n, 32, shp, h_gcz, h_gcx)
+
 
     clocks = ClockSampler(local_rank)
     if rank == 0:

@@ -67,6 +67,8 @@ int get_ctx(int device, DeviceCtx** out) {
     GCZ_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
     GCZ_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    GCZ_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    GCZ_CUDA(cudaEventCreateWithFlags(&ctx->copy_event, cudaEventDisableTiming));
     *out = ctx.get();
     g_ctx[device] = std::move(ctx);
     return GCZ_OK;
@@ -83,6 +85,9 @@ void destroy_all_ctx() {
         cudaSetDevice(kv.first);
         kv.second->arena.destroy();
         if (kv.second->own_stream) cudaStreamDestroy(kv.second->own_stream);
+        if (kv.second->copy_stream) cudaStreamDestroy(kv.second->copy_stream);
+        if (kv.second->copy_event) cudaEventDestroy(kv.second->copy_event);
+        if (kv.second->staged_dev) cudaFree(kv.second->staged_dev);
     }
     g_ctx.clear();
 }
@@ -140,20 +145,28 @@ static int count_symbols(int device, const uint8_t* text, int64_t n, int64_t cou
     cudaStream_t st = stream_of(ctx);
     ctx->arena.reset();
     const bool on_dev = is_device_ptr(text);
-    const size_t need = (on_dev ? 0 : (size_t)n) + (1 << 20);
-    if (ctx->arena.capacity < need) GCZ_TRY(ctx->arena.reserve(need));
+    if (ctx->arena.capacity < (1 << 20)) GCZ_TRY(ctx->arena.reserve(1 << 20));
     const uint8_t* d_text = text;
     if (!on_dev) {
-        uint8_t* d = ctx->arena.get<uint8_t>((size_t)n + 64);
-        if (!d) return fail(GCZ_E_NOMEM, "text staging");
-        GCZ_CUDA(cudaMemcpyAsync(d, text, (size_t)n, cudaMemcpyHostToDevice, st));
-        d_text = d;
+        // the upload is kept: the gcz_build_block that follows on the same host buffer finds the text on the device
+        ctx->staged_host = nullptr;
+        if (ctx->staged_cap < (size_t)n + 64) {
+            if (ctx->staged_dev) cudaFree(ctx->staged_dev);
+            ctx->staged_dev = nullptr; ctx->staged_cap = 0;
+            const size_t want = ((size_t)n + 64 + ((size_t)1 << 20)) & ~(((size_t)1 << 20) - 1);
+            cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ctx->staged_dev), want);
+            if (e != cudaSuccess) { cudaGetLastError(); ctx->staged_dev = nullptr; return fail(GCZ_E_NOMEM, "text staging of %zu bytes", want); }
+            ctx->staged_cap = want;
+        }
+        GCZ_CUDA(cudaMemcpyAsync(ctx->staged_dev, text, (size_t)n, cudaMemcpyHostToDevice, st));
+        d_text = ctx->staged_dev;
     }
     unsigned long long* d_counts = ctx->arena.get<unsigned long long>(256);
     if (!d_counts) return fail(GCZ_E_NOMEM, "histogram scratch");
     GCZ_TRY(histogram_device(ctx, st, d_text, n, d_counts));
     GCZ_CUDA(cudaMemcpyAsync(counts, d_counts, 256 * 8, cudaMemcpyDeviceToHost, st));
     GCZ_CUDA(cudaStreamSynchronize(st));
+    if (!on_dev) { ctx->staged_host = text; ctx->staged_n = n; }
     return GCZ_OK;
 }
 
@@ -177,7 +190,9 @@ static int build_block(int device, const uint8_t* text, int64_t n, int32_t sampl
     const int64_t launches0 = ctx->launches;
     std::memset(&t_timing, 0, sizeof(t_timing));
 
-    const bool text_dev = is_device_ptr(text), gcz_dev = is_device_ptr(gcz_body), gcx_dev = is_device_ptr(gcx_body);
+    const bool text_staged = ctx->staged_host == text && ctx->staged_n == n && ctx->staged_dev != nullptr;
+    ctx->staged_host = nullptr;                                   // one use: the host buffer may change afterwards
+    const bool text_dev = text_staged || is_device_ptr(text), gcz_dev = is_device_ptr(gcz_body), gcx_dev = is_device_ptr(gcx_body);
     const bool sa_dev = sa_out && is_device_ptr(sa_out), bwt_dev = bwt_out && is_device_ptr(bwt_out);
 
     const size_t fixed = (text_dev ? 0 : (size_t)n + 256) + (size_t)n * 4 + (size_t)n + 256 +
@@ -191,7 +206,7 @@ static int build_block(int device, const uint8_t* text, int64_t n, int32_t sampl
     for (auto& e : ev) GCZ_CUDA(cudaEventCreate(&e));
     GCZ_CUDA(cudaEventRecord(ev[0], st));
 
-    const uint8_t* d_text = text;
+    const uint8_t* d_text = text_staged ? ctx->staged_dev : text;
     if (!text_dev) {
         uint8_t* d = arena.get<uint8_t>((size_t)n + 64);
         if (!d) return fail(GCZ_E_NOMEM, "text staging");
@@ -222,10 +237,11 @@ static int build_block(int device, const uint8_t* text, int64_t n, int32_t sampl
     int carry_shift = std::getenv("GCZ_BWT_GATHER") ? 0 : 1;
     GCZ_TRY(suffix_sort(ctx, st, d_text, n, counts, d_sa, arena, &ss, &carry_shift));
     WaveletStats ws;
-    GCZ_TRY(build_wavelet_structures(ctx, st, d_text, d_sa, carry_shift, sa_out != nullptr, n, shape, sf, d_bwt, d_gcz, d_gcx, arena, &ws));
+    GCZ_TRY(build_wavelet_structures(ctx, st, d_text, d_sa, carry_shift, sa_out != nullptr, n, shape, sf, d_bwt, d_gcz, d_gcx, arena, &ws,
+                                     gcz_dev ? nullptr : gcz_body, ctx->copy_stream, ctx->copy_event));
     GCZ_CUDA(cudaEventRecord(ev[2], st));
 
-    if (!gcz_dev) GCZ_CUDA(cudaMemcpyAsync(gcz_body, d_gcz, (size_t)gcz_body_len, cudaMemcpyDeviceToHost, st));
+    if (!gcz_dev) GCZ_CUDA(cudaStreamWaitEvent(st, ctx->copy_event, 0));         // the .gcz body went out while the index was built
     if (!gcx_dev) GCZ_CUDA(cudaMemcpyAsync(gcx_body, d_gcx, (size_t)gcx_body_len, cudaMemcpyDeviceToHost, st));
     if (sa_out && !sa_dev) GCZ_CUDA(cudaMemcpyAsync(sa_out, d_sa, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     if (bwt_out && !bwt_dev) GCZ_CUDA(cudaMemcpyAsync(bwt_out, d_bwt, (size_t)n, cudaMemcpyDeviceToHost, st));

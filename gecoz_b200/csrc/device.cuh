@@ -48,6 +48,13 @@ struct DeviceCtx {
     int          device = -1;
     int          sm_count = 0;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;       // device-to-host copies that overlap the build
+    cudaEvent_t  copy_event = nullptr;
+    // text left on the device by gcz_count_symbols for the gcz_build_block that follows on the same host buffer
+    const void*  staged_host = nullptr;
+    int64_t      staged_n = 0;
+    uint8_t*     staged_dev = nullptr;
+    size_t       staged_cap = 0;
     std::mutex   mu;                          // one build / query batch at a time per device (shared arena)
     Arena        arena;
     void*        pinned = nullptr;            // small pinned scratch for read-backs

@@ -421,9 +421,9 @@ struct VectorDesc {
 
 // ones per 65536-bit superblock (one warp each)
 __global__ void superblock_popcount_kernel(const uint32_t* __restrict__ raw, const VectorDesc* __restrict__ vecs, int nvec,
-                                           int64_t total_sb, uint32_t* __restrict__ sb_ones) {
-    const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (g >= total_sb) return;
+                                           int64_t sb_begin, int64_t sb_end, uint32_t* __restrict__ sb_ones) {
+    const int64_t g = sb_begin + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (g >= sb_end) return;
     int v = 0;
     while (v + 1 < nvec && vecs[v + 1].sb_first <= g) v++;
     const uint4* p = reinterpret_cast<const uint4*>(raw + vecs[v].raw_word + (uint64_t)(g - vecs[v].sb_first) * 2048u);
@@ -465,11 +465,11 @@ superblock_scan_kernel(uint32_t* __restrict__ sb_ones, const VectorDesc* __restr
 // superblock, or a uint64 absolute count after the 128th chunk — only when more data follows
 // (algo/tree/RankedWTNode.java:228-245, layout in SURVEY.md A.3).
 __global__ void __launch_bounds__(128)
-ranked_layout_kernel(const uint32_t* __restrict__ raw, const VectorDesc* __restrict__ vecs, int nvec,
+ranked_layout_kernel(const uint32_t* __restrict__ raw, const VectorDesc* __restrict__ vecs, int nvec, int64_t sb_begin,
                      const uint32_t* __restrict__ sb_excl) {
     __shared__ __align__(16) uint16_t s_out[4232];
     __shared__ uint32_t s_warp[4];
-    const int64_t g = blockIdx.x;
+    const int64_t g = sb_begin + blockIdx.x;
     int v = 0;
     while (v + 1 < nvec && vecs[v + 1].sb_first <= g) v++;
     const VectorDesc vd = vecs[v];
@@ -516,6 +516,16 @@ ranked_layout_kernel(const uint32_t* __restrict__ raw, const VectorDesc* __restr
 
 inline int64_t superblocks(int64_t len) { return (len + 65535) >> 16; }
 
+// counters + final byte layout of vectors [v0, v1) of `vecs` (their superblocks are [sb0, sb1))
+int layout_vectors(DeviceCtx* ctx, cudaStream_t st, const uint32_t* d_raw, const VectorDesc* d_vecs, int nvec, int v0, int v1,
+                   int64_t sb0, int64_t sb1, uint32_t* d_sb) {
+    if (v1 <= v0 || sb1 <= sb0) return GCZ_OK;
+    GCZ_LAUNCH(ctx, superblock_popcount_kernel, (unsigned)(((sb1 - sb0) * 32 + 255) / 256), 256, 0, st, d_raw, d_vecs, nvec, sb0, sb1, d_sb);
+    GCZ_LAUNCH(ctx, superblock_scan_kernel, (unsigned)(v1 - v0), 1024, 0, st, d_sb, d_vecs + v0);
+    GCZ_LAUNCH(ctx, ranked_layout_kernel, (unsigned)(sb1 - sb0), 128, 0, st, d_raw, d_vecs, nvec, sb0, d_sb);
+    return GCZ_OK;
+}
+
 // All levels of an IndexWaveletTree over the m values in d_ssa[0] (d_ssa[1]: scratch of the same size): the high
 // levels with three launches each over global memory, the low ones in one launch (iwt_low_levels_kernel).
 int iwt_levels(DeviceCtx* ctx, cudaStream_t st, uint32_t* const d_ssa[2], int64_t m, int levels, uint32_t* d_raw,
@@ -561,7 +571,8 @@ size_t wavelet_workspace_bytes(int64_t n, int sampling_factor) {
 
 int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, uint32_t* d_sa, int carry_shift, bool clean_sa,
                              int64_t n, const gcz_shape* shape, int sampling_factor, uint8_t* d_bwt,
-                             uint8_t* d_gcz_body, uint8_t* d_gcx_body, Arena& arena, WaveletStats* stats) {
+                             uint8_t* d_gcz_body, uint8_t* d_gcx_body, Arena& arena, WaveletStats* stats,
+                             uint8_t* h_gcz_out, cudaStream_t copy_stream, cudaEvent_t gcz_copied) {
     const size_t mark0 = arena.mark();
     // ---- host tables -------------------------------------------------------------------------------
     SymbolTables h_tab;
@@ -674,6 +685,15 @@ int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_t
     } else {
         GCZ_LAUNCH(ctx, hswt_emit_kernel, wt_grid, kWtThreads, 0, st, d_bwt, n, d_tab, d_tile_counts, tiles, d_node_raw, d_raw);
     }
+    // the .gcz body is complete once its nodes are laid out: its copy to the host overlaps the index build
+    const int64_t sb_nodes = vecs[marker_vec].sb_first;
+    GCZ_TRY(layout_vectors(ctx, st, d_raw, d_vecs, (int)vecs.size(), 0, marker_vec, 0, sb_nodes, d_sb));
+    if (h_gcz_out) {
+        GCZ_CUDA(cudaEventRecord(gcz_copied, st));
+        GCZ_CUDA(cudaStreamWaitEvent(copy_stream, gcz_copied, 0));
+        GCZ_CUDA(cudaMemcpyAsync(h_gcz_out, d_gcz_body, (size_t)shape->size, cudaMemcpyDeviceToHost, copy_stream));
+        GCZ_CUDA(cudaEventRecord(gcz_copied, copy_stream));
+    }
     if (stats) GCZ_CUDA(cudaEventRecord(ev1, st));
 
     // ---- sampled SA + IndexWaveletTree ---------------------------------------------------------------------
@@ -683,10 +703,7 @@ int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_t
     GCZ_TRY(iwt_levels(ctx, st, d_ssa, m, levels, d_raw, vecs, level_vec0, d_zeros, d_block_zeros, d_level_raw));
 
     // ---- counters + final byte layout of every vector ---------------------------------------------------------
-    GCZ_LAUNCH(ctx, superblock_popcount_kernel, (unsigned)((total_sb * 32 + 255) / 256), 256, 0, st, d_raw, d_vecs,
-               (int)vecs.size(), total_sb, d_sb);
-    GCZ_LAUNCH(ctx, superblock_scan_kernel, (unsigned)vecs.size(), 1024, 0, st, d_sb, d_vecs);
-    GCZ_LAUNCH(ctx, ranked_layout_kernel, (unsigned)total_sb, 128, 0, st, d_raw, d_vecs, (int)vecs.size(), d_sb);
+    GCZ_TRY(layout_vectors(ctx, st, d_raw, d_vecs, (int)vecs.size(), marker_vec, (int)vecs.size(), sb_nodes, total_sb, d_sb));
 
     if (stats) {
         GCZ_CUDA(cudaEventRecord(ev2, st));
@@ -728,9 +745,7 @@ int ranked_vector_from_bits(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_bi
     GCZ_CUDA(cudaMemcpyAsync(d_vec, &d, sizeof(d), cudaMemcpyHostToDevice, st));
     GCZ_CUDA(cudaStreamSynchronize(st));
     GCZ_LAUNCH(ctx, pack_bits_kernel, ctx->sm_count * 4, 256, 0, st, d_bits, len, d_raw);
-    GCZ_LAUNCH(ctx, superblock_popcount_kernel, (unsigned)((d.sb_count * 32 + 255) / 256), 256, 0, st, d_raw, d_vec, 1, d.sb_count, d_sb);
-    GCZ_LAUNCH(ctx, superblock_scan_kernel, 1, 1024, 0, st, d_sb, d_vec);
-    GCZ_LAUNCH(ctx, ranked_layout_kernel, (unsigned)d.sb_count, 128, 0, st, d_raw, d_vec, 1, d_sb);
+    GCZ_TRY(layout_vectors(ctx, st, d_raw, d_vec, 1, 0, 1, 0, d.sb_count, d_sb));
     GCZ_CUDA(cudaStreamSynchronize(st));
     arena.release(mark0);
     return GCZ_OK;
@@ -761,9 +776,7 @@ int index_wavelet_tree_from_values(DeviceCtx* ctx, cudaStream_t st, const uint32
     GCZ_CUDA(cudaMemcpyAsync(d_ssa[0], d_vals, (size_t)m * 4, cudaMemcpyDeviceToDevice, st));
     GCZ_CUDA(cudaStreamSynchronize(st));
     GCZ_TRY(iwt_levels(ctx, st, d_ssa, m, levels, d_raw, vecs, 0, d_zeros, d_block_zeros, d_level_raw));
-    GCZ_LAUNCH(ctx, superblock_popcount_kernel, (unsigned)((total_sb * 32 + 255) / 256), 256, 0, st, d_raw, d_vecs, (int)vecs.size(), total_sb, d_sb);
-    GCZ_LAUNCH(ctx, superblock_scan_kernel, (unsigned)vecs.size(), 1024, 0, st, d_sb, d_vecs);
-    GCZ_LAUNCH(ctx, ranked_layout_kernel, (unsigned)total_sb, 128, 0, st, d_raw, d_vecs, (int)vecs.size(), d_sb);
+    GCZ_TRY(layout_vectors(ctx, st, d_raw, d_vecs, (int)vecs.size(), 0, (int)vecs.size(), 0, total_sb, d_sb));
     GCZ_CUDA(cudaStreamSynchronize(st));
     arena.release(mark0);
     return GCZ_OK;

@@ -74,7 +74,11 @@ int64_t gcz_ranked_bytes(int64_t len_bits);                    /* RankedWTNode.b
 int64_t gcz_index_size(int64_t n, int32_t sampling_factor);    /* GSSAIndex.getIndexSize  algo/ssa/GSSAIndex.java:200-205 */
 
 /* ---- build ------------------------------------------------------------------------------------ */
-/* The counting loop of GecozFileWriter.write  fmt/GecozFileWriter.java:127-130 (GPU histogram). */
+/* The counting loop of GecozFileWriter.write  fmt/GecozFileWriter.java:127-130 (GPU histogram).
+ * When `text` is a host buffer its upload stays on the device: the gcz_build_block that follows for the SAME
+ * buffer and length (what GecozFileWriter.write does: count, reserve the file slices, queue the block) finds the
+ * text there and does not copy it a second time.  The buffer must not change between the two calls; any other
+ * gcz_build_block / gcz_count_symbols on the device drops the staged copy. */
 int gcz_count_symbols(int device, const uint8_t* text, int64_t n, int64_t counts[256]);
 
 /* One call == BlockWriter.run  fmt/GecozFileWriter.java:256-284:

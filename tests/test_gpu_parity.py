@@ -181,6 +181,26 @@ def test_build_block_gather_path(G, O, monkeypatch):
     assert np.array_equal(gcz, ref["gcz_body"]) and np.array_equal(gcx, ref["gcx_body"])
 
 
+def test_text_staging_follows_the_buffer(G, O):
+    """gcz_count_symbols leaves the upload for the build of the SAME host buffer; any other buffer is uploaded."""
+    from gecoz_b200 import synth
+    a = synth.cfg2_text(200_000, seed=21)
+    b = synth.cfg2_text(200_000, seed=22)
+    assert len(a) == len(b)
+    shape_b = G.shape_from_counts(np.bincount(b, minlength=256).astype(np.int64))
+    G.symbol_counts(a)                                       # stages a
+    gcz = np.zeros(shape_b.size, np.uint8)
+    gcx = np.zeros(G.index_size(len(b), 5), np.uint8)
+    G.build_block(0, b, len(b), 32, shape_b, gcz, gcx)       # same length, other buffer: must not see a
+    ref = O.build_block(b, 32)
+    assert np.array_equal(gcz, ref["gcz_body"]) and np.array_equal(gcx, ref["gcx_body"])
+    shape_a = G.shape_from_counts(G.symbol_counts(a))        # staged and used
+    gcz = np.zeros(shape_a.size, np.uint8)
+    G.build_block(0, a, len(a), 32, shape_a, gcz, gcx)
+    ref = O.build_block(a, 32)
+    assert np.array_equal(gcz, ref["gcz_body"]) and np.array_equal(gcx, ref["gcx_body"])
+
+
 def test_provisional_golden_blocks(G):
     prov = json.loads((GOLD / "provisional_blocks.json").read_text())
     for name, p in prov.items():
