@@ -199,11 +199,20 @@ def count_sharded(gssas: Sequence, data, off, *, rank: int = 0, world: int = 1, 
     lo, hi = shard_bounds(n, world)[rank]
     sdata, soff = _shard_patterns(data, off, lo, hi)
     k = len(gssas)
-    local = np.zeros((k, 2, hi - lo), dtype=np.int64)
-    for b, g in enumerate(gssas):
-        if hi > lo:
-            sp, ep = g.count_batch(packed=(sdata, soff))
-            local[b, 0], local[b, 1] = np.asarray(sp), np.asarray(ep)
+    if device is not None and str(device).startswith("cuda") and hi > lo:
+        # the shard goes to the device once and is searched there against every block
+        import torch
+        t_data, t_off = torch.from_numpy(sdata).to(device), torch.from_numpy(soff).to(device)
+        t_out = torch.empty((k, 2, hi - lo), dtype=torch.int64, device=device)
+        for b, g in enumerate(gssas):
+            g.count_batch(packed=(t_data, t_off), out=(t_out[b, 0], t_out[b, 1]))
+        local = t_out.cpu().numpy()
+    else:
+        local = np.zeros((k, 2, hi - lo), dtype=np.int64)
+        for b, g in enumerate(gssas):
+            if hi > lo:
+                sp, ep = g.count_batch(packed=(sdata, soff))
+                local[b, 0], local[b, 1] = np.asarray(sp), np.asarray(ep)
     parts = gather_varlen(local, rank=rank, world=world, group=group, device=device)
     if parts is None:
         return None

@@ -415,3 +415,91 @@ def test_sharded_two_gpus_nccl(G, O, tmp_path, mode):
             assert np.array_equal(got["sp"][b], sp) and np.array_equal(got["ep"][b], ep)
             per, pos, poff = og.find_batch_raw((data, off))
             assert np.array_equal(got[f"per{b}"], per) and np.array_equal(got[f"pos{b}"], pos) and np.array_equal(got[f"off{b}"], poff)
+
+
+# ---- callers: GecoMatch (-c / -s) and SimpleGFFGenerator (-s patterns.fa) ------------------------------------------------
+def _small_genome(tmp_path, G):
+    from gecoz_b200 import synth
+    recs = [(f"chr{i} test", synth.iid_acgtn(int(ln), 60 + i, p_n=0.0)) for i, ln in enumerate([40_000, 25_000, 12_000, 11_000, 700, 650])]
+    info = G.index_records(recs, tmp_path / "g.gcz")
+    return recs, info
+
+
+def _oracle_blocks(O, recs, info):
+    from gecoz_b200 import synth
+    by = {h: s for h, s in recs}
+    out = []
+    for headers in info["blocks"]:
+        text = synth.block_of([by[h] for h in headers])
+        r = O.build_block(text, 32)
+        out.append((headers, O.GSSA(r["gcz_body"], len(text), r["gcx_body"])))
+    return out
+
+
+def test_geco_match_count_and_search(G, O, tmp_path):
+    from gecoz_b200 import geco_match
+    recs, info = _small_genome(tmp_path, G)
+    blocks = _oracle_blocks(O, recs, info)
+    assert len(blocks) < len(recs)                                       # merged blocks: per-string split matters
+    pats = [recs[0][1][100:108].tobytes(), recs[3][1][5:11].tobytes(), recs[5][1][:4].tobytes(), b"ACGTACGTACGTACGTACGTAC", b"A"]
+    for pat in pats:
+        for want_pos in (False, True):
+            exp = []
+            for headers, og in blocks:
+                res = og.find(pat)
+                if res is None:
+                    continue
+                for h, r in zip(headers, res):
+                    if r is not None and len(r):
+                        exp.append(f">{h} found : {len(r)}")
+                        if want_pos:
+                            exp += [str(int(p)) for p in r]
+            got = (geco_match.match if want_pos else geco_match.count)(tmp_path / "g.gcz", None, pat)
+            assert got == exp, pat
+    # -s / -c with a header: only that string of that block
+    hdr = recs[3][0]
+    headers, og = next(b for b in blocks if hdr in b[0])
+    res = og.find(pats[1])
+    r = res[headers.index(hdr)] if res is not None else None
+    exp = ([f">{hdr} found : {len(r)}"] + [str(int(p)) for p in r]) if r is not None and len(r) else []
+    assert geco_match.match(tmp_path / "g.gcz", hdr, pats[1]) == exp
+    with pytest.raises(KeyError):
+        geco_match.count(tmp_path / "g.gcz", "chrZ", b"ACGT")
+
+
+def test_simple_gff_generator(G, O, tmp_path):
+    from gecoz_b200 import geco_match
+    recs, info = _small_genome(tmp_path, G)
+    blocks = _oracle_blocks(O, recs, info)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    s0, s2 = recs[0][1], recs[2][1]
+    pats = [("p1|first note|second", s0[200:230].tobytes()), ("rna", s0[300:320].tobytes().replace(b"T", b"U")),
+            ("revcomp|", s2[50:75].tobytes().translate(comp)[::-1]), ("absent", b"ACGT" * 9), ("|", s2[10:22].tobytes()),
+            ("short", b"ACG")]
+    fa = tmp_path / "p.fa"
+    with open(fa, "wb") as f:
+        for i, (h, s) in enumerate(pats):
+            if i == 1:                                                    # a FASTQ record in the middle
+                f.write(b"@" + h.encode() + b"\r\n" + s[:10] + b"\r\n" + s[10:] + b"\n+\n" + b"I" * len(s) + b"\n")
+            else:
+                f.write(b">" + h.encode() + b"\n" + s + b"\n")
+        f.write(b">empty\n>last\nACGTAC\n")
+    exp = []
+    for h, s in pats + [("last", b"ACGTAC")]:
+        fwd = s.replace(b"U", b"T")
+        for strand, seq in (("+", fwd), ("-", fwd.translate(comp)[::-1])):
+            for headers, og in blocks:
+                res = og.find(seq)
+                if res is None:
+                    continue
+                for name, r in zip(headers, res):
+                    if r is None:
+                        continue
+                    parts = h.split("|")
+                    while parts and parts[-1] == "":
+                        parts.pop()
+                    attrs = ("ID=" + parts[0] if parts else "") + "".join(";Note=" + x for x in parts[1:])
+                    exp += [f"{name}\tgecotools\tdna\t{int(p) + 1}\t{int(p) + len(seq)}\t1.000\t{strand}\t.\t{attrs}" for p in r]
+    got = geco_match.search(tmp_path / "g.gcz", fa)
+    assert got == exp
+    assert any("\t-\t" in x for x in got) and any("\t+\t" in x for x in got) and len(got) > 10
