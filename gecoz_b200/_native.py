@@ -74,7 +74,7 @@ EXPORTS = [
     "gcz_shape_from_counts", "gcz_shape_write", "gcz_shape_read", "gcz_ranked_bytes", "gcz_index_size",
     "gcz_count_symbols", "gcz_build_block", "gcz_last_build_timing",
     "gcz_open_block", "gcz_close_block", "gcz_text_length", "gcz_sampling_factor", "gcz_num_strings",
-    "gcz_string_ends", "gcz_c_array", "gcz_count_batch", "gcz_locate_rows", "gcz_find_batch", "gcz_free",
+    "gcz_string_ends", "gcz_c_array", "gcz_count_batch", "gcz_locate_rows", "gcz_find_batch", "gcz_extract", "gcz_free",
     "gcz_dbg_sort_pairs", "gcz_dbg_suffix_array", "gcz_dbg_ranked_vector", "gcz_dbg_index_wavelet_tree",
 ]
 
@@ -127,6 +127,7 @@ def lib() -> C.CDLL:
         "gcz_count_batch": (C.c_int, [P, P, P, i64, P, P]),
         "gcz_locate_rows": (C.c_int, [P, P, i64, P]),
         "gcz_find_batch": (C.c_int, [P, P, P, i64, P, C.POINTER(P), C.POINTER(P)]),
+        "gcz_extract": (C.c_int, [P, i32, i64, P, i64, C.POINTER(i64)]),
         "gcz_free": (None, [P]),
         "gcz_dbg_sort_pairs": (C.c_int, [C.c_int, P, P, i64, i32, i32]),
         "gcz_dbg_suffix_array": (C.c_int, [C.c_int, P, i64, P]),

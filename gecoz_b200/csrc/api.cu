@@ -383,6 +383,10 @@ int gcz_find_batch(gcz_index* idx, const uint8_t* pats, const int64_t* pat_off, 
     clear_error();
     return find_batch(idx, pats, pat_off, n_pats, per_string_counts, positions, pos_off);
 }
+int gcz_extract(gcz_index* idx, int32_t nstr, int64_t from, uint8_t* out, int64_t cap, int64_t* written) {
+    clear_error();
+    return extract(idx, nstr, from, out, cap, written);
+}
 void gcz_free(void* p) { std::free(p); }
 
 // ---- stage hooks ---------------------------------------------------------------------------------------------------

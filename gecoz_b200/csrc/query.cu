@@ -178,6 +178,122 @@ __device__ __forceinline__ long long iwt_get(const QueryTables* __restrict__ t, 
     return code;
 }
 
+
+// ---- select / inverse lookups (extract) -----------------------------------------------------------------------------
+// Position of the n-th (1-based, counted from the start of the vector) bit equal to `want` among bits [lo, hi] of a
+// sector vector, or -1.  RankedWTNode.findZero/findOne(n, lo, hi)  algo/tree/RankedWTNode.java:154-205: the
+// reference steers an interpolation search with doubles; the position it returns is the exact select computed here.
+__device__ long long sector_select(const uint32_t* __restrict__ sectors, uint64_t sector0, long long lo, long long hi,
+                                   long long n, unsigned want) {
+    if (hi < lo || n <= 0) return -1;
+    long long jlo = lo / kSectorBits, jhi = hi / kSectorBits;
+    auto before = [&](long long j) -> long long {
+        const long long ones = __ldg(sectors + (sector0 + (uint64_t)j) * 8);
+        return want ? ones : j * kSectorBits - ones;
+    };
+    if (before(jlo) >= n) return -1;
+    while (jlo < jhi) {                                     // last sector with fewer than n matches before it
+        const long long mid = (jlo + jhi + 1) >> 1;
+        if (before(mid) < n) jlo = mid; else jhi = mid - 1;
+    }
+    long long r = n - before(jlo);
+    const uint4* p = reinterpret_cast<const uint4*>(sectors + (sector0 + (uint64_t)jlo) * 8);
+    const uint4 a = __ldg(p), b = __ldg(p + 1);
+    const uint32_t w[7] = { a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+    for (int k = 0; k < 7; k++) {
+        const uint32_t m = want ? w[k] : ~w[k];
+        const int c = __popc(m);
+        if (r <= c) {
+            const long long pos = jlo * kSectorBits + 32 * k + __fns(m, 0, (int)r);
+            return (pos >= lo && pos <= hi) ? pos : -1;
+        }
+        r -= c;
+    }
+    return -1;
+}
+
+// IndexWaveletTree.find  algo/tree/IndexWaveletTree.java:152-165: where the value idx sits in the sequence
+__device__ long long iwt_find(const QueryTables* __restrict__ t, const uint32_t* __restrict__ sectors, long long idx) {
+    long long pos = 0;
+    for (int i = 0; i < t->iwt_levels; i++) {
+        const unsigned bit = (unsigned)((unsigned long long)idx >> i) & 1u;
+        const long long block = (long long)((unsigned long long)idx & (0xFFFFFFFFFFFFFFFEull << i));
+        const long long hi = min(block + (2ll << i), (long long)t->iwt_m) - 1;
+        pos = sector_select(sectors, t->iwt_sector0[i], block, hi, (long long)((unsigned long long)block >> 1) + pos + 1, bit);
+        pos -= block;
+    }
+    return pos;
+}
+
+// GSSAIndex.find  algo/ssa/GSSAIndex.java:184-187: the SA row of a sampled text position
+__device__ long long index_find(const QueryTables* __restrict__ t, const uint32_t* __restrict__ sectors, long long text_pos) {
+    const long long sidx = text_pos >> t->sampling_factor;
+    if (text_pos != (sidx << t->sampling_factor)) return (long long)INT_MIN;
+    return sector_select(sectors, t->marker_sector0, 0, t->n - 1, iwt_find(t, sectors, sidx) + 1, 1u);
+}
+
+// One step of the LF walk: HSWT.getRS  algo/tree/HuffmanShapedWaveletTree.java:300-314 followed by
+// idx = (int)(c[symbol] + rank)  algo/ssa/GSSA.java:116,123.  Returns the BWT symbol of row idx.
+__device__ __forceinline__ int lf_step(const QueryTables* __restrict__ t, const uint32_t* __restrict__ sectors, long long& idx) {
+    long long pos = idx;
+    int v = 0;
+    while (v >= 0) {
+        const BitRank br = sector_bit_rank(sectors, t->node_sector0[v], (uint32_t)pos);
+        pos = br.bit ? (long long)br.rank - 1 : pos - (long long)br.rank;
+        v = t->child[v][br.bit];
+    }
+    const int symbol = ~v;
+    idx = (long long)(int)(t->c[symbol] + pos);
+    return symbol;
+}
+
+// GSSA.extract  algo/ssa/GSSA.java:90-126 for generalized-string positions [from, pos] into out[0 .. pos - from].
+// Thread 0 does what the reference does at the top: it starts at the sampled position after `pos` (sapos, or row 0
+// when that is past the text), skips down to pos and emits until the last sampled position low <= pos.  Every other
+// thread owns one sampled position s in (from, low]: row by index_find, then up to 2^sf symbols backwards.  Both are
+// the same walk as long as thread 0 reaches the row index_find(low) names; flag[0] tells whether it did (it does not
+// when the walk crossed a separator the LF mapping gets wrong) and flag[1] keeps its row.
+__global__ void __launch_bounds__(128)
+extract_kernel(const QueryTables* __restrict__ tables, const uint32_t* __restrict__ sectors, long long from, long long pos,
+               uint8_t* __restrict__ out, long long* __restrict__ flag) {
+    __shared__ QueryTables t;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&t);
+        for (int i = threadIdx.x; i < (int)(sizeof(QueryTables) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int sf = t.sampling_factor;
+    const long long step = 1ll << sf;
+    const long long low = max(from, (pos >> sf) << sf);               // thread 0 emits [low, pos]
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g == 0) {
+        const long long sapos = ((pos >> sf) + 1) << sf;
+        long long idx = sapos < (long long)t.n ? index_find(&t, sectors, sapos) : 0;
+        long long n = min(sapos, (long long)t.n - 1) - pos;
+        while (--n > 0) lf_step(&t, sectors, idx);
+        for (long long p = pos; p >= low; p--) out[p - from] = (uint8_t)lf_step(&t, sectors, idx);
+        // idx is now the row of position low (as the reference sees it)
+        flag[1] = idx;
+        flag[0] = (low > from && idx != index_find(&t, sectors, low)) ? 1 : 0;
+        return;
+    }
+    // anchor g - 1 counts sampled positions downwards from low
+    const long long s = low - (g - 1) * step;
+    if (s <= from || low <= from) return;
+    long long idx = index_find(&t, sectors, s);
+    const long long stop = max(from, s - step);
+    for (long long p = s - 1; p >= stop; p--) out[p - from] = (uint8_t)lf_step(&t, sectors, idx);
+}
+
+// the reference's own sequential walk, for the calls where it leaves the text's true LF chain
+__global__ void extract_sequential_kernel(const QueryTables* __restrict__ tables, const uint32_t* __restrict__ sectors,
+                                          long long from, long long low, long long row, uint8_t* __restrict__ out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    long long idx = row;
+    for (long long p = low - 1; p >= from; p--) out[p - from] = (uint8_t)lf_step(tables, sectors, idx);
+}
+
 // GSSA.locate  algo/ssa/GSSA.java:241-251 with GSSAIndex.get :171-173 and HSWT.getRS :300-314
 __device__ long long locate_row(const QueryTables* __restrict__ t, const uint32_t* __restrict__ sectors, long long idx) {
     long long steps = 0;
@@ -594,6 +710,49 @@ int find_batch(gcz_index* idx, const uint8_t* pats, const int64_t* pat_off, int6
     }
     *positions = h_pos;
     *pos_off = h_off;
+    return GCZ_OK;
+}
+
+// GSSA.extract(ByteBuffer buf, int nstr, long from)  algo/ssa/GSSA.java:90-126
+int extract(gcz_index* idx, int32_t nstr, int64_t from, uint8_t* out, int64_t cap, int64_t* written) {
+    if (!idx || !out || !written || cap < 0 || from < 0) return fail(GCZ_E_ARG, "extract arguments");
+    const int64_t ns = (int64_t)idx->e.size();
+    if (nstr < 0 || nstr >= ns) return fail(GCZ_E_RANGE, "String index %d is out of bound", nstr);
+    if (nstr > 0) from += idx->e[(size_t)nstr - 1] + 1;
+    const int64_t pos = std::min(idx->e[(size_t)nstr], from + cap) - 1;
+    *written = 0;
+    // the reference ends with buf.position(bpos + 1), bpos = (int)(pos - from): IllegalArgumentException below zero
+    // (strings whose end the index mislocates)
+    if (pos - from + 1 < 0) return fail(GCZ_E_RANGE, "newPosition < 0: the string ends before position %lld", (long long)from);
+    if (pos < from) return GCZ_OK;
+    const int64_t count = pos - from + 1;
+    DeviceCtx* ctx = idx->ctx;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    GCZ_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream_of(ctx);
+    ctx->arena.reset();
+    const bool out_dev = is_device_ptr(out);
+    const size_t need = (out_dev ? 0 : (size_t)count + 256) + (1 << 20);
+    if (ctx->arena.capacity < need) GCZ_TRY(ctx->arena.reserve(need));
+    uint8_t* d_out = out_dev ? out : ctx->arena.get<uint8_t>((size_t)count + 64);
+    long long* d_flag = ctx->arena.get<long long>(2);
+    if (!d_out || !d_flag) return fail(GCZ_E_NOMEM, "extract staging");
+    const int sf = idx->sampling_factor;
+    const int64_t low = std::max(from, (pos >> sf) << sf);
+    const int64_t anchors = low > from ? ((low - from) >> sf) + 1 : 0;              // sampled positions in (from, low]
+    const int64_t threads = 1 + anchors;
+    GCZ_LAUNCH(ctx, extract_kernel, (unsigned)((threads + 127) / 128), 128, 0, st, idx->d_tables, idx->d_sectors,
+               (long long)from, (long long)pos, d_out, d_flag);
+    long long h_flag[2] = { 0, 0 };
+    GCZ_CUDA(cudaMemcpyAsync(h_flag, d_flag, sizeof(h_flag), cudaMemcpyDeviceToHost, st));
+    GCZ_CUDA(cudaStreamSynchronize(st));
+    if (h_flag[0]) {
+        GCZ_LAUNCH(ctx, extract_sequential_kernel, 1, 32, 0, st, idx->d_tables, idx->d_sectors, (long long)from, (long long)low,
+                   h_flag[1], d_out);
+    }
+    if (!out_dev) GCZ_CUDA(cudaMemcpyAsync(out, d_out, (size_t)count, cudaMemcpyDeviceToHost, st));
+    GCZ_CUDA(cudaStreamSynchronize(st));
+    *written = count;
     return GCZ_OK;
 }
 

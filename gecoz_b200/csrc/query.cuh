@@ -47,6 +47,7 @@ int  open_block(DeviceCtx* ctx, const uint8_t* gcz_body, int64_t body_len, int64
 void close_block(gcz_index* idx);
 int  count_batch(gcz_index* idx, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats, int64_t* sp, int64_t* ep);
 int  locate_rows(gcz_index* idx, const int64_t* rows, int64_t n_rows, int64_t* positions);
+int  extract(gcz_index* idx, int32_t nstr, int64_t from, uint8_t* out, int64_t cap, int64_t* written);
 int  find_batch(gcz_index* idx, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats,
                 int64_t* per_string_counts, int64_t** positions, int64_t** pos_off);
 

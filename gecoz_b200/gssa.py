@@ -129,6 +129,18 @@ class GSSA:
             res.append(one)
         return res
 
+    def extract(self, nstr: int, start: int = 0, length: int | None = None, out=None) -> np.ndarray:
+        """GSSA.extract(buf, nstr, from)  :90-126: up to `length` symbols of string nstr from `start` (never past the
+        string's end).  Returns the bytes written (a view of `out` when one is given)."""
+        if nstr < 0 or nstr >= self.n_strings:
+            raise IndexError(f"String index {nstr} is out of bound")
+        cap = self.getLength(nstr) - start if length is None else length
+        cap = max(int(cap), 0)
+        buf = np.zeros(max(cap, 1), dtype=np.uint8) if out is None else out
+        w = C.c_int64()
+        N.check(N.lib().gcz_extract(self._h, nstr, int(start), N.ptr(buf), cap, C.byref(w)))
+        return buf[:w.value]
+
     def find(self, pattern: bytes):                                    # :160-185
         return self.find_batch([pattern])[0]
 

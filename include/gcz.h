@@ -142,6 +142,13 @@ int  gcz_locate_rows(gcz_index* idx, const int64_t* rows, int64_t n_rows, int64_
  * callee-allocated host memory, released with gcz_free. */
 int  gcz_find_batch(gcz_index* idx, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats,
                     int64_t* per_string_counts, int64_t** positions, int64_t** pos_off);
+/* GSSA.extract(ByteBuffer buf, int nstr, long from)  :90-126: the symbols of string nstr from position `from`
+ * (0-based inside the string), at most `cap` of them and never past the string's end, into out[0 ..]; *written =
+ * the buffer position the reference leaves behind.  One thread per sampled text position walks 2^sampling_factor
+ * LF steps (GSSAIndex.find :184-187, IndexWaveletTree.find, RankedWTNode.findZero/findOne for the anchors); a call
+ * whose reference walk leaves the true LF chain (merged blocks) is replayed sequentially so that
+ * the bytes stay the reference's. */
+int  gcz_extract(gcz_index* idx, int32_t nstr, int64_t from, uint8_t* out, int64_t cap, int64_t* written);
 void gcz_free(void* p);
 
 /* ---- stage-level hooks used by the parity tests (each one is a stage of gcz_build_block) ------- */

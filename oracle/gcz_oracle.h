@@ -99,6 +99,8 @@ int64_t   orc_get_rs(const orc_gssa*, int64_t pos);                /* HSWT.getRS
 /* backward search GSSA.search :187-197; returns number of RankedWTNode.count calls made */
 int64_t   orc_search(orc_gssa*, const uint8_t* pat, int64_t len, int64_t* sp, int64_t* ep);
 int64_t   orc_locate(orc_gssa*, int64_t row);               /* GSSA.locate :241-251 */
+int64_t   orc_index_find(orc_gssa*, int64_t pos);           /* GSSAIndex.find  algo/ssa/GSSAIndex.java:184-187 */
+int64_t   orc_extract(orc_gssa*, int32_t nstr, int64_t from, uint8_t* out, int64_t cap);   /* GSSA.extract :90-126 */
 /* GSSA.find :160-185.  Returns total hits k (0 == Java null).  positions (cap ints) receives the
  * per-string relative positions concatenated in string order; per_string[ns] the counts. */
 int64_t   orc_find(orc_gssa*, const uint8_t* pat, int64_t len,

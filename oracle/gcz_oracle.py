@@ -87,6 +87,8 @@ def lib():
             "orc_get_rs": (i64, [P, i64]),
             "orc_search": (i64, [P, P, i64, P, P]),
             "orc_locate": (i64, [P, i64]),
+            "orc_index_find": (i64, [P, i64]),
+            "orc_extract": (i64, [P, C.c_int32, i64, P, i64]),
             "orc_find": (i64, [P, P, i64, P, P, i64]),
             "orc_search_batch": (i64, [P, P, P, i64, P, P]),
             "orc_rank_calls": (C.c_uint64, []),
@@ -343,6 +345,19 @@ class GSSA:
 
     def locate(self, row: int) -> int:
         return int(lib().orc_locate(self.h, row))
+
+    def index_find(self, pos: int) -> int:
+        return int(lib().orc_index_find(self.h, pos))
+
+    def extract(self, nstr: int, start: int, cap: int) -> np.ndarray:
+        """GSSA.extract into a fresh buffer of `cap` bytes: the bytes written (string nstr from `start`)."""
+        out = np.zeros(max(cap, 1), np.uint8)
+        w = int(lib().orc_extract(self.h, nstr, start, _p(out), cap))
+        if w == -(1 << 63):
+            raise IndexError(f"String index {nstr} is out of bound")
+        if w < 0:
+            raise ValueError("newPosition < 0")            # IllegalArgumentException from buf.position(bpos + 1)
+        return out[:w].copy()
 
     def find(self, pat: bytes):
         """GSSA.find: list (per string) of ascending relative positions, or None when no hit."""

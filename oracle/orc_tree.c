@@ -352,6 +352,14 @@ static int64_t gssa_locate(const orc_gssa* g, int64_t idx) {
     return sa + len;
 }
 
+/* GSSAIndex.find  algo/ssa/GSSAIndex.java:184-187: the suffix-array row that holds text position idx (sampled ones only) */
+static int64_t gssa_index_find(const orc_gssa* g, int64_t idx) {
+    const jlong sidx = j_lshr(idx, g->sampling_factor);
+    return idx == j_lshl(sidx, g->sampling_factor)
+        ? orc_ranked_find_one(g->rank, g->tree.length, iwt_find(&g->wsa, sidx) + 1)
+        : (int64_t)INT32_MIN;
+}
+
 static int cmp_jlong2(const void* a, const void* b) {
     const jlong x = *(const jlong*)a, y = *(const jlong*)b;
     return x < y ? -1 : (x > y ? 1 : 0);
@@ -493,3 +501,29 @@ int64_t orc_find(orc_gssa* g, const uint8_t* pat, int64_t len,
     free(sa);
     return w;
 }
+
+/* GSSA.extract(ByteBuffer buf, int nstr, long from)  algo/ssa/GSSA.java:90-126 with buf.position() == 0 and
+ * buf.remaining() == cap.  Returns the new buffer position (= bytes written; negative where Java's
+ * buf.position(bpos + 1) throws IllegalArgumentException), or INT64_MIN for a bad string index. */
+int64_t orc_extract(orc_gssa* g, int32_t nstr, int64_t from, uint8_t* out, int64_t cap) {
+    if (nstr < 0 || nstr >= g->ne) return INT64_MIN;
+    if (nstr > 0) from += g->e[nstr - 1] + 1;                                 /* :97-100 */
+    const jlong lim = from + cap;
+    jlong pos = (g->e[nstr] < lim ? g->e[nstr] : lim) - 1;                     /* :104 */
+    const jlong sapos = j_lshl(j_lshr(pos, g->sampling_factor) + 1, g->sampling_factor);   /* :107 */
+    jlong idx = sapos < g->tree.length ? gssa_index_find(g, sapos) : 0;       /* :110 */
+    jlong n = (sapos < g->tree.length - 1 ? sapos : g->tree.length - 1) - pos; /* :113 */
+    while (--n > 0) {
+        const jlong rs = hswt_get_rs(&g->tree, idx);
+        idx = (jint)(g->c[(jint)rs] + j_lushr(rs, 32));
+    }
+    const jint bpos = (jint)(pos - from);                                     /* :119 */
+    for (jint i = bpos; i >= 0; i--) {
+        const jlong rs = hswt_get_rs(&g->tree, idx);
+        out[i] = (uint8_t)(rs & 0xFF);
+        idx = (jint)(g->c[(jint)rs] + j_lushr(rs, 32));
+    }
+    return (int64_t)bpos + 1;
+}
+
+int64_t orc_index_find(orc_gssa* g, int64_t pos) { return gssa_index_find(g, pos); }

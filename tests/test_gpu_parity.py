@@ -503,3 +503,79 @@ def test_simple_gff_generator(G, O, tmp_path):
     got = geco_match.search(tmp_path / "g.gcz", fa)
     assert got == exp
     assert any("\t-\t" in x for x in got) and any("\t+\t" in x for x in got) and len(got) > 10
+
+
+# ---- extract (GSSA.extract, GSSAIndex.find, IndexWaveletTree.find, select) and GecoRead -----------------------------------
+def test_extract_single_string(G, O):
+    from gecoz_b200 import synth
+    seq = synth.chromosome_shaped(300_000, 9)
+    text = synth.block_of([seq])
+    ref = O.build_block(text, 32)
+    g = G.GSSA.open(0, ref["gcz_body"], len(text), ref["gcx_body"])
+    og = O.GSSA(ref["gcz_body"], len(text), ref["gcx_body"])
+    rng = np.random.default_rng(3)
+    cases = [(0, len(seq)), (0, len(seq) + 100), (0, 1), (31, 2), (32, 32), (33, 31), (len(seq) - 1, 5), (len(seq) - 40, 40),
+             (12345, 70_000)] + [(int(a), int(b)) for a, b in zip(rng.integers(0, len(seq), 20), rng.integers(1, 5000, 20))]
+    for start, cap in cases:
+        got = g.extract(0, start, cap)
+        exp = og.extract(0, start, cap)
+        assert np.array_equal(got, exp), (start, cap)
+        assert np.array_equal(got, seq[start:start + cap])                 # single-string blocks extract exactly
+    with pytest.raises(IndexError):
+        g.extract(1, 0, 10)
+    g.close()
+
+
+@pytest.mark.parametrize("rate", [32, 4])
+def test_extract_merged_block_like_the_reference(G, O, rate):
+    """Merged block: calls whose walk starts beyond the string end cross a separator the LF mapping gets wrong
+     — the bytes must be the reference's (the oracle's literal walk), right or wrong."""
+    from gecoz_b200 import synth
+    seqs = [synth.iid_acgtn(5000, 31), synth.iid_acgtn(3000, 32), synth.iid_acgtn(2987, 33), synth.iid_acgtn(19, 34),
+            synth.iid_acgtn(64, 35), synth.iid_acgtn(1, 36)]
+    seqs[0][:4] = np.frombuffer(b"TTTT", np.uint8)
+    text = synth.block_of(seqs)
+    ref = O.build_block(text, rate)
+    g = G.GSSA.open(0, ref["gcz_body"], len(text), ref["gcx_body"])
+    og = O.GSSA(ref["gcz_body"], len(text), ref["gcx_body"])
+    differs = 0
+    for nstr, s in enumerate(seqs):
+        for start, cap in ((0, len(s) + 10), (0, len(s)), (0, 100), (17, 64), (max(len(s) - 5, 0), 100), (len(s) // 2, 1), (0, 31)):
+            if start >= len(s):
+                continue
+            try:
+                exp = og.extract(nstr, start, cap)
+            except ValueError:                                              # Java: IllegalArgumentException
+                with pytest.raises(G.GczError):
+                    g.extract(nstr, start, cap)
+                differs += 1
+                continue
+            got = g.extract(nstr, start, cap)
+            assert np.array_equal(got, exp), (nstr, start, cap)
+            differs += not np.array_equal(got, s[start:start + cap])
+    assert differs > 0 or rate != 32                                        # the quirk is exercised at rate 32
+    g.close()
+
+
+def test_geco_read_fasta_and_sequence(G, O, tmp_path):
+    from gecoz_b200 import geco_read
+    recs, info = _small_genome(tmp_path, G)
+    blocks = _oracle_blocks(O, recs, info)
+    n = geco_read.fasta(tmp_path / "g.gcz", tmp_path / "out.fa")
+    assert n == len(recs)
+    exp = b""
+    for headers, og in blocks:
+        for nstr, h in enumerate(headers):
+            length = int(og.string_ends()[nstr] - (og.string_ends()[nstr - 1] + 1 if nstr else 0))
+            seq = og.extract(nstr, 0, 4 * 1024 * 1024)[:length]
+            body = bytearray()
+            for i in range(0, length, 50):
+                body += seq[i:i + 50].tobytes() + b"\n"
+            if length % 50 == 0:
+                body += b"\n"
+            exp += b">" + h.encode() + b"\n" + bytes(body)
+    assert (tmp_path / "out.fa").read_bytes() == exp
+    hdr, seq = recs[1]
+    assert geco_read.sequence(tmp_path / "g.gcz", hdr, 100, 1100, tmp_path / "sub.bin") == 1000
+    blk = next(b for b in blocks if hdr in b[0])
+    assert (tmp_path / "sub.bin").read_bytes() == blk[1].extract(blk[0].index(hdr), 100, 1000).tobytes()

@@ -283,3 +283,21 @@ def test_write_files_two_blocks():
     assert gcz.count(b"GecozBWT") == 2 and gcx.count(b"GecozSSA") == 2
     size0 = int.from_bytes(gcz[9:17], "little")
     assert gcz[size0:size0 + 8] == b"GecozBWT"
+
+
+# ---- extract (GSSA.extract :90-126, GSSAIndex.find :184-187) ------------------------------------------------------------
+def test_oracle_extract_and_index_find():
+    from gecoz_b200 import synth
+    seq = synth.chromosome_shaped(40_000, 5)
+    text = synth.block_of([seq])
+    r = O.build_block(text, 32, want_sa=True)
+    g = O.GSSA(r["gcz_body"], len(text), r["gcx_body"])
+    isa = np.zeros(len(text), np.int64)
+    isa[r["sa"]] = np.arange(len(text))
+    for p in (0, 32, 64, 4096, 39_968, 40_000):                  # sampled positions (40 000 is the separator)
+        assert g.index_find(p) == isa[p]
+    assert g.index_find(33) == -(1 << 31)                        # Integer.MIN_VALUE for an unsampled position
+    for start, cap in ((0, 40_000), (0, 50_000), (0, 1), (31, 2), (39_990, 100), (12_345, 6_789)):
+        assert np.array_equal(g.extract(0, start, cap), seq[start:start + cap])
+    with pytest.raises(IndexError):
+        g.extract(1, 0, 5)
