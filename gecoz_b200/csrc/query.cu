@@ -124,11 +124,61 @@ __device__ __forceinline__ long long hswt_occ(const QueryTables* __restrict__ t,
     return pos;
 }
 
+// ones in [0, off] of one loaded rank sector
+__device__ __forceinline__ uint32_t sector_rank_at(const uint32_t (&w)[8], uint32_t off) {
+    const uint32_t wi = off >> 5, bi = off & 31;
+    uint32_t r = w[0], cur = 0;
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+        r += (uint32_t)k < wi ? __popc(w[1 + k]) : 0u;
+        cur = (uint32_t)k == wi ? w[1 + k] : cur;
+    }
+    return r + __popc(cur << (31 - bi));
+}
+
+// The two occ() of one backward-search step, occ(symbol, p1) and occ(symbol, p2) with p1 <= p2, walking the
+// symbol's path once: on every node the two positions usually fall into the same rank sector (always, once the
+// interval has shrunk to a few suffixes), and that sector is loaded once.
+__device__ __forceinline__ void hswt_occ2(const QueryTables* __restrict__ t, const uint32_t* __restrict__ sectors,
+                                          int symbol, long long& p1, long long& p2) {
+    const int len = t->len[symbol];
+    if (len == 0) { p1 = -1; p2 = -1; return; }
+    const unsigned code = t->code[symbol];
+    for (int d = 0; d < len && p2 >= 0; d++) {
+        const uint64_t s0 = t->node_sector0[t->node_of[symbol][d]];
+        const bool one = (code >> d) & 1u;
+        const uint32_t q2 = (uint32_t)p2, sec2 = q2 / kSectorBits;
+        uint32_t w[8];
+        {
+            const uint4* p = reinterpret_cast<const uint4*>(sectors + (s0 + sec2) * 8);
+            const uint4 a = __ldg(p), b = __ldg(p + 1);
+            w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+        }
+        const uint32_t r2 = sector_rank_at(w, q2 - sec2 * kSectorBits);
+        if (p1 >= 0) {
+            const uint32_t q1 = (uint32_t)p1, sec1 = q1 / kSectorBits;
+            uint32_t r1;
+            if (sec1 == sec2) {
+                r1 = sector_rank_at(w, q1 - sec1 * kSectorBits);
+            } else {
+                r1 = sector_bit_rank(sectors, s0, q1).rank;
+            }
+            p1 = one ? (long long)r1 - 1 : p1 - (long long)r1;
+        }
+        p2 = one ? (long long)r2 - 1 : p2 - (long long)r2;
+    }
+    if (p2 < 0) p1 = -1;                                   // p1 <= p2 throughout
+}
+
 // ---- count: backward search ---------------------------------------------------------------------------------
+// Patterns differ in length (15..100 symbols) and half of a typical batch dies after ~14 steps, so a lane per pattern
+// would idle most of the time.  Lanes are refilled instead: a lane that finishes its pattern takes the next one from its
+// warp's reservation (64 patterns per atomic on the global counter), and every trip of the loop is one backward-search
+// step for all 32 lanes.
 __global__ void __launch_bounds__(256)
 count_kernel(const QueryTables* __restrict__ tables, const uint32_t* __restrict__ sectors,
              const uint8_t* __restrict__ pats, const int64_t* __restrict__ pat_off, int64_t n_pats,
-             int64_t* __restrict__ sp_out, int64_t* __restrict__ ep_out) {
+             int64_t* __restrict__ sp_out, int64_t* __restrict__ ep_out, unsigned long long* __restrict__ next_pattern) {
     __shared__ QueryTables t;
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
@@ -136,25 +186,60 @@ count_kernel(const QueryTables* __restrict__ tables, const uint32_t* __restrict_
         for (int i = threadIdx.x; i < (int)(sizeof(QueryTables) / 4); i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_pats; q += stride) {
-        const int64_t b = pat_off[q], e = pat_off[q + 1];
-        long long sp = 0, ep = -1;
-        if (e > b) {
-            int ch = pats[e - 1];
-            if (ch < 128) {                                  // the reference indexes c[] with a signed byte
-                sp = t.c[ch];
-                ep = (ch < 255 ? t.c[ch + 1] : t.n) - 1;
-                for (int64_t i = e - 2; sp <= ep && i >= b; i--) {
-                    ch = pats[i];
-                    if (ch >= 128) { sp = 0; ep = -1; break; }
-                    sp = t.c[ch] + hswt_occ(&t, sectors, ch, sp - 1) + 1;
-                    ep = t.c[ch] + hswt_occ(&t, sectors, ch, ep);
+    constexpr int kReserve = 64;
+    const unsigned lane = lane_id(), lt = lanemask_lt();
+    long long wnext = 0, wend = 0;                       // the warp's reservation [wnext, wend), uniform across lanes
+    long long q = -1, i = 0, b = 0, sp = 0, ep = -1;     // q: my pattern, -1 = none
+    bool drained = false;                                // the global counter ran past n_pats
+    while (true) {
+        // hand patterns to the idle lanes
+        unsigned idle = __ballot_sync(0xffffffffu, q < 0);
+        while (idle && !drained) {
+            if (wnext >= wend) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(next_pattern, (unsigned long long)kReserve);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                wnext = (long long)base;
+                wend = min((long long)base + kReserve, (long long)n_pats);
+                if (wnext >= wend) { drained = true; break; }
+            }
+            const long long mine = wnext + __popc(idle & lt);
+            if (q < 0 && mine < wend) {
+                q = mine;
+                b = pat_off[q];
+                const long long e = pat_off[q + 1];
+                sp = 0; ep = -1; i = b - 1;              // empty pattern / byte >= 0x80: reported as not found
+                if (e > b) {
+                    const int ch = pats[e - 1];
+                    if (ch < 128) {                      // the reference indexes c[] with a signed byte
+                        sp = t.c[ch];
+                        ep = (ch < 255 ? t.c[ch + 1] : t.n) - 1;
+                        i = e - 2;
+                    }
                 }
             }
+            wnext = min(wend, wnext + (long long)__popc(idle));
+            idle = __ballot_sync(0xffffffffu, q < 0);
         }
-        sp_out[q] = sp;
-        ep_out[q] = ep;
+        if (__ballot_sync(0xffffffffu, q >= 0) == 0) break;
+        if (q >= 0) {
+            if (sp <= ep && i >= b) {                    // GSSA.search :193-196, one symbol
+                const int ch = pats[i];
+                if (ch >= 128) {
+                    sp = 0; ep = -1;
+                } else {
+                    long long o1 = sp - 1, o2 = ep;
+                    hswt_occ2(&t, sectors, ch, o1, o2);
+                    sp = t.c[ch] + o1 + 1;
+                    ep = t.c[ch] + o2;
+                }
+                i--;
+            } else {
+                sp_out[q] = sp;
+                ep_out[q] = ep;
+                q = -1;
+            }
+        }
     }
 }
 
@@ -586,7 +671,11 @@ int count_batch(gcz_index* idx, const uint8_t* pats, const int64_t* pat_off, int
     int64_t* d_ep = out_dev ? ep : ctx->arena.get<int64_t>((size_t)n_pats);
     if (!d_sp || !d_ep) return fail(GCZ_E_NOMEM, "query staging");
 
-    GCZ_LAUNCH(ctx, count_kernel, launch_grid(ctx, n_pats, 256), 256, 0, st, idx->d_tables, idx->d_sectors, d_pats, d_off, n_pats, d_sp, d_ep);
+    unsigned long long* d_next = ctx->arena.get<unsigned long long>(1);
+    if (!d_next) return fail(GCZ_E_NOMEM, "query staging");
+    GCZ_CUDA(cudaMemsetAsync(d_next, 0, 8, st));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_pats + 255) / 256, (int64_t)ctx->sm_count * 8));
+    GCZ_LAUNCH(ctx, count_kernel, grid, 256, 0, st, idx->d_tables, idx->d_sectors, d_pats, d_off, n_pats, d_sp, d_ep, d_next);
     if (!out_dev) {
         GCZ_CUDA(cudaMemcpyAsync(sp, d_sp, (size_t)n_pats * 8, cudaMemcpyDeviceToHost, st));
         GCZ_CUDA(cudaMemcpyAsync(ep, d_ep, (size_t)n_pats * 8, cudaMemcpyDeviceToHost, st));

@@ -188,6 +188,34 @@ def _shard_patterns(data, off, lo: int, hi: int):
     return sdata, np.ascontiguousarray(off[lo:hi + 1] - b)
 
 
+def count_totals_sharded(gssas: Sequence, data, off, *, rank: int = 0, world: int = 1, group=None, device=None):
+    """Occurrences of every pattern summed over all blocks (what `gecotools -c PATTERN` logs as "total found",
+    tools/GecoMatch.java:110-133), query-sharded: int64[n_patterns] on rank 0, None elsewhere.  On a CUDA `device`
+    the shard is uploaded once, searched against every block there, reduced there, and 8 bytes per pattern come
+    back."""
+    n = len(off) - 1
+    lo, hi = shard_bounds(n, world)[rank]
+    sdata, soff = _shard_patterns(data, off, lo, hi)
+    if device is not None and str(device).startswith("cuda") and hi > lo:
+        import torch
+        t_data, t_off = torch.from_numpy(sdata).to(device), torch.from_numpy(soff).to(device)
+        sp = torch.empty(hi - lo, dtype=torch.int64, device=device)
+        ep = torch.empty(hi - lo, dtype=torch.int64, device=device)
+        tot = torch.zeros(hi - lo, dtype=torch.int64, device=device)
+        for g in gssas:
+            g.count_batch(packed=(t_data, t_off), out=(sp, ep))
+            tot += (ep - sp + 1).clamp_(min=0)
+        local = tot.cpu().numpy()
+    else:
+        local = np.zeros(hi - lo, dtype=np.int64)
+        for g in gssas:
+            if hi > lo:
+                sp, ep = g.count_batch(packed=(sdata, soff))
+                local += np.maximum(np.asarray(ep) - np.asarray(sp) + 1, 0)
+    parts = gather_varlen(local, rank=rank, world=world, group=group, device=device)
+    return None if parts is None else np.concatenate(parts)
+
+
 def count_sharded(gssas: Sequence, data, off, *, rank: int = 0, world: int = 1, group=None, device=None):
     """Backward-search intervals of a packed pattern batch against every block, query-sharded.
 

@@ -99,7 +99,9 @@ def main():
                 gssas.append(G.GSSA.open(rank, r["gcz_body"], len(t), r["gcx_body"]))
             c = sharding.count_sharded(gssas, data, off, rank=rank, world=world, device=device)
             f = sharding.find_sharded(gssas, data, off, rank=rank, world=world, device=device)
+            tot = sharding.count_totals_sharded(gssas, data, off, rank=rank, world=world, device=device)
             if rank == 0:
+                assert np.array_equal(tot, np.maximum(c[1] - c[0] + 1, 0).sum(axis=0))
                 np.savez(out_dir / "query.npz", sp=c[0], ep=c[1],
                          **{f"per{b}": x[0] for b, x in enumerate(f)}, **{f"pos{b}": x[1] for b, x in enumerate(f)},
                          **{f"off{b}": x[2] for b, x in enumerate(f)})
@@ -111,7 +113,9 @@ def main():
             gssas = [OracleGSSA(t) for t in texts]
             c = sharding.count_sharded(gssas, data, off, rank=rank, world=world)
             f = sharding.find_sharded(gssas, data, off, rank=rank, world=world)
+            tot = sharding.count_totals_sharded(gssas, data, off, rank=rank, world=world)
             if rank == 0:
+                assert np.array_equal(tot, np.maximum(c[1] - c[0] + 1, 0).sum(axis=0))
                 np.savez(out_dir / "query.npz", sp=c[0], ep=c[1],
                          **{f"per{b}": x[0] for b, x in enumerate(f)}, **{f"pos{b}": x[1] for b, x in enumerate(f)},
                          **{f"off{b}": x[2] for b, x in enumerate(f)})
