@@ -178,7 +178,8 @@ def main() -> None:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=4))
     steps, warm = max(1, args.steps), max(3, args.warmup)
 
     def barrier():
@@ -303,24 +304,35 @@ def main() -> None:
         else:
             r_gcz, r_gcx, n0 = d_gcz, d_gcx, n
         g = G.GSSA.open(local_rank, r_gcz, n0, r_gcx)
-        npat = max(1000, args.patterns) * world
+        per_rank = max(1000, args.patterns)
+        npat = per_rank * world
         lo, hi = sharding.shard_bounds(npat, world)[rank]
-        width = sharding.shard_bounds(npat, world)[0][1]
-        if world > 1:                                     # every rank needs the same batch: rank 0 draws it
+        width = per_rank
+        # the batch is drawn shard by shard on rank 0 (it holds the text the index was built from; a shard is 4 M
+        # patterns, so no rank ever materialises the whole batch) and shard r goes to rank r
+        if world > 1:
+            meta = torch.zeros(1, dtype=torch.int64, device=dev)
             if rank == 0:
-                pdata, poff = synth.patterns(text, npat, 15, 100, seed=5)
-                tot = torch.tensor([len(pdata)], dtype=torch.int64, device=dev)
+                keep = None
+                for r in range(world - 1, -1, -1):
+                    sd, so = synth.patterns(text, per_rank, 15, 100, seed=5 + r)
+                    if r == 1:
+                        keep = (sd, so)                   # shard 1 is checked against rank 0's own search below
+                    if r > 0:
+                        meta[0] = len(sd)
+                        dist.send(meta, r)
+                        dist.send(torch.from_numpy(sd).to(dev), r)
+                        dist.send(torch.from_numpy(so).to(dev), r)
+                sdata, soff = sd, so
             else:
-                tot = torch.zeros(1, dtype=torch.int64, device=dev)
-            dist.broadcast(tot, 0)
-            t_data = torch.from_numpy(pdata).to(dev) if rank == 0 else torch.empty(int(tot.item()), dtype=torch.uint8, device=dev)
-            t_off = torch.from_numpy(poff).to(dev) if rank == 0 else torch.empty(npat + 1, dtype=torch.int64, device=dev)
-            dist.broadcast(t_data, 0)
-            dist.broadcast(t_off, 0)
-            pdata, poff = t_data.cpu().numpy(), t_off.cpu().numpy()
+                dist.recv(meta, 0)
+                t_data = torch.empty(int(meta.item()), dtype=torch.uint8, device=dev)
+                t_off = torch.empty(per_rank + 1, dtype=torch.int64, device=dev)
+                dist.recv(t_data, 0)
+                dist.recv(t_off, 0)
+                sdata, soff = t_data.cpu().numpy(), t_off.cpu().numpy()
         else:
-            pdata, poff = synth.patterns(text, npat, 15, 100, seed=5)
-        sdata, soff = sharding._shard_patterns(pdata, poff, lo, hi)
+            sdata, soff = synth.patterns(text, per_rank, 15, 100, seed=5)
         hp, ho = torch.from_numpy(sdata).pin_memory(), torch.from_numpy(soff).pin_memory()
         dp, do = hp.to(dev), ho.to(dev)
         d_res = torch.full((2, width), -1, dtype=torch.int64, device=dev)        # row 0 = sp, row 1 = ep
@@ -350,15 +362,15 @@ def main() -> None:
         cms_e2e = max_over_ranks(cms_e2e / 5)
         torch.cuda.synchronize()
         assert torch.equal(h_res[:, :hi - lo], d_res[:, :hi - lo].cpu())
-        if rank == 0 and world > 1:                        # gathered shards == what rank 0 computes for them itself
-            chk_sp, chk_ep = g.count_batch(packed=(pdata, poff))
-            got = torch.cat([p[:, :b - a] for p, (a, b) in zip(parts, sharding.shard_bounds(npat, world))], dim=1).cpu().numpy()
+        if rank == 0 and world > 1:                        # a gathered shard == what rank 0 computes for it itself
+            chk_sp, chk_ep = g.count_batch(packed=keep)
+            got = parts[1].cpu().numpy()
             assert np.array_equal(got[0], chk_sp) and np.array_equal(got[1], chk_ep), "sharded count differs"
         found = int(sum_over_ranks(float((d_res[1, :hi - lo] >= d_res[0, :hi - lo]).sum().item())))
         count = {"metric": "count queries/s (backward-search intervals)", "value": npat / (cms / 1e3), "unit": "queries/s",
                  "patterns": int(npat), "pattern_length": "uniform 15..100, 50% text-sampled / 50% random", "found": found,
                  "ms_per_batch": cms, "sharding": f"{world} contiguous shard(s), replicated index" + (", one NCCL gather to rank 0" if world > 1 else ""),
-                 "e2e": {"value": npat / (cms_e2e / 1e3), "unit": "queries/s", "h2d_bytes_per_step": int(pdata.nbytes + poff.nbytes),
+                 "e2e": {"value": npat / (cms_e2e / 1e3), "unit": "queries/s", "h2d_bytes_per_step": int((sdata.nbytes + soff.nbytes) * world),
                          "d2h_bytes_per_step": int(npat * 16)}}
 
         # ---- locate leg (rank 0's shard only at N>1 is not the point: every rank runs its shard, no gather timed) ----
