@@ -152,3 +152,37 @@ def test_synthetic_workloads_are_seeded():
     d2, o2 = synth.patterns(a, 1000, 15, 100, seed=5)
     assert np.array_equal(d1, d2) and np.array_equal(o1, o2) and set(np.unique(d1)) <= set(b"ACGT")
     assert len(synth.hg38_shaped_records(1e-5)) == 25
+
+
+# ---- callers' host logic (no device needed) ---------------------------------------------------------------------------
+def test_gff_attribute_column_follows_java_split():
+    """String.split("\\|") drops trailing empty strings (tools/SimpleGFFGenerator.java:146-154)."""
+    from gecoz_b200.geco_match import _attributes
+    assert _attributes("abc") == "ID=abc"
+    assert _attributes("a|b|c") == "ID=a;Note=b;Note=c"
+    assert _attributes("a||") == "ID=a"
+    assert _attributes("|a") == "ID=;Note=a"
+    assert _attributes("") == "ID="
+    assert _attributes("|") == ""
+
+
+def test_pattern_file_records(tmp_path):
+    """The record loop of SimpleGFFGenerator.search :59-86: '>' / '@' open, '+' closes, empty records are dropped."""
+    from gecoz_b200.geco_match import read_patterns
+    p = tmp_path / "p.fq"
+    p.write_bytes(b"ignored before any header\n>r1 desc\nACGT\r\nAC\n>empty\n@r2\nGGU\n+\nIII\n@IIIquality-looking header\nTT\n>r3\n\nA\n")
+    assert list(read_patterns(p)) == [("r1 desc", b"ACGTAC"), ("r2", b"GGU"), ("IIIquality-looking header", b"TT"), ("r3", b"A")]
+
+
+def test_fasta_record_layout():
+    """fasta/FastaFileWriter.java:132-215 for a multi-line sequence: a break after every 50 symbols and one more."""
+    from gecoz_b200.geco_read import fasta_record_bytes
+    for n in (49, 50, 51, 100, 149, 150):
+        seq = np.frombuffer(bytes((65 + i % 4) for i in range(n)), np.uint8)
+        rec = fasta_record_bytes("h d", seq)
+        assert rec.startswith(b">h d\n")
+        body = rec[len(b">h d\n"):]
+        assert len(body) == n + n // 50 + 1
+        lines = body.split(b"\n")
+        assert b"".join(lines) == seq.tobytes()
+        assert all(len(x) == 50 for x in lines[:n // 50])
