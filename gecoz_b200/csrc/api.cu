@@ -68,6 +68,8 @@ int get_ctx(int device, DeviceCtx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     GCZ_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     GCZ_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    GCZ_CUDA(cudaStreamCreateWithFlags(&ctx->stage_stream, cudaStreamNonBlocking));
+    GCZ_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->stage_counts), 256 * 8));
     GCZ_CUDA(cudaEventCreateWithFlags(&ctx->copy_event, cudaEventDisableTiming));
     *out = ctx.get();
     g_ctx[device] = std::move(ctx);
@@ -87,7 +89,9 @@ void destroy_all_ctx() {
         if (kv.second->own_stream) cudaStreamDestroy(kv.second->own_stream);
         if (kv.second->copy_stream) cudaStreamDestroy(kv.second->copy_stream);
         if (kv.second->copy_event) cudaEventDestroy(kv.second->copy_event);
-        if (kv.second->staged_dev) cudaFree(kv.second->staged_dev);
+        if (kv.second->stage_stream) cudaStreamDestroy(kv.second->stage_stream);
+        if (kv.second->stage_counts) cudaFree(kv.second->stage_counts);
+        for (auto& slot : kv.second->staged) if (slot.dev) cudaFree(slot.dev);
     }
     g_ctx.clear();
 }
@@ -136,37 +140,74 @@ static int histogram_device(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_te
     return GCZ_OK;
 }
 
+// 64 bytes of a host text at fixed places: a staged copy is only used for a buffer that still shows the same bytes
+// (a buffer freed and reallocated at the same address with the same length must not find the old text)
+constexpr int64_t kStageChunk = 4 << 20;
+
+static void text_probe(const uint8_t* text, int64_t n, uint8_t out[64]) {
+    for (int i = 0; i < 64; i++) out[i] = text[(int64_t)((__int128)(n - 1) * i / 63)];
+}
+
 static int count_symbols(int device, const uint8_t* text, int64_t n, int64_t counts[256]) {
     if (!text || !counts || n <= 0) return fail(GCZ_E_ARG, "count_symbols arguments");
     DeviceCtx* ctx = nullptr;
     GCZ_TRY(get_ctx(device, &ctx));
-    std::lock_guard<std::mutex> lock(ctx->mu);
-    GCZ_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = stream_of(ctx);
-    ctx->arena.reset();
-    const bool on_dev = is_device_ptr(text);
-    if (ctx->arena.capacity < (1 << 20)) GCZ_TRY(ctx->arena.reserve(1 << 20));
-    const uint8_t* d_text = text;
-    if (!on_dev) {
-        // the upload is kept: the gcz_build_block that follows on the same host buffer finds the text on the device
-        ctx->staged_host = nullptr;
-        if (ctx->staged_cap < (size_t)n + 64) {
-            if (ctx->staged_dev) cudaFree(ctx->staged_dev);
-            ctx->staged_dev = nullptr; ctx->staged_cap = 0;
-            const size_t want = ((size_t)n + 64 + ((size_t)1 << 20)) & ~(((size_t)1 << 20) - 1);
-            cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ctx->staged_dev), want);
-            if (e != cudaSuccess) { cudaGetLastError(); ctx->staged_dev = nullptr; return fail(GCZ_E_NOMEM, "text staging of %zu bytes", want); }
-            ctx->staged_cap = want;
-        }
-        GCZ_CUDA(cudaMemcpyAsync(ctx->staged_dev, text, (size_t)n, cudaMemcpyHostToDevice, st));
-        d_text = ctx->staged_dev;
+    if (is_device_ptr(text)) {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        GCZ_CUDA(cudaSetDevice(ctx->device));
+        cudaStream_t st = stream_of(ctx);
+        ctx->arena.reset();
+        if (ctx->arena.capacity < (1 << 20)) GCZ_TRY(ctx->arena.reserve(1 << 20));
+        unsigned long long* d_counts = ctx->arena.get<unsigned long long>(256);
+        if (!d_counts) return fail(GCZ_E_NOMEM, "histogram scratch");
+        GCZ_TRY(histogram_device(ctx, st, text, n, d_counts));
+        GCZ_CUDA(cudaMemcpyAsync(counts, d_counts, 256 * 8, cudaMemcpyDeviceToHost, st));
+        GCZ_CUDA(cudaStreamSynchronize(st));
+        return GCZ_OK;
     }
-    unsigned long long* d_counts = ctx->arena.get<unsigned long long>(256);
-    if (!d_counts) return fail(GCZ_E_NOMEM, "histogram scratch");
-    GCZ_TRY(histogram_device(ctx, st, d_text, n, d_counts));
-    GCZ_CUDA(cudaMemcpyAsync(counts, d_counts, 256 * 8, cudaMemcpyDeviceToHost, st));
+    // host text: the upload is kept in one of two slots, so that the gcz_build_block that follows on the same host
+    // buffer finds the text on the device — and this call may overlap the build of the previous block.
+    // stage_io_mu: one staging at a time (stream, counters); stage_mu: slot bookkeeping only, never held across a copy.
+    std::lock_guard<std::mutex> io(ctx->stage_io_mu);
+    GCZ_CUDA(cudaSetDevice(ctx->device));
+    struct Filling {
+        DeviceCtx* ctx; DeviceCtx::StagedText* slot = nullptr; bool done = false;
+        ~Filling() { if (slot && !done) { std::lock_guard<std::mutex> l(ctx->stage_mu); slot->state = 0; slot->host = nullptr; } }
+    } fill{ctx};
+    {
+        std::lock_guard<std::mutex> l(ctx->stage_mu);
+        DeviceCtx::StagedText* slot = nullptr;
+        for (auto& c : ctx->staged) if (c.state == 0) { slot = &c; break; }
+        if (!slot) for (auto& c : ctx->staged) if (c.state == 1 && (!slot || c.stamp < slot->stamp)) slot = &c;
+        if (!slot) return fail(GCZ_E_INTERNAL, "both text slots are in use by builds");
+        slot->state = 3;                                      // being filled: nobody else looks at it
+        slot->host = nullptr;
+        fill.slot = slot;
+    }
+    DeviceCtx::StagedText* slot = fill.slot;
+    if (slot->cap < (size_t)n + 64) {
+        if (slot->dev) cudaFree(slot->dev);
+        slot->dev = nullptr; slot->cap = 0;
+        const size_t want = ((size_t)n + 64 + ((size_t)1 << 20)) & ~(((size_t)1 << 20) - 1);
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&slot->dev), want);
+        if (e != cudaSuccess) { cudaGetLastError(); slot->dev = nullptr; return fail(GCZ_E_NOMEM, "text staging of %zu bytes", want); }
+        slot->cap = want;
+    }
+    cudaStream_t st = ctx->stage_stream;
+    // in pieces: the small uploads of a build running on the other stream share the copy engine and must not
+    // queue behind one transfer of the whole text
+    for (int64_t off = 0; off < n; off += kStageChunk) {
+        GCZ_CUDA(cudaMemcpyAsync(slot->dev + off, text + off, (size_t)std::min<int64_t>(kStageChunk, n - off), cudaMemcpyHostToDevice, st));
+    }
+    GCZ_TRY(histogram_device(ctx, st, slot->dev, n, ctx->stage_counts));
+    GCZ_CUDA(cudaMemcpyAsync(counts, ctx->stage_counts, 256 * 8, cudaMemcpyDeviceToHost, st));
     GCZ_CUDA(cudaStreamSynchronize(st));
-    if (!on_dev) { ctx->staged_host = text; ctx->staged_n = n; }
+    {
+        std::lock_guard<std::mutex> l(ctx->stage_mu);
+        slot->host = text; slot->n = n; slot->state = 1; slot->stamp = ++ctx->stage_clock;
+        text_probe(text, n, slot->probe);
+        fill.done = true;
+    }
     return GCZ_OK;
 }
 
@@ -190,8 +231,24 @@ static int build_block(int device, const uint8_t* text, int64_t n, int32_t sampl
     const int64_t launches0 = ctx->launches;
     std::memset(&t_timing, 0, sizeof(t_timing));
 
-    const bool text_staged = ctx->staged_host == text && ctx->staged_n == n && ctx->staged_dev != nullptr;
-    ctx->staged_host = nullptr;                                   // one use: the host buffer may change afterwards
+    // a text staged by gcz_count_symbols for this host buffer is used once (the buffer may change afterwards)
+    struct StageClaim {
+        DeviceCtx* ctx; DeviceCtx::StagedText* slot = nullptr;
+        ~StageClaim() { if (slot) { std::lock_guard<std::mutex> l(ctx->stage_mu); slot->state = 0; slot->host = nullptr; } }
+    } claim{ctx};
+    {
+        std::lock_guard<std::mutex> l(ctx->stage_mu);
+        uint8_t probe[64];
+        bool probed = false;
+        for (auto& c : ctx->staged) {
+            if (c.state != 1 || c.host != text || c.n != n) continue;
+            if (!probed) { text_probe(text, n, probe); probed = true; }
+            if (std::memcmp(probe, c.probe, 64) != 0) { c.state = 0; c.host = nullptr; continue; }     // stale
+            if (!claim.slot || c.stamp < claim.slot->stamp) claim.slot = &c;
+        }
+        if (claim.slot) claim.slot->state = 2;
+    }
+    const bool text_staged = claim.slot != nullptr;
     const bool text_dev = text_staged || is_device_ptr(text), gcz_dev = is_device_ptr(gcz_body), gcx_dev = is_device_ptr(gcx_body);
     const bool sa_dev = sa_out && is_device_ptr(sa_out), bwt_dev = bwt_out && is_device_ptr(bwt_out);
 
@@ -206,7 +263,7 @@ static int build_block(int device, const uint8_t* text, int64_t n, int32_t sampl
     for (auto& e : ev) GCZ_CUDA(cudaEventCreate(&e));
     GCZ_CUDA(cudaEventRecord(ev[0], st));
 
-    const uint8_t* d_text = text_staged ? ctx->staged_dev : text;
+    const uint8_t* d_text = text_staged ? claim.slot->dev : text;
     if (!text_dev) {
         uint8_t* d = arena.get<uint8_t>((size_t)n + 64);
         if (!d) return fail(GCZ_E_NOMEM, "text staging");

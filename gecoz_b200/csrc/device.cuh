@@ -5,6 +5,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <mutex>
 
 namespace gcz {
@@ -50,16 +51,29 @@ struct DeviceCtx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;       // device-to-host copies that overlap the build
     cudaEvent_t  copy_event = nullptr;
-    // text left on the device by gcz_count_symbols for the gcz_build_block that follows on the same host buffer
-    const void*  staged_host = nullptr;
-    int64_t      staged_n = 0;
-    uint8_t*     staged_dev = nullptr;
-    size_t       staged_cap = 0;
+    // Texts left on the device by gcz_count_symbols for the gcz_build_block that follows on the same host buffer.
+    // Two slots and a stream and lock of their own: the upload + histogram of block k + 1 runs while block k is
+    // being built (the build holds `mu`, the staging only `stage_mu`).
+    struct StagedText {
+        const void* host = nullptr;           // key: host buffer and length
+        int64_t     n = 0;
+        uint8_t*    dev = nullptr;
+        size_t      cap = 0;
+        int         state = 0;                // 0 free, 1 staged, 2 in use by a build, 3 being filled
+        uint64_t    stamp = 0;                // staging order (the older staged text is overwritten first)
+        uint8_t     probe[64] = {};           // bytes of the host buffer at fixed places, compared again at build time
+    };
+    std::mutex   stage_mu;                   // slot bookkeeping (short critical sections only)
+    std::mutex   stage_io_mu;                // one staging at a time
+    cudaStream_t stage_stream = nullptr;
+    StagedText   staged[2];
+    uint64_t     stage_clock = 0;
+    unsigned long long* stage_counts = nullptr;   // device, 256 counters
     std::mutex   mu;                          // one build / query batch at a time per device (shared arena)
     Arena        arena;
     void*        pinned = nullptr;            // small pinned scratch for read-backs
     size_t       pinned_bytes = 0;
-    int64_t      launches = 0;                // kernels launched by this library on this device
+    std::atomic<int64_t> launches{0};        // kernels launched by this library on this device
     bool         iwt_attr = false;             // dynamic-smem opt-in done for iwt_low_levels_kernel
     bool         sort_attr[3] = { false, false, false };   // dynamic-smem opt-in done for the onesweep kernels
 };

@@ -154,9 +154,10 @@ def build_block(device: int, text, n: int, sampling_rate: int, shape: N.Shape, g
 class GecozFileWriter:
     """Writes blocks to `ref_path` (.gcz) and `ssa_path` (.gcx).
 
-    `devices` replaces the reference's `threads`: one in-flight block per GPU (the reference runs up to
-    `-t` BlockWriters on a JDK pool).  File offsets are fixed in write() before the block is computed,
-    exactly as in the reference, so blocks may finish in any order.
+    `devices` replaces the reference's `threads`: two blocks in flight per GPU — one being built, the next one
+    being counted, which is also its upload (gcz_count_symbols leaves the text on the device for the build) — where
+    the reference runs up to `-t` BlockWriters on a JDK pool.  File offsets are fixed in write() before the block
+    is computed, exactly as in the reference, so blocks may finish in any order.
     """
 
     def __init__(self, ref_path, ssa_path=None, sampling_rate: int = 32, devices: Sequence[int] = (0,)):
@@ -170,8 +171,8 @@ class GecozFileWriter:
         self._ssa = open(self.ssa_path, "w+b")
         self._ref_pos = 0
         self._ssa_pos = 0
-        self._pool = ThreadPoolExecutor(max_workers=len(self.devices))
-        self._free = list(self.devices)
+        self._pool = ThreadPoolExecutor(max_workers=2 * len(self.devices))
+        self._free = list(self.devices) * 2               # two tokens per device: the library has two text slots
         self._cv = threading.Condition()
         self._jobs: list[Future] = []
         self.timings: list[dict] = []
@@ -218,7 +219,7 @@ class GecozFileWriter:
                     if attempts > 1:
                         raise
                     with self._cv:                       # wait until nothing else is in flight, then retry once
-                        self._cv.wait_for(lambda: len(self._free) == len(self.devices) - 1, timeout=600)
+                        self._cv.wait_for(lambda: len(self._free) == 2 * len(self.devices) - 1, timeout=600)
                 finally:
                     ref_map.close()
                     ssa_map.close()

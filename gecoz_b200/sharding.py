@@ -155,9 +155,15 @@ def sharded_index_records(records: Iterable[tuple[str, object]], opath, xpath=No
     _barrier(world, group)
 
     timings = []
-    with open(opath, "r+b") as fref, open(xpath, "r+b") as fssa:
-        for i in mine:
+    # block k + 1 is uploaded (re-counted: that is what stages its text on the device) while block k is being built
+    from concurrent.futures import ThreadPoolExecutor
+    with open(opath, "r+b") as fref, open(xpath, "r+b") as fssa, ThreadPoolExecutor(1) as stager:
+        staged = stager.submit(engine.symbol_counts, prepared[mine[0]][1]) if mine else None
+        for k, i in enumerate(mine):
             headers, text, shape = prepared.pop(i)
+            staged.result()
+            if k + 1 < len(mine):
+                staged = stager.submit(engine.symbol_counts, prepared[mine[k + 1]][1])
             n = len(text)
             idx_size = index_size(n, sf)
             hdr = GecozRefBlockHeader(headers, GecozRefBlockHeader.block_header_length(headers) + int(shape.size), n)

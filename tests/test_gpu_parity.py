@@ -201,6 +201,20 @@ def test_text_staging_follows_the_buffer(G, O):
     assert np.array_equal(gcz, ref["gcz_body"]) and np.array_equal(gcx, ref["gcx_body"])
 
 
+def test_stale_staged_text_is_not_used(G, O):
+    """A buffer that changed after gcz_count_symbols (or was reallocated at the same address) is uploaded again."""
+    from gecoz_b200 import synth
+    a = synth.cfg2_text(150_000, seed=31)
+    G.symbol_counts(a)                                       # stages the old content under a's address
+    a[:-1] = synth.cfg2_text(150_000, seed=32)[:-1]          # same buffer, new text
+    shape = G.shape_from_counts(np.bincount(a, minlength=256).astype(np.int64))
+    gcz = np.zeros(shape.size, np.uint8)
+    gcx = np.zeros(G.index_size(len(a), 5), np.uint8)
+    G.build_block(0, a, len(a), 32, shape, gcz, gcx)
+    ref = O.build_block(a, 32)
+    assert np.array_equal(gcz, ref["gcz_body"]) and np.array_equal(gcx, ref["gcx_body"])
+
+
 def test_provisional_golden_blocks(G):
     prov = json.loads((GOLD / "provisional_blocks.json").read_text())
     for name, p in prov.items():
