@@ -9,11 +9,11 @@ from .gecoz_file import (GecozFileReader, GecozFileWriter, GecozRefBlockHeader, 
                          index_size, shape_from_counts, symbol_counts)
 from .gssa import GSSA, pack_patterns
 from .geco_index import FastaSequence, GecozRefBlock, index, index_records, merge_blocks, read_fasta
-from . import geco_match, geco_read, sharding
+from . import geco_match, geco_read, native_file, sharding
 
 __all__ = [
     "GczError", "GczFormatError", "GczOutOfMemory", "Shape", "build", "lib",
     "GecozFileReader", "GecozFileWriter", "GecozRefBlockHeader", "GecozSSABlockHeader", "build_block", "index_size",
     "shape_from_counts", "symbol_counts", "GSSA", "pack_patterns",
-    "FastaSequence", "GecozRefBlock", "index", "index_records", "merge_blocks", "read_fasta", "sharding", "geco_match", "geco_read",
+    "FastaSequence", "GecozRefBlock", "index", "index_records", "merge_blocks", "read_fasta", "sharding", "geco_match", "geco_read", "native_file",
 ]

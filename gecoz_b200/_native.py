@@ -78,6 +78,28 @@ EXPORTS = [
     "gcz_dbg_sort_pairs", "gcz_dbg_suffix_array", "gcz_dbg_ranked_vector", "gcz_dbg_index_wavelet_tree",
 ]
 
+# include/gcz_file.h — the native host layer (FASTA records, block planning, .gcz/.gcx writer and reader)
+FILE_EXPORTS = [
+    "gcz_fasta_open", "gcz_fasta_open_buffer", "gcz_fasta_count", "gcz_fasta_record", "gcz_fasta_read", "gcz_fasta_close",
+    "gcz_plan_blocks", "gcz_ref_header_length", "gcz_header_hash", "gcz_ref_header_write", "gcz_ssa_header_write",
+    "gcz_index_fasta",
+    "gcz_reader_open", "gcz_reader_num_blocks", "gcz_reader_block", "gcz_reader_header", "gcz_reader_find",
+    "gcz_reader_sampling_factor", "gcz_reader_open_block", "gcz_reader_close",
+]
+
+COUNT_SYMBOLS_FN = C.CFUNCTYPE(C.c_int, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64))
+BUILD_BLOCK_FN = C.CFUNCTYPE(C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(Shape), C.c_void_p, C.c_int64,
+                             C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p)
+
+
+class Engine(C.Structure):
+    """struct gcz_engine (include/gcz_file.h): the per-block device work; null members = the CUDA entry points."""
+    _fields_ = [("count_symbols", COUNT_SYMBOLS_FN), ("build_block", BUILD_BLOCK_FN)]
+
+
+class IndexReport(C.Structure):
+    _fields_ = [("blocks", C.c_int64), ("sequences", C.c_int64), ("symbols", C.c_int64), ("seconds", C.c_double)]
+
 
 def build(force: bool = False) -> Path:
     """Compile the CUDA sources for sm_100a with nvcc (cross-compiles without a GPU)."""
@@ -135,6 +157,30 @@ def lib() -> C.CDLL:
         "gcz_dbg_index_wavelet_tree": (C.c_int, [C.c_int, P, i64, P]),
     }
     assert sorted(sig) == sorted(EXPORTS)
+    PP = C.POINTER(C.c_char_p)
+    sig.update({
+        "gcz_fasta_open": (C.c_int, [C.c_char_p, C.POINTER(P)]),
+        "gcz_fasta_open_buffer": (C.c_int, [P, i64, C.POINTER(P)]),
+        "gcz_fasta_count": (i64, [P]),
+        "gcz_fasta_record": (C.c_int, [P, i64, PP, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]),
+        "gcz_fasta_read": (C.c_int, [P, i64, P, i64]),
+        "gcz_fasta_close": (None, [P]),
+        "gcz_plan_blocks": (i64, [P, PP, i64, P, P]),
+        "gcz_ref_header_length": (i64, [PP, i32]),
+        "gcz_header_hash": (i64, [PP, i32]),
+        "gcz_ref_header_write": (i64, [PP, i32, i64, i64, P, i64]),
+        "gcz_ssa_header_write": (i64, [PP, i32, i64, P]),
+        "gcz_index_fasta": (C.c_int, [P, C.c_char_p, C.c_char_p, i32, i32, P, C.POINTER(Engine), C.POINTER(IndexReport)]),
+        "gcz_reader_open": (C.c_int, [C.c_char_p, C.POINTER(P)]),
+        "gcz_reader_num_blocks": (i32, [P]),
+        "gcz_reader_block": (C.c_int, [P, i32, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]),
+        "gcz_reader_header": (C.c_char_p, [P, i32, i32]),
+        "gcz_reader_find": (C.c_int, [P, C.c_char_p, C.POINTER(i32), C.POINTER(i32)]),
+        "gcz_reader_sampling_factor": (i32, [P]),
+        "gcz_reader_open_block": (C.c_int, [P, i32, C.c_int, C.POINTER(P)]),
+        "gcz_reader_close": (None, [P]),
+    })
+    assert sorted(sig) == sorted(EXPORTS + FILE_EXPORTS)
     for name, (res, args) in sig.items():
         f = getattr(L, name)
         f.restype = res

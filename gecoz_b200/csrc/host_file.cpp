@@ -1,0 +1,624 @@
+// Native host layer above the C ABI (include/gcz_file.h): FASTA records, block planning, the .gcz/.gcx writer and
+// reader.  C++ counterpart of the reference's host classes for this path — every function cites the Java lines it
+// follows.  No CUDA kernels here; the per-block device work goes through a gcz_engine (default: this library's
+// gcz_count_symbols / gcz_build_block).
+#include "../../include/gcz_file.h"
+#include "gcz_host.h"
+
+#include <cuda_runtime.h>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#define GCZ_TRY_HOST(expr)                  \
+    do {                                    \
+        int rc__ = (expr);                  \
+        if (rc__ != GCZ_OK) return rc__;    \
+    } while (0)
+
+namespace gcz {
+namespace {
+
+// ---- read-only file mapping ---------------------------------------------------------------------------------------
+struct MappedFile {
+    const uint8_t* data = nullptr;
+    int64_t size = 0;
+    int fd = -1;
+    int open_ro(const char* path) {
+        fd = ::open(path, O_RDONLY);
+        if (fd < 0) return fail(GCZ_E_ARG, "cannot open %s", path);
+        struct stat st;
+        if (fstat(fd, &st) != 0) return fail(GCZ_E_ARG, "cannot stat %s", path);
+        size = (int64_t)st.st_size;
+        if (size > 0) {
+            void* p = mmap(nullptr, (size_t)size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (p == MAP_FAILED) return fail(GCZ_E_NOMEM, "cannot map %s", path);
+            data = static_cast<const uint8_t*>(p);
+        }
+        return GCZ_OK;
+    }
+    ~MappedFile() {
+        if (data) munmap(const_cast<uint8_t*>(data), (size_t)size);
+        if (fd >= 0) ::close(fd);
+    }
+};
+
+// ---- FastaIterator (lazy) ------------------------------------------------------------------------------------------
+struct FastaRecord {
+    std::string header;
+    int64_t position = 0, length = 0;
+    bool multiline = false;
+};
+
+// The character-level state machine of fasta/FastaIterator.java:39-127, kept literal (hasNext :40-69, next :72-127):
+// which byte opens a record, what counts as sequence, how FASTQ qualities are skipped — all of it decides which
+// bytes end up in the index.
+void scan_fasta(const uint8_t* buf, int64_t size, std::vector<FastaRecord>& out) {
+    int64_t p = 0;
+    auto rd = [&]() -> int { return p < size ? (int)buf[p++] : -1; };
+    int ch = '\r';                                          // FastaIterator(InputStream, boolean) :33
+    int64_t position = 0;
+    while (true) {
+        while (ch >= 0 && ch != '>' && ch != '@') { ch = rd(); position++; }          // hasNext :46-49
+        if (ch < 0) break;
+        FastaRecord rec;
+        while ((ch = rd()) >= 0 && ch != '\n') {                                       // :55-61
+            position++;
+            if (ch != '\r') rec.header.push_back((char)ch);
+        }
+        position++;
+        int lines = 0;                                                                 // next :81-96
+        int64_t length = 0, posnew = position;
+        do {
+            if (ch >= 0 && ch != '\r' && ch != '\n') {
+                lines++;
+                do { posnew++; length++; } while ((ch = rd()) >= 0 && ch != '\r' && ch != '\n');
+            }
+            posnew++;
+        } while ((ch = rd()) >= 0 && ch != '>' && ch != '@' && ch != '+');
+        if (ch == '+') {                                                               // skip qualities :98-113
+            int qlines = -1;
+            int64_t qlength = 0;
+            do {
+                while ((ch = rd()) >= 0 && ch != '\r' && ch != '\n') { qlength++; posnew++; }
+                posnew++;
+                qlines++;
+            } while (qlength < length && qlines < lines);
+        }
+        rec.position = position;
+        rec.length = length;
+        rec.multiline = lines > 1;
+        out.push_back(std::move(rec));
+        position = posnew;
+    }
+}
+
+}  // namespace
+}  // namespace gcz
+
+struct gcz_fasta {
+    std::unique_ptr<gcz::MappedFile> file;
+    const uint8_t* data = nullptr;
+    int64_t size = 0;
+    std::vector<gcz::FastaRecord> records;
+};
+
+namespace gcz {
+namespace {
+
+// FastaFileReader.read  fasta/FastaFileReader.java:109-160 (plain file): one-line sequences are `length` raw bytes
+// at `position`; multi-line ones are read from there with CR/LF dropped until `length` bytes are in
+int64_t read_sequence(const gcz_fasta* f, const FastaRecord& r, uint8_t* out, int64_t cap) {
+    const int64_t want = std::min(r.length, cap);
+    if (!r.multiline) {
+        const int64_t avail = std::max<int64_t>(0, std::min(want, f->size - r.position));
+        std::memcpy(out, f->data + r.position, (size_t)avail);
+        return avail;
+    }
+    int64_t i = 0;
+    for (int64_t p = r.position; i < want && p < f->size; p++) {
+        const uint8_t c = f->data[p];
+        if (c != '\r' && c != '\n') out[i++] = c;
+    }
+    return i;
+}
+
+// ---- GecoIndex: one block per sequence, greedy merge, file order  tools/GecoIndex.java:57-98 ------------------------
+inline int32_t java_int(int64_t v) { return (int32_t)(uint32_t)(uint64_t)v; }   // int arithmetic wraps
+
+struct Seq { int64_t length; const char* header; int64_t id; };
+
+// TFastaSequence.compareTo  fasta/TFastaSequence.java:46-52: longer first, then header (String.compareTo)
+int cmp_seq(const Seq& a, const Seq& b) {
+    if (a.length != b.length) return a.length > b.length ? -1 : 1;
+    const int c = std::strcmp(a.header, b.header);          // bytes < 0x80: same order as UTF-16 code units
+    return c < 0 ? -1 : (c > 0 ? 1 : 0);
+}
+
+struct Block {                                               // fmt/GecozRefBlock.java:38-71
+    std::vector<Seq> sequences;                              // TreeSet<TFastaSequence>
+    int32_t size = 0;
+    explicit Block(const Seq& s) : sequences{ s }, size(java_int(s.length + 1)) {}
+    void add(const Seq& s) {                                 // :45-48
+        size_t lo = 0, hi = sequences.size();
+        bool dup = false;
+        while (lo < hi) {
+            const size_t mid = (lo + hi) / 2;
+            const int c = cmp_seq(s, sequences[mid]);
+            if (c == 0) { dup = true; break; }
+            if (c < 0) hi = mid; else lo = mid + 1;
+        }
+        if (!dup) sequences.insert(sequences.begin() + (long)lo, s);
+        size = java_int((int64_t)size + s.length + 1);
+    }
+};
+
+int cmp_block(const Block& a, const Block& b) {              // compareTo :62-69
+    if (a.size != b.size) return a.size > b.size ? 1 : -1;
+    return cmp_seq(a.sequences[0], b.sequences[0]);
+}
+
+template <class Cmp>
+bool tree_add(std::vector<Block>& set, Block&& b, Cmp cmp) {     // TreeSet.add: equal elements are rejected
+    size_t lo = 0, hi = set.size();
+    while (lo < hi) {
+        const size_t mid = (lo + hi) / 2;
+        const int c = cmp(b, set[mid]);
+        if (c == 0) return false;
+        if (c < 0) hi = mid; else lo = mid + 1;
+    }
+    set.insert(set.begin() + (long)lo, std::move(b));
+    return true;
+}
+
+std::vector<Block> plan_blocks(const std::vector<Seq>& seqs) {
+    std::vector<Block> blocks;
+    for (const Seq& s : seqs) tree_add(blocks, Block(s), cmp_block);
+    if (blocks.empty()) return blocks;
+    const int32_t max_size = blocks.back().size;                                   // :72
+    while (blocks.size() > 1) {                                                     // :73-85
+        Block first = std::move(blocks[0]), second = std::move(blocks[1]);
+        blocks.erase(blocks.begin(), blocks.begin() + 2);
+        const int32_t size = java_int((int64_t)first.size + second.size);
+        if (size > 0 && size <= max_size) {
+            for (const Seq& s : second.sequences) first.add(s);
+            tree_add(blocks, std::move(first), cmp_block);
+        } else {
+            tree_add(blocks, std::move(first), cmp_block);
+            tree_add(blocks, std::move(second), cmp_block);
+            break;
+        }
+    }
+    auto by_longest = [](const Block& a, const Block& b) {                          // :88-96
+        if (a.sequences[0].length != b.sequences[0].length) return a.sequences[0].length > b.sequences[0].length ? -1 : 1;
+        return cmp_block(a, b);
+    };
+    std::vector<Block> sorted;
+    for (Block& b : blocks) tree_add(sorted, std::move(b), by_longest);
+    return sorted;
+}
+
+// ---- headers ------------------------------------------------------------------------------------------------------------
+void put_le64(uint8_t* p, int64_t v) { for (int i = 0; i < 8; i++) p[i] = (uint8_t)((uint64_t)v >> (8 * i)); }
+int64_t get_le64(const uint8_t* p) { uint64_t v = 0; for (int i = 0; i < 8; i++) v |= (uint64_t)p[i] << (8 * i); return (int64_t)v; }
+
+int64_t ref_header_length(const char* const* headers, int32_t n) {                  // getBlockHeaderLength :130-136
+    int64_t len = 26;
+    for (int32_t i = 0; i < n; i++) len += (int64_t)std::strlen(headers[i]) + 1;
+    return len;
+}
+
+int64_t header_hash(const char* const* headers, int32_t n) {                        // getBlockHeaderHash :120-128
+    uint64_t h = 1125899906842597ull;
+    for (int32_t i = 0; i < n; i++) {
+        for (const unsigned char* c = reinterpret_cast<const unsigned char*>(headers[i]); *c; c++) h = 31 * h + *c;
+    }
+    return (int64_t)h;
+}
+
+std::string ssa_path_for(const std::string& ref) {                                  // fmt/GecozFileWriter.java:97-104
+    const size_t slash = ref.find_last_of('/');
+    std::string dir = slash == std::string::npos ? "" : ref.substr(0, slash + 1);
+    std::string name = slash == std::string::npos ? ref : ref.substr(slash + 1);
+    if (name.size() >= 4 && name.compare(name.size() - 4, 4, ".gcz") == 0) name.resize(name.size() - 3);
+    return dir + name + "gcx";
+}
+
+// a writable mapping of file bytes [off, off + len)
+struct MappedSlice {
+    uint8_t* base = nullptr;
+    size_t mapped = 0;
+    uint8_t* data = nullptr;
+    int map(int fd, int64_t off, int64_t len) {
+        const int64_t page = sysconf(_SC_PAGESIZE);
+        const int64_t start = off - off % page;
+        mapped = (size_t)(len + (off - start));
+        if (mapped == 0) mapped = 1;
+        void* p = mmap(nullptr, mapped, PROT_READ | PROT_WRITE, MAP_SHARED, fd, start);
+        if (p == MAP_FAILED) return fail(GCZ_E_NOMEM, "cannot map %lld bytes of the output file", (long long)len);
+        base = static_cast<uint8_t*>(p);
+        data = base + (off - start);
+        return GCZ_OK;
+    }
+    ~MappedSlice() { if (base) munmap(base, mapped); }
+};
+
+// host buffer for one block's text: pinned when a CUDA device is there (full-speed DMA), plain otherwise
+struct TextBuffer {
+    uint8_t* data = nullptr;
+    bool pinned = false;
+    explicit TextBuffer(size_t bytes) {
+        if (cudaHostAlloc(reinterpret_cast<void**>(&data), bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess) { pinned = true; return; }
+        cudaGetLastError();
+        data = static_cast<uint8_t*>(std::malloc(bytes ? bytes : 1));
+    }
+    ~TextBuffer() { if (pinned) cudaFreeHost(data); else std::free(data); }
+    TextBuffer(const TextBuffer&) = delete;
+    TextBuffer& operator=(const TextBuffer&) = delete;
+};
+
+}  // namespace
+}  // namespace gcz
+
+using namespace gcz;
+
+// =====================================================================================================================
+extern "C" {
+
+int gcz_fasta_open(const char* path, gcz_fasta** out) {
+    clear_error();
+    if (!path || !out) return fail(GCZ_E_ARG, "null argument");
+    std::unique_ptr<gcz_fasta> f(new gcz_fasta());
+    f->file.reset(new MappedFile());
+    GCZ_TRY_HOST(f->file->open_ro(path));
+    f->data = f->file->data;
+    f->size = f->file->size;
+    if (f->size >= 2 && f->data[0] == 0x1f && f->data[1] == 0x8b)
+        return fail(GCZ_E_FORMAT, "%s is gzipped: decompress it on the host side and use gcz_fasta_open_buffer", path);
+    scan_fasta(f->data, f->size, f->records);
+    *out = f.release();
+    return GCZ_OK;
+}
+
+int gcz_fasta_open_buffer(const uint8_t* data, int64_t size, gcz_fasta** out) {
+    clear_error();
+    if ((!data && size > 0) || size < 0 || !out) return fail(GCZ_E_ARG, "null argument");
+    std::unique_ptr<gcz_fasta> f(new gcz_fasta());
+    f->data = data;
+    f->size = size;
+    scan_fasta(data, size, f->records);
+    *out = f.release();
+    return GCZ_OK;
+}
+
+int64_t gcz_fasta_count(const gcz_fasta* f) { return f ? (int64_t)f->records.size() : 0; }
+
+int gcz_fasta_record(const gcz_fasta* f, int64_t i, const char** header, int64_t* position, int64_t* length, int32_t* multiline) {
+    if (!f || i < 0 || i >= (int64_t)f->records.size()) return fail(GCZ_E_ARG, "record index");
+    const FastaRecord& r = f->records[(size_t)i];
+    if (header) *header = r.header.c_str();
+    if (position) *position = r.position;
+    if (length) *length = r.length;
+    if (multiline) *multiline = r.multiline ? 1 : 0;
+    return GCZ_OK;
+}
+
+int gcz_fasta_read(const gcz_fasta* f, int64_t i, uint8_t* out, int64_t cap) {
+    if (!f || !out || i < 0 || i >= (int64_t)f->records.size()) return fail(GCZ_E_ARG, "record index");
+    const FastaRecord& r = f->records[(size_t)i];
+    if (cap < r.length) return fail(GCZ_E_ARG, "buffer of %lld bytes for a sequence of %lld", (long long)cap, (long long)r.length);
+    read_sequence(f, r, out, cap);
+    return GCZ_OK;
+}
+
+void gcz_fasta_close(gcz_fasta* f) { delete f; }
+
+int64_t gcz_plan_blocks(const int64_t* lengths, const char* const* headers, int64_t n, int64_t* block_of, int64_t* order_in_block) {
+    clear_error();
+    if (n < 0 || (n > 0 && (!lengths || !headers || !block_of || !order_in_block))) return fail(GCZ_E_ARG, "null argument");
+    std::vector<Seq> seqs((size_t)n);
+    for (int64_t i = 0; i < n; i++) { seqs[(size_t)i] = Seq{ lengths[i], headers[i], i }; block_of[i] = -1; order_in_block[i] = -1; }
+    const std::vector<Block> blocks = plan_blocks(seqs);
+    for (size_t b = 0; b < blocks.size(); b++) {
+        for (size_t k = 0; k < blocks[b].sequences.size(); k++) {
+            block_of[blocks[b].sequences[k].id] = (int64_t)b;
+            order_in_block[blocks[b].sequences[k].id] = (int64_t)k;
+        }
+    }
+    return (int64_t)blocks.size();
+}
+
+int64_t gcz_ref_header_length(const char* const* headers, int32_t n) { return ref_header_length(headers, n); }
+int64_t gcz_header_hash(const char* const* headers, int32_t n) { return header_hash(headers, n); }
+
+int64_t gcz_ref_header_write(const char* const* headers, int32_t n, int64_t block_size, int64_t text_len, uint8_t* out, int64_t cap) {
+    clear_error();                                                                   // write(ByteBuffer) :90-101
+    const int64_t len = ref_header_length(headers, n);
+    if (!out || cap < len) return fail(GCZ_E_ARG, "header buffer of %lld bytes, %lld needed", (long long)cap, (long long)len);
+    std::memcpy(out, "GecozBWT", 8);
+    out[8] = 1;
+    put_le64(out + 9, block_size);
+    put_le64(out + 17, text_len);
+    int64_t p = 25;
+    for (int32_t i = 0; i < n; i++) {
+        const size_t l = std::strlen(headers[i]);
+        std::memcpy(out + p, headers[i], l);
+        p += (int64_t)l;
+        out[p++] = 0;
+    }
+    out[p++] = 0;
+    return p;
+}
+
+int64_t gcz_ssa_header_write(const char* const* headers, int32_t n, int64_t index_len, uint8_t out[25]) {
+    std::memcpy(out, "GecozSSA", 8);                                                 // fmt/GecozSSABlockHeader.java:69-74
+    out[8] = 1;
+    put_le64(out + 9, index_len);
+    put_le64(out + 17, header_hash(headers, n));
+    return 25;
+}
+
+// ---- writer -------------------------------------------------------------------------------------------------------------
+int gcz_index_fasta(const gcz_fasta* fasta, const char* gcz_path, const char* gcx_path, int32_t sampling_rate,
+                    int32_t n_devices, const int* devices, const gcz_engine* engine, gcz_index_report* report) {
+    clear_error();
+    if (!fasta || !gcz_path) return fail(GCZ_E_ARG, "null argument");
+    if (sampling_rate <= 0 || (sampling_rate & (sampling_rate - 1)) != 0) return fail(GCZ_E_ARG, "sampling rate must be a power of two");
+    const int sf = 31 - __builtin_clz((unsigned)sampling_rate);
+    gcz_engine eng;
+    eng.count_symbols = engine && engine->count_symbols ? engine->count_symbols : gcz_count_symbols;
+    eng.build_block = engine && engine->build_block ? engine->build_block : gcz_build_block;
+    std::vector<int> devs;
+    for (int32_t i = 0; i < n_devices; i++) devs.push_back(devices ? devices[i] : i);
+    if (devs.empty()) devs.push_back(0);
+    const auto t_start = std::chrono::steady_clock::now();
+
+    // blocks in file order (tools/GecoIndex.java:57-98)
+    std::vector<Seq> seqs;
+    for (size_t i = 0; i < fasta->records.size(); i++) seqs.push_back(Seq{ fasta->records[i].length, fasta->records[i].header.c_str(), (int64_t)i });
+    const std::vector<Block> blocks = plan_blocks(seqs);
+    if (blocks.empty()) return fail(GCZ_E_ARG, "no data found");
+
+    const std::string ref_path = gcz_path, ssa_path = gcx_path ? std::string(gcx_path) : ssa_path_for(ref_path);
+    const int ref_fd = ::open(ref_path.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0644);
+    const int ssa_fd = ::open(ssa_path.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0644);
+    if (ref_fd < 0 || ssa_fd < 0) {
+        if (ref_fd >= 0) ::close(ref_fd);
+        if (ssa_fd >= 0) ::close(ssa_fd);
+        return fail(GCZ_E_ARG, "cannot create %s / %s", ref_path.c_str(), ssa_path.c_str());
+    }
+
+    // two tokens per device: one block being built, the next one being counted (= uploaded)
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<int> free_tokens;
+    for (int rep = 0; rep < 2; rep++) for (int d : devs) free_tokens.push_back(d);
+    const size_t all_tokens = free_tokens.size();
+    int first_error = GCZ_OK;
+    std::string first_message;
+    std::vector<std::thread> workers;
+    int64_t ref_pos = 0, ssa_pos = 0, symbols = 0, sequences = 0;
+
+    auto release = [&](int d) { std::lock_guard<std::mutex> l(mu); free_tokens.push_back(d); cv.notify_all(); };
+    auto record_error = [&](int rc) {
+        std::lock_guard<std::mutex> l(mu);
+        if (first_error == GCZ_OK) { first_error = rc; first_message = gcz_last_error(); }
+    };
+
+    for (const Block& block : blocks) {
+        {
+            std::lock_guard<std::mutex> l(mu);
+            if (first_error != GCZ_OK) break;
+        }
+        int device;
+        {
+            std::unique_lock<std::mutex> l(mu);
+            cv.wait(l, [&] { return !free_tokens.empty(); });
+            device = free_tokens.front();
+            free_tokens.erase(free_tokens.begin());
+        }
+        // writeBlock (tools/GecoIndex.java:119-146): the member sequences in block order, each followed by '\0'
+        int64_t n = 0;
+        for (const Seq& s : block.sequences) n += s.length + 1;
+        std::shared_ptr<TextBuffer> text(new TextBuffer((size_t)n));
+        if (!text->data) { release(device); record_error(fail(GCZ_E_NOMEM, "host buffer of %lld bytes", (long long)n)); break; }
+        std::vector<const char*> hdrs;
+        int64_t p = 0;
+        for (const Seq& s : block.sequences) {
+            read_sequence(fasta, fasta->records[(size_t)s.id], text->data + p, s.length);
+            p += s.length;
+            text->data[p++] = 0;
+            hdrs.push_back(s.header);
+        }
+        // GecozFileWriter.write (fmt/GecozFileWriter.java:124-159): counts, shape, slices, headers, queue the block
+        int64_t counts[256];
+        std::shared_ptr<gcz_shape> shape(new gcz_shape());
+        int rc = eng.count_symbols(device, text->data, n, counts);
+        if (rc == GCZ_OK) rc = gcz_shape_from_counts(counts, shape.get());
+        if (rc != GCZ_OK) { release(device); record_error(rc); break; }
+        const int64_t hlen = ref_header_length(hdrs.data(), (int32_t)hdrs.size());
+        const int64_t idx_size = index_size(n, sf);
+        const int64_t my_ref = ref_pos, my_ssa = ssa_pos;
+        ref_pos += hlen + shape->size;
+        ssa_pos += 25 + idx_size;
+        std::vector<uint8_t> hb((size_t)hlen);
+        uint8_t sb[25];
+        gcz_ref_header_write(hdrs.data(), (int32_t)hdrs.size(), hlen + shape->size, n, hb.data(), hlen);
+        gcz_ssa_header_write(hdrs.data(), (int32_t)hdrs.size(), idx_size, sb);
+        if (ftruncate(ref_fd, ref_pos) != 0 || ftruncate(ssa_fd, ssa_pos) != 0 ||
+            pwrite(ref_fd, hb.data(), (size_t)hlen, my_ref) != hlen || pwrite(ssa_fd, sb, 25, my_ssa) != 25) {
+            release(device);
+            record_error(fail(GCZ_E_ARG, "cannot write %s / %s", ref_path.c_str(), ssa_path.c_str()));
+            break;
+        }
+        symbols += n;
+        sequences += (int64_t)block.sequences.size();
+        // BlockWriter.run (:256-284) on its own thread; GCZ_E_NOMEM: once more when nothing else is in flight
+        // (WriterPoolExecutor.afterExecute :203-226)
+        workers.emplace_back([&, device, text, shape, n, my_ref, my_ssa, hlen, idx_size] {
+            int attempts = 0;
+            while (true) {
+                MappedSlice ref_map, ssa_map;
+                int rc2 = ref_map.map(ref_fd, my_ref + hlen, shape->size);
+                if (rc2 == GCZ_OK) rc2 = ssa_map.map(ssa_fd, my_ssa + 25, idx_size);
+                if (rc2 == GCZ_OK) rc2 = eng.build_block(device, text->data, n, sampling_rate, shape.get(), ref_map.data, shape->size,
+                                                         ssa_map.data, idx_size, nullptr, nullptr);
+                if (rc2 == GCZ_E_NOMEM && attempts++ == 0) {
+                    std::unique_lock<std::mutex> l(mu);
+                    cv.wait(l, [&] { return free_tokens.size() == all_tokens - 1; });
+                    continue;
+                }
+                if (rc2 != GCZ_OK) record_error(rc2);
+                break;
+            }
+            release(device);
+        });
+    }
+    for (std::thread& t : workers) t.join();
+    ::close(ref_fd);
+    ::close(ssa_fd);
+    if (report) {
+        report->blocks = (int64_t)workers.size();
+        report->sequences = sequences;
+        report->symbols = symbols;
+        report->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+    }
+    if (first_error != GCZ_OK) return fail(first_error, "%s", first_message.c_str());
+    return GCZ_OK;
+}
+
+}  // extern "C"
+
+// ---- reader -------------------------------------------------------------------------------------------------------------
+struct gcz_reader {
+    gcz::MappedFile ref, ssa;
+    bool has_ssa = false;
+    struct BlockInfo {
+        int64_t position = 0, size = 0, len = 0, header_len = 0;
+        std::vector<std::string> headers;
+    };
+    std::vector<BlockInfo> blocks;
+    int32_t sampling_factor = -1;
+};
+
+extern "C" {
+
+int gcz_reader_open(const char* gcz_path, gcz_reader** out) {
+    clear_error();
+    if (!gcz_path || !out) return fail(GCZ_E_ARG, "null argument");
+    std::unique_ptr<gcz_reader> r(new gcz_reader());
+    GCZ_TRY_HOST(r->ref.open_ro(gcz_path));
+    if (r->ref.size < 26) return fail(GCZ_E_FORMAT, "%s is too short for a gecoz file", gcz_path);
+    // GecozFileReader(Path) :65-91: walk the block headers by `size` (do / while)
+    int64_t position = 0;
+    const int64_t total = r->ref.size;
+    do {
+        if (position + 26 > total) return fail(GCZ_E_FORMAT, "truncated block header at %lld", (long long)position);
+        gcz_reader::BlockInfo b;
+        const uint8_t* h = r->ref.data + position;
+        b.position = position;
+        b.size = get_le64(h + 9);
+        b.len = get_le64(h + 17);
+        int64_t p = position + 25;
+        while (p < total && r->ref.data[p] > 0) {                                   // GecozRefBlockHeader(InputStream) :59-82
+            const void* q = std::memchr(r->ref.data + p, 0, (size_t)(total - p));
+            if (!q) return fail(GCZ_E_FORMAT, "unterminated header at %lld", (long long)p);
+            const int64_t e = static_cast<const uint8_t*>(q) - r->ref.data;
+            b.headers.emplace_back(reinterpret_cast<const char*>(r->ref.data + p), (size_t)(e - p));
+            p = e + 1;
+        }
+        b.header_len = 26;
+        for (const std::string& s : b.headers) b.header_len += (int64_t)s.size() + 1;
+        const int64_t size = b.size;
+        r->blocks.push_back(std::move(b));
+        position += size;
+        if (size <= 0) break;
+    } while (position < total);
+
+    const std::string ssa_path = ssa_path_for(gcz_path);
+    if (access(ssa_path.c_str(), R_OK) == 0 && r->ssa.open_ro(ssa_path.c_str()) == GCZ_OK) {
+        r->has_ssa = true;
+        // the sampling factor is not stored: the smallest one whose index fits the file  :134-149
+        const int64_t data_len = r->ssa.size - (int64_t)r->blocks.size() * 25;
+        int sf = -1;
+        while (true) {
+            if (++sf > 30) return fail(GCZ_E_FORMAT, "invalid index file");
+            int64_t need = 0;
+            for (const auto& b : r->blocks) need += index_size(b.len, sf);
+            if (data_len >= need) break;
+        }
+        r->sampling_factor = sf;
+    }
+    clear_error();
+    *out = r.release();
+    return GCZ_OK;
+}
+
+int32_t gcz_reader_num_blocks(const gcz_reader* r) { return r ? (int32_t)r->blocks.size() : 0; }
+
+int gcz_reader_block(const gcz_reader* r, int32_t block, int64_t* text_len, int64_t* block_size, int32_t* n_headers) {
+    if (!r || block < 0 || block >= (int32_t)r->blocks.size()) return fail(GCZ_E_ARG, "block index");
+    const auto& b = r->blocks[(size_t)block];
+    if (text_len) *text_len = b.len;
+    if (block_size) *block_size = b.size;
+    if (n_headers) *n_headers = (int32_t)b.headers.size();
+    return GCZ_OK;
+}
+
+const char* gcz_reader_header(const gcz_reader* r, int32_t block, int32_t i) {
+    if (!r || block < 0 || block >= (int32_t)r->blocks.size()) return nullptr;
+    const auto& b = r->blocks[(size_t)block];
+    return (i >= 0 && i < (int32_t)b.headers.size()) ? b.headers[(size_t)i].c_str() : nullptr;
+}
+
+int gcz_reader_find(const gcz_reader* r, const char* header, int32_t* block, int32_t* nstr) {
+    if (!r || !header) return fail(GCZ_E_ARG, "null argument");
+    for (size_t b = 0; b < r->blocks.size(); b++) {                                  // findBlockHeader :93-101 + findHeader
+        for (size_t i = 0; i < r->blocks[b].headers.size(); i++) {
+            if (r->blocks[b].headers[i] == header) {
+                if (block) *block = (int32_t)b;
+                if (nstr) *nstr = (int32_t)i;
+                return GCZ_OK;
+            }
+        }
+    }
+    return fail(GCZ_E_ARG, "no sequence found: %s", header);
+}
+
+int32_t gcz_reader_sampling_factor(const gcz_reader* r) { return r ? r->sampling_factor : -1; }
+
+int gcz_reader_open_block(const gcz_reader* r, int32_t block, int device, gcz_index** out) {
+    clear_error();
+    if (!r || !out || block < 0 || block >= (int32_t)r->blocks.size()) return fail(GCZ_E_ARG, "block index");
+    if (!r->has_ssa) return fail(GCZ_E_ARG, "the .gcx index is missing: queries need it");
+    const auto& b = r->blocks[(size_t)block];
+    const int sf = r->sampling_factor;
+    int64_t ssa_pos = 0;
+    for (int32_t i = 0; i < block; i++) ssa_pos += 25 + index_size(r->blocks[(size_t)i].len, sf);
+    const int64_t ssa_size = index_size(b.len, sf);
+    if (ssa_pos + 25 + ssa_size > r->ssa.size || b.position + b.size > r->ref.size || b.size < b.header_len)
+        return fail(GCZ_E_FORMAT, "invalid index file");
+    std::vector<const char*> hdrs;
+    for (const std::string& s : b.headers) hdrs.push_back(s.c_str());
+    const uint8_t* sh = r->ssa.data + ssa_pos;
+    if (get_le64(sh + 17) != header_hash(hdrs.data(), (int32_t)hdrs.size()) || get_le64(sh + 9) != ssa_size)
+        return fail(GCZ_E_FORMAT, "invalid index file");                             // :165-172
+    return gcz_open_block(device, r->ref.data + b.position + b.header_len, b.size - b.header_len, b.len,
+                          sh + 25, ssa_size, out);
+}
+
+void gcz_reader_close(gcz_reader* r) { delete r; }
+
+}  // extern "C"

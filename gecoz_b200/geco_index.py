@@ -118,32 +118,17 @@ def merge_blocks(sequences: Sequence[FastaSequence]) -> list[GecozRefBlock]:
 
 # ---- FASTA (host I/O; stays on the CPU like nova-gzip / fasta in the reference) -------------------------------
 def read_fasta(path) -> Iterator[tuple[str, bytes]]:
-    """Records as the reference sees them: header = the full line after '>' (or '@'), sequence bytes verbatim
-    with CR/LF removed; a line starting with '+' ends the record and its quality lines are skipped
-    (fasta/FastaIterator.java:49-127, fasta/FastaFileReader.java:109-160)."""
+    """Records as the reference sees them (fasta/FastaIterator.java:39-127, fasta/FastaFileReader.java:109-160): the
+    native record scanner (csrc/host_file.cpp) is the one implementation of that state machine; gzipped files are
+    decompressed here first (nova-gzip's job in the reference; it stays on the host)."""
+    from .native_file import Fasta
     path = Path(path)
-    opener = gzip.open if path.suffix == ".gz" else open
-    header, parts, in_quality, qleft = None, [], False, 0
-    with opener(path, "rb") as f:
-        for raw in f:
-            line = raw.rstrip(b"\r\n")
-            if in_quality:
-                qleft -= len(line)
-                if qleft <= 0:
-                    in_quality = False
-                continue
-            if line[:1] in (b">", b"@"):
-                if header is not None:
-                    yield header, b"".join(parts)
-                header, parts = line[1:].replace(b"\r", b"").decode("latin-1"), []
-            elif line[:1] == b"+" and header is not None:
-                seq = b"".join(parts)
-                yield header, seq
-                header, parts, in_quality, qleft = None, [], len(seq) > 0, len(seq)
-            elif header is not None:
-                parts.append(line.replace(b"\r", b""))
-    if header is not None:
-        yield header, b"".join(parts)
+    with open(path, "rb") as f:
+        magic = f.read(2)
+    source = gzip.open(path, "rb").read() if magic == b"\x1f\x8b" else path
+    with Fasta(source) as fasta:
+        for i in range(len(fasta)):
+            yield fasta.record(i)[0], fasta.read(i).tobytes()
 
 
 def block_text(block: GecozRefBlock) -> tuple[list[str], np.ndarray]:

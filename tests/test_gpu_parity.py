@@ -593,3 +593,28 @@ def test_geco_read_fasta_and_sequence(G, O, tmp_path):
     assert geco_read.sequence(tmp_path / "g.gcz", hdr, 100, 1100, tmp_path / "sub.bin") == 1000
     blk = next(b for b in blocks if hdr in b[0])
     assert (tmp_path / "sub.bin").read_bytes() == blk[1].extract(blk[0].index(hdr), 100, 1000).tobytes()
+
+
+# ---- the native host layer (include/gcz_file.h) with the CUDA engine -------------------------------------------------------
+def test_native_writer_and_reader_on_the_gpu(G, O, tmp_path):
+    from gecoz_b200 import native_file as NF, synth
+    recs = [(f"n{i} d", synth.iid_acgtn(int(ln), 80 + i)) for i, ln in enumerate([30_000, 21_000, 9_500, 9_000, 300, 300, 11])]
+    fa = tmp_path / "n.fa"
+    with open(fa, "wb") as f:
+        for h, s in recs:
+            f.write(b">" + h.encode() + b"\n")
+            for i in range(0, len(s), 70):
+                f.write(s[i:i + 70].tobytes() + b"\n")
+    with NF.Fasta(fa) as fasta:
+        rep = NF.index(fasta, tmp_path / "n.gcz")                            # engine = the library's CUDA entry points
+    gcz, gcx, blocks = O.write_files([(h, s.tobytes()) for h, s in recs])
+    assert (tmp_path / "n.gcz").read_bytes() == gcz and (tmp_path / "n.gcx").read_bytes() == gcx
+    assert rep["blocks"] == len(blocks)
+    with NF.Reader(tmp_path / "n.gcz") as r:
+        b, s = r.find(recs[2][0])
+        g = r.open_block(b)
+        pat = recs[2][1][100:120].tobytes()
+        res = g.find(pat)
+        assert res is not None and res[s] is not None and 100 in res[s].tolist()
+        assert np.array_equal(g.extract(s, 50, 500), recs[2][1][50:550])
+        g.close()

@@ -18,12 +18,13 @@ ROOT = Path(__file__).resolve().parent.parent
 
 
 def test_library_exports_every_declared_symbol():
-    header = (ROOT / "include" / "gcz.h").read_text()
-    declared = set(re.findall(r"^\s*(?:int|void|int64_t|const char\*)\s+(gcz_[a-z0-9_]+)\s*\(", header, re.M))
-    assert declared == set(N.EXPORTS)
     lib = N.lib()
-    for name in declared:
-        assert hasattr(lib, name), name
+    for header_name, exports in (("gcz.h", N.EXPORTS), ("gcz_file.h", N.FILE_EXPORTS)):
+        header = (ROOT / "include" / header_name).read_text()
+        declared = set(re.findall(r"^\s*(?:int|void|int32_t|int64_t|const char\*)\s+(gcz_[a-z0-9_]+)\s*\(", header, re.M))
+        assert declared == set(exports), header_name
+        for name in declared:
+            assert hasattr(lib, name), name
     assert b"sm_100a" in lib.gcz_version()
 
 
