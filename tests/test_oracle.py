@@ -301,3 +301,35 @@ def test_oracle_extract_and_index_find():
         assert np.array_equal(g.extract(0, start, cap), seq[start:start + cap])
     with pytest.raises(IndexError):
         g.extract(1, 0, 5)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_select_and_inverse_lookups_are_exact(seed):
+    """RankedWTNode.findOne/findZero (:130-205) return the exact select; IndexWaveletTree.find (:152-165) inverts get;
+    GSSAIndex.find (:184-187) inverts locate at the sampled positions — on random small inputs."""
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(1, 200_000))
+    bits = (rng.random(n) < rng.choice([0.02, 0.5, 0.97])).astype(np.uint8)
+    buf = O.ranked_write(bits)
+    ones, zeros = np.flatnonzero(bits), np.flatnonzero(bits == 0)
+    for k in rng.integers(1, max(2, len(ones) + 1), 40):
+        if k <= len(ones):
+            assert O.ranked_find_one(buf, n, int(k)) == ones[k - 1]
+    for k in rng.integers(1, max(2, len(zeros) + 1), 40):
+        if k <= len(zeros):
+            assert O.ranked_find_zero(buf, n, int(k)) == zeros[k - 1]
+    m = int(rng.integers(1, 5000))
+    vals = rng.permutation(m).astype(np.int32)
+    iwt = O.iwt_write(vals)
+    for p in rng.integers(0, m, 60):
+        assert O.iwt_find(iwt, m, int(vals[p])) == p
+    text = synth.block_of([synth.iid_acgtn(int(rng.integers(40, 3000)), seed)])
+    rate = int(rng.choice([2, 8, 32]))
+    r = O.build_block(text, rate, want_sa=True)
+    g = O.GSSA(r["gcz_body"], len(text), r["gcx_body"])
+    isa = np.zeros(len(text), np.int64)
+    isa[r["sa"]] = np.arange(len(text))
+    for p in range(0, len(text), rate):
+        assert g.index_find(p) == isa[p]
+    start = int(rng.integers(0, len(text) - 1))
+    assert np.array_equal(g.extract(0, start, 10_000), text[start:-1])
