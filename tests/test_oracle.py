@@ -323,6 +323,7 @@ def test_select_and_inverse_lookups_are_exact(seed):
     iwt = O.iwt_write(vals)
     for p in rng.integers(0, m, 60):
         assert O.iwt_find(iwt, m, int(vals[p])) == p
+    from gecoz_b200 import synth
     text = synth.block_of([synth.iid_acgtn(int(rng.integers(40, 3000)), seed)])
     rate = int(rng.choice([2, 8, 32]))
     r = O.build_block(text, rate, want_sa=True)
