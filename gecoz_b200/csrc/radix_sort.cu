@@ -191,7 +191,10 @@ __device__ __forceinline__ unsigned peers_with_same_digit(unsigned d) {
 //   7 write digit runs out, coalesced
 //   1' (FROM_TEXT) the tile's keys are computed from the text instead: codes to shared memory, a k-symbol window
 //      slid over ITEMS consecutive positions per thread, transposed to the warp-striped order through shared memory
-template <int THREADS, int ITEMS, bool HAS_VALS, int MIN_BLOCKS, bool USE_MATCH, bool FROM_TEXT>
+// OPT (tuning variants, GCZ_SORT_VARIANT; 0 = what the benchmarks use): bit 0 = 32-bit destination offsets and no
+// bounds test in the write-out of a full tile; bit 1 = the first look-back window is requested before the shared-memory
+// reorder, so that its latency overlaps the scatter.
+template <int THREADS, int ITEMS, bool HAS_VALS, int MIN_BLOCKS, bool USE_MATCH, bool FROM_TEXT, int OPT = 0>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
                 const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
@@ -358,6 +361,16 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
     }
     __syncthreads();
 
+    constexpr int kEarly = 4;
+    unsigned long long early[kEarly];
+    if ((OPT & 2) && threadIdx.x < kRadix) {
+#pragma unroll
+        for (int j = 0; j < kEarly; j++) {
+            const long long t = (long long)tile - 1 - j;
+            early[j] = t >= 0 ? ld_relaxed_u64(&status[(size_t)t * kRadix + threadIdx.x]) : kFlagPrefix;
+        }
+    }
+
     // 5. reorder the tile in shared memory (padding keys are digit 255 and rank last: they land at >= count)
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
@@ -373,6 +386,19 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
         unsigned long long excl = 0;
         long long t = (long long)tile - 1;
         bool done = tile == 0;
+        if (OPT & 2) {                                   // the window requested before the reorder
+            int used = 0;
+#pragma unroll
+            for (int j = 0; j < kEarly; j++) {
+                const unsigned long long flag = early[j] & ~kValueMask;
+                if (!done && used == j && flag != 0) {
+                    excl += early[j] & kValueMask;
+                    used = j + 1;
+                    done = flag == kFlagPrefix;
+                }
+            }
+            t -= used;
+        }
         while (!done) {
             unsigned long long v[kLookWindow];
 #pragma unroll
@@ -392,17 +418,34 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
             t -= used;                                   // a status word that was not ready yet is polled again
         }
         if (tile > 0) st_relaxed_u64(&status[(size_t)tile * kRadix + threadIdx.x], (excl + total) | kFlagPrefix);
-        s_gofs[threadIdx.x] = (long long)(digit_base[threadIdx.x] + excl) - (long long)s_digit_start[threadIdx.x];
+        if (OPT & 1) {                                   // destinations are below 2^32: unsigned wrap-around arithmetic
+            reinterpret_cast<unsigned*>(s_gofs)[threadIdx.x] = (unsigned)(digit_base[threadIdx.x] + excl) - s_digit_start[threadIdx.x];
+        } else {
+            s_gofs[threadIdx.x] = (long long)(digit_base[threadIdx.x] + excl) - (long long)s_digit_start[threadIdx.x];
+        }
     }
     __syncthreads();
 
     // 7. digit runs are contiguous both in shared memory and at their destination
+    if ((OPT & 1) && count == TILE) {
+        const unsigned* gofs32 = reinterpret_cast<const unsigned*>(s_gofs);
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            const unsigned j = i * THREADS + threadIdx.x;
+            const uint64_t k = s_keys[j];
+            const unsigned dst = gofs32[(unsigned)(k >> shift) & 255u] + j;
+            keys_out[dst] = k;
+            if (HAS_VALS) vals_out[dst] = s_vals[j];
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
         const int j = i * THREADS + threadIdx.x;
         if (j < count) {
             const uint64_t k = s_keys[j];
-            const long long dst = s_gofs[(unsigned)(k >> shift) & 255u] + j;
+            const long long dst = (OPT & 1) ? (long long)(reinterpret_cast<const unsigned*>(s_gofs)[(unsigned)(k >> shift) & 255u] + (unsigned)j)
+                                            : s_gofs[(unsigned)(k >> shift) & 255u] + j;
             keys_out[dst] = k;
             if (HAS_VALS) vals_out[dst] = s_vals[j];
         }
@@ -419,14 +462,14 @@ struct OnesweepConfig {
     int tile() const { return threads * items; }
 };
 
-template <int THREADS, int ITEMS, int MIN_BLOCKS, bool USE_MATCH>
+template <int THREADS, int ITEMS, int MIN_BLOCKS, bool USE_MATCH, int OPT = 0>
 OnesweepConfig make_config() {
     const size_t fixed = (size_t)(THREADS / 32) * kRadix * 4 + kRadix * 8 + kRadix * 4 + 64;
     OnesweepConfig c;
     c.threads = THREADS; c.items = ITEMS;
-    c.pairs = onesweep_kernel<THREADS, ITEMS, true, MIN_BLOCKS, USE_MATCH, false>;
-    c.keys_only = onesweep_kernel<THREADS, ITEMS, false, MIN_BLOCKS, USE_MATCH, false>;
-    c.from_text = onesweep_kernel<THREADS, ITEMS, true, MIN_BLOCKS, USE_MATCH, true>;
+    c.pairs = onesweep_kernel<THREADS, ITEMS, true, MIN_BLOCKS, USE_MATCH, false, OPT>;
+    c.keys_only = onesweep_kernel<THREADS, ITEMS, false, MIN_BLOCKS, USE_MATCH, false, OPT>;
+    c.from_text = onesweep_kernel<THREADS, ITEMS, true, MIN_BLOCKS, USE_MATCH, true, OPT>;
     c.smem_pairs = (size_t)THREADS * ITEMS * 12 + fixed;
     c.smem_keys = (size_t)THREADS * ITEMS * 8 + fixed;
     return c;
@@ -444,6 +487,9 @@ const OnesweepConfig& config() {
         make_config<512, 8, 3, false>(),      // 5: 4096 pairs, 3 CTAs/SM (48 warps, 40 regs)
         make_config<1024, 6, 1, false>(),     // 6: 6144 pairs, 1 CTA/SM
         make_config<512, 16, 1, false>(),     // 7: 8192 pairs, 1 CTA/SM
+        make_config<512, 12, 2, false, 1>(),  // 8: as 0, 32-bit destination offsets              (untested on hardware yet)
+        make_config<512, 12, 2, false, 2>(),  // 9: as 0, early look-back window                  (untested on hardware yet)
+        make_config<512, 12, 2, false, 3>(),  // 10: both                                         (untested on hardware yet)
     };
     static const int pick = [] {
         const char* e = getenv("GCZ_SORT_VARIANT");
