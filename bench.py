@@ -307,6 +307,46 @@ def main() -> None:
         except Exception:
             pass
 
+    line = None
+    if rank == 0:
+        line = {
+            "metric": "FM-index build throughput (SA+BWT+HSWT+SSA per block)", "value": value, "unit": "Mbp/s",
+            "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 (64-bit packed keys)", "data": "synthetic",
+            "config": {"workload": CFG[args.workload]["name"] + (f" (length overridden to {args.length})" if args.length else ""),
+                       "symbols_per_block": n, "blocks": world, "sampling_rate": 32,
+                       "l2": "inputs larger than L2 (249 MB text, ~3 GB sort working set per pass vs 126 MB L2)",
+                       "parallelism": f"{world} independent block(s), one per GPU, no collective"},
+            "e2e": {"value": e2e_value, "unit": "Mbp/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(n),
+                    "d2h_bytes_per_step": int(shape.size) + gcx_len,
+                    "pipelining": "the upload + histogram of step i + 1 overlaps the build of step i (two text slots per device), as in "
+                                  "GecozFileWriter; K steps timed as one region",
+                    "serial": {"value": total_bases / 1e6 / (ms_e2e_serial / 1e3), "ms_per_step": ms_e2e_serial,
+                               "what": "the same calls strictly one after the other"}},
+            "gpu_launches": int(sum(i["kernel_launches"] for i in infos)),
+            "clocks": clk,
+            "roofline": roofline,
+            "cpu_baseline": None, "count": None, "locate": None,
+            "phases_ms": {k: float(np.mean([i[k] for i in infos])) for k in
+                          ("sort_initial_ms", "sort_refine_ms", "bwt_hswt_ms", "ssa_ms", "total_ms")},
+            "refine_rounds": int(infos[-1]["refine_rounds"]),
+            "sorter": {"symbols_per_key": int(infos[-1]["symbols_per_key"]), "long_runs": int(infos[-1]["long_runs"]),
+                       "unresolved_after_first_sort": int(infos[-1]["unresolved_after_first_sort"])},
+        }
+
+    # The headline numbers are complete here.  The query legs below use collectives; if one of them hangs (a rank that
+    # died, a lost peer) the line is still printed and every rank leaves with status 0 instead of waiting for NCCL's
+    # watchdog to abort the job.
+    def give_up():
+        if rank == 0:
+            line["count"] = line["count"] or {"error": "query legs did not finish within the deadline"}
+            print(json.dumps(line), flush=True)
+        os._exit(0)
+
+    deadline = threading.Timer(300.0, give_up)
+    deadline.daemon = True
+    deadline.start()
+
     # ---- count leg: query-sharded batch against a replicated index ---------------------------------------
     # The index of rank 0's block is replicated (NCCL broadcast of the two bodies); the global batch of
     # world x --patterns patterns is cut into contiguous shards; every rank counts its shard and the intervals
@@ -412,6 +452,8 @@ def main() -> None:
         count = count or {"error": repr(ex)}
         locate = locate or {"error": repr(ex)}
 
+    deadline.cancel()
+
     # ---- CPU baseline (rank 0, N=1 only) --------------------------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -426,32 +468,7 @@ def main() -> None:
                          f"Java path (no JVM on the box); one block can use 2 threads (SA-IS, then HSWT || SSA); host has {os.cpu_count()} cores"}
 
     if rank == 0:
-        line = {
-            "metric": "FM-index build throughput (SA+BWT+HSWT+SSA per block)", "value": value, "unit": "Mbp/s",
-            "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 (64-bit packed keys)", "data": "synthetic",
-            "config": {"workload": CFG[args.workload]["name"] + (f" (length overridden to {args.length})" if args.length else ""),
-                       "symbols_per_block": n, "blocks": world, "sampling_rate": 32,
-                       "l2": "inputs larger than L2 (249 MB text, ~3 GB sort working set per pass vs 126 MB L2)",
-                       "parallelism": f"{world} independent block(s), one per GPU, no collective"},
-            "e2e": {"value": e2e_value, "unit": "Mbp/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(n),
-                    "d2h_bytes_per_step": int(shape.size) + gcx_len,
-                    "pipelining": "the upload + histogram of step i + 1 overlaps the build of step i (two text slots per device), as in "
-                                  "GecozFileWriter; K steps timed as one region",
-                    "serial": {"value": total_bases / 1e6 / (ms_e2e_serial / 1e3), "ms_per_step": ms_e2e_serial,
-                               "what": "the same calls strictly one after the other"}},
-            "gpu_launches": int(sum(i["kernel_launches"] for i in infos)),
-            "clocks": clk,
-            "roofline": roofline,
-            "cpu_baseline": cpu,
-            "count": count,
-            "locate": locate,
-            "phases_ms": {k: float(np.mean([i[k] for i in infos])) for k in
-                          ("sort_initial_ms", "sort_refine_ms", "bwt_hswt_ms", "ssa_ms", "total_ms")},
-            "refine_rounds": int(infos[-1]["refine_rounds"]),
-            "sorter": {"symbols_per_key": int(infos[-1]["symbols_per_key"]), "long_runs": int(infos[-1]["long_runs"]),
-                       "unresolved_after_first_sort": int(infos[-1]["unresolved_after_first_sort"])},
-        }
+        line["cpu_baseline"], line["count"], line["locate"] = cpu, count, locate
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
