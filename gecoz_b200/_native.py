@@ -85,6 +85,7 @@ FILE_EXPORTS = [
     "gcz_index_fasta",
     "gcz_reader_open", "gcz_reader_num_blocks", "gcz_reader_block", "gcz_reader_header", "gcz_reader_find",
     "gcz_reader_sampling_factor", "gcz_reader_open_block", "gcz_reader_close",
+    "gcz_match", "gcz_gff_search", "gcz_extract_fasta",
 ]
 
 COUNT_SYMBOLS_FN = C.CFUNCTYPE(C.c_int, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64))
@@ -95,6 +96,20 @@ BUILD_BLOCK_FN = C.CFUNCTYPE(C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int32,
 class Engine(C.Structure):
     """struct gcz_engine (include/gcz_file.h): the per-block device work; null members = the CUDA entry points."""
     _fields_ = [("count_symbols", COUNT_SYMBOLS_FN), ("build_block", BUILD_BLOCK_FN)]
+
+
+class QueryEngine(C.Structure):
+    """struct gcz_query_engine (include/gcz_file.h); null members = the CUDA entry points."""
+    _fields_ = [
+        ("open_block", C.CFUNCTYPE(C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p))),
+        ("close_block", C.CFUNCTYPE(None, C.c_void_p)),
+        ("num_strings", C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_int32))),
+        ("string_ends", C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_int64))),
+        ("find_batch", C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64),
+                                   C.POINTER(C.c_void_p), C.POINTER(C.c_void_p))),
+        ("extract", C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64))),
+        ("release", C.CFUNCTYPE(None, C.c_void_p)),
+    ]
 
 
 class IndexReport(C.Structure):
@@ -179,6 +194,9 @@ def lib() -> C.CDLL:
         "gcz_reader_sampling_factor": (i32, [P]),
         "gcz_reader_open_block": (C.c_int, [P, i32, C.c_int, C.POINTER(P)]),
         "gcz_reader_close": (None, [P]),
+        "gcz_match": (C.c_int, [P, C.c_int, C.c_char_p, P, i64, i32, C.POINTER(QueryEngine), C.POINTER(P), C.POINTER(i64)]),
+        "gcz_gff_search": (C.c_int, [P, C.c_int, P, i64, C.POINTER(QueryEngine), C.POINTER(P), C.POINTER(i64)]),
+        "gcz_extract_fasta": (C.c_int, [P, C.c_int, C.c_char_p, C.POINTER(QueryEngine), C.POINTER(i64)]),
     })
     assert sorted(sig) == sorted(EXPORTS + FILE_EXPORTS)
     for name, (res, args) in sig.items():

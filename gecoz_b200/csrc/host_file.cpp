@@ -599,9 +599,10 @@ int gcz_reader_find(const gcz_reader* r, const char* header, int32_t* block, int
 
 int32_t gcz_reader_sampling_factor(const gcz_reader* r) { return r ? r->sampling_factor : -1; }
 
-int gcz_reader_open_block(const gcz_reader* r, int32_t block, int device, gcz_index** out) {
-    clear_error();
-    if (!r || !out || block < 0 || block >= (int32_t)r->blocks.size()) return fail(GCZ_E_ARG, "block index");
+// read(header) :115-177 up to the point where the GSSA is made: the two slices of a block, checked
+static int block_slices(const gcz_reader* r, int32_t block, const uint8_t** body, int64_t* body_len, int64_t* text_len,
+                        const uint8_t** ssa_body, int64_t* ssa_len) {
+    if (!r || block < 0 || block >= (int32_t)r->blocks.size()) return fail(GCZ_E_ARG, "block index");
     if (!r->has_ssa) return fail(GCZ_E_ARG, "the .gcx index is missing: queries need it");
     const auto& b = r->blocks[(size_t)block];
     const int sf = r->sampling_factor;
@@ -615,10 +616,308 @@ int gcz_reader_open_block(const gcz_reader* r, int32_t block, int device, gcz_in
     const uint8_t* sh = r->ssa.data + ssa_pos;
     if (get_le64(sh + 17) != header_hash(hdrs.data(), (int32_t)hdrs.size()) || get_le64(sh + 9) != ssa_size)
         return fail(GCZ_E_FORMAT, "invalid index file");                             // :165-172
-    return gcz_open_block(device, r->ref.data + b.position + b.header_len, b.size - b.header_len, b.len,
-                          sh + 25, ssa_size, out);
+    *body = r->ref.data + b.position + b.header_len;
+    *body_len = b.size - b.header_len;
+    *text_len = b.len;
+    *ssa_body = sh + 25;
+    *ssa_len = ssa_size;
+    return GCZ_OK;
+}
+
+int gcz_reader_open_block(const gcz_reader* r, int32_t block, int device, gcz_index** out) {
+    clear_error();
+    if (!out) return fail(GCZ_E_ARG, "null argument");
+    const uint8_t *body = nullptr, *ssa = nullptr;
+    int64_t body_len = 0, text_len = 0, ssa_len = 0;
+    GCZ_TRY_HOST(block_slices(r, block, &body, &body_len, &text_len, &ssa, &ssa_len));
+    return gcz_open_block(device, body, body_len, text_len, ssa, ssa_len, out);
 }
 
 void gcz_reader_close(gcz_reader* r) { delete r; }
+
+// ---- callers ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+// this library's CUDA entry points behind the engine signature
+int  def_open(int device, const uint8_t* a, int64_t al, int64_t tl, const uint8_t* b, int64_t bl, void** out) {
+    gcz_index* idx = nullptr;
+    const int rc = gcz_open_block(device, a, al, tl, b, bl, &idx);
+    *out = idx;
+    return rc;
+}
+void def_close(void* idx) { gcz_close_block(static_cast<gcz_index*>(idx)); }
+int  def_num_strings(const void* idx, int32_t* out) { return gcz_num_strings(static_cast<const gcz_index*>(idx), out); }
+int  def_string_ends(const void* idx, int64_t* e) { return gcz_string_ends(static_cast<const gcz_index*>(idx), e); }
+int  def_find(void* idx, const uint8_t* p, const int64_t* o, int64_t n, int64_t* per, int64_t** pos, int64_t** off) {
+    return gcz_find_batch(static_cast<gcz_index*>(idx), p, o, n, per, pos, off);
+}
+int  def_extract(void* idx, int32_t nstr, int64_t from, uint8_t* out, int64_t cap, int64_t* w) {
+    return gcz_extract(static_cast<gcz_index*>(idx), nstr, from, out, cap, w);
+}
+void def_release(void* p) { gcz_free(p); }
+
+gcz_query_engine resolve(const gcz_query_engine* e) {
+    gcz_query_engine q;
+    q.open_block = e && e->open_block ? e->open_block : def_open;
+    q.close_block = e && e->close_block ? e->close_block : def_close;
+    q.num_strings = e && e->num_strings ? e->num_strings : def_num_strings;
+    q.string_ends = e && e->string_ends ? e->string_ends : def_string_ends;
+    q.find_batch = e && e->find_batch ? e->find_batch : def_find;
+    q.extract = e && e->extract ? e->extract : def_extract;
+    q.release = e && e->release ? e->release : def_release;
+    return q;
+}
+
+// one open block, closed on scope exit
+struct OpenBlock {
+    const gcz_query_engine& q;
+    void* idx = nullptr;
+    int32_t n_strings = 0;
+    explicit OpenBlock(const gcz_query_engine& engine) : q(engine) {}
+    int open(const gcz_reader* r, int32_t block, int device) {
+        const uint8_t *body = nullptr, *ssa = nullptr;
+        int64_t body_len = 0, text_len = 0, ssa_len = 0;
+        GCZ_TRY_HOST(block_slices(r, block, &body, &body_len, &text_len, &ssa, &ssa_len));
+        GCZ_TRY_HOST(q.open_block(device, body, body_len, text_len, ssa, ssa_len, &idx));
+        return q.num_strings(idx, &n_strings);
+    }
+    ~OpenBlock() { if (idx) q.close_block(idx); }
+};
+
+// GSSA.find of a batch against one block: per-string counts [n_pats x n_strings], positions, offsets
+struct Found {
+    const gcz_query_engine& q;
+    std::vector<int64_t> per;
+    int64_t* pos = nullptr;
+    int64_t* off = nullptr;
+    explicit Found(const gcz_query_engine& engine) : q(engine) {}
+    int run(OpenBlock& b, const std::vector<uint8_t>& data, const std::vector<int64_t>& offsets) {
+        const int64_t n = (int64_t)offsets.size() - 1;
+        per.assign((size_t)std::max<int64_t>(1, n * b.n_strings), 0);
+        static const uint8_t none = 0;
+        return q.find_batch(b.idx, data.empty() ? &none : data.data(), offsets.data(), n, per.data(), &pos, &off);
+    }
+    ~Found() { if (pos) q.release(pos); if (off) q.release(off); }
+};
+
+int give_text(const std::string& text, char** out_text, int64_t* out_len) {
+    char* p = static_cast<char*>(std::malloc(text.size() + 1));
+    if (!p) return fail(GCZ_E_NOMEM, "result text of %zu bytes", text.size());
+    std::memcpy(p, text.data(), text.size());
+    p[text.size()] = 0;
+    *out_text = p;
+    if (out_len) *out_len = (int64_t)text.size();
+    return GCZ_OK;
+}
+
+// GecoMatch.print :143-157 for one block
+void print_found(const std::vector<std::string>& headers, const int64_t* per, const int64_t* pos, bool with_positions, std::string& out) {
+    int64_t o = 0;
+    for (size_t i = 0; i < headers.size(); i++) {
+        const int64_t k = per[i];
+        if (k > 0) {
+            out += ">" + headers[i] + " found : " + std::to_string(k) + "\n";
+            if (with_positions) for (int64_t j = 0; j < k; j++) out += std::to_string(pos[o + j]) + "\n";
+        }
+        o += k;
+    }
+}
+
+// String.split("\\|") + the ID= / ;Note= column of SimpleGFFGenerator :146-154 (trailing empty strings are dropped)
+std::string gff_attributes(const std::string& header) {
+    std::vector<std::string> parts;
+    size_t start = 0;
+    while (true) {
+        const size_t bar = header.find('|', start);
+        parts.push_back(header.substr(start, bar == std::string::npos ? std::string::npos : bar - start));
+        if (bar == std::string::npos) break;
+        start = bar + 1;
+    }
+    while (!parts.empty() && parts.back().empty()) parts.pop_back();
+    if (parts.empty() && header.find('|') == std::string::npos) parts.push_back(header);     // "" -> [""]
+    std::string s;
+    if (!parts.empty()) s += "ID=" + parts[0];
+    for (size_t i = 1; i < parts.size(); i++) s += ";Note=" + parts[i];
+    return s;
+}
+
+struct PatternRecord { std::string header; std::vector<uint8_t> seq; };
+
+// the record loop of SimpleGFFGenerator.search :59-86 (BufferedReader.readLine: \n, \r or \r\n end a line)
+void read_pattern_records(const uint8_t* data, int64_t size, std::vector<PatternRecord>& out) {
+    bool open = false;
+    PatternRecord cur;
+    auto flush = [&] { if (open && !cur.seq.empty()) out.push_back(cur); };
+    int64_t p = 0;
+    while (p < size) {
+        int64_t e = p;
+        while (e < size && data[e] != '\n' && data[e] != '\r') e++;
+        const uint8_t* line = data + p;
+        const int64_t len = e - p;
+        p = e;
+        if (p < size) { if (data[p] == '\r' && p + 1 < size && data[p + 1] == '\n') p += 2; else p += 1; }
+        if (len > 0 && (line[0] == '>' || line[0] == '@')) {
+            flush();
+            cur.header.assign(reinterpret_cast<const char*>(line + 1), (size_t)(len - 1));
+            cur.seq.clear();
+            open = true;
+        } else if (len > 0 && line[0] == '+') {
+            flush();
+            open = false;
+            cur.seq.clear();
+        } else if (open) {
+            cur.seq.insert(cur.seq.end(), line, line + len);
+        }
+    }
+    flush();
+}
+
+uint8_t complement(uint8_t b) {                                                       // reverse(byte) :110-118
+    switch (b) { case 'A': return 'T'; case 'T': return 'A'; case 'C': return 'G'; case 'G': return 'C'; default: return b; }
+}
+
+}  // namespace
+
+int gcz_match(const gcz_reader* r, int device, const char* header, const uint8_t* pattern, int64_t pattern_len,
+              int32_t with_positions, const gcz_query_engine* engine, char** out_text, int64_t* out_len) {
+    clear_error();
+    if (!r || !pattern || pattern_len <= 0 || !out_text) return fail(GCZ_E_ARG, "match arguments");
+    const gcz_query_engine q = resolve(engine);
+    const std::vector<uint8_t> data(pattern, pattern + pattern_len);
+    const std::vector<int64_t> off = { 0, pattern_len };
+    std::string text;
+    if (header) {                                                                     // :79-108
+        int32_t block = -1, nstr = -1;
+        GCZ_TRY_HOST(gcz_reader_find(r, header, &block, &nstr));
+        OpenBlock b(q);
+        GCZ_TRY_HOST(b.open(r, block, device));
+        Found f(q);
+        GCZ_TRY_HOST(f.run(b, data, off));
+        if (nstr < b.n_strings && f.per[(size_t)nstr] > 0) {
+            int64_t o = 0;
+            for (int32_t i = 0; i < nstr; i++) o += f.per[(size_t)i];
+            text += ">" + std::string(header) + " found : " + std::to_string(f.per[(size_t)nstr]) + "\n";
+            if (with_positions) for (int64_t j = 0; j < f.per[(size_t)nstr]; j++) text += std::to_string(f.pos[o + j]) + "\n";
+        }
+    } else {                                                                          // :109-134
+        for (int32_t block = 0; block < (int32_t)r->blocks.size(); block++) {
+            OpenBlock b(q);
+            GCZ_TRY_HOST(b.open(r, block, device));
+            Found f(q);
+            GCZ_TRY_HOST(f.run(b, data, off));
+            std::vector<std::string> headers = r->blocks[(size_t)block].headers;
+            headers.resize((size_t)b.n_strings);
+            print_found(headers, f.per.data(), f.pos, with_positions != 0, text);
+        }
+    }
+    return give_text(text, out_text, out_len);
+}
+
+int gcz_gff_search(const gcz_reader* r, int device, const uint8_t* patterns, int64_t patterns_len,
+                   const gcz_query_engine* engine, char** out_text, int64_t* out_len) {
+    clear_error();
+    if (!r || (!patterns && patterns_len > 0) || patterns_len < 0 || !out_text) return fail(GCZ_E_ARG, "gff arguments");
+    const gcz_query_engine q = resolve(engine);
+    std::vector<PatternRecord> recs;
+    read_pattern_records(patterns, patterns_len, recs);
+    const int64_t nrec = (int64_t)recs.size();
+    // forward (U -> T :96-100) then reverse complement (:104-108) of every record: one batch of 2 x nrec patterns
+    std::vector<uint8_t> data;
+    std::vector<int64_t> off(1, 0);
+    for (PatternRecord& rec : recs) {
+        for (uint8_t& c : rec.seq) if (c == 'U') c = 'T';
+        data.insert(data.end(), rec.seq.begin(), rec.seq.end());
+        off.push_back((int64_t)data.size());
+    }
+    for (const PatternRecord& rec : recs) {
+        for (size_t i = rec.seq.size(); i-- > 0;) data.push_back(complement(rec.seq[i]));
+        off.push_back((int64_t)data.size());
+    }
+    const int32_t nblocks = (int32_t)r->blocks.size();
+    std::vector<std::unique_ptr<OpenBlock>> blocks;
+    std::vector<std::unique_ptr<Found>> found;
+    for (int32_t b = 0; b < nblocks && nrec > 0; b++) {                                // :52-56: every block is opened
+        blocks.emplace_back(new OpenBlock(q));
+        GCZ_TRY_HOST(blocks.back()->open(r, b, device));
+        found.emplace_back(new Found(q));
+        GCZ_TRY_HOST(found.back()->run(*blocks.back(), data, off));
+    }
+    std::string text;
+    for (int64_t rec = 0; rec < nrec; rec++) {
+        const std::string attrs = gff_attributes(recs[(size_t)rec].header);
+        const int64_t length = (int64_t)recs[(size_t)rec].seq.size();
+        for (int strand = 0; strand < 2; strand++) {
+            const int64_t qi = strand == 0 ? rec : nrec + rec;
+            for (int32_t b = 0; b < nblocks; b++) {
+                const Found& f = *found[(size_t)b];
+                const int32_t ns = blocks[(size_t)b]->n_strings;
+                int64_t o = f.off[qi];
+                for (int32_t j = 0; j < ns; j++) {
+                    const int64_t k = f.per[(size_t)(qi * ns + j)];
+                    const std::string& name = j < (int32_t)r->blocks[(size_t)b].headers.size() ? r->blocks[(size_t)b].headers[(size_t)j] : std::string();
+                    for (int64_t x = 0; x < k; x++) {                                  // :134-156
+                        const int64_t p = f.pos[o + x];
+                        text += name + "\tgecotools\tdna\t" + std::to_string(p + 1) + "\t" + std::to_string(p + length) + "\t1.000\t" +
+                                (strand ? "-" : "+") + "\t.\t" + attrs + "\n";
+                    }
+                    o += k;
+                }
+            }
+        }
+    }
+    return give_text(text, out_text, out_len);
+}
+
+int gcz_extract_fasta(const gcz_reader* r, int device, const char* fasta_path, const gcz_query_engine* engine, int64_t* n_sequences) {
+    clear_error();
+    if (!r || !fasta_path) return fail(GCZ_E_ARG, "extract arguments");
+    const gcz_query_engine q = resolve(engine);
+    const int fd = ::open(fasta_path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return fail(GCZ_E_ARG, "cannot create %s", fasta_path);
+    struct Closer { int fd; ~Closer() { ::close(fd); } } closer{ fd };
+    constexpr int64_t kBuffer = 1024 * 1024 * 4;                                      // tools/GecoRead.java:163
+    constexpr int64_t kLine = 50;                                                     // fasta/FastaFileWriter.java:32
+    std::vector<uint8_t> buf((size_t)kBuffer);
+    int64_t count = 0;
+    for (int32_t block = 0; block < (int32_t)r->blocks.size(); block++) {
+        OpenBlock b(q);
+        GCZ_TRY_HOST(b.open(r, block, device));
+        std::vector<int64_t> e((size_t)std::max(1, b.n_strings));
+        GCZ_TRY_HOST(q.string_ends(b.idx, e.data()));
+        const auto& headers = r->blocks[(size_t)block].headers;
+        for (const std::string& header : headers) {
+            int32_t nstr = -1;                                                        // findHeader: the FIRST string of that name
+            for (size_t i = 0; i < headers.size(); i++) if (headers[i] == header) { nstr = (int32_t)i; break; }
+            if (nstr < 0 || nstr >= b.n_strings) continue;
+            const int64_t len = nstr == 0 ? e[0] : e[(size_t)nstr] - e[(size_t)nstr - 1] - 1;   // GSSA.getLength :71-88
+            std::vector<uint8_t> seq((size_t)std::max<int64_t>(len, 0));
+            int64_t from = 0;
+            do {                                                                      // SequenceExtractor.run :155-174
+                int64_t w = 0;
+                GCZ_TRY_HOST(q.extract(b.idx, nstr, from, buf.data(), kBuffer, &w));
+                if (w <= 0) break;
+                const int64_t take = std::min(w, std::max<int64_t>(len - from, 0));
+                std::memcpy(seq.data() + from, buf.data(), (size_t)take);
+                from += w;
+            } while (from < len);
+            // FastaFileWriter.write(TFastaSequence) + FastaSequenceWriter.run: a break after every 50 symbols, one more at the end
+            std::string rec = ">" + header + "\n";
+            rec.reserve(rec.size() + (size_t)(len + len / kLine + 1));
+            for (int64_t i = 0; i < len; i += kLine) {
+                rec.append(reinterpret_cast<const char*>(seq.data() + i), (size_t)std::min(kLine, len - i));
+                rec.push_back('\n');
+            }
+            if (len % kLine == 0) rec.push_back('\n');
+            for (size_t done = 0; done < rec.size();) {
+                const ssize_t wr = ::write(fd, rec.data() + done, rec.size() - done);
+                if (wr <= 0) return fail(GCZ_E_ARG, "cannot write %s", fasta_path);
+                done += (size_t)wr;
+            }
+            count++;
+        }
+    }
+    if (n_sequences) *n_sequences = count;
+    return GCZ_OK;
+}
 
 }  // extern "C"

@@ -141,6 +141,36 @@ class Reader:
         N.check(N.lib().gcz_reader_open_block(self._h, b, device, C.byref(h)))
         return GSSA(h, device, self.block(b)["headers"])
 
+    def _text(self, rc: int, out: C.c_void_p, n: C.c_int64) -> list[str]:
+        N.check(rc)
+        try:
+            return C.string_at(out, n.value).decode("latin-1").splitlines()
+        finally:
+            N.lib().gcz_free(out)
+
+    def match(self, header: str | None, pattern: bytes, with_positions: bool = True, device: int = 0,
+              engine: N.QueryEngine | None = None) -> list[str]:
+        """GecoMatch.match / count (tools/GecoMatch.java:51-157): the lines the tool prints."""
+        out, n = C.c_void_p(), C.c_int64()
+        pat = np.frombuffer(bytes(pattern), dtype=np.uint8)
+        rc = N.lib().gcz_match(self._h, device, None if header is None else header.encode("latin-1"), N.ptr(pat), len(pat),
+                               1 if with_positions else 0, C.byref(engine) if engine is not None else None, C.byref(out), C.byref(n))
+        return self._text(rc, out, n)
+
+    def gff_search(self, patterns: bytes, device: int = 0, engine: N.QueryEngine | None = None) -> list[str]:
+        """SimpleGFFGenerator.search (tools/SimpleGFFGenerator.java:45-163) for the bytes of a pattern file."""
+        out, n = C.c_void_p(), C.c_int64()
+        data = np.frombuffer(bytes(patterns), dtype=np.uint8)
+        rc = N.lib().gcz_gff_search(self._h, device, N.ptr(data) if len(data) else None, len(data),
+                                    C.byref(engine) if engine is not None else None, C.byref(out), C.byref(n))
+        return self._text(rc, out, n)
+
+    def extract_fasta(self, path, device: int = 0, engine: N.QueryEngine | None = None) -> int:
+        """GecoRead.fasta (tools/GecoRead.java:83-175)."""
+        n = C.c_int64()
+        N.check(N.lib().gcz_extract_fasta(self._h, device, str(path).encode(), C.byref(engine) if engine is not None else None, C.byref(n)))
+        return n.value
+
     def close(self):
         if self._h:
             N.lib().gcz_reader_close(self._h)

@@ -82,6 +82,39 @@ int32_t gcz_reader_sampling_factor(const gcz_reader* r);                        
 int     gcz_reader_open_block(const gcz_reader* r, int32_t block, int device, gcz_index** out);
 void    gcz_reader_close(gcz_reader* r);
 
+/* ---- the callers: gecotools -c / -s / -s file / -o  --------------------------------------------------------------
+ * The query-side device work goes through a gcz_query_engine; NULL (or a NULL member) selects this library's CUDA
+ * entry points (gcz_open_block, gcz_find_batch, gcz_extract, ...).  Handles are opaque to the host layer. */
+typedef struct gcz_query_engine {
+    int  (*open_block)(int device, const uint8_t* gcz_body, int64_t body_len, int64_t text_len,
+                       const uint8_t* gcx_body, int64_t gcx_len, void** out);
+    void (*close_block)(void* idx);
+    int  (*num_strings)(const void* idx, int32_t* out);
+    int  (*string_ends)(const void* idx, int64_t* e);
+    int  (*find_batch)(void* idx, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats,
+                       int64_t* per_string_counts, int64_t** positions, int64_t** pos_off);
+    int  (*extract)(void* idx, int32_t nstr, int64_t from, uint8_t* out, int64_t cap, int64_t* written);
+    void (*release)(void* p);                    /* frees what find_batch allocated */
+} gcz_query_engine;
+
+/* GecoMatch.match / count  tools/GecoMatch.java:51-157: the lines the tool prints (">hdr found : k", then the 0-based
+ * positions when with_positions), '\n'-terminated, in *out_text (malloc'd, release with gcz_free).  header NULL:
+ * every block; else only the block that holds it and only that string (GCZ_E_ARG when there is none). */
+int gcz_match(const gcz_reader* r, int device, const char* header, const uint8_t* pattern, int64_t pattern_len,
+              int32_t with_positions, const gcz_query_engine* engine, char** out_text, int64_t* out_len);
+
+/* SimpleGFFGenerator.search  tools/SimpleGFFGenerator.java:45-163: every record of a FASTA/FASTQ pattern file (bytes in
+ * `patterns`), as given (U -> T) and reverse-complemented, against every block; one GFF line per occurrence in the
+ * reference's order.  The searches are batched: one find_batch call per block. */
+int gcz_gff_search(const gcz_reader* r, int device, const uint8_t* patterns, int64_t patterns_len,
+                   const gcz_query_engine* engine, char** out_text, int64_t* out_len);
+
+/* GecoRead.fasta  tools/GecoRead.java:83-175: every sequence of every block into a FASTA file — 4 MiB extract calls
+ * (SequenceExtractor :155-174), 50 symbols per line and one more line break at the end of a record
+ * (fasta/FastaFileWriter.java:132-215). */
+int gcz_extract_fasta(const gcz_reader* r, int device, const char* fasta_path, const gcz_query_engine* engine,
+                      int64_t* n_sequences);
+
 #ifdef __cplusplus
 }
 #endif

@@ -618,3 +618,21 @@ def test_native_writer_and_reader_on_the_gpu(G, O, tmp_path):
         assert res is not None and res[s] is not None and 100 in res[s].tolist()
         assert np.array_equal(g.extract(s, 50, 500), recs[2][1][50:550])
         g.close()
+
+
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: the same code passes on CPU with the "
+                                        "oracle as the query engine (tests/test_native_host_cpu.py); first hardware run pending")
+def test_native_callers_on_the_gpu(G, O, tmp_path):
+    """gcz_match / gcz_gff_search / gcz_extract_fasta with the library's own CUDA entry points as the engine."""
+    from gecoz_b200 import geco_match, geco_read, native_file as NF
+    recs, info = _small_genome(tmp_path, G)
+    pat = recs[0][1][100:112].tobytes()
+    fa = tmp_path / "p.fa"
+    fa.write_bytes(b">p1|note\n" + recs[2][1][50:80].tobytes() + b"\n>p2\n" + recs[0][1][10:40].tobytes() + b"\n")
+    with NF.Reader(tmp_path / "g.gcz") as r:
+        assert r.match(None, pat, True) == geco_match.match(tmp_path / "g.gcz", None, pat)
+        assert r.match(recs[0][0], pat, False) == geco_match.count(tmp_path / "g.gcz", recs[0][0], pat)
+        assert r.gff_search(fa.read_bytes()) == geco_match.search(tmp_path / "g.gcz", fa)
+        assert r.extract_fasta(tmp_path / "native.fa") == len(recs)
+    geco_read.fasta(tmp_path / "g.gcz", tmp_path / "python.fa")
+    assert (tmp_path / "native.fa").read_bytes() == (tmp_path / "python.fa").read_bytes()

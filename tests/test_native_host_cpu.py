@@ -153,7 +153,7 @@ def _oracle_engine(fail_first_build_with=None):
 
     def count(device, text, n, counts):
         t = np.ctypeslib.as_array(C.cast(text, C.POINTER(C.c_uint8)), shape=(n,))
-        c = np.bincount(t, minlength=256).astype(np.int64)
+        c = np.bincount(t, minlength=256).astype(np.int64)                                    # kept alive across the copy
         C.memmove(counts, c.ctypes.data, 256 * 8)
         return 0
 
@@ -229,3 +229,169 @@ def test_native_writer_retries_a_block_that_ran_out_of_memory(tmp_path):
 def test_native_writer_empty_input(tmp_path):
     with NF.Fasta(b"no records here\n") as f, pytest.raises(N.GczError, match="no data found"):
         NF.index(f, tmp_path / "e.gcz", engine=_oracle_engine()[0])
+
+
+# ---- the callers (gcz_match, gcz_gff_search, gcz_extract_fasta) with the oracle as the query engine ---------------------
+class _OracleQueryEngine:
+    """gcz_query_engine whose members call the oracle: lets the native callers run without a GPU."""
+
+    def __init__(self):
+        self.libc = C.CDLL(None)
+        self.libc.malloc.restype = C.c_void_p
+        self.libc.malloc.argtypes = [C.c_size_t]
+        self.libc.free.argtypes = [C.c_void_p]
+        self.open = {}
+        self.next_id = 1
+        E = N.QueryEngine
+        types = dict(E._fields_)
+        self.struct = E(types["open_block"](self._open), types["close_block"](self._close), types["num_strings"](self._num_strings),
+                        types["string_ends"](self._string_ends), types["find_batch"](self._find), types["extract"](self._extract),
+                        types["release"](self._release))
+
+    def _open(self, device, gcz, gcz_len, text_len, gcx, gcx_len, out):
+        a = np.ctypeslib.as_array(C.cast(gcz, C.POINTER(C.c_uint8)), shape=(gcz_len,)).copy()
+        b = np.ctypeslib.as_array(C.cast(gcx, C.POINTER(C.c_uint8)), shape=(gcx_len,)).copy()
+        self.open[self.next_id] = O.GSSA(a, text_len, b)
+        out[0] = self.next_id
+        self.next_id += 1
+        return 0
+
+    def _close(self, h):
+        self.open.pop(h).close()
+
+    def _num_strings(self, h, out):
+        out[0] = self.open[h].n_strings
+        return 0
+
+    def _string_ends(self, h, e):
+        ends = self.open[h].string_ends()
+        C.memmove(e, ends.ctypes.data, ends.nbytes)
+        return 0
+
+    def _find(self, h, pats, off, n, per, pos_out, off_out):
+        g = self.open[h]
+        o = np.ctypeslib.as_array(off, shape=(n + 1,))
+        data = np.ctypeslib.as_array(C.cast(pats, C.POINTER(C.c_uint8)), shape=(max(int(o[n]), 1),))
+        counts, positions, offs = [], [], [0]
+        for i in range(n):
+            res = g.find(data[o[i]:o[i + 1]].tobytes())
+            row = [0] * g.n_strings
+            if res is not None:
+                for s, a in enumerate(res):
+                    if a is not None:
+                        row[s] = len(a)
+                        positions.extend(int(x) for x in a)
+            counts.extend(row)
+            offs.append(len(positions))
+        for k, v in enumerate(counts):
+            per[k] = v
+        pbuf = self.libc.malloc(8 * max(len(positions), 1))
+        obuf = self.libc.malloc(8 * (n + 1))
+        parr, oarr = np.asarray(positions + [0], np.int64), np.asarray(offs, np.int64)      # kept alive across the copies
+        C.memmove(pbuf, parr.ctypes.data, 8 * max(len(positions), 1))
+        C.memmove(obuf, oarr.ctypes.data, 8 * (n + 1))
+        pos_out[0], off_out[0] = pbuf, obuf
+        return 0
+
+    def _extract(self, h, nstr, start, out, cap, written):
+        try:
+            got = self.open[h].extract(nstr, start, cap)
+        except (ValueError, IndexError):
+            return N.GCZ_E_RANGE
+        C.memmove(out, got.ctypes.data, len(got))
+        written[0] = len(got)
+        return 0
+
+    def _release(self, p):
+        self.libc.free(p)
+
+
+@pytest.fixture(scope="module")
+def small_index(tmp_path_factory):
+    d = tmp_path_factory.mktemp("native_callers")
+    recs = [(f"chr{i} test", synth.iid_acgtn(int(ln), 60 + i, p_n=0.0)) for i, ln in enumerate([4_000, 2_500, 1_200, 1_100, 150, 100])]
+    _write_fasta(d / "g.fa", recs)
+    eng, _ = _oracle_engine()
+    with NF.Fasta(d / "g.fa") as f:
+        NF.index(f, d / "g.gcz", engine=eng)
+    _, _, blocks = O.write_files([(h, s.tobytes()) for h, s in recs])
+    oracle_blocks = []
+    for ids in blocks:
+        text = synth.block_of([recs[i][1] for i in ids])
+        r = O.build_block(text, 32)
+        oracle_blocks.append(([recs[i][0] for i in ids], O.GSSA(r["gcz_body"], len(text), r["gcx_body"])))
+    return d, recs, oracle_blocks
+
+
+def test_native_match_lines(small_index):
+    d, recs, blocks = small_index
+    q = _OracleQueryEngine()
+    pats = [recs[0][1][100:108].tobytes(), recs[3][1][5:11].tobytes(), recs[5][1][:4].tobytes(), b"ACGTACGTACGTACGTACGTAC", b"A"]
+    with NF.Reader(d / "g.gcz") as r:
+        for pat in pats:
+            for want_pos in (False, True):
+                exp = []
+                for headers, og in blocks:
+                    res = og.find(pat)
+                    for h, a in zip(headers, res or []):
+                        if a is not None and len(a):
+                            exp.append(f">{h} found : {len(a)}")
+                            if want_pos:
+                                exp += [str(int(p)) for p in a]
+                assert r.match(None, pat, want_pos, engine=q.struct) == exp
+        hdr = recs[3][0]
+        headers, og = next(b for b in blocks if hdr in b[0])
+        res = og.find(pats[1])
+        a = res[headers.index(hdr)] if res is not None else None
+        exp = ([f">{hdr} found : {len(a)}"] + [str(int(p)) for p in a]) if a is not None and len(a) else []
+        assert r.match(hdr, pats[1], True, engine=q.struct) == exp
+        with pytest.raises(N.GczError):
+            r.match("chrZ", b"ACGT", engine=q.struct)
+    assert not q.open                                                       # every block was closed again
+
+
+def test_native_gff_lines(small_index):
+    from gecoz_b200.geco_match import _attributes
+    d, recs, blocks = small_index
+    q = _OracleQueryEngine()
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    s0, s2 = recs[0][1], recs[2][1]
+    pats = [("p1|first note|second", s0[200:230].tobytes()), ("rna", s0[300:320].tobytes().replace(b"T", b"U")),
+            ("revcomp|", s2[50:75].tobytes().translate(comp)[::-1]), ("absent", b"ACGT" * 9), ("|", s2[10:22].tobytes()), ("short", b"ACG")]
+    data = b""
+    for i, (h, s) in enumerate(pats):
+        data += (b"@" + h.encode() + b"\r\n" + s[:10] + b"\r\n" + s[10:] + b"\n+\n" + b"I" * len(s) + b"\n") if i == 1 else (b">" + h.encode() + b"\n" + s + b"\n")
+    data += b">empty\n>last\nACGTAC"
+    exp = []
+    for h, s in pats + [("last", b"ACGTAC")]:
+        fwd = s.replace(b"U", b"T")
+        for strand, seq in (("+", fwd), ("-", fwd.translate(comp)[::-1])):
+            for headers, og in blocks:
+                res = og.find(seq)
+                for name, a in zip(headers, res or []):
+                    if a is not None:
+                        exp += [f"{name}\tgecotools\tdna\t{int(p) + 1}\t{int(p) + len(seq)}\t1.000\t{strand}\t.\t{_attributes(h)}" for p in a]
+    with NF.Reader(d / "g.gcz") as r:
+        got = r.gff_search(data, engine=q.struct)
+        assert r.gff_search(b"", engine=q.struct) == []
+    assert got == exp and len(got) > 10
+
+
+def test_native_extract_fasta(small_index, tmp_path):
+    d, recs, blocks = small_index
+    q = _OracleQueryEngine()
+    with NF.Reader(d / "g.gcz") as r:
+        assert r.extract_fasta(tmp_path / "out.fa", engine=q.struct) == len(recs)
+    from gecoz_b200.geco_read import fasta_record_bytes
+    exp = b""
+    for headers, og in blocks:
+        ends = og.string_ends()
+        for nstr, h in enumerate(headers):
+            length = int(ends[nstr] - (ends[nstr - 1] + 1 if nstr else 0))
+            exp += fasta_record_bytes(h, og.extract(nstr, 0, 4 * 1024 * 1024)[:length])
+    assert (tmp_path / "out.fa").read_bytes() == exp
+    by_header = {h: s for h, s in recs}
+    with NF.Fasta(tmp_path / "out.fa") as f:                               # single-string blocks come back verbatim
+        back = dict(f.records())
+    first = blocks[0][0][0]
+    assert np.array_equal(back[first], by_header[first])
