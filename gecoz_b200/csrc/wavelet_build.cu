@@ -20,7 +20,6 @@ namespace {
 
 constexpr int kWarpTile = 1024;             // BWT positions per warp
 constexpr int kWtThreads = 256;             // 8 warps
-constexpr int kWtBlockTile = kWarpTile * (kWtThreads / 32);
 constexpr int kNoNode = 0xFFFF;
 
 // symbol tables of one block, resident in global memory for the duration of the build
@@ -579,7 +578,6 @@ int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_t
     std::memset(&h_tab, 0, sizeof(h_tab));
     std::memset(h_tab.dense, 0xFF, sizeof(h_tab.dense));
     int sigma = 0, max_len = 0;
-    int dense_to_byte[256];
     for (int c = 0; c < 256; c++) {
         if (shape->bit_lengths[c] > 0) {
             h_tab.dense[c] = (uint8_t)sigma;
@@ -587,10 +585,9 @@ int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_t
             h_tab.code[sigma] = (uint16_t)shape->codes[c];
             h_tab.len[sigma] = (uint8_t)shape->bit_lengths[c];
             max_len = std::max(max_len, (int)shape->bit_lengths[c]);
-            dense_to_byte[sigma++] = c;
+            sigma++;
         }
     }
-    (void)dense_to_byte;
     const int n_nodes = shape->n_nodes;
     if (n_nodes <= 0 || n_nodes > 255 || max_len > 15) return fail(GCZ_E_RANGE, "unsupported tree shape");
     for (int v = 0; v < n_nodes; v++) {
