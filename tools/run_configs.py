@@ -71,8 +71,29 @@ def main() -> None:
             print(json.dumps(d), flush=True)
 
     # ---- cfg3: sharded build ---------------------------------------------------------------------------------------
+    # sequences are synthesised on demand, so that a rank only pays for the blocks it builds (eight GPUs must not wait
+    # for eight copies of the same host work)
+    class LazySequence:
+        def __init__(self, length, seed):
+            self.length, self.seed, self._data = length, seed, None
+
+        def __len__(self):
+            return self.length
+
+        def __call__(self):
+            if self._data is None:
+                self._data = synth.chromosome_shaped(self.length, self.seed)
+            return self._data
+
     t0 = time.perf_counter()
-    recs = synth.hg38_shaped_records(args.scale)
+    recs = [(name, LazySequence(max(8, int(length * args.scale)), 4 + i))
+            for i, (name, length) in enumerate(zip(synth.HG38_NAMES, synth.HG38_LENGTHS))]
+    from gecoz_b200.geco_index import FastaSequence, merge_blocks
+    plan = merge_blocks([FastaSequence(h, len(s), None, i) for i, (h, s) in enumerate(recs)])
+    for b, r in zip(plan, sharding.lpt_assign([b.size for b in plan], world)):
+        if r == rank:
+            for seq in b.sequences:
+                recs[seq.id][1]()                         # my blocks' sequences exist before the clock starts
     gen_s = time.perf_counter() - t0
     bases = sum(len(s) for _, s in recs)
     if world > 1:
@@ -105,10 +126,26 @@ def main() -> None:
     open_s = time.perf_counter() - t0
     by_header = {h: s for h, s in recs}
 
+    # A few distinct chunks, drawn once on rank 0 and broadcast, are cycled through: pattern synthesis on the host is
+    # slower than the searches and must not run on every rank while the GPUs are held.
+    distinct = {}
+
     def pattern_chunk(i: int, count: int):
-        # half of each chunk sampled from one sequence (rotating), half random
-        name = synth.HG38_NAMES[i % 24]
-        return synth.patterns(by_header[name], count, 15, 100, seed=5000 + i)
+        key = (i % 3, count)
+        if key not in distinct:
+            if rank == 0:
+                name = synth.HG38_NAMES[(i % 3) * 7 % 24]
+                data, off = synth.patterns(by_header[name](), count, 15, 100, seed=5000 + i % 3)
+            if world > 1:
+                size = torch.tensor([len(data) if rank == 0 else 0], dtype=torch.int64, device=dev)
+                dist.broadcast(size, 0)
+                t_data = torch.from_numpy(data).to(dev) if rank == 0 else torch.empty(int(size.item()), dtype=torch.uint8, device=dev)
+                t_off = torch.from_numpy(off).to(dev) if rank == 0 else torch.empty(count + 1, dtype=torch.int64, device=dev)
+                dist.broadcast(t_data, 0)
+                dist.broadcast(t_off, 0)
+                data, off = t_data.cpu().numpy(), t_off.cpu().numpy()
+            distinct[key] = (data, off)
+        return distinct[key]
 
     # ---- cfg4: count ---------------------------------------------------------------------------------------------------
     done, found, ms = 0, 0, 0.0
@@ -167,7 +204,7 @@ def main() -> None:
     g11 = gssas[bheaders.index(bh)]
     nstr = bh.findHeader("chr11")
     cnt = min(args.chunk, args.locate_patterns)
-    data, off = synth.patterns(by_header["chr11"], cnt, 15, 100, seed=77)
+    data, off = synth.patterns(by_header["chr11"](), cnt, 15, 100, seed=77)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     per, pos, poff = g11.find_batch_raw(packed=(data, off))
