@@ -7,6 +7,8 @@
 
 #include <cuda_runtime.h>
 
+#include <dlfcn.h>
+
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -110,6 +112,7 @@ void scan_fasta(const uint8_t* buf, int64_t size, std::vector<FastaRecord>& out)
 
 struct gcz_fasta {
     std::unique_ptr<gcz::MappedFile> file;
+    std::vector<uint8_t> inflated;                 // gzipped input: the decompressed bytes
     const uint8_t* data = nullptr;
     int64_t size = 0;
     std::vector<gcz::FastaRecord> records;
@@ -285,8 +288,29 @@ int gcz_fasta_open(const char* path, gcz_fasta** out) {
     GCZ_TRY_HOST(f->file->open_ro(path));
     f->data = f->file->data;
     f->size = f->file->size;
-    if (f->size >= 2 && f->data[0] == 0x1f && f->data[1] == 0x8b)
-        return fail(GCZ_E_FORMAT, "%s is gzipped: decompress it on the host side and use gcz_fasta_open_buffer", path);
+    if (f->size >= 2 && f->data[0] == 0x1f && f->data[1] == 0x8b) {
+        // FastaFileReader(Path) probes for GZIP (fasta/FastaFileReader.java:71-81) and then reads the decompressed stream
+        // (lazy loading is off for gzipped files).  nova-gzip's job in the reference; zlib here — host I/O either way.
+        // zlib is looked up at run time: the library itself must load on a machine without it
+        void* z = dlopen("libz.so.1", RTLD_NOW | RTLD_LOCAL);
+        if (!z) return fail(GCZ_E_FORMAT, "%s is gzipped and libz.so.1 is not available: decompress it and use gcz_fasta_open_buffer", path);
+        auto z_open = reinterpret_cast<void* (*)(const char*, const char*)>(dlsym(z, "gzopen"));
+        auto z_read = reinterpret_cast<int (*)(void*, void*, unsigned)>(dlsym(z, "gzread"));
+        auto z_close = reinterpret_cast<int (*)(void*)>(dlsym(z, "gzclose"));
+        if (!z_open || !z_read || !z_close) { dlclose(z); return fail(GCZ_E_FORMAT, "libz.so.1 lacks the gz* functions"); }
+        void* gz = z_open(path, "rb");
+        if (!gz) { dlclose(z); return fail(GCZ_E_ARG, "cannot open %s", path); }
+        std::vector<uint8_t> chunk((size_t)8 << 20);
+        int got;
+        while ((got = z_read(gz, chunk.data(), (unsigned)chunk.size())) > 0) f->inflated.insert(f->inflated.end(), chunk.begin(), chunk.begin() + got);
+        const bool bad = got < 0;
+        z_close(gz);
+        dlclose(z);
+        if (bad) return fail(GCZ_E_FORMAT, "%s: corrupt gzip stream", path);
+        f->file.reset();
+        f->data = f->inflated.data();
+        f->size = (int64_t)f->inflated.size();
+    }
     scan_fasta(f->data, f->size, f->records);
     *out = f.release();
     return GCZ_OK;

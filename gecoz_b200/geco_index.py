@@ -118,15 +118,17 @@ def merge_blocks(sequences: Sequence[FastaSequence]) -> list[GecozRefBlock]:
 
 # ---- FASTA (host I/O; stays on the CPU like nova-gzip / fasta in the reference) -------------------------------
 def read_fasta(path) -> Iterator[tuple[str, bytes]]:
-    """Records as the reference sees them (fasta/FastaIterator.java:39-127, fasta/FastaFileReader.java:109-160): the
+    """Records as the reference sees them (fasta/FastaIterator.java:39-127, fasta/FastaFileReader.java:71-160): the
     native record scanner (csrc/host_file.cpp) is the one implementation of that state machine; gzipped files are
-    decompressed here first (nova-gzip's job in the reference; it stays on the host)."""
+    decompressed on the host (nova-gzip's job in the reference), by the scanner's zlib or, failing that, here."""
+    from . import _native as N
     from .native_file import Fasta
     path = Path(path)
-    with open(path, "rb") as f:
-        magic = f.read(2)
-    source = gzip.open(path, "rb").read() if magic == b"\x1f\x8b" else path
-    with Fasta(source) as fasta:
+    try:
+        fasta = Fasta(path)
+    except N.GczFormatError:
+        fasta = Fasta(gzip.open(path, "rb").read())
+    with fasta:
         for i in range(len(fasta)):
             yield fasta.record(i)[0], fasta.read(i).tobytes()
 

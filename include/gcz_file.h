@@ -7,8 +7,9 @@
  *   tools/ = nova-gecoz/src/main/java/es/elixir/bsc/ngs/nova/gecoz/tools/
  * Same conventions as gcz.h (0 / negative gcz_status, gcz_last_error()).  The per-block device work goes through a
  * gcz_engine; NULL selects this library's CUDA entry points (gcz_count_symbols, gcz_build_block) — the tests on a
- * machine without a GPU pass an engine of their own to exercise the host logic.  Gzipped FASTA is not read here
- * (nova-gzip stays on the host side of the caller): hand the decompressed bytes to gcz_fasta_open_buffer.
+ * machine without a GPU pass an engine of their own to exercise the host logic.  Gzipped FASTA (nova-gzip in the
+ * reference; host I/O either way) is inflated with zlib, looked up at run time; without libz.so.1 gcz_fasta_open
+ * fails with GCZ_E_FORMAT and the caller hands the decompressed bytes to gcz_fasta_open_buffer.
  */
 #ifndef GCZ_FILE_H
 #define GCZ_FILE_H
