@@ -303,8 +303,7 @@ int gcz_fasta_open(const char* path, gcz_fasta** out) {
         std::vector<uint8_t> chunk((size_t)8 << 20);
         int got;
         while ((got = z_read(gz, chunk.data(), (unsigned)chunk.size())) > 0) f->inflated.insert(f->inflated.end(), chunk.begin(), chunk.begin() + got);
-        const bool bad = got < 0;
-        z_close(gz);
+        const bool bad = z_close(gz) != 0 || got < 0;           // gzclose reports a stream that ended early
         dlclose(z);
         if (bad) return fail(GCZ_E_FORMAT, "%s: corrupt gzip stream", path);
         f->file.reset();
