@@ -187,3 +187,27 @@ def test_fasta_record_layout():
         lines = body.split(b"\n")
         assert b"".join(lines) == seq.tobytes()
         assert all(len(x) == 50 for x in lines[:n // 50])
+
+
+def test_headers_are_plain_c_and_the_c_example_links(tmp_path):
+    """include/*.h must be usable from C (the Java/JNI side and any other FFI bind the same symbols); the example
+    program links against the library and, without a device, fails loudly instead of computing on the CPU."""
+    import shutil
+    import subprocess
+    import torch
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    for h in ("gcz.h", "gcz_file.h"):
+        subprocess.run([gcc, "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c",
+                        str(ROOT / "include" / h)], check=True)
+    exe = tmp_path / "index_and_count"
+    subprocess.run([gcc, "-std=c11", "-Wall", "-Werror", f"-I{ROOT / 'include'}", str(ROOT / "examples" / "index_and_count.c"),
+                    f"-L{ROOT / 'gecoz_b200'}", "-lgcz_b200", f"-Wl,-rpath,{ROOT / 'gecoz_b200'}", "-o", str(exe)], check=True)
+    fa = tmp_path / "t.fa"
+    fa.write_bytes(b">s\nACGTACGTTTGACA\n")
+    r = subprocess.run([str(exe), str(fa), str(tmp_path / "t.gcz"), "ACGT"], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and ">s found : 2" in r.stdout
+    else:
+        assert r.returncode == 1 and "no CPU path" in r.stderr
