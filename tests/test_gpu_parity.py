@@ -5,6 +5,7 @@ BASELINE.json full sizes are covered by size-independent properties in test_gpu_
 """
 import ctypes as C
 import json
+import os
 from pathlib import Path
 
 import numpy as np
@@ -620,8 +621,9 @@ def test_native_writer_and_reader_on_the_gpu(G, O, tmp_path):
         g.close()
 
 
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: the same code passes on CPU with the "
-                                        "oracle as the query engine (tests/test_native_host_cpu.py); first hardware run pending")
+@pytest.mark.skipif(os.environ.get("GCZ_TEST_PENDING") != "1",
+                    reason="written after the round's GPU budget was spent: the same code passes on CPU with the oracle as the query "
+                           "engine (tests/test_native_host_cpu.py); set GCZ_TEST_PENDING=1 for its first hardware run")
 def test_native_callers_on_the_gpu(G, O, tmp_path):
     """gcz_match / gcz_gff_search / gcz_extract_fasta with the library's own CUDA entry points as the engine."""
     from gecoz_b200 import geco_match, geco_read, native_file as NF
