@@ -81,23 +81,30 @@ def patterns(text: np.ndarray, count: int, min_len: int, max_len: int, seed: int
     data = ACGT[rng.integers(0, 4, int(off[-1]), dtype=np.uint8)]
     n = len(text)
     from_text = np.flatnonzero(rng.random(count) < 0.5)
-    bad = (text == N) | (text == 0)
-    cum_bad = np.concatenate([[0], np.cumsum(bad, dtype=np.int64)])
+    bad_pos = np.flatnonzero((text == N) | (text == 0))  # sorted; a window [s, e) is clean when no position falls in it
+
+    def touches_bad(s, e):
+        return np.searchsorted(bad_pos, s) != np.searchsorted(bad_pos, e)
+
     starts = rng.integers(0, max(1, n - max_len - 1), len(from_text))
+    tlen = lens[from_text]
+    check = np.arange(len(starts))                       # windows not yet known to be clean
     for _ in range(8):                                   # re-draw windows that touch N / '\0'
-        ends = np.minimum(starts + lens[from_text], n)
-        dirty = (cum_bad[ends] - cum_bad[starts]) > 0
-        if not dirty.any():
+        s_c = starts[check]
+        check = check[touches_bad(s_c, np.minimum(s_c + tlen[check], n))]
+        if not len(check):
             break
-        starts[dirty] = rng.integers(0, max(1, n - max_len - 1), int(dirty.sum()))
-    ends = np.minimum(starts + lens[from_text], n)
-    clean = (cum_bad[ends] - cum_bad[starts]) == 0
+        starts[check] = rng.integers(0, max(1, n - max_len - 1), len(check))
+    clean = np.ones(len(starts), dtype=bool)
+    if len(check):
+        s_c = starts[check]
+        clean[check] = ~touches_bad(s_c, np.minimum(s_c + tlen[check], n))
     sel, st = from_text[clean], starts[clean]
-    if len(sel):
-        ln = lens[sel]
-        tot = int(ln.sum())
-        first = np.zeros(len(sel), dtype=np.int64)
+    for c in range(0, len(sel), 1 << 18):                # bounded temporaries: 256 K patterns at a time
+        s_c, st_c = sel[c:c + (1 << 18)], st[c:c + (1 << 18)]
+        ln = lens[s_c]
+        first = np.zeros(len(s_c), dtype=np.int64)
         np.cumsum(ln[:-1], out=first[1:])
-        within = np.arange(tot, dtype=np.int64) - np.repeat(first, ln)
-        data[np.repeat(off[sel], ln) + within] = text[np.repeat(st, ln) + within]
+        within = np.arange(int(ln.sum()), dtype=np.int64) - np.repeat(first, ln)
+        data[np.repeat(off[s_c], ln) + within] = text[np.repeat(st_c, ln) + within]
     return data, off
