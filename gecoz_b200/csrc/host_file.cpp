@@ -7,6 +7,10 @@
 
 #include <cuda_runtime.h>
 
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+
 #include <dlfcn.h>
 
 #include <fcntl.h>
@@ -15,8 +19,11 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <cerrno>
 #include <chrono>
 #include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -61,13 +68,48 @@ struct MappedFile {
 struct FastaRecord {
     std::string header;
     int64_t position = 0, length = 0;
+    int64_t span_end = 0;        // the sequence's characters are the non-CR/LF bytes of [position, span_end)
     bool multiline = false;
 };
 
-// The character-level state machine of fasta/FastaIterator.java:39-127, kept literal (hasNext :40-69, next :72-127):
-// which byte opens a record, what counts as sequence, how FASTQ qualities are skipped — all of it decides which
-// bytes end up in the index.
-void scan_fasta(const uint8_t* buf, int64_t size, std::vector<FastaRecord>& out) {
+// first byte of [p, end) that is one of the two, or end
+template <char A, char B>
+inline const uint8_t* find_either(const uint8_t* p, const uint8_t* end) {
+#if defined(__SSE2__)
+    const __m128i a = _mm_set1_epi8(A), b = _mm_set1_epi8(B);
+    while (p + 16 <= end) {
+        const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(p));
+        const int m = _mm_movemask_epi8(_mm_or_si128(_mm_cmpeq_epi8(v, a), _mm_cmpeq_epi8(v, b)));
+        if (m) return p + __builtin_ctz((unsigned)m);
+        p += 16;
+    }
+#endif
+    while (p < end && *p != (uint8_t)A && *p != (uint8_t)B) p++;
+    return p;
+}
+inline const uint8_t* find_eol(const uint8_t* p, const uint8_t* end) { return find_either<'\r', '\n'>(p, end); }
+
+// number of CR and LF bytes in [p, end)
+inline int64_t count_eol(const uint8_t* p, const uint8_t* end) {
+    int64_t c = 0;
+#if defined(__SSE2__)
+    const __m128i a = _mm_set1_epi8('\r'), b = _mm_set1_epi8('\n');
+    while (p + 16 <= end) {
+        const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(p));
+        c += __builtin_popcount((unsigned)_mm_movemask_epi8(_mm_or_si128(_mm_cmpeq_epi8(v, a), _mm_cmpeq_epi8(v, b))));
+        p += 16;
+    }
+#endif
+    for (; p < end; p++) c += (*p == '\r') | (*p == '\n');
+    return c;
+}
+
+// The character-level state machine of fasta/FastaIterator.java:39-127 (hasNext :40-69, next :72-127): which byte opens a
+// record, what counts as sequence, how FASTQ qualities are skipped — all of it decides which bytes end up in the index.
+// scan_fasta_literal reads one character at a time exactly like the Java code; scan_fasta is the same machine with its
+// three run loops (skip to the next record, one sequence line, one quality line) replaced by vector searches for the byte
+// that ends the run.  GCZ_FASTA_LITERAL=1 selects the literal one (the tests compare the two on adversarial inputs).
+void scan_fasta_literal(const uint8_t* buf, int64_t size, std::vector<FastaRecord>& out) {
     int64_t p = 0;
     auto rd = [&]() -> int { return p < size ? (int)buf[p++] : -1; };
     int ch = '\r';                                          // FastaIterator(InputStream, boolean) :33
@@ -90,6 +132,7 @@ void scan_fasta(const uint8_t* buf, int64_t size, std::vector<FastaRecord>& out)
             }
             posnew++;
         } while ((ch = rd()) >= 0 && ch != '>' && ch != '@' && ch != '+');
+        rec.span_end = ch >= 0 ? p - 1 : size;
         if (ch == '+') {                                                               // skip qualities :98-113
             int qlines = -1;
             int64_t qlength = 0;
@@ -102,6 +145,127 @@ void scan_fasta(const uint8_t* buf, int64_t size, std::vector<FastaRecord>& out)
         rec.position = position;
         rec.length = length;
         rec.multiline = lines > 1;
+        out.push_back(std::move(rec));
+        position = posnew;
+    }
+}
+
+// One sequence, as the machine's loop :81-96 sees it, without going line by line.  Every test for the character that ends
+// a sequence ('>', '@', '+') is made on the byte that follows a CR or LF (the first one follows the header's LF), so the
+// sequence region is [from, k) with k the first such byte whose predecessor is CR/LF, or the end of the input; `length` is
+// the number of non-CR/LF bytes in the region and `lines` the number of maximal runs of them.
+struct SliceScan { int64_t hit = -1, eol = 0, runs = 0; };      // hit: index of the ending byte in the slice, counts before it
+
+int host_threads();
+
+// [a, b) with a >= 1 (buf[a - 1] is read)
+SliceScan scan_slice(const uint8_t* buf, int64_t a, int64_t b) {
+    SliceScan r;
+    int64_t i = a;
+#if defined(__SSE2__)
+    const __m128i cr = _mm_set1_epi8('\r'), lf = _mm_set1_epi8('\n'), gt = _mm_set1_epi8('>'), at = _mm_set1_epi8('@'), plus = _mm_set1_epi8('+');
+    const __m128i zero = _mm_setzero_si128();
+    __m128i eol_acc = zero, run_acc = zero;
+    for (; i + 16 <= b; i += 16) {
+        const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(buf + i));
+        const __m128i w = _mm_loadu_si128(reinterpret_cast<const __m128i*>(buf + i - 1));          // the predecessors
+        const __m128i eol_v = _mm_or_si128(_mm_cmpeq_epi8(v, cr), _mm_cmpeq_epi8(v, lf));
+        const __m128i eol_w = _mm_or_si128(_mm_cmpeq_epi8(w, cr), _mm_cmpeq_epi8(w, lf));
+        const __m128i special = _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(v, gt), _mm_cmpeq_epi8(v, at)), _mm_cmpeq_epi8(v, plus));
+        if (_mm_movemask_epi8(_mm_and_si128(special, eol_w))) break;                               // finish this block one byte at a time
+        eol_acc = _mm_add_epi64(eol_acc, _mm_sad_epu8(_mm_sub_epi8(zero, eol_v), zero));           // 0xFF -> 1 per byte, summed
+        run_acc = _mm_add_epi64(run_acc, _mm_sad_epu8(_mm_sub_epi8(zero, _mm_andnot_si128(eol_v, eol_w)), zero));
+    }
+    uint64_t lanes[2];
+    _mm_storeu_si128(reinterpret_cast<__m128i*>(lanes), eol_acc);
+    r.eol = (int64_t)(lanes[0] + lanes[1]);
+    _mm_storeu_si128(reinterpret_cast<__m128i*>(lanes), run_acc);
+    r.runs = (int64_t)(lanes[0] + lanes[1]);
+#endif
+    for (; i < b; i++) {
+        const uint8_t c = buf[i], q = buf[i - 1];
+        const bool eol_c = c == '\r' || c == '\n', eol_q = q == '\r' || q == '\n';
+        if (eol_q && (c == '>' || c == '@' || c == '+')) { r.hit = i; return r; }
+        r.eol += eol_c;
+        r.runs += !eol_c && eol_q;
+    }
+    return r;
+}
+
+struct Region { int64_t end, length, lines; };
+
+// slice: bytes per thread and step; the first step is a short one on the calling thread
+Region scan_region(const uint8_t* buf, int64_t from, int64_t size, int64_t slice, int threads) {
+    int64_t eol = 0, runs = 0, at = from, hit = -1;
+    bool first = true;
+    while (at < size && hit < 0) {
+        const int64_t step = first || threads <= 1 ? std::min<int64_t>(slice / 8 + 1, size - at) : std::min<int64_t>(slice * threads, size - at);
+        if (first || threads <= 1) {                         // short sequences (reads, contigs) never leave this branch
+            const SliceScan r = scan_slice(buf, at, at + step);
+            eol += r.eol; runs += r.runs; hit = r.hit;
+        } else {
+            std::vector<SliceScan> part((size_t)threads);
+            std::vector<std::thread> pool;
+            for (int t = 0; t < threads; t++)
+                pool.emplace_back([&, t] { part[(size_t)t] = scan_slice(buf, at + step * t / threads, at + step * (t + 1) / threads); });
+            for (std::thread& th : pool) th.join();
+            for (int t = 0; t < threads && hit < 0; t++) { eol += part[(size_t)t].eol; runs += part[(size_t)t].runs; hit = part[(size_t)t].hit; }
+        }
+        first = false;
+        at += step;
+    }
+    const int64_t end = hit >= 0 ? hit : size;
+    return Region{ end, (end - from) - eol, runs };
+}
+
+void scan_fasta(const uint8_t* buf, int64_t size, std::vector<FastaRecord>& out) {
+    const char* lit = std::getenv("GCZ_FASTA_LITERAL");
+    if (lit && lit[0] == '1') { scan_fasta_literal(buf, size, out); return; }
+    const uint8_t* const end = buf + size;
+    const char* slice_env = std::getenv("GCZ_FASTA_SLICE");               // the tests shrink it to reach the threaded steps
+    const int64_t slice = slice_env && std::atoll(slice_env) > 0 ? (int64_t)std::atoll(slice_env) : (int64_t)8 << 20;
+    const int threads = host_threads();
+    int64_t p = 0;
+    auto rd = [&]() -> int { return p < size ? (int)buf[p++] : -1; };
+    // the reads of one run: everything up to the byte that ends it (consumed too), or up to the end of the input (where the
+    // machine's last read returns -1 and consumes nothing); returns how many bytes the run itself holds
+    auto run_to = [&](const uint8_t* stop, int& ch) -> int64_t {
+        const int64_t k = stop - buf, n = k - p;
+        if (k < size) { ch = buf[k]; p = k + 1; } else { ch = -1; p = size; }
+        return n;
+    };
+    int ch = '\r';
+    int64_t position = 0;
+    while (true) {
+        if (ch >= 0 && ch != '>' && ch != '@') position += run_to(find_either<'>', '@'>(buf + p, end), ch) + 1;    // hasNext :46-49
+        if (ch < 0) break;
+        FastaRecord rec;
+        while ((ch = rd()) >= 0 && ch != '\n') {                                       // :55-61
+            position++;
+            if (ch != '\r') rec.header.push_back((char)ch);
+        }
+        position++;
+        rec.position = position;
+        if (ch < 0) {                                                                  // the input ends inside the header line
+            rec.span_end = size;
+            out.push_back(std::move(rec));
+            break;
+        }
+        const Region seq = scan_region(buf, position, size, slice, threads);                           // next :81-96 (p == position here)
+        rec.span_end = seq.end;
+        rec.length = seq.length;
+        rec.multiline = seq.lines > 1;
+        int64_t posnew = seq.end + 1;                                                  // == p after the ending byte was read
+        run_to(buf + seq.end, ch);
+        if (ch == '+') {                                                               // skip qualities :98-113
+            int64_t qlines = -1, qlength = 0;
+            do {
+                const int64_t n = run_to(find_eol(buf + p, end), ch);
+                qlength += n;
+                posnew += n + 1;
+                qlines++;
+            } while (qlength < seq.length && qlines < seq.lines);
+        }
         out.push_back(std::move(rec));
         position = posnew;
     }
@@ -121,8 +285,55 @@ struct gcz_fasta {
 namespace gcz {
 namespace {
 
+// how many host threads the bulk loops (record scan, sequence assembly) may use: GCZ_HOST_THREADS, else the machine's, at most 16
+int host_threads() {
+    if (const char* e = std::getenv("GCZ_HOST_THREADS")) {
+        const int v = std::atoi(e);
+        if (v > 0) return std::min(v, 64);
+    }
+    const unsigned hw = std::thread::hardware_concurrency();
+    return (int)std::min(16u, std::max(1u, hw));
+}
+
+// the non-CR/LF bytes of [src, end) -> out, at most `want` of them; returns how many
+int64_t strip_eol(const uint8_t* src, const uint8_t* end, uint8_t* out, int64_t want) {
+    int64_t i = 0;
+    while (src < end && i < want) {
+        const uint8_t* e = find_eol(src, end);
+        const int64_t n = std::min<int64_t>(e - src, want - i);
+        std::memcpy(out + i, src, (size_t)n);
+        i += n;
+        src = e + 1;
+    }
+    return i;
+}
+
+// the same over `threads` pieces of the source: count per piece, prefix, copy per piece
+int64_t strip_eol_parallel(const uint8_t* src, const uint8_t* end, uint8_t* out, int64_t want, int threads) {
+    const int64_t bytes = end - src;
+    threads = (int)std::min<int64_t>(threads, bytes >> 22);                  // >= 4 MiB of source per thread
+    if (threads <= 1) return strip_eol(src, end, out, want);
+    std::vector<const uint8_t*> cut((size_t)threads + 1);
+    for (int t = 0; t <= threads; t++) cut[(size_t)t] = src + bytes * t / threads;
+    std::vector<int64_t> first((size_t)threads + 1, 0);
+    {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; t++)
+            pool.emplace_back([&, t] { first[(size_t)t + 1] = (cut[(size_t)t + 1] - cut[(size_t)t]) - count_eol(cut[(size_t)t], cut[(size_t)t + 1]); });
+        for (std::thread& th : pool) th.join();
+    }
+    for (int t = 0; t < threads; t++) first[(size_t)t + 1] += first[(size_t)t];
+    if (first[(size_t)threads] > want) return strip_eol(src, end, out, want);  // a buffer shorter than the sequence: in order
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++)
+        pool.emplace_back([&, t] { strip_eol(cut[(size_t)t], cut[(size_t)t + 1], out + first[(size_t)t], first[(size_t)t + 1] - first[(size_t)t]); });
+    for (std::thread& th : pool) th.join();
+    return first[(size_t)threads];
+}
+
 // FastaFileReader.read  fasta/FastaFileReader.java:109-160 (plain file): one-line sequences are `length` raw bytes
-// at `position`; multi-line ones are read from there with CR/LF dropped until `length` bytes are in
+// at `position`; multi-line ones are read from there with CR/LF dropped until `length` bytes are in — which are the
+// non-CR/LF bytes of [position, span_end) (scan_fasta)
 int64_t read_sequence(const gcz_fasta* f, const FastaRecord& r, uint8_t* out, int64_t cap) {
     const int64_t want = std::min(r.length, cap);
     if (!r.multiline) {
@@ -130,12 +341,7 @@ int64_t read_sequence(const gcz_fasta* f, const FastaRecord& r, uint8_t* out, in
         std::memcpy(out, f->data + r.position, (size_t)avail);
         return avail;
     }
-    int64_t i = 0;
-    for (int64_t p = r.position; i < want && p < f->size; p++) {
-        const uint8_t c = f->data[p];
-        if (c != '\r' && c != '\n') out[i++] = c;
-    }
-    return i;
+    return strip_eol_parallel(f->data + r.position, f->data + r.span_end, out, want, host_threads());
 }
 
 // ---- GecoIndex: one block per sequence, greedy merge, file order  tools/GecoIndex.java:57-98 ------------------------
@@ -239,43 +445,77 @@ std::string ssa_path_for(const std::string& ref) {                              
     return dir + name + "gcx";
 }
 
-// a writable mapping of file bytes [off, off + len)
-struct MappedSlice {
-    uint8_t* base = nullptr;
-    size_t mapped = 0;
+// host buffer: pinned when a CUDA device is there (full-speed DMA both ways), plain otherwise
+struct HostBuffer {
     uint8_t* data = nullptr;
-    int map(int fd, int64_t off, int64_t len) {
-        const int64_t page = sysconf(_SC_PAGESIZE);
-        const int64_t start = off - off % page;
-        mapped = (size_t)(len + (off - start));
-        if (mapped == 0) mapped = 1;
-        void* p = mmap(nullptr, mapped, PROT_READ | PROT_WRITE, MAP_SHARED, fd, start);
-        if (p == MAP_FAILED) return fail(GCZ_E_NOMEM, "cannot map %lld bytes of the output file", (long long)len);
-        base = static_cast<uint8_t*>(p);
-        data = base + (off - start);
-        return GCZ_OK;
+    size_t cap = 0;
+    bool pinned = false;
+    explicit HostBuffer(size_t bytes) : cap(bytes ? bytes : 1) {
+        if (cudaHostAlloc(reinterpret_cast<void**>(&data), cap, cudaHostAllocDefault) == cudaSuccess) { pinned = true; return; }
+        cudaGetLastError();
+        data = static_cast<uint8_t*>(std::malloc(cap));
     }
-    ~MappedSlice() { if (base) munmap(base, mapped); }
+    ~HostBuffer() { if (pinned) cudaFreeHost(data); else std::free(data); }
+    HostBuffer(const HostBuffer&) = delete;
+    HostBuffer& operator=(const HostBuffer&) = delete;
 };
 
-// host buffer for one block's text: pinned when a CUDA device is there (full-speed DMA), plain otherwise
-struct TextBuffer {
-    uint8_t* data = nullptr;
-    bool pinned = false;
-    explicit TextBuffer(size_t bytes) {
-        if (cudaHostAlloc(reinterpret_cast<void**>(&data), bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess) { pinned = true; return; }
-        cudaGetLastError();
-        data = static_cast<uint8_t*>(std::malloc(bytes ? bytes : 1));
+// Buffers of one kind, reused from block to block: pinning a quarter of a gigabyte costs more than building the block.
+// At most `limit` are out at a time (take() waits); a returned buffer that is too small for the next request is dropped.
+class BufferPool {
+public:
+    explicit BufferPool(size_t limit) : limit_(limit) {}
+    std::unique_ptr<HostBuffer> take(size_t bytes) {
+        std::unique_lock<std::mutex> l(mu_);
+        cv_.wait(l, [&] { return out_ < limit_; });
+        out_++;
+        size_t best = free_.size();
+        for (size_t i = 0; i < free_.size(); i++)
+            if (free_[i]->cap >= bytes && (best == free_.size() || free_[i]->cap < free_[best]->cap)) best = i;
+        if (best < free_.size()) {
+            std::unique_ptr<HostBuffer> b = std::move(free_[best]);
+            free_.erase(free_.begin() + (long)best);
+            return b;
+        }
+        free_.clear();                                      // all too small: their memory goes first
+        largest_ = std::max(largest_, bytes);
+        l.unlock();
+        return std::unique_ptr<HostBuffer>(new HostBuffer(largest_));
     }
-    ~TextBuffer() { if (pinned) cudaFreeHost(data); else std::free(data); }
-    TextBuffer(const TextBuffer&) = delete;
-    TextBuffer& operator=(const TextBuffer&) = delete;
+    void expect(size_t bytes) { std::lock_guard<std::mutex> l(mu_); largest_ = std::max(largest_, bytes); }
+    void give(std::unique_ptr<HostBuffer> b) {
+        std::lock_guard<std::mutex> l(mu_);
+        if (b && b->data) free_.push_back(std::move(b));
+        out_--;
+        cv_.notify_all();
+    }
+private:
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::vector<std::unique_ptr<HostBuffer>> free_;
+    size_t limit_, out_ = 0, largest_ = 0;
 };
+
+// all of buf[0, len) at file offset off
+bool write_fully(int fd, const uint8_t* buf, int64_t len, int64_t off) {
+    while (len > 0) {
+        const ssize_t w = pwrite(fd, buf, (size_t)std::min<int64_t>(len, (int64_t)1 << 30), off);
+        if (w < 0 && errno == EINTR) continue;
+        if (w <= 0) return false;
+        buf += w; off += w; len -= w;
+    }
+    return true;
+}
 
 }  // namespace
 }  // namespace gcz
 
 using namespace gcz;
+
+namespace {
+bool host_trace() { static const bool on = [] { const char* e = std::getenv("GCZ_HOST_TRACE"); return e && e[0] == '1'; }(); return on; }
+double seconds_since(std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); }
+}  // namespace
 
 // =====================================================================================================================
 extern "C" {
@@ -434,6 +674,18 @@ int gcz_index_fasta(const gcz_fasta* fasta, const char* gcz_path, const char* gc
     std::vector<std::thread> workers;
     int64_t ref_pos = 0, ssa_pos = 0, symbols = 0, sequences = 0;
 
+    // One text buffer per token, sized for the largest block.  The bodies come back into buffers of a second pool and go
+    // to the files with pwrite AFTER the device token is released: writing into the page cache is the slow part of the host
+    // side (about 2 GB/s per thread) and must not sit between two builds.
+    int64_t largest = 0;
+    for (const Block& block : blocks) {
+        int64_t n = 0;
+        for (const Seq& s : block.sequences) n += s.length + 1;
+        largest = std::max(largest, n);
+    }
+    BufferPool texts(all_tokens), bodies(all_tokens + 2);
+    texts.expect((size_t)largest);
+
     auto release = [&](int d) { std::lock_guard<std::mutex> l(mu); free_tokens.push_back(d); cv.notify_all(); };
     auto record_error = [&](int rc) {
         std::lock_guard<std::mutex> l(mu);
@@ -455,7 +707,9 @@ int gcz_index_fasta(const gcz_fasta* fasta, const char* gcz_path, const char* gc
         // writeBlock (tools/GecoIndex.java:119-146): the member sequences in block order, each followed by '\0'
         int64_t n = 0;
         for (const Seq& s : block.sequences) n += s.length + 1;
-        std::shared_ptr<TextBuffer> text(new TextBuffer((size_t)n));
+        auto t0 = std::chrono::steady_clock::now();
+        std::shared_ptr<HostBuffer> text(texts.take((size_t)n).release(), [&texts](HostBuffer* b) { texts.give(std::unique_ptr<HostBuffer>(b)); });
+        const double t_alloc = seconds_since(t0);
         if (!text->data) { release(device); record_error(fail(GCZ_E_NOMEM, "host buffer of %lld bytes", (long long)n)); break; }
         std::vector<const char*> hdrs;
         int64_t p = 0;
@@ -465,10 +719,12 @@ int gcz_index_fasta(const gcz_fasta* fasta, const char* gcz_path, const char* gc
             text->data[p++] = 0;
             hdrs.push_back(s.header);
         }
+        const double t_read = seconds_since(t0) - t_alloc;
         // GecozFileWriter.write (fmt/GecozFileWriter.java:124-159): counts, shape, slices, headers, queue the block
         int64_t counts[256];
         std::shared_ptr<gcz_shape> shape(new gcz_shape());
         int rc = eng.count_symbols(device, text->data, n, counts);
+        const double t_count = seconds_since(t0) - t_alloc - t_read;
         if (rc == GCZ_OK) rc = gcz_shape_from_counts(counts, shape.get());
         if (rc != GCZ_OK) { release(device); record_error(rc); break; }
         const int64_t hlen = ref_header_length(hdrs.data(), (int32_t)hdrs.size());
@@ -476,37 +732,46 @@ int gcz_index_fasta(const gcz_fasta* fasta, const char* gcz_path, const char* gc
         const int64_t my_ref = ref_pos, my_ssa = ssa_pos;
         ref_pos += hlen + shape->size;
         ssa_pos += 25 + idx_size;
-        std::vector<uint8_t> hb((size_t)hlen);
-        uint8_t sb[25];
+        std::vector<uint8_t> hb((size_t)hlen), sb(25);
         gcz_ref_header_write(hdrs.data(), (int32_t)hdrs.size(), hlen + shape->size, n, hb.data(), hlen);
-        gcz_ssa_header_write(hdrs.data(), (int32_t)hdrs.size(), idx_size, sb);
-        if (ftruncate(ref_fd, ref_pos) != 0 || ftruncate(ssa_fd, ssa_pos) != 0 ||
-            pwrite(ref_fd, hb.data(), (size_t)hlen, my_ref) != hlen || pwrite(ssa_fd, sb, 25, my_ssa) != 25) {
-            release(device);
-            record_error(fail(GCZ_E_ARG, "cannot write %s / %s", ref_path.c_str(), ssa_path.c_str()));
-            break;
-        }
+        gcz_ssa_header_write(hdrs.data(), (int32_t)hdrs.size(), idx_size, sb.data());
         symbols += n;
         sequences += (int64_t)block.sequences.size();
+        if (host_trace())
+            std::fprintf(stderr, "[gcz host] block n=%lld: buffer %.1f ms, assemble %.1f ms, count %.1f ms\n", (long long)n,
+                         t_alloc * 1e3, t_read * 1e3, t_count * 1e3);
         // BlockWriter.run (:256-284) on its own thread; GCZ_E_NOMEM: once more when nothing else is in flight
         // (WriterPoolExecutor.afterExecute :203-226)
-        workers.emplace_back([&, device, text, shape, n, my_ref, my_ssa, hlen, idx_size] {
-            int attempts = 0;
-            while (true) {
-                MappedSlice ref_map, ssa_map;
-                int rc2 = ref_map.map(ref_fd, my_ref + hlen, shape->size);
-                if (rc2 == GCZ_OK) rc2 = ssa_map.map(ssa_fd, my_ssa + 25, idx_size);
-                if (rc2 == GCZ_OK) rc2 = eng.build_block(device, text->data, n, sampling_rate, shape.get(), ref_map.data, shape->size,
-                                                         ssa_map.data, idx_size, nullptr, nullptr);
-                if (rc2 == GCZ_E_NOMEM && attempts++ == 0) {
-                    std::unique_lock<std::mutex> l(mu);
-                    cv.wait(l, [&] { return free_tokens.size() == all_tokens - 1; });
-                    continue;
-                }
-                if (rc2 != GCZ_OK) record_error(rc2);
-                break;
+        workers.emplace_back([&, device, text, shape, n, my_ref, my_ssa, hlen, idx_size, hb, sb]() mutable {
+            const auto b0 = std::chrono::steady_clock::now();
+            // one buffer: [.. ref header | .gcz body .. ssa header | .gcx body], both bodies on a 4 KiB boundary, so that each
+            // file gets its header and body with one write
+            const int64_t ref_at = (hlen + 4095) & ~(int64_t)4095;
+            const int64_t ssa_at = ((ref_at + shape->size + 4095) & ~(int64_t)4095) + 4096;
+            std::unique_ptr<HostBuffer> out = bodies.take((size_t)(ssa_at + idx_size));
+            int rc2 = out->data ? GCZ_OK : fail(GCZ_E_NOMEM, "host buffer of %lld bytes", (long long)(ssa_at + idx_size));
+            for (int attempts = 0; rc2 == GCZ_OK; ) {
+                rc2 = eng.build_block(device, text->data, n, sampling_rate, shape.get(), out->data + ref_at, shape->size, out->data + ssa_at,
+                                      idx_size, nullptr, nullptr);
+                if (rc2 != GCZ_E_NOMEM || attempts++ > 0) break;
+                std::unique_lock<std::mutex> l(mu);
+                cv.wait(l, [&] { return free_tokens.size() == all_tokens - 1; });
+                rc2 = GCZ_OK;
             }
+            if (rc2 != GCZ_OK) record_error(rc2);
+            text.reset();                                                            // the text buffer goes back with the token
             release(device);
+            const double t_build = seconds_since(b0);
+            if (rc2 == GCZ_OK) {
+                std::memcpy(out->data + ref_at - hlen, hb.data(), (size_t)hlen);
+                std::memcpy(out->data + ssa_at - 25, sb.data(), 25);
+                if (!write_fully(ref_fd, out->data + ref_at - hlen, hlen + shape->size, my_ref) ||
+                    !write_fully(ssa_fd, out->data + ssa_at - 25, 25 + idx_size, my_ssa))
+                    record_error(fail(GCZ_E_ARG, "cannot write %s / %s", ref_path.c_str(), ssa_path.c_str()));
+            }
+            bodies.give(std::move(out));
+            if (host_trace()) std::fprintf(stderr, "[gcz host] block n=%lld: build %.1f ms, write %.1f ms\n", (long long)n, t_build * 1e3,
+                                           (seconds_since(b0) - t_build) * 1e3);
         });
     }
     for (std::thread& t : workers) t.join();

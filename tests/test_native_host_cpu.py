@@ -113,6 +113,53 @@ def test_fasta_random_files():
             assert [f.record(i) + (f.read(i).tobytes(),) for i in range(len(f))] == exp
 
 
+def _scan(data: bytes):
+    with NF.Fasta(data) as f:
+        return [f.record(i) + (f.read(i).tobytes(),) for i in range(len(f))]
+
+
+@pytest.mark.parametrize("slice_bytes,threads", [("5", "3"), ("64", "2"), ("1000000", "1")])
+def test_fast_scanner_equals_the_literal_machine(monkeypatch, slice_bytes, threads):
+    """scan_fasta (vector searches, sequence regions counted by several threads) against scan_fasta_literal (the Java loop,
+    one character at a time) on inputs made of the characters the machine reacts to; tiny slices force the threaded steps."""
+    rng = np.random.default_rng(int(slice_bytes) + int(threads))
+    alphabets = [np.frombuffer(b"ACGTN>@+\r\n\n\nacgt ", np.uint8), np.frombuffer(b"AC\n\r>@+", np.uint8),
+                 np.frombuffer(b"ACGTACGTACGTACGTACGTACGTACGTACGT\n>", np.uint8), np.frombuffer(b"A\n+@I", np.uint8)]
+    for it in range(1200):
+        alpha = alphabets[it % len(alphabets)]
+        data = alpha[rng.integers(0, len(alpha), int(rng.integers(0, 2500 if it % 10 == 0 else 200)))].tobytes()
+        monkeypatch.setenv("GCZ_FASTA_LITERAL", "1")
+        exp = _scan(data)
+        monkeypatch.delenv("GCZ_FASTA_LITERAL")
+        monkeypatch.setenv("GCZ_FASTA_SLICE", slice_bytes)
+        monkeypatch.setenv("GCZ_HOST_THREADS", threads)
+        got = _scan(data)
+        monkeypatch.delenv("GCZ_FASTA_SLICE")
+        monkeypatch.delenv("GCZ_HOST_THREADS")
+        assert got == exp, data
+
+
+def test_long_multiline_sequence_is_assembled_by_several_threads(monkeypatch):
+    """A record large enough for the threaded reader (>= 4 MiB of source per thread), mixed line ends and widths."""
+    rng = np.random.default_rng(9)
+    seq = synth.iid_acgtn(12_000_000, seed=3)
+    parts, p = [b">big one\r\n"], 0
+    while p < len(seq):
+        w = int(rng.integers(1, 200)) if p < 50_000 else 61
+        parts.append(seq[p:p + w].tobytes())
+        parts.append((b"\n", b"\r\n", b"\n\n")[int(rng.integers(0, 3))] if p < 50_000 else b"\n")
+        p += w
+    parts.append(b">next\nAC\nGT\n")
+    data = b"".join(parts)
+    monkeypatch.setenv("GCZ_HOST_THREADS", "3")
+    with NF.Fasta(data) as f:
+        assert len(f) == 2 and f.record(0)[2:] == (len(seq), True)
+        assert np.array_equal(f.read(0), seq)
+        assert f.read(1).tobytes() == b"ACGT"
+        short = np.zeros(len(seq) - 1, np.uint8)                       # a buffer shorter than the sequence is refused
+        assert N.lib().gcz_fasta_read(f._h, 0, N.ptr(short), len(short)) == N.GCZ_E_ARG
+
+
 def test_gzipped_fasta(tmp_path):
     """FastaFileReader probes for GZIP and reads the decompressed stream (fasta/FastaFileReader.java:71-96); here through
     zlib looked up at run time, multi-member files (BGZF) included."""
