@@ -461,28 +461,54 @@ struct HostBuffer {
 };
 
 // Buffers of one kind, reused from block to block: pinning a quarter of a gigabyte costs more than building the block.
-// At most `limit` are out at a time (take() waits); a returned buffer that is too small for the next request is dropped.
+// At most `limit` are out at a time (take() waits); returned buffers that are too small for a request are dropped.
+// prefill() allocates in the background, so that the second text buffer and the first body buffers are being pinned
+// while the first block is assembled.
 class BufferPool {
 public:
     explicit BufferPool(size_t limit) : limit_(limit) {}
+    ~BufferPool() { if (filler_.joinable()) filler_.join(); }
+    void prefill(size_t count, size_t bytes) {
+        {
+            std::lock_guard<std::mutex> l(mu_);
+            largest_ = std::max(largest_, bytes);
+            pending_ += count;
+        }
+        filler_ = std::thread([this, count] {
+            for (size_t i = 0; i < count; i++) {
+                size_t bytes;
+                { std::lock_guard<std::mutex> l(mu_); bytes = largest_; }
+                std::unique_ptr<HostBuffer> b(new HostBuffer(bytes));
+                std::lock_guard<std::mutex> l(mu_);
+                pending_--;
+                if (b->data) free_.push_back(std::move(b));
+                cv_.notify_all();
+            }
+        });
+    }
     std::unique_ptr<HostBuffer> take(size_t bytes) {
         std::unique_lock<std::mutex> l(mu_);
-        cv_.wait(l, [&] { return out_ < limit_; });
+        size_t best = 0;
+        auto fits = [&] {
+            best = free_.size();
+            for (size_t i = 0; i < free_.size(); i++)
+                if (free_[i]->cap >= bytes && (best == free_.size() || free_[i]->cap < free_[best]->cap)) best = i;
+            return best < free_.size();
+        };
+        // a buffer the filler is about to deliver is worth waiting for only if it will be large enough
+        cv_.wait(l, [&] { return out_ < limit_ && (fits() || pending_ == 0 || largest_ < bytes); });
         out_++;
-        size_t best = free_.size();
-        for (size_t i = 0; i < free_.size(); i++)
-            if (free_[i]->cap >= bytes && (best == free_.size() || free_[i]->cap < free_[best]->cap)) best = i;
-        if (best < free_.size()) {
+        if (fits()) {
             std::unique_ptr<HostBuffer> b = std::move(free_[best]);
             free_.erase(free_.begin() + (long)best);
             return b;
         }
         free_.clear();                                      // all too small: their memory goes first
         largest_ = std::max(largest_, bytes);
+        const size_t want = largest_;
         l.unlock();
-        return std::unique_ptr<HostBuffer>(new HostBuffer(largest_));
+        return std::unique_ptr<HostBuffer>(new HostBuffer(want));
     }
-    void expect(size_t bytes) { std::lock_guard<std::mutex> l(mu_); largest_ = std::max(largest_, bytes); }
     void give(std::unique_ptr<HostBuffer> b) {
         std::lock_guard<std::mutex> l(mu_);
         if (b && b->data) free_.push_back(std::move(b));
@@ -493,7 +519,8 @@ private:
     std::mutex mu_;
     std::condition_variable cv_;
     std::vector<std::unique_ptr<HostBuffer>> free_;
-    size_t limit_, out_ = 0, largest_ = 0;
+    std::thread filler_;
+    size_t limit_, out_ = 0, largest_ = 0, pending_ = 0;
 };
 
 // all of buf[0, len) at file offset off
@@ -684,7 +711,9 @@ int gcz_index_fasta(const gcz_fasta* fasta, const char* gcz_path, const char* gc
         largest = std::max(largest, n);
     }
     BufferPool texts(all_tokens), bodies(all_tokens + 2);
-    texts.expect((size_t)largest);
+    texts.prefill(std::min(all_tokens, blocks.size()), (size_t)largest);
+    // the bodies of a DNA block take about 0.3 n + n / 8 + 23 levels of n / 256 bytes; other alphabets grow the pool on demand
+    bodies.prefill(std::min<size_t>(2, blocks.size()), (size_t)(largest * 0.32) + (size_t)index_size(largest, sf) + 3 * 4096);
 
     auto release = [&](int d) { std::lock_guard<std::mutex> l(mu); free_tokens.push_back(d); cv.notify_all(); };
     auto record_error = [&](int rc) {
