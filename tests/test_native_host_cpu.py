@@ -265,6 +265,52 @@ def test_native_writer_with_the_oracle_engine(tmp_path, rate, devices):
             r.find("no such header")
 
 
+def test_native_writer_many_blocks_and_a_large_alphabet(tmp_path):
+    """More blocks than body buffers (workers wait for one to come back) and bodies larger than the pool's DNA estimate
+    (the prefilled buffers are dropped for larger ones)."""
+    rng = np.random.default_rng(3)
+    alpha = np.frombuffer(b"ACGTNacgtnRYKMSWBDHVrykmswbdhv", np.uint8)
+    recs = [(f"s{i}", alpha[rng.integers(0, len(alpha), 2000 - i)]) for i in range(30)]
+    fa = tmp_path / "m.fa"
+    _write_fasta(fa, recs, width=70)
+    eng, state = _oracle_engine()
+    with NF.Fasta(fa) as f:
+        rep = NF.index(f, tmp_path / "m.gcz", sampling=8, devices=(0,), engine=eng)
+    gcz, gcx, blocks = O.write_files([(h, s.tobytes()) for h, s in recs], 8)
+    assert len(blocks) == 30 == rep["blocks"] == state["builds"]
+    assert (tmp_path / "m.gcz").read_bytes() == gcz and (tmp_path / "m.gcx").read_bytes() == gcx
+
+
+def test_native_writer_with_a_concurrent_engine(tmp_path):
+    """The same pipeline with an engine that does not hold the GIL (tools/hostbench.py's stand-in, compiled with gcc):
+    builds, buffer hand-overs and file writes really overlap.  Every block's header and both bodies must be where the
+    reader expects them."""
+    import sys
+    sys.path.insert(0, str(__import__("pathlib").Path(__file__).resolve().parent.parent / "tools"))
+    import hostbench
+    eng = hostbench.standin_engine(50.0)
+    recs = [(f"c{i}", synth.iid_acgtn(40_000 - 137 * i, 70 + i)) for i in range(40)]
+    fa = tmp_path / "c.fa"
+    _write_fasta(fa, recs)
+    for devices in ((0,), (0, 1, 2, 3)):
+        with NF.Fasta(fa) as f:
+            rep = NF.index(f, tmp_path / "c.gcz", sampling=32, devices=devices, engine=eng)
+        assert rep["blocks"] == 40
+        ref, ssa = (tmp_path / "c.gcz").read_bytes(), (tmp_path / "c.gcx").read_bytes()
+        rp = sp = 0
+        for b in range(40):
+            n = 40_000 - 137 * b + 1                                       # file order: longest first
+            assert ref[rp:rp + 8] == b"GecozBWT" and ssa[sp:sp + 8] == b"GecozSSA"
+            size, text_len = int.from_bytes(ref[rp + 9:rp + 17], "little"), int.from_bytes(ref[rp + 17:rp + 25], "little")
+            assert text_len == n
+            hlen = GecozRefBlockHeader.block_header_length([f"c{b}"])
+            assert set(ref[rp + hlen:rp + size]) == {n % 251}
+            idx = int.from_bytes(ssa[sp + 9:sp + 17], "little")
+            assert idx == O.index_size(n, 5) and set(ssa[sp + 25:sp + 25 + idx]) == {n % 241}
+            rp, sp = rp + size, sp + 25 + idx
+        assert rp == len(ref) and sp == len(ssa)
+
+
 def test_native_writer_retries_a_block_that_ran_out_of_memory(tmp_path):
     recs = [("a", synth.iid_acgtn(3000, 1)), ("b", synth.iid_acgtn(2900, 2))]
     fa = tmp_path / "y.fa"

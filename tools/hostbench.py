@@ -4,7 +4,8 @@
     python tools/hostbench.py [--fasta PATH | --scale 1.0] [--out DIR] [--gpu-gbps 12.6]
 
 The per-block device work is replaced by a stand-in engine (compiled here with gcc): count_symbols samples the text,
-build_block sleeps for n / --gpu-gbps (the measured device throughput of a block build) and fills both output slices.
+build_block sleeps for n / --gpu-gbps (the measured device throughput of a block build) and fills both output slices
+(with n % 251 and n % 241).
 What remains is what the host has to do around the GPU: scan the FASTA, assemble the block texts, create the files and
 take the bodies.  The output files are NOT valid indexes; the tool reports seconds per stage.
 """
@@ -45,8 +46,8 @@ int standin_build(int device, const uint8_t* text, int64_t n, int32_t rate, cons
     ts.tv_sec = (time_t)s;
     ts.tv_nsec = (long)((s - (double)ts.tv_sec) * 1e9);
     nanosleep(&ts, 0);
-    memset(gcz_body, 0x5a, (size_t)gcz_len);
-    memset(gcx_body, 0xa5, (size_t)gcx_len);
+    memset(gcz_body, (int)(n % 251), (size_t)gcz_len);               /* recognisable per block: the tests check the files */
+    memset(gcx_body, (int)(n % 241), (size_t)gcx_len);
     return 0;
 }
 """
