@@ -450,7 +450,9 @@ struct HostBuffer {
     uint8_t* data = nullptr;
     size_t cap = 0;
     bool pinned = false;
-    explicit HostBuffer(size_t bytes) : cap(bytes ? bytes : 1) {
+    // device: the one whose context the pinning goes through (a thread that never chose one would bring up device 0's)
+    HostBuffer(size_t bytes, int device) : cap(bytes ? bytes : 1) {
+        if (device >= 0 && cudaSetDevice(device) != cudaSuccess) cudaGetLastError();
         if (cudaHostAlloc(reinterpret_cast<void**>(&data), cap, cudaHostAllocDefault) == cudaSuccess) { pinned = true; return; }
         cudaGetLastError();
         data = static_cast<uint8_t*>(std::malloc(cap));
@@ -466,7 +468,7 @@ struct HostBuffer {
 // while the first block is assembled.
 class BufferPool {
 public:
-    explicit BufferPool(size_t limit) : limit_(limit) {}
+    BufferPool(size_t limit, int device) : limit_(limit), device_(device) {}
     ~BufferPool() { if (filler_.joinable()) filler_.join(); }
     void prefill(size_t count, size_t bytes) {
         {
@@ -478,7 +480,7 @@ public:
             for (size_t i = 0; i < count; i++) {
                 size_t bytes;
                 { std::lock_guard<std::mutex> l(mu_); bytes = largest_; }
-                std::unique_ptr<HostBuffer> b(new HostBuffer(bytes));
+                std::unique_ptr<HostBuffer> b(new HostBuffer(bytes, device_));
                 std::lock_guard<std::mutex> l(mu_);
                 pending_--;
                 if (b->data) free_.push_back(std::move(b));
@@ -507,7 +509,7 @@ public:
         largest_ = std::max(largest_, bytes);
         const size_t want = largest_;
         l.unlock();
-        return std::unique_ptr<HostBuffer>(new HostBuffer(want));
+        return std::unique_ptr<HostBuffer>(new HostBuffer(want, device_));
     }
     void give(std::unique_ptr<HostBuffer> b) {
         std::lock_guard<std::mutex> l(mu_);
@@ -521,6 +523,7 @@ private:
     std::vector<std::unique_ptr<HostBuffer>> free_;
     std::thread filler_;
     size_t limit_, out_ = 0, largest_ = 0, pending_ = 0;
+    int device_;
 };
 
 // all of buf[0, len) at file offset off
@@ -710,7 +713,7 @@ int gcz_index_fasta(const gcz_fasta* fasta, const char* gcz_path, const char* gc
         for (const Seq& s : block.sequences) n += s.length + 1;
         largest = std::max(largest, n);
     }
-    BufferPool texts(all_tokens), bodies(all_tokens + 2);
+    BufferPool texts(all_tokens, devs[0]), bodies(all_tokens + 2, devs[0]);
     texts.prefill(std::min(all_tokens, blocks.size()), (size_t)largest);
     // the bodies of a DNA block take about 0.3 n + n / 8 + 23 levels of n / 256 bytes; other alphabets grow the pool on demand
     bodies.prefill(std::min<size_t>(2, blocks.size()), (size_t)(largest * 0.32) + (size_t)index_size(largest, sf) + 3 * 4096);
