@@ -211,3 +211,26 @@ def test_headers_are_plain_c_and_the_c_example_links(tmp_path):
         assert r.returncode == 0 and ">s found : 2" in r.stdout
     else:
         assert r.returncode == 1 and "no CPU path" in r.stderr
+
+
+def test_native_host_layer_under_thread_sanitizer(tmp_path):
+    """The host layer alone (FASTA scan and assembly threads, the writer's buffer pools and block workers) compiled with
+    -fsanitize=thread against stand-ins for the CUDA runtime and entry points (tests/host_tsan): no data race reports."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    cuda_inc = Path("/usr/local/cuda/include")
+    if gxx is None or not (cuda_inc / "cuda_runtime.h").exists():
+        pytest.skip("needs g++ and the CUDA headers")
+    src = ROOT / "tests" / "host_tsan"
+    csrc = ROOT / "gecoz_b200" / "csrc"
+    exe = tmp_path / "host_tsan"
+    build = subprocess.run([gxx, "-std=c++17", "-O1", "-g", "-fsanitize=thread", f"-I{csrc}", f"-I{ROOT / 'include'}", f"-I{cuda_inc}",
+                            "-o", str(exe), str(src / "main.cpp"), str(src / "stubs.cpp"), str(csrc / "host_file.cpp"), str(csrc / "shape.cpp"),
+                            "-ldl", "-lpthread"], capture_output=True, text=True)
+    if build.returncode != 0 and "tsan" in build.stderr.lower():
+        pytest.skip("no ThreadSanitizer runtime")
+    assert build.returncode == 0, build.stderr
+    r = subprocess.run([str(exe), str(tmp_path / "o.gcz")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr, r.stderr[-4000:]
+    assert r.stdout.count("rc 0 blocks") == 2
