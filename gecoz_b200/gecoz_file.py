@@ -13,7 +13,6 @@ the C ABI is Python; the Java shim a maintainer would use instead is shown in IN
 from __future__ import annotations
 
 import ctypes as C
-import mmap
 import os
 import threading
 from concurrent.futures import Future, ThreadPoolExecutor
@@ -151,6 +150,86 @@ def build_block(device: int, text, n: int, sampling_rate: int, shape: N.Shape, g
     return t.as_dict()
 
 
+class _BodyWriter:
+    """Where block bodies go before they reach the files: reusable host buffers, written with pwrite on helper threads.
+
+    The reference hands BlockWriter two mapped file slices.  A mapping takes a page fault per 4 KiB while the build call
+    fills it (125 ms per 128 MB measured) and the next block waits behind that; a buffer that is reused does
+    not fault, and its pwrite overlaps the next build.  One buffer holds a whole block: ref header | .gcz body, then
+    ssa header | .gcx body, so each file gets one write per block."""
+
+    def __init__(self, max_buffers: int, threads: int = 2):
+        self._pool = ThreadPoolExecutor(max_workers=threads)
+        self._cv = threading.Condition()
+        self._free: list[np.ndarray] = []
+        self._out, self._max = 0, max(1, max_buffers)
+        self._pending: list[Future] = []
+
+    def take(self, nbytes: int) -> np.ndarray:
+        with self._cv:
+            self._cv.wait_for(lambda: self._out < self._max)
+            self._out += 1
+            best = None
+            for k, b in enumerate(self._free):
+                if len(b) >= nbytes and (best is None or len(b) < len(self._free[best])):
+                    best = k
+            if best is not None:
+                return self._free.pop(best)
+            self._free.clear()                                    # all too small
+        return np.empty(max(nbytes, 1), dtype=np.uint8)
+
+    def give(self, buf: np.ndarray) -> None:
+        with self._cv:
+            self._free.append(buf)
+            self._out -= 1
+            self._cv.notify_all()
+
+    def commit(self, buf: np.ndarray, writes: Sequence[tuple[int, int, int, int]]) -> None:
+        """writes: (fd, file offset, buffer offset, length); the buffer comes back to the pool when they are done."""
+        fut = self._pool.submit(self._write, buf, list(writes))
+        with self._cv:
+            self._pending.append(fut)
+
+    def _write(self, buf, writes):
+        try:
+            mv = memoryview(buf)
+            for fd, off, at, length in writes:
+                done = 0
+                while done < length:
+                    done += os.pwrite(fd, mv[at + done:at + length], off + done)
+        finally:
+            self.give(buf)
+
+    def drain(self) -> None:
+        with self._cv:
+            pending, self._pending = self._pending, []
+        for f in pending:
+            f.result()
+
+    def close(self) -> None:
+        try:
+            self.drain()
+        finally:
+            self._pool.shutdown(wait=True)
+
+
+def _block_layout(header_len: int, ref_len: int, ssa_len: int) -> tuple[int, int, int]:
+    """Offsets of the .gcz body and the .gcx body in a block buffer (64-byte aligned, their headers just before), and its size."""
+    ref_at = (header_len + 63) & ~63
+    ssa_at = ((ref_at + ref_len + 63) & ~63) + 64
+    return ref_at, ssa_at, ssa_at + ssa_len
+
+
+class _CudaEngine:
+    """The CUDA path behind the C ABI (the only engine the product uses; the CPU tests inject the oracle here)."""
+
+    def symbol_counts(self, text, device):
+        return symbol_counts(text, device)
+
+    def build_block(self, device, text, n, sampling_rate, shape, gcz_out, gcx_out):
+        return build_block(device, text, n, sampling_rate, shape, gcz_out, gcx_out)
+
+
 class GecozFileWriter:
     """Writes blocks to `ref_path` (.gcz) and `ssa_path` (.gcx).
 
@@ -160,13 +239,14 @@ class GecozFileWriter:
     is computed, exactly as in the reference, so blocks may finish in any order.
     """
 
-    def __init__(self, ref_path, ssa_path=None, sampling_rate: int = 32, devices: Sequence[int] = (0,)):
+    def __init__(self, ref_path, ssa_path=None, sampling_rate: int = 32, devices: Sequence[int] = (0,), engine=None):
         self.ref_path = Path(ref_path)
         self.ssa_path = Path(ssa_path) if ssa_path is not None else ssa_path_for(self.ref_path)
         if sampling_rate <= 0 or sampling_rate & (sampling_rate - 1):
             raise ValueError("sampling rate must be a power of two")
         self.sampling_rate = sampling_rate
         self.devices = list(devices)
+        self._engine = engine or _CudaEngine()
         self._ref = open(self.ref_path, "w+b")
         self._ssa = open(self.ssa_path, "w+b")
         self._ref_pos = 0
@@ -175,6 +255,7 @@ class GecozFileWriter:
         self._free = list(self.devices) * 2               # two tokens per device: the library has two text slots
         self._cv = threading.Condition()
         self._jobs: list[Future] = []
+        self._bodies = _BodyWriter(max_buffers=2 * len(self.devices) + 2)
         self.timings: list[dict] = []
 
     def write(self, headers: Sequence[str], text) -> None:
@@ -183,48 +264,51 @@ class GecozFileWriter:
         n = len(text)
         device = self._acquire()
         try:
-            counts = symbol_counts(text, device)
+            counts = self._engine.symbol_counts(text, device)
             shape = shape_from_counts(counts)
             hdr = GecozRefBlockHeader(headers, GecozRefBlockHeader.block_header_length(headers) + shape.size, n)
             idx_size = index_size(n, self.sampling_rate.bit_length() - 1)
             ref_pos, ssa_pos = self._ref_pos, self._ssa_pos
             self._ref_pos += hdr.size
             self._ssa_pos += GecozSSABlockHeader.LENGTH + idx_size
-            os.ftruncate(self._ref.fileno(), self._ref_pos)
-            os.ftruncate(self._ssa.fileno(), self._ssa_pos)
             hb = hdr.to_bytes()
-            os.pwrite(self._ref.fileno(), hb, ref_pos)
-            os.pwrite(self._ssa.fileno(), GecozSSABlockHeader(headers, idx_size).to_bytes(), ssa_pos)
+            sb = GecozSSABlockHeader(headers, idx_size).to_bytes()
         except BaseException:
             self._release(device)
             raise
-        fut = self._pool.submit(self._block_writer, device, text, n, shape, ref_pos + len(hb), int(shape.size),
-                                ssa_pos + GecozSSABlockHeader.LENGTH, idx_size)
+        fut = self._pool.submit(self._block_writer, device, text, n, shape, hb, ref_pos, int(shape.size), sb, ssa_pos, idx_size)
         self._jobs.append(fut)
 
     # BlockWriter.run :256-284 — plus the retry contract of WriterPoolExecutor.afterExecute :203-226
-    def _block_writer(self, device, text, n, shape, ref_off, ref_len, ssa_off, ssa_len):
+    def _block_writer(self, device, text, n, shape, hb, ref_pos, ref_len, sb, ssa_pos, ssa_len):
         try:
-            attempts = 0
-            while True:
-                ref_map = _map_slice(self._ref, ref_off, ref_len)
-                ssa_map = _map_slice(self._ssa, ssa_off, ssa_len)
-                try:
-                    t = build_block(device, text, n, self.sampling_rate, shape, ref_map.array, ssa_map.array)
-                    t["n"] = n
-                    self.timings.append(t)
-                    return
-                except N.GczOutOfMemory:
-                    attempts += 1
-                    if attempts > 1:
-                        raise
-                    with self._cv:                       # wait until nothing else is in flight, then retry once
-                        self._cv.wait_for(lambda: len(self._free) == 2 * len(self.devices) - 1, timeout=600)
-                finally:
-                    ref_map.close()
-                    ssa_map.close()
+            ref_at, ssa_at, size = _block_layout(len(hb), ref_len, ssa_len)
+            buf = self._bodies.take(size)
+            try:
+                attempts = 0
+                while True:
+                    try:
+                        t = self._engine.build_block(device, text, n, self.sampling_rate, shape, buf[ref_at:ref_at + ref_len],
+                                                     buf[ssa_at:ssa_at + ssa_len])
+                        break
+                    except N.GczOutOfMemory:
+                        attempts += 1
+                        if attempts > 1:
+                            raise
+                        with self._cv:                   # wait until nothing else is in flight, then retry once
+                            self._cv.wait_for(lambda: len(self._free) == 2 * len(self.devices) - 1, timeout=600)
+            except BaseException:
+                self._bodies.give(buf)
+                raise
+            t = dict(t or {})
+            t["n"] = n
+            self.timings.append(t)
         finally:
-            self._release(device)
+            self._release(device)                        # the files are written after the device is free again
+        buf[ref_at - len(hb):ref_at] = np.frombuffer(hb, np.uint8)
+        buf[ssa_at - len(sb):ssa_at] = np.frombuffer(sb, np.uint8)
+        self._bodies.commit(buf, [(self._ref.fileno(), ref_pos, ref_at - len(hb), len(hb) + ref_len),
+                                  (self._ssa.fileno(), ssa_pos, ssa_at - len(sb), len(sb) + ssa_len)])
 
     def _acquire(self) -> int:
         with self._cv:
@@ -241,37 +325,18 @@ class GecozFileWriter:
             for f in self._jobs:
                 f.result()
         finally:
-            self._pool.shutdown(wait=True)
-            self._ref.close()
-            self._ssa.close()
+            try:
+                self._pool.shutdown(wait=True)
+                self._bodies.close()                      # the pending writes finish while the files are open
+            finally:
+                self._ref.close()
+                self._ssa.close()
 
     def __enter__(self):
         return self
 
     def __exit__(self, *exc):
         self.close()
-
-
-class _MappedSlice:
-    """A writable mmap of file bytes [off, off + length) exposed as a numpy uint8 array."""
-
-    def __init__(self, f, off: int, length: int):
-        gran = mmap.ALLOCATIONGRANULARITY
-        start = off - off % gran
-        self._mm = mmap.mmap(f.fileno(), length + (off - start), access=mmap.ACCESS_WRITE, offset=start)
-        self.array = np.frombuffer(self._mm, dtype=np.uint8, count=length, offset=off - start)
-
-    def close(self):
-        self.array = None
-        try:
-            self._mm.flush()
-            self._mm.close()
-        except BufferError:
-            pass
-
-
-def _map_slice(f, off, length):
-    return _MappedSlice(f, off, length)
 
 
 class GecozFileReader:

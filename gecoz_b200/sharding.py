@@ -25,8 +25,8 @@ from typing import Iterable, Sequence
 import numpy as np
 
 from . import _native as N
-from .gecoz_file import (GecozRefBlockHeader, GecozSSABlockHeader, _map_slice, build_block, index_size, shape_from_counts,
-                         ssa_path_for, symbol_counts)
+from .gecoz_file import (GecozRefBlockHeader, GecozSSABlockHeader, _BodyWriter, _block_layout, build_block, index_size,
+                         shape_from_counts, ssa_path_for, symbol_counts)
 from .geco_index import FastaSequence, block_text, merge_blocks
 
 
@@ -155,31 +155,38 @@ def sharded_index_records(records: Iterable[tuple[str, object]], opath, xpath=No
     _barrier(world, group)
 
     timings = []
-    # block k + 1 is uploaded (re-counted: that is what stages its text on the device) while block k is being built
+    # block k + 1 is uploaded (re-counted: that is what stages its text on the device) while block k is being built, and
+    # the bodies of block k - 1 are on their way to the files (reused host buffers, pwrite on helper threads)
     from concurrent.futures import ThreadPoolExecutor
+    bodies = _BodyWriter(max_buffers=3)
     with open(opath, "r+b") as fref, open(xpath, "r+b") as fssa, ThreadPoolExecutor(1) as stager:
-        staged = stager.submit(engine.symbol_counts, prepared[mine[0]][1]) if mine else None
-        for k, i in enumerate(mine):
-            headers, text, shape = prepared.pop(i)
-            staged.result()
-            if k + 1 < len(mine):
-                staged = stager.submit(engine.symbol_counts, prepared[mine[k + 1]][1])
-            n = len(text)
-            idx_size = index_size(n, sf)
-            hdr = GecozRefBlockHeader(headers, GecozRefBlockHeader.block_header_length(headers) + int(shape.size), n)
-            hb = hdr.to_bytes()
-            os.pwrite(fref.fileno(), hb, ref_off[i])
-            os.pwrite(fssa.fileno(), GecozSSABlockHeader(headers, idx_size).to_bytes(), ssa_off[i])
-            ref_map = _map_slice(fref, ref_off[i] + len(hb), int(shape.size))
-            ssa_map = _map_slice(fssa, ssa_off[i] + GecozSSABlockHeader.LENGTH, idx_size)
-            try:
-                t = engine.build_block(text, n, sampling, shape, ref_map.array, ssa_map.array)
-            finally:
-                ref_map.close()
-                ssa_map.close()
-            t = dict(t or {})
-            t["n"], t["block"] = n, i
-            timings.append(t)
+        try:
+            staged = stager.submit(engine.symbol_counts, prepared[mine[0]][1]) if mine else None
+            for k, i in enumerate(mine):
+                headers, text, shape = prepared.pop(i)
+                staged.result()
+                if k + 1 < len(mine):
+                    staged = stager.submit(engine.symbol_counts, prepared[mine[k + 1]][1])
+                n = len(text)
+                idx_size = index_size(n, sf)
+                hdr = GecozRefBlockHeader(headers, GecozRefBlockHeader.block_header_length(headers) + int(shape.size), n)
+                hb, sb = hdr.to_bytes(), GecozSSABlockHeader(headers, idx_size).to_bytes()
+                ref_at, ssa_at, size = _block_layout(len(hb), int(shape.size), idx_size)
+                buf = bodies.take(size)
+                try:
+                    t = engine.build_block(text, n, sampling, shape, buf[ref_at:ref_at + int(shape.size)], buf[ssa_at:ssa_at + idx_size])
+                except BaseException:
+                    bodies.give(buf)
+                    raise
+                buf[ref_at - len(hb):ref_at] = np.frombuffer(hb, np.uint8)
+                buf[ssa_at - len(sb):ssa_at] = np.frombuffer(sb, np.uint8)
+                bodies.commit(buf, [(fref.fileno(), ref_off[i], ref_at - len(hb), len(hb) + int(shape.size)),
+                                    (fssa.fileno(), ssa_off[i], ssa_at - len(sb), len(sb) + idx_size)])
+                t = dict(t or {})
+                t["n"], t["block"] = n, i
+                timings.append(t)
+        finally:
+            bodies.close()                                       # the pending writes finish while the files are open
     _barrier(world, group)
     return {"blocks": [[s.header for s in b.sequences] for b in blocks], "owner": owner, "mine": mine,
             "seconds": time.perf_counter() - t0, "timings": timings}

@@ -89,3 +89,47 @@ def test_sharded_queries_gloo_world2(tmp_path):
         assert np.array_equal(got[f"pos{b}"], pos)
         assert np.array_equal(got[f"off{b}"], poff)
     assert int((got["ep"] >= got["sp"]).sum()) > 100
+
+
+class _OracleFileEngine:
+    """Engine for gecoz_file.GecozFileWriter (device passed per call) backed by the oracle."""
+
+    def __init__(self, fail_first=False):
+        self.fail_first, self.builds = fail_first, 0
+
+    def symbol_counts(self, text, device):
+        return np.bincount(np.asarray(text), minlength=256).astype(np.int64)
+
+    def build_block(self, device, text, n, sampling_rate, shape, gcz_out, gcx_out):
+        from gecoz_b200 import _native as N
+        from oracle import gcz_oracle as O
+        self.builds += 1
+        if self.fail_first and self.builds == 1:
+            raise N.GczOutOfMemory(N.GCZ_E_NOMEM, "injected")
+        r = O.build_block(np.asarray(text), sampling_rate)
+        assert len(r["gcz_body"]) == len(gcz_out) and len(r["gcx_body"]) == len(gcx_out)
+        gcz_out[:] = r["gcz_body"]
+        gcx_out[:] = r["gcx_body"]
+        return {"total_ms": 0.0}
+
+
+@pytest.mark.parametrize("devices,fail_first", [((0,), False), ((0, 1, 2), False), ((0,), True)])
+def test_python_file_writer_with_the_oracle_engine(tmp_path, devices, fail_first):
+    """gecoz_file.GecozFileWriter (pooled block buffers, header + body written with one pwrite per file after the device
+    token is released) produces the oracle's files, with several blocks in flight and across the out-of-memory retry."""
+    from gecoz_b200 import synth
+    from gecoz_b200.geco_index import index_records
+    from gecoz_b200.gecoz_file import GecozFileWriter
+    from oracle import gcz_oracle as O
+    recs = [(f"r{i} d", synth.iid_acgtn(int(ln), 60 + i)) for i, ln in enumerate([7000, 6900, 6800, 3000, 2900, 800, 40, 0])]
+    eng = _OracleFileEngine(fail_first)
+    import gecoz_b200.geco_index as GI
+    real = GI.GecozFileWriter
+    GI.GecozFileWriter = lambda o, x, s, d: GecozFileWriter(o, x, s, d, engine=eng)
+    try:
+        info = index_records(recs, tmp_path / "p.gcz", sampling=16, devices=devices)
+    finally:
+        GI.GecozFileWriter = real
+    gcz, gcx, blocks = O.write_files([(h, s.tobytes()) for h, s in recs], 16)
+    assert (tmp_path / "p.gcz").read_bytes() == gcz and (tmp_path / "p.gcx").read_bytes() == gcx
+    assert len(info["blocks"]) == len(blocks) and eng.builds == len(blocks) + (1 if fail_first else 0)
