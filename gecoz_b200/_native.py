@@ -85,7 +85,7 @@ FILE_EXPORTS = [
     "gcz_index_fasta",
     "gcz_reader_open", "gcz_reader_num_blocks", "gcz_reader_block", "gcz_reader_header", "gcz_reader_find",
     "gcz_reader_sampling_factor", "gcz_reader_open_block", "gcz_reader_close",
-    "gcz_match", "gcz_gff_search", "gcz_extract_fasta",
+    "gcz_match", "gcz_gff_search", "gcz_extract_fasta", "gcz_extract_sequence",
 ]
 
 COUNT_SYMBOLS_FN = C.CFUNCTYPE(C.c_int, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64))
@@ -197,6 +197,7 @@ def lib() -> C.CDLL:
         "gcz_match": (C.c_int, [P, C.c_int, C.c_char_p, P, i64, i32, C.POINTER(QueryEngine), C.POINTER(P), C.POINTER(i64)]),
         "gcz_gff_search": (C.c_int, [P, C.c_int, P, i64, C.POINTER(QueryEngine), C.POINTER(P), C.POINTER(i64)]),
         "gcz_extract_fasta": (C.c_int, [P, C.c_int, C.c_char_p, C.POINTER(QueryEngine), C.POINTER(i64)]),
+        "gcz_extract_sequence": (C.c_int, [P, C.c_int, C.c_char_p, i64, i64, C.c_char_p, C.POINTER(QueryEngine), C.POINTER(i64)]),
     })
     assert sorted(sig) == sorted(EXPORTS + FILE_EXPORTS)
     for name, (res, args) in sig.items():

@@ -1240,4 +1240,33 @@ int gcz_extract_fasta(const gcz_reader* r, int device, const char* fasta_path, c
     return GCZ_OK;
 }
 
+// GecoRead.sequence  tools/GecoRead.java:33-81: the raw symbols [from, min(to, length)) of one sequence into `path`, one
+// GSSA.extract call (ssa.extract(buf, nstr, from) :72 with a buffer of to - from bytes)
+int gcz_extract_sequence(const gcz_reader* r, int device, const char* header, int64_t from, int64_t to, const char* path,
+                         const gcz_query_engine* engine, int64_t* written) {
+    clear_error();
+    if (!r || !header || !path) return fail(GCZ_E_ARG, "extract arguments");
+    const gcz_query_engine q = resolve(engine);
+    int32_t block = -1, nstr = -1;
+    GCZ_TRY_HOST(gcz_reader_find(r, header, &block, &nstr));                              // "no sequence found"
+    OpenBlock b(q);
+    GCZ_TRY_HOST(b.open(r, block, device));
+    if (nstr >= b.n_strings) return fail(GCZ_E_ARG, "no sequence found: %s", header);
+    std::vector<int64_t> e((size_t)std::max(1, b.n_strings));
+    GCZ_TRY_HOST(q.string_ends(b.idx, e.data()));
+    const int64_t len = nstr == 0 ? e[0] : e[(size_t)nstr] - e[(size_t)nstr - 1] - 1;     // GSSA.getLength :71-88
+    to = std::min(to, len);                                                               // :66
+    if (from < 0 || to < from) return fail(GCZ_E_RANGE, "range [%lld, %lld) of a sequence of %lld symbols", (long long)from, (long long)to, (long long)len);
+    std::vector<uint8_t> buf((size_t)std::max<int64_t>(to - from, 1));
+    int64_t w = 0;
+    if (to > from) GCZ_TRY_HOST(q.extract(b.idx, nstr, from, buf.data(), to - from, &w));
+    const int fd = ::open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return fail(GCZ_E_ARG, "cannot create %s", path);
+    const bool ok = write_fully(fd, buf.data(), w, 0);
+    ::close(fd);
+    if (!ok) return fail(GCZ_E_ARG, "cannot write %s", path);
+    if (written) *written = w;
+    return GCZ_OK;
+}
+
 }  // extern "C"

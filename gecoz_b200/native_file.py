@@ -171,6 +171,13 @@ class Reader:
         N.check(N.lib().gcz_extract_fasta(self._h, device, str(path).encode(), C.byref(engine) if engine is not None else None, C.byref(n)))
         return n.value
 
+    def extract_sequence(self, header: str, start: int, end: int, path, device: int = 0, engine: N.QueryEngine | None = None) -> int:
+        """GecoRead.sequence (tools/GecoRead.java:33-81): symbols [start, min(end, length)) of one sequence into `path`."""
+        n = C.c_int64()
+        N.check(N.lib().gcz_extract_sequence(self._h, device, header.encode("latin-1"), start, end, str(path).encode(),
+                                             C.byref(engine) if engine is not None else None, C.byref(n)))
+        return n.value
+
     def close(self):
         if self._h:
             N.lib().gcz_reader_close(self._h)

@@ -116,6 +116,12 @@ int gcz_gff_search(const gcz_reader* r, int device, const uint8_t* patterns, int
 int gcz_extract_fasta(const gcz_reader* r, int device, const char* fasta_path, const gcz_query_engine* engine,
                       int64_t* n_sequences);
 
+/* GecoRead.sequence  tools/GecoRead.java:33-81 (`gecotools -i x.gcz -o out.seq header [from] [to]`): the raw symbols
+ * [from, min(to, length)) of the sequence `header` into `path` with one extract call.  GCZ_E_ARG: no such sequence;
+ * GCZ_E_RANGE: from < 0 or from beyond the end (where the reference fails mapping a negative size). */
+int gcz_extract_sequence(const gcz_reader* r, int device, const char* header, int64_t from, int64_t to, const char* path,
+                         const gcz_query_engine* engine, int64_t* written);
+
 #ifdef __cplusplus
 }
 #endif

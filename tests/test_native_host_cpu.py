@@ -495,3 +495,28 @@ def test_native_extract_fasta(small_index, tmp_path):
         back = dict(f.records())
     first = blocks[0][0][0]
     assert np.array_equal(back[first], by_header[first])
+
+
+def test_native_extract_sequence(small_index, tmp_path):
+    """gcz_extract_sequence == GecoRead.sequence: [from, min(to, length)) of one sequence with one extract call."""
+    d, recs, blocks = small_index
+    q = _OracleQueryEngine()
+    out = tmp_path / "s.seq"
+    with NF.Reader(d / "g.gcz") as r:
+        for headers, og in blocks:
+            ends = og.string_ends()
+            for nstr, h in enumerate(headers):
+                length = int(ends[nstr] - (ends[nstr - 1] + 1 if nstr else 0))
+                for start, end in ((0, 2 ** 31 - 1), (7, 61), (length - 3, length + 10), (5, 5)):
+                    if start < 0 or start > length:
+                        continue
+                    n = r.extract_sequence(h, start, end, out, engine=q.struct)
+                    want = og.extract(nstr, start, max(min(end, length) - start, 0)) if min(end, length) > start else np.zeros(0, np.uint8)
+                    assert n == len(want) and out.read_bytes() == want.tobytes()
+        first = blocks[0][0][0]                                            # a single-string block: the text itself
+        r.extract_sequence(first, 10, 90, out, engine=q.struct)
+        assert out.read_bytes() == dict(recs)[first][10:90].tobytes()
+        with pytest.raises(N.GczError):
+            r.extract_sequence("no such header", 0, 10, out, engine=q.struct)
+        with pytest.raises(N.GczError):
+            r.extract_sequence(first, 50, 40, out, engine=q.struct)
