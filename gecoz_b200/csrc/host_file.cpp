@@ -478,9 +478,9 @@ public:
         }
         filler_ = std::thread([this, count] {
             for (size_t i = 0; i < count; i++) {
-                size_t bytes;
-                { std::lock_guard<std::mutex> l(mu_); bytes = largest_; }
-                std::unique_ptr<HostBuffer> b(new HostBuffer(bytes, device_));
+                size_t want;
+                { std::lock_guard<std::mutex> l(mu_); want = largest_; }
+                std::unique_ptr<HostBuffer> b(new HostBuffer(want, device_));
                 std::lock_guard<std::mutex> l(mu_);
                 pending_--;
                 if (b->data) free_.push_back(std::move(b));
