@@ -1,4 +1,4 @@
-// LSD radix sort of (u64 key, u32 value) pairs, 8-bit digits, one HBM round trip per digit.
+// LSD radix sort of (u64 key, u32 value) pairs, 8-bit digits (9-bit in the experimental variants), one HBM round trip per digit.
 //
 // This is the workhorse of the suffix sorter (replaces the induced-sorting loops of
 // algo/string/SAIS.java:103-137 by a data-parallel sort; only the resulting order is shared).
@@ -19,7 +19,7 @@ namespace gcz {
 
 namespace {
 
-constexpr int kRadix = 256;
+// digits are RB bits wide (template parameter of every kernel below; 8 unless a GCZ_SORT_VARIANT says otherwise)
 constexpr int kHistThreads = 512;
 constexpr int kLookWindow = 8;
 
@@ -28,9 +28,11 @@ constexpr unsigned long long kFlagPrefix = 2ull << 62;
 constexpr unsigned long long kValueMask = (1ull << 62) - 1;
 
 // ---- histogram of every digit in one pass -------------------------------------------------------
+template <int RB>
 __global__ void __launch_bounds__(kHistThreads)
 radix_hist_kernel(const uint64_t* __restrict__ keys, int64_t n, int begin_bit, int npass,
-                  unsigned long long* __restrict__ hist /* [npass][256] */) {
+                  unsigned long long* __restrict__ hist /* [npass][radix] */) {
+    constexpr int kRadix = 1 << RB;
     __shared__ unsigned s_hist[8 * kRadix];
     for (int i = threadIdx.x; i < npass * kRadix; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
@@ -38,7 +40,7 @@ radix_hist_kernel(const uint64_t* __restrict__ keys, int64_t n, int begin_bit, i
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint64_t k = keys[i] >> begin_bit;
 #pragma unroll 8
-        for (int p = 0; p < npass; p++) atomicAdd(&s_hist[p * kRadix + (int)((k >> (8 * p)) & 255)], 1u);
+        for (int p = 0; p < npass; p++) atomicAdd(&s_hist[p * kRadix + (int)((k >> (RB * p)) & (kRadix - 1))], 1u);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < npass * kRadix; i += blockDim.x) {
@@ -60,8 +62,10 @@ __device__ __forceinline__ uint64_t slide_key(uint64_t key, uint32_t c_out, uint
     return key * radix + c_in;
 }
 
+template <int RB>
 __global__ void __launch_bounds__(kTextThreads)
-text_hist_kernel(TextKeySource src, int npass, unsigned long long* __restrict__ hist /* [npass][256] */, int64_t tiles) {
+text_hist_kernel(TextKeySource src, int npass, unsigned long long* __restrict__ hist /* [npass][radix] */, int64_t tiles) {
+    constexpr int kRadix = 1 << RB;
     __shared__ unsigned s_hist[8 * kRadix];
     __shared__ uint8_t s_code_of[256];
     __shared__ __align__(16) uint8_t s_codes[16 + kTextTile + kMaxKeySymbols + 16];    // index 16 = first position of the tile
@@ -113,7 +117,7 @@ text_hist_kernel(TextKeySource src, int npass, unsigned long long* __restrict__ 
             if (p < n) {
 #pragma unroll
                 for (int d = 0; d < 8; d++) {
-                    if (d < npass) atomicAdd(&s_hist[d * kRadix + (int)((key >> (8 * d)) & 255)], 1u);
+                    if (d < npass) atomicAdd(&s_hist[d * kRadix + (int)((key >> (RB * d)) & (kRadix - 1))], 1u);
                 }
                 const uint32_t c = s_codes[first + i];
                 if (src.run_marks && key == (uint64_t)c * unit) {
@@ -136,9 +140,11 @@ text_hist_kernel(TextKeySource src, int npass, unsigned long long* __restrict__ 
     }
 }
 
-// exclusive scan of each pass's 256 bins, in place
+// exclusive scan of each pass's bins, in place (one thread per bin)
+template <int RB>
 __global__ void radix_scan_kernel(unsigned long long* hist, int npass) {
-    __shared__ unsigned long long s_warp[8];
+    constexpr int kRadix = 1 << RB;
+    __shared__ unsigned long long s_warp[kRadix / 32];
     for (int p = 0; p < npass; p++) {
         unsigned long long v = hist[p * kRadix + threadIdx.x];
         unsigned long long incl = v;
@@ -156,9 +162,11 @@ __global__ void radix_scan_kernel(unsigned long long* hist, int npass) {
     }
 }
 
-// Lanes of the warp whose 8-bit digit equals mine: one ballot per bit, each folded in with two logic ops
+// Lanes of the warp whose RB-bit digit equals mine: one ballot per bit, each folded in with two logic ops
 // (written in PTX: the compiler's own expansion of the C form spends six instructions per bit).
+template <int RB>
 __device__ __forceinline__ unsigned peers_with_same_digit(unsigned d) {
+    static_assert(RB == 8 || RB == 9, "digit widths the ballot chain is written for");
     unsigned acc;
     asm(
         "{\n"
@@ -175,6 +183,15 @@ __device__ __forceinline__ unsigned peers_with_same_digit(unsigned d) {
         "and.b32 t, %1, 128; setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; selp.b32 m, 0, 0xffffffff, p; lop3.b32 %0, %0, v, m, 0x60;\n"
         "}\n"
         : "=&r"(acc) : "r"(d));
+    if (RB == 9) {
+        asm(
+            "{\n"
+            ".reg .pred p;\n"
+            ".reg .b32 t, v, m;\n"
+            "and.b32 t, %1, 256; setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; selp.b32 m, 0, 0xffffffff, p; lop3.b32 %0, %0, v, m, 0x60;\n"
+            "}\n"
+            : "+r"(acc) : "r"(d));
+    }
     return acc;
 }
 
@@ -194,7 +211,7 @@ __device__ __forceinline__ unsigned peers_with_same_digit(unsigned d) {
 // OPT (tuning variants, GCZ_SORT_VARIANT; 0 = what the benchmarks use): bit 0 = 32-bit destination offsets and no
 // bounds test in the write-out of a full tile; bit 1 = the first look-back window is requested before the shared-memory
 // reorder, so that its latency overlaps the scatter.
-template <int THREADS, int ITEMS, bool HAS_VALS, int MIN_BLOCKS, bool USE_MATCH, bool FROM_TEXT, int OPT = 0>
+template <int THREADS, int ITEMS, bool HAS_VALS, int MIN_BLOCKS, bool USE_MATCH, bool FROM_TEXT, int OPT = 0, int RB = 8>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
                 const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
@@ -202,6 +219,7 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
                 unsigned long long* __restrict__ status, unsigned* __restrict__ ticket, TextKeySource src) {
     constexpr int TILE = THREADS * ITEMS;
     constexpr int WARPS = THREADS / 32;
+    constexpr int kRadix = 1 << RB;
     static_assert(THREADS >= kRadix, "one thread per digit is needed for the look-back");
     static_assert(!FROM_TEXT || HAS_VALS, "text input produces (key, position) pairs");
     static_assert(TILE * 4 >= TILE + kMaxKeySymbols + 8 + 256, "the value staging area holds the tile's symbol codes");
@@ -296,12 +314,12 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
     unsigned* my_hist = s_warp_hist + warp * kRadix;
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
-        const unsigned d = (unsigned)(key[i] >> shift) & 255u;
+        const unsigned d = (unsigned)(key[i] >> shift) & (unsigned)(kRadix - 1);
         unsigned peers;
         if (USE_MATCH) {
             peers = __match_any_sync(0xffffffffu, d);
         } else {
-            peers = peers_with_same_digit(d);
+            peers = peers_with_same_digit<RB>(d);
         }
         const unsigned below = __popc(peers & lt);
         unsigned base = 0;
@@ -346,7 +364,7 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
             s_warp_hist[w * kRadix + threadIdx.x] = total;
             total += c;
         }
-        if (threadIdx.x == kRadix - 1) total -= (unsigned)(TILE - count);     // padding keys are all digit 255
+        if (threadIdx.x == kRadix - 1) total -= (unsigned)(TILE - count);     // padding keys are all the last digit
         st_relaxed_u64(&status[(size_t)tile * kRadix + threadIdx.x],
                        (unsigned long long)total | (tile == 0 ? kFlagPrefix : kFlagAgg));
         const unsigned incl = warp_incl_sum(total);
@@ -371,10 +389,10 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
         }
     }
 
-    // 5. reorder the tile in shared memory (padding keys are digit 255 and rank last: they land at >= count)
+    // 5. reorder the tile in shared memory (padding keys are the last digit and rank last: they land at >= count)
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
-        const unsigned d = (unsigned)(key[i] >> shift) & 255u;
+        const unsigned d = (unsigned)(key[i] >> shift) & (unsigned)(kRadix - 1);
         const unsigned pos = s_digit_start[d] + my_hist[d] + ((i & 1) ? rank2[i >> 1] >> 16 : rank2[i >> 1] & 0xffffu);
         s_keys[pos] = key[i];
         if (HAS_VALS) s_vals[pos] = val[i];
@@ -433,7 +451,7 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
         for (int i = 0; i < ITEMS; i++) {
             const unsigned j = i * THREADS + threadIdx.x;
             const uint64_t k = s_keys[j];
-            const unsigned dst = gofs32[(unsigned)(k >> shift) & 255u] + j;
+            const unsigned dst = gofs32[(unsigned)(k >> shift) & (unsigned)(kRadix - 1)] + j;
             keys_out[dst] = k;
             if (HAS_VALS) vals_out[dst] = s_vals[j];
         }
@@ -444,8 +462,8 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
         const int j = i * THREADS + threadIdx.x;
         if (j < count) {
             const uint64_t k = s_keys[j];
-            const long long dst = (OPT & 1) ? (long long)(reinterpret_cast<const unsigned*>(s_gofs)[(unsigned)(k >> shift) & 255u] + (unsigned)j)
-                                            : s_gofs[(unsigned)(k >> shift) & 255u] + j;
+            const long long dst = (OPT & 1) ? (long long)(reinterpret_cast<const unsigned*>(s_gofs)[(unsigned)(k >> shift) & (unsigned)(kRadix - 1)] + (unsigned)j)
+                                            : s_gofs[(unsigned)(k >> shift) & (unsigned)(kRadix - 1)] + j;
             keys_out[dst] = k;
             if (HAS_VALS) vals_out[dst] = s_vals[j];
         }
@@ -454,28 +472,39 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
 
 typedef void (*OnesweepFn)(const uint64_t*, uint64_t*, const uint32_t*, uint32_t*, int64_t, int, const unsigned long long*,
                            unsigned long long*, unsigned*, TextKeySource);
+typedef void (*HistFn)(const uint64_t*, int64_t, int, int, unsigned long long*);
+typedef void (*TextHistFn)(TextKeySource, int, unsigned long long*, int64_t);
+typedef void (*ScanFn)(unsigned long long*, int);
 
 struct OnesweepConfig {
-    int threads, items;
+    int threads, items, bits;
     OnesweepFn pairs, keys_only, from_text;
+    HistFn hist;
+    TextHistFn text_hist;
+    ScanFn scan;
     size_t smem_pairs, smem_keys;
     int tile() const { return threads * items; }
+    int radix() const { return 1 << bits; }
 };
 
-template <int THREADS, int ITEMS, int MIN_BLOCKS, bool USE_MATCH, int OPT = 0>
+template <int THREADS, int ITEMS, int MIN_BLOCKS, bool USE_MATCH, int OPT = 0, int RB = 8>
 OnesweepConfig make_config() {
+    constexpr int kRadix = 1 << RB;
     const size_t fixed = (size_t)(THREADS / 32) * kRadix * 4 + kRadix * 8 + kRadix * 4 + 64;
     OnesweepConfig c;
-    c.threads = THREADS; c.items = ITEMS;
-    c.pairs = onesweep_kernel<THREADS, ITEMS, true, MIN_BLOCKS, USE_MATCH, false, OPT>;
-    c.keys_only = onesweep_kernel<THREADS, ITEMS, false, MIN_BLOCKS, USE_MATCH, false, OPT>;
-    c.from_text = onesweep_kernel<THREADS, ITEMS, true, MIN_BLOCKS, USE_MATCH, true, OPT>;
+    c.threads = THREADS; c.items = ITEMS; c.bits = RB;
+    c.pairs = onesweep_kernel<THREADS, ITEMS, true, MIN_BLOCKS, USE_MATCH, false, OPT, RB>;
+    c.keys_only = onesweep_kernel<THREADS, ITEMS, false, MIN_BLOCKS, USE_MATCH, false, OPT, RB>;
+    c.from_text = onesweep_kernel<THREADS, ITEMS, true, MIN_BLOCKS, USE_MATCH, true, OPT, RB>;
+    c.hist = radix_hist_kernel<RB>;
+    c.text_hist = text_hist_kernel<RB>;
+    c.scan = radix_scan_kernel<RB>;
     c.smem_pairs = (size_t)THREADS * ITEMS * 12 + fixed;
     c.smem_keys = (size_t)THREADS * ITEMS * 8 + fixed;
     return c;
 }
 
-// GCZ_SORT_VARIANT selects the tile shape / ranking primitive (tuning knob; 0 is what the benchmarks use).
+// GCZ_SORT_VARIANT selects the tile shape / ranking primitive / digit width (tuning knob; 0 is what the benchmarks use).
 // profiles/sort_variants_r01.md holds the sweep these were picked from.
 const OnesweepConfig& config() {
     static const OnesweepConfig table[] = {
@@ -490,6 +519,10 @@ const OnesweepConfig& config() {
         make_config<512, 12, 2, false, 1>(),  // 8: as 0, 32-bit destination offsets              (untested on hardware yet)
         make_config<512, 12, 2, false, 2>(),  // 9: as 0, early look-back window                  (untested on hardware yet)
         make_config<512, 12, 2, false, 3>(),  // 10: both                                         (untested on hardware yet)
+        // 9-bit digits: a 44-bit key (17 symbols of ACGTN + separator) takes 5 passes instead of 6; 512 bins, one per thread,
+        // 110.6 KB of shared memory per CTA (two still fit an SM), status words twice as many
+        make_config<512, 12, 2, false, 0, 9>(),  // 11: as 0, 9-bit digits                        (untested on hardware yet)
+        make_config<512, 12, 2, false, 3, 9>(),  // 12: as 10, 9-bit digits                       (untested on hardware yet)
     };
     static const int pick = [] {
         const char* e = getenv("GCZ_SORT_VARIANT");
@@ -503,27 +536,36 @@ constexpr int kMinTile = 4096;          // smallest tile of any variant: sizes t
 
 }  // namespace
 
+int radix_sort_passes(int bits) { return (bits + config().bits - 1) / config().bits; }
+
 size_t radix_sort_temp_bytes(int64_t n) {
     const int64_t tiles = (n + kMinTile - 1) / kMinTile;
-    // [8][256] histogram + per-pass (status[tiles][256] + ticket)
-    return 8 * kRadix * 8 + 256 + ((size_t)tiles * kRadix * 8 + 256);
+    const size_t radix = (size_t)config().radix();
+    // [8][radix] histogram + per-pass (status[tiles][radix] + ticket)
+    return 8 * radix * 8 + 256 + ((size_t)tiles * radix * 8 + 256);
 }
 
 int radix_sort_pairs(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n, int begin_bit, int end_bit,
                      void* temp, SortStats* stats, const TextKeySource* src) {
     if (n <= 0 || end_bit <= begin_bit) return GCZ_OK;
     if (end_bit - begin_bit > 64 || begin_bit < 0) return fail(GCZ_E_ARG, "radix sort bit range");
-    const int npass = (end_bit - begin_bit + 7) / 8;
+    const OnesweepConfig& cfg = config();
+    const int npass = radix_sort_passes(end_bit - begin_bit);
+    const int kRadix = cfg.radix();
     const bool has_vals = b.vals[0] != nullptr;
     if (src && (!has_vals || begin_bit != 0 || src->n != n)) return fail(GCZ_E_ARG, "radix sort from text: arguments");
-    const OnesweepConfig& cfg = config();
+    // two CTAs of the 9-bit variants need 221 KB of an SM's 228: ask for the largest shared-memory carve-out
+    const bool wide = cfg.bits > 8;
     if (!ctx->sort_attr[has_vals ? 1 : 0]) {
         GCZ_CUDA(cudaFuncSetAttribute(has_vals ? cfg.pairs : cfg.keys_only, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(has_vals ? cfg.smem_pairs : cfg.smem_keys)));
+        if (wide) GCZ_CUDA(cudaFuncSetAttribute(has_vals ? cfg.pairs : cfg.keys_only, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                (int)cudaSharedmemCarveoutMaxShared));
         ctx->sort_attr[has_vals ? 1 : 0] = true;
     }
     if (src && !ctx->sort_attr[2]) {
         GCZ_CUDA(cudaFuncSetAttribute(cfg.from_text, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_pairs));
+        if (wide) GCZ_CUDA(cudaFuncSetAttribute(cfg.from_text, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         ctx->sort_attr[2] = true;
     }
     auto* hist = static_cast<unsigned long long*>(temp);
@@ -532,21 +574,21 @@ int radix_sort_pairs(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n
     auto* ticket = reinterpret_cast<unsigned*>(status + (size_t)tiles * kRadix);
     const TextKeySource none;
 
-    GCZ_CUDA(cudaMemsetAsync(hist, 0, 8 * kRadix * 8, st));
+    GCZ_CUDA(cudaMemsetAsync(hist, 0, (size_t)8 * kRadix * 8, st));
     if (src) {
         const int64_t ttiles = (n + kTextTile - 1) / kTextTile;
         const int grid = (int)std::min<int64_t>(ttiles, (int64_t)ctx->sm_count * 8);
-        GCZ_LAUNCH(ctx, text_hist_kernel, grid, kTextThreads, 0, st, *src, npass, hist, ttiles);
+        GCZ_LAUNCH(ctx, cfg.text_hist, grid, kTextThreads, 0, st, *src, npass, hist, ttiles);
     } else {
         const int hist_grid = (int)std::min<int64_t>((n + kHistThreads * 8 - 1) / (kHistThreads * 8), (int64_t)ctx->sm_count * 4);
-        GCZ_LAUNCH(ctx, radix_hist_kernel, hist_grid, kHistThreads, 0, st, b.keys[b.cur], n, begin_bit, npass, hist);
+        GCZ_LAUNCH(ctx, cfg.hist, hist_grid, kHistThreads, 0, st, b.keys[b.cur], n, begin_bit, npass, hist);
     }
-    GCZ_LAUNCH(ctx, radix_scan_kernel, 1, kRadix, 0, st, hist, npass);
+    GCZ_LAUNCH(ctx, cfg.scan, 1, kRadix, 0, st, hist, npass);
 
     for (int p = 0; p < npass; p++) {
         GCZ_CUDA(cudaMemsetAsync(status, 0, (size_t)tiles * kRadix * 8 + 64, st));
         const int in = b.cur, out = b.cur ^ 1;
-        const int shift = begin_bit + 8 * p;
+        const int shift = begin_bit + cfg.bits * p;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (stats) {
             GCZ_CUDA(cudaEventCreate(&e0)); GCZ_CUDA(cudaEventCreate(&e1));

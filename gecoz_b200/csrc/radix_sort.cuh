@@ -47,6 +47,7 @@ struct SortStats {
 };
 
 size_t radix_sort_temp_bytes(int64_t n);
+int    radix_sort_passes(int bits);         // digit passes a sort of `bits` key bits takes (8-bit digits unless GCZ_SORT_VARIANT says otherwise)
 
 // Sorts bits [begin_bit, end_bit) of the keys, stable, ascending.  Result is in b.keys[b.cur] / b.vals[b.cur].
 // With `src` the input is the text (see TextKeySource; begin_bit must be 0 and values are required).

@@ -501,7 +501,7 @@ int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t 
     GCZ_CUDA(cudaMemsetAsync(d_rank, 0xFF, (size_t)n * 4, st));
 
     // full sort by the first k symbols; start in the buffer that makes the result land in d_sa
-    const int npass = (key_bits + 7) / 8;
+    const int npass = radix_sort_passes(key_bits);
     RadixBuffers b;
     b.keys[0] = d_keys0; b.keys[1] = d_keys1;
     b.vals[0] = d_sa;    b.vals[1] = d_vals1;
