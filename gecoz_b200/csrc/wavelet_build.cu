@@ -11,6 +11,7 @@
 #include "wavelet_build.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -265,6 +266,112 @@ hswt_emit_small_kernel(const uint8_t* __restrict__ bwt, int64_t n, const SymbolT
         }
     }
     if (fill > 0 && (uint32_t)acc != 0) atomicOr(&raw[word], (uint32_t)acc);
+}
+
+// Experimental (GCZ_EMIT_VARIANT=1; the build uses hswt_emit_small_kernel unless asked): trees of at most kLutNodes nodes,
+// i.e. alphabets of up to 8 symbols.  Every lane takes 32 consecutive BWT symbols and appends to its own per-node
+// accumulators, four symbols at a time through a table indexed by the four dense codes (entry: for every node one byte,
+// the branch bits of those of the four symbols that pass the node, low bit first, and how many they are above bit 4).
+// A warp-wide prefix over the per-lane bit counts places each lane's fragment; fragments meet in shared memory and the
+// tile's words go out with plain stores, except the first and last word of a node, which neighbouring tiles share.
+// About 12 instructions per symbol and lane instead of one ballot + reduction per node and 32 symbols.
+constexpr int kLutNodes = 8;
+constexpr int kLutStageWords = 34;                      // 31 + 1024 bits of one tile in one node, + 1 for the carry word
+
+template <int NODES>
+__global__ void __launch_bounds__(kWtThreads)
+hswt_emit_lut_kernel(const uint8_t* __restrict__ bwt, int64_t n, const SymbolTables* __restrict__ tab,
+                     const uint2* __restrict__ lut, int lut_entries,
+                     const uint32_t* __restrict__ tile_prefix /* [sigma][tiles], exclusive */, int64_t tiles,
+                     const uint64_t* __restrict__ node_raw_word, uint32_t* __restrict__ raw) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    uint2* s_lut = reinterpret_cast<uint2*>(s_dyn);
+    uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_lut + lut_entries);          // [warps][NODES][kLutStageWords]
+    __shared__ uint32_t s_path[256], s_bit[256];
+    __shared__ uint8_t s_dense[256];
+    for (int i = threadIdx.x; i < lut_entries; i += kWtThreads) s_lut[i] = lut[i];
+    s_path[threadIdx.x] = tab->path_mask[threadIdx.x];
+    s_bit[threadIdx.x] = tab->bit_mask[threadIdx.x];
+    s_dense[threadIdx.x] = tab->dense[threadIdx.x];
+    __syncthreads();
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    const unsigned sigma = (unsigned)tab->sigma;
+    uint32_t* stage = s_stage + warp * (NODES * kLutStageWords);
+    const bool aligned = (reinterpret_cast<uintptr_t>(bwt) & 15) == 0;
+
+    for (int64_t tile = (int64_t)blockIdx.x * (kWtThreads / 32) + warp; tile < tiles; tile += (int64_t)gridDim.x * (kWtThreads / 32)) {
+        // where this tile's bits start in "my" node: symbols routed through it, summed over earlier tiles
+        uint32_t my_word = 0, my_fill = 0;
+        if ((int)lane < NODES) {
+            unsigned long long bit0 = node_raw_word[lane] * 32ull;
+            for (unsigned s = 0; s < sigma; s++) {
+                if ((s_path[s] >> lane) & 1u) bit0 += tile_prefix[(size_t)s * tiles + tile];
+            }
+            my_word = (uint32_t)(bit0 >> 5);                   // raw areas are far below 2^32 words
+            my_fill = (uint32_t)(bit0 & 31);
+        }
+        for (int i = lane; i < NODES * kLutStageWords; i += 32) stage[i] = 0;
+        __syncwarp();
+
+        uint32_t acc[NODES], cnt[NODES];
+#pragma unroll
+        for (int v = 0; v < NODES; v++) { acc[v] = 0; cnt[v] = 0; }
+        const int64_t p0 = tile * kWarpTile + (int64_t)lane * 32;
+        if (aligned && p0 + 32 <= n) {
+            const uint4 q0 = *reinterpret_cast<const uint4*>(bwt + p0), q1 = *reinterpret_cast<const uint4*>(bwt + p0 + 16);
+            const uint32_t w[8] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w };
+#pragma unroll
+            for (int g = 0; g < 8; g++) {
+                const uint32_t x = w[g];                       // four symbols, the first one in the low byte
+                const unsigned idx = (((unsigned)s_dense[x & 255] * sigma + s_dense[(x >> 8) & 255]) * sigma + s_dense[(x >> 16) & 255]) * sigma
+                                     + s_dense[x >> 24];
+                const uint2 e = s_lut[idx];
+#pragma unroll
+                for (int v = 0; v < NODES; v++) {
+                    const uint32_t b = ((v < 4 ? e.x : e.y) >> (8 * (v & 3))) & 255u;
+                    acc[v] |= (b & 15u) << cnt[v];             // never shifted out: a lane holds 32 symbols
+                    cnt[v] += b >> 4;
+                }
+            }
+        } else {
+            for (int i = 0; i < 32 && p0 + i < n; i++) {
+                const unsigned d = s_dense[bwt[p0 + i]];
+                const uint32_t pm = s_path[d], bm = s_bit[d] & pm;
+#pragma unroll
+                for (int v = 0; v < NODES; v++) {
+                    acc[v] |= (((pm >> v) & 1u) ? ((bm >> v) & 1u) : 0u) << cnt[v];
+                    cnt[v] += (pm >> v) & 1u;
+                }
+            }
+        }
+
+#pragma unroll
+        for (int v = 0; v < NODES; v++) {
+            unsigned incl = cnt[v];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)lane >= o) incl += t;
+            }
+            const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+            const unsigned fill0 = __shfl_sync(0xffffffffu, my_fill, v), word0 = __shfl_sync(0xffffffffu, my_word, v);
+            uint32_t* node_stage = stage + v * kLutStageWords;
+            if (cnt[v]) {
+                const unsigned o = fill0 + (incl - cnt[v]), wi = o >> 5, sh = o & 31;
+                atomicOr(&node_stage[wi], acc[v] << sh);
+                if (sh && sh + cnt[v] > 32) atomicOr(&node_stage[wi + 1], acc[v] >> (32 - sh));
+            }
+            __syncwarp();
+            const unsigned bits = fill0 + total, words = (bits + 31) >> 5;
+            for (unsigned wd = lane; wd < words; wd += 32) {
+                const uint32_t val = node_stage[wd];
+                const bool shared_word = (wd == 0 && fill0 != 0) || (wd == words - 1 && (bits & 31) != 0);
+                if (!shared_word) raw[word0 + wd] = val;       // this tile owns every bit of the word
+                else if (val) atomicOr(&raw[word0 + wd], val);
+            }
+        }
+        __syncwarp();
+    }
 }
 
 // ---- sampled suffix array values in SA order -----------------------------------------------------------
@@ -661,6 +768,31 @@ int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_t
     GCZ_CUDA(cudaMemcpyAsync(d_vecs, vecs.data(), sizeof(VectorDesc) * vecs.size(), cudaMemcpyHostToDevice, st));
     GCZ_CUDA(cudaMemsetAsync(d_raw, 0, ((size_t)raw_words + 16) * 4, st));
 
+    // experimental table-driven node emission (GCZ_EMIT_VARIANT=1): alphabets of up to 8 symbols
+    const char* emit_env = std::getenv("GCZ_EMIT_VARIANT");
+    const bool emit_lut = emit_env && emit_env[0] == '1' && sigma <= 8 && n_nodes <= kLutNodes;
+    std::vector<uint2> h_lut;
+    uint2* d_lut = nullptr;
+    if (emit_lut) {
+        const int entries = sigma * sigma * sigma * sigma;
+        h_lut.assign((size_t)entries, make_uint2(0u, 0u));
+        for (int g = 0; g < entries; g++) {
+            const int d[4] = { g / (sigma * sigma * sigma), (g / (sigma * sigma)) % sigma, (g / sigma) % sigma, g % sigma };   // text order
+            uint8_t bytes[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+            for (int v = 0; v < n_nodes; v++) {
+                unsigned p = 0, c = 0;
+                for (int i = 0; i < 4; i++) {
+                    if ((h_tab.path_mask[d[i]] >> v) & 1u) { p |= ((h_tab.bit_mask[d[i]] >> v) & 1u) << c; c++; }
+                }
+                bytes[v] = (uint8_t)(p | (c << 4));
+            }
+            std::memcpy(&h_lut[(size_t)g], bytes, 8);
+        }
+        d_lut = arena.get<uint2>((size_t)entries);
+        if (!d_lut) return fail(GCZ_E_NOMEM, "wavelet workspace for n=%lld", (long long)n);
+        GCZ_CUDA(cudaMemcpyAsync(d_lut, h_lut.data(), sizeof(uint2) * (size_t)entries, cudaMemcpyHostToDevice, st));   // synchronised below
+    }
+
     // shape table at the head of the body
     {
         std::vector<uint8_t> tbl((size_t)shape->table_bytes + 8);
@@ -677,7 +809,17 @@ int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_t
     GCZ_LAUNCH(ctx, bwt_count_kernel, wt_grid, kWtThreads, 0, st, d_text, d_sa, n, d_tab, sample_mask, carry_shift,
                (carry_shift && clean_sa) ? d_sa : (uint32_t*)nullptr, d_bwt, d_marker_raw, d_tile_counts, tiles);
     GCZ_LAUNCH(ctx, row_scan_kernel, (unsigned)(sigma + 1), 1024, 0, st, d_tile_counts, tiles, (uint32_t*)nullptr);
-    if (n_nodes <= 32) {
+    if (emit_lut) {
+        const int entries = (int)h_lut.size();
+        const size_t smem = sizeof(uint2) * (size_t)entries + (size_t)(kWtThreads / 32) * n_nodes * kLutStageWords * 4;
+        const unsigned grid = (unsigned)std::min<int64_t>((int64_t)wt_grid, (int64_t)ctx->sm_count * 8);
+        switch (n_nodes) {
+#define GCZ_EMIT_LUT(N) case N: GCZ_LAUNCH(ctx, hswt_emit_lut_kernel<N>, grid, kWtThreads, smem, st, d_bwt, n, d_tab, d_lut, entries, \
+                                           d_tile_counts, tiles, d_node_raw, d_raw); break;
+            GCZ_EMIT_LUT(1) GCZ_EMIT_LUT(2) GCZ_EMIT_LUT(3) GCZ_EMIT_LUT(4) GCZ_EMIT_LUT(5) GCZ_EMIT_LUT(6) GCZ_EMIT_LUT(7) GCZ_EMIT_LUT(8)
+#undef GCZ_EMIT_LUT
+        }
+    } else if (n_nodes <= 32) {
         GCZ_LAUNCH(ctx, hswt_emit_small_kernel, wt_grid, kWtThreads, 0, st, d_bwt, n, d_tab, d_tile_counts, tiles, d_node_raw, d_raw);
     } else {
         GCZ_LAUNCH(ctx, hswt_emit_kernel, wt_grid, kWtThreads, 0, st, d_bwt, n, d_tab, d_tile_counts, tiles, d_node_raw, d_raw);
