@@ -62,7 +62,9 @@ __device__ __forceinline__ uint64_t slide_key(uint64_t key, uint32_t c_out, uint
     return key * radix + c_in;
 }
 
-template <int RB>
+// UNIFORM (experimental, GCZ_TEXT_HIST_VARIANT=1): inside a long run of one symbol all 32 lanes of a warp hold the same key
+// and their six shared-memory atomics hit one counter each; such a warp lets lane 0 add 32 instead.
+template <int RB, bool UNIFORM = false>
 __global__ void __launch_bounds__(kTextThreads)
 text_hist_kernel(TextKeySource src, int npass, unsigned long long* __restrict__ hist /* [npass][radix] */, int64_t tiles) {
     constexpr int kRadix = 1 << RB;
@@ -114,10 +116,21 @@ text_hist_kernel(TextKeySource src, int npass, unsigned long long* __restrict__ 
         for (int i = 0; i < kTextItems; i++) {
             key = slide_key(key, i > 0 ? s_codes[first + i - 1] : 0u, s_codes[first + i + k - 1], radix, top);
             const int64_t p = base + first - 16 + i;
+            bool counted = false;
+            if (UNIFORM) {
+                const uint64_t key0 = __shfl_sync(0xffffffffu, key, 0);
+                counted = __all_sync(0xffffffffu, p < n && key == key0);
+                if (counted && (threadIdx.x & 31) == 0) {
+#pragma unroll
+                    for (int d = 0; d < 8; d++) {
+                        if (d < npass) atomicAdd(&s_hist[d * kRadix + (int)((key >> (RB * d)) & (kRadix - 1))], 32u);
+                    }
+                }
+            }
             if (p < n) {
 #pragma unroll
                 for (int d = 0; d < 8; d++) {
-                    if (d < npass) atomicAdd(&s_hist[d * kRadix + (int)((key >> (RB * d)) & (kRadix - 1))], 1u);
+                    if (d < npass && !counted) atomicAdd(&s_hist[d * kRadix + (int)((key >> (RB * d)) & (kRadix - 1))], 1u);
                 }
                 const uint32_t c = s_codes[first + i];
                 if (src.run_marks && key == (uint64_t)c * unit) {
@@ -487,6 +500,11 @@ struct OnesweepConfig {
     int radix() const { return 1 << bits; }
 };
 
+bool text_hist_uniform() {
+    const char* e = getenv("GCZ_TEXT_HIST_VARIANT");
+    return e && e[0] == '1';
+}
+
 template <int THREADS, int ITEMS, int MIN_BLOCKS, bool USE_MATCH, int OPT = 0, int RB = 8>
 OnesweepConfig make_config() {
     constexpr int kRadix = 1 << RB;
@@ -497,7 +515,7 @@ OnesweepConfig make_config() {
     c.keys_only = onesweep_kernel<THREADS, ITEMS, false, MIN_BLOCKS, USE_MATCH, false, OPT, RB>;
     c.from_text = onesweep_kernel<THREADS, ITEMS, true, MIN_BLOCKS, USE_MATCH, true, OPT, RB>;
     c.hist = radix_hist_kernel<RB>;
-    c.text_hist = text_hist_kernel<RB>;
+    c.text_hist = text_hist_uniform() ? text_hist_kernel<RB, true> : text_hist_kernel<RB, false>;
     c.scan = radix_scan_kernel<RB>;
     c.smem_pairs = (size_t)THREADS * ITEMS * 12 + fixed;
     c.smem_keys = (size_t)THREADS * ITEMS * 8 + fixed;
