@@ -42,6 +42,10 @@ struct SymbolTables {
 // ---- BWT gather + per-tile symbol counts + marker bits -----------------------------------------------
 // carry_shift != 0: SA entries hold the dense code (1..sigma) of the preceding text symbol above bit carry_shift
 // (suffix_sort.cuh) — the BWT is read off the entries and, when sa_clean is set, plain positions are written back.
+// PACKED (experimental, GCZ_BWT_VARIANT=1, alphabets of up to 8 symbols): every lane counts its own symbols in eight 8-bit
+// fields of one register (32 symbols per lane and tile, so no field overflows) and the warp adds the fields up once per
+// tile, instead of one ballot round per distinct symbol of every 32-symbol chunk.
+template <bool PACKED>
 __global__ void __launch_bounds__(kWtThreads)
 bwt_count_kernel(const uint8_t* __restrict__ text, const uint32_t* __restrict__ sa, int64_t n,
                  const SymbolTables* __restrict__ tab, uint32_t sample_mask, int carry_shift, uint32_t* __restrict__ sa_clean,
@@ -61,6 +65,7 @@ bwt_count_kernel(const uint8_t* __restrict__ text, const uint32_t* __restrict__ 
     const uint32_t pos_mask = carry_shift ? (1u << carry_shift) - 1u : 0xFFFFFFFFu;
     uint32_t* cnt = s_cnt[warp];
     unsigned marks = 0;
+    unsigned long long packed = 0;
 #pragma unroll 1
     for (int c0 = 0; c0 < kWarpTile / 32; c0 += 4) {
         uint32_t s[4];
@@ -89,6 +94,10 @@ bwt_count_kernel(const uint8_t* __restrict__ text, const uint32_t* __restrict__ 
             const unsigned mk = __ballot_sync(0xffffffffu, valid && (s[u] & sample_mask) == 0);
             if (lane == 0 && base + (c0 + u) * 32 < n) marker_raw[(base >> 5) + c0 + u] = mk;
             marks += (lane == 0) ? __popc(mk) : 0;
+            if (PACKED) {
+                if (valid) packed += 1ull << (8 * d[u]);
+                continue;
+            }
             // count every distinct symbol of this chunk once
             unsigned todo = __ballot_sync(0xffffffffu, valid);
             while (todo) {
@@ -100,6 +109,16 @@ bwt_count_kernel(const uint8_t* __restrict__ text, const uint32_t* __restrict__ 
             }
             __syncwarp();
         }
+    }
+    if (PACKED) {
+        // symbols 0, 2, 4, 6 and 1, 3, 5, 7 in 16-bit fields: a tile holds 1024 symbols
+        unsigned long long even = packed & 0x00FF00FF00FF00FFull, odd = (packed >> 8) & 0x00FF00FF00FF00FFull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            even += __shfl_xor_sync(0xffffffffu, even, o);
+            odd += __shfl_xor_sync(0xffffffffu, odd, o);
+        }
+        if ((int)lane < sigma) cnt[lane] = (uint32_t)(((lane & 1u) ? odd : even) >> (16 * (lane >> 1))) & 0xFFFFu;
     }
     __syncwarp();
     if (lane == 0) cnt[sigma] = marks;
@@ -806,8 +825,14 @@ int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_t
     const unsigned wt_grid = (unsigned)((tiles + kWtThreads / 32 - 1) / (kWtThreads / 32));
     const uint32_t sample_mask = (1u << sampling_factor) - 1u;
     uint32_t* d_marker_raw = d_raw + vecs[marker_vec].raw_word;
-    GCZ_LAUNCH(ctx, bwt_count_kernel, wt_grid, kWtThreads, 0, st, d_text, d_sa, n, d_tab, sample_mask, carry_shift,
-               (carry_shift && clean_sa) ? d_sa : (uint32_t*)nullptr, d_bwt, d_marker_raw, d_tile_counts, tiles);
+    const char* bwt_env = std::getenv("GCZ_BWT_VARIANT");
+    if (bwt_env && bwt_env[0] == '1' && sigma <= 8) {
+        GCZ_LAUNCH(ctx, bwt_count_kernel<true>, wt_grid, kWtThreads, 0, st, d_text, d_sa, n, d_tab, sample_mask, carry_shift,
+                   (carry_shift && clean_sa) ? d_sa : (uint32_t*)nullptr, d_bwt, d_marker_raw, d_tile_counts, tiles);
+    } else {
+        GCZ_LAUNCH(ctx, bwt_count_kernel<false>, wt_grid, kWtThreads, 0, st, d_text, d_sa, n, d_tab, sample_mask, carry_shift,
+                   (carry_shift && clean_sa) ? d_sa : (uint32_t*)nullptr, d_bwt, d_marker_raw, d_tile_counts, tiles);
+    }
     GCZ_LAUNCH(ctx, row_scan_kernel, (unsigned)(sigma + 1), 1024, 0, st, d_tile_counts, tiles, (uint32_t*)nullptr);
     if (emit_lut) {
         const int entries = (int)h_lut.size();
