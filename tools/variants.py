@@ -1,0 +1,148 @@
+#!/usr/bin/env python
+"""variants.py — check and time every experimental kernel variant in ONE GPU call.
+
+    python tools/variants.py [--length 248956422] [--steps 5] [--out gpurun_out/variants.jsonl] [--only NAME ...]
+
+The variants are selected by environment variables read once per process, so each one runs in a child process:
+  1. parity: a block of every "family" below is built and compared byte for byte with the build of the DEFAULT kernels
+     (which the GPU parity tests compare with the oracle) — suffix array, BWT, .gcz body, .gcx body;
+  2. time: --steps device-resident builds of the chr1-shaped block; mean of total / sort / wavelet phase times and of the
+     digit passes (gcz_last_build_timing).
+One JSON line per variant.  Needs a GPU; nothing here is a bench value (no clock sampling, no e2e).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+VARIANTS = {
+    "default": {},
+    "sort8_dst32": {"GCZ_SORT_VARIANT": "8"},
+    "sort9_early_lookback": {"GCZ_SORT_VARIANT": "9"},
+    "sort10_both": {"GCZ_SORT_VARIANT": "10"},
+    "sort11_9bit": {"GCZ_SORT_VARIANT": "11"},
+    "sort12_9bit_both": {"GCZ_SORT_VARIANT": "12"},
+    "emit_lut": {"GCZ_EMIT_VARIANT": "1"},
+    "text_hist_uniform": {"GCZ_TEXT_HIST_VARIANT": "1"},
+    "bwt_packed": {"GCZ_BWT_VARIANT": "1"},
+    "all_small": {"GCZ_EMIT_VARIANT": "1", "GCZ_TEXT_HIST_VARIANT": "1", "GCZ_BWT_VARIANT": "1"},
+    "all_small_9bit": {"GCZ_EMIT_VARIANT": "1", "GCZ_TEXT_HIST_VARIANT": "1", "GCZ_BWT_VARIANT": "1", "GCZ_SORT_VARIANT": "11"},
+}
+
+
+def families():
+    import numpy as np
+    from gecoz_b200 import synth
+    rng = np.random.default_rng(11)
+    acgtn = np.frombuffer(b"ACGTN", np.uint8)
+    yield "tiny", np.frombuffer(b"GATTACA\0", np.uint8).copy()
+    yield "two_strings", np.frombuffer(b"ACGTN\0ACG\0", np.uint8).copy()
+    yield "iid_300k", synth.cfg1_text(300_000)
+    yield "chr_shaped_3M", synth.cfg2_text(3_000_000)
+    yield "all_same", synth.block_of([np.full(50_000, ord("A"), np.uint8)])
+    yield "tandem", synth.block_of([np.frombuffer(b"ACACACACGT" * 30_000, np.uint8)])
+    yield "multi", synth.block_of([synth.iid_acgtn(30_000, 5), synth.iid_acgtn(20_000, 6), synth.iid_acgtn(7, 7),
+                                   np.zeros(0, np.uint8), synth.iid_acgtn(20_000, 6)])
+    yield "lower_iupac", synth.block_of([np.frombuffer(b"ACGTNacgtnRYKM", np.uint8)[rng.integers(0, 14, 150_000)]])
+    lens = rng.integers(1, 200, 4000)
+    yield "runs_mixed", synth.block_of([np.repeat(acgtn[rng.integers(0, 5, len(lens))], lens)])
+    yield "acgt_only", synth.block_of([np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 1_000_003)]])
+    yield "eight_symbols", synth.block_of([np.frombuffer(b"ACGTNRY", np.uint8)[rng.integers(0, 7, 400_001)]])
+
+
+def build(G, text, rate=32):
+    import numpy as np
+    shape = G.shape_from_counts(G.symbol_counts(text))
+    gcz = np.zeros(int(shape.size), np.uint8)
+    gcx = np.zeros(G.index_size(len(text), rate.bit_length() - 1), np.uint8)
+    sa = np.zeros(len(text), np.int32)
+    bwt = np.zeros(len(text), np.uint8)
+    t = G.build_block(0, text, len(text), rate, shape, gcz, gcx, sa, bwt)
+    return gcz, gcx, sa, bwt, t
+
+
+def child(args) -> None:
+    """Runs under the variant's environment: builds every family, stores or compares the results, then times cfg2."""
+    import hashlib
+    import numpy as np
+    import torch
+    import gecoz_b200 as G
+    from gecoz_b200 import synth
+    G.lib()
+    ref_path = Path(args.ref)
+    ref = json.loads(ref_path.read_text()) if ref_path.exists() else None
+    digests, mismatches = {}, []
+    for name, text in families():
+        for rate in (32, 4):
+            gcz, gcx, sa, bwt, _ = build(G, text, rate)
+            d = [hashlib.sha256(a.tobytes()).hexdigest() for a in (gcz, gcx, sa, bwt)]
+            digests[f"{name}/{rate}"] = d
+            if ref is not None and ref.get(f"{name}/{rate}") != d:
+                what = [w for w, x, y in zip(("gcz", "gcx", "sa", "bwt"), ref.get(f"{name}/{rate}", [None] * 4), d) if x != y]
+                mismatches.append(f"{name}/{rate}: {','.join(what)}")
+    if ref is None:
+        ref_path.write_text(json.dumps(digests))
+    # timing: device-resident builds of the chr1-shaped block
+    text = synth.cfg2_text(args.length, seed=3)
+    n = len(text)
+    d_text = torch.from_numpy(text).cuda()
+    shape = G.shape_from_counts(G.symbol_counts(d_text, 0))
+    d_gcz = torch.empty(int(shape.size), dtype=torch.uint8, device="cuda")
+    d_gcx = torch.empty(G.index_size(n, 5), dtype=torch.uint8, device="cuda")
+    infos = []
+    for i in range(2 + args.steps):
+        t = G.build_block(0, d_text, n, 32, shape, d_gcz, d_gcx)
+        if i >= 2:
+            infos.append(t)
+    keys = ("total_ms", "sort_initial_ms", "sort_refine_ms", "bwt_hswt_ms", "ssa_ms", "radix_ms", "radix_full_ms", "radix_text_ms",
+            "radix_launches", "radix_full_launches", "kernel_launches")
+    mean = {k: float(np.mean([t[k] for t in infos])) for k in keys}
+    big = hashlib.sha256(d_gcz.cpu().numpy().tobytes()).hexdigest()[:16] + hashlib.sha256(d_gcx.cpu().numpy().tobytes()).hexdigest()[:16]
+    print("RESULT " + json.dumps({"variant": args.child, "env": VARIANTS[args.child], "parity_vs_default": "stored" if ref is None else
+                                  ("ok" if not mismatches else mismatches), "cfg2_digest": big, "n": n, **mean}), flush=True)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--length", type=int, default=248_956_422)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--out", default=str(ROOT / "gpurun_out" / "variants.jsonl"))
+    ap.add_argument("--only", nargs="*", default=None)
+    ap.add_argument("--child", default=None)
+    ap.add_argument("--ref", default="/tmp/gcz_variants_ref.json")
+    args = ap.parse_args()
+    if args.child:
+        child(args)
+        return
+    out = Path(args.out)
+    out.parent.mkdir(parents=True, exist_ok=True)
+    Path(args.ref).unlink(missing_ok=True)
+    names = ["default"] + [v for v in VARIANTS if v != "default" and (not args.only or v in args.only)]
+    base_digest = None
+    with open(out, "w") as f:
+        for name in names:
+            env = dict(os.environ, **VARIANTS[name])
+            r = subprocess.run([sys.executable, __file__, "--child", name, "--length", str(args.length), "--steps", str(args.steps),
+                                "--ref", args.ref], env=env, capture_output=True, text=True, timeout=900)
+            line = next((l[7:] for l in r.stdout.splitlines() if l.startswith("RESULT ")), None)
+            rec = json.loads(line) if line else {"variant": name, "env": VARIANTS[name], "failed": r.returncode,
+                                                 "stderr": r.stderr[-1500:]}
+            if name == "default" and line:
+                base_digest = rec["cfg2_digest"]
+            elif line:
+                rec["cfg2_same_as_default"] = rec["cfg2_digest"] == base_digest
+            f.write(json.dumps(rec) + "\n")
+            f.flush()
+            print(json.dumps({k: rec.get(k) for k in ("variant", "parity_vs_default", "cfg2_same_as_default", "total_ms", "sort_initial_ms",
+                                                      "bwt_hswt_ms", "radix_full_ms", "radix_text_ms", "failed")}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
