@@ -223,7 +223,7 @@ __device__ __forceinline__ unsigned peers_with_same_digit(unsigned d) {
 //      slid over ITEMS consecutive positions per thread, transposed to the warp-striped order through shared memory
 // OPT (tuning variants, GCZ_SORT_VARIANT; 0 = what the benchmarks use): bit 0 = 32-bit destination offsets and no
 // bounds test in the write-out of a full tile; bit 1 = the first look-back window is requested before the shared-memory
-// reorder, so that its latency overlaps the scatter.
+// reorder, so that its latency overlaps the scatter; bit 2 = the tile's values are prefetched into L2 while the keys are ranked.
 template <int THREADS, int ITEMS, bool HAS_VALS, int MIN_BLOCKS, bool USE_MATCH, bool FROM_TEXT, int OPT = 0, int RB = 8>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
@@ -314,6 +314,13 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
             const int e = warp_base + i * 32 + lane;
             key[i] = e < count ? keys_in[tile_base + e] : ~0ull;
         }
+    }
+
+    // OPT bit 2: the values are not wanted in registers before the ranking is done, but their lines can be on their way to L2
+    if ((OPT & 4) && HAS_VALS && !FROM_TEXT && count == TILE) {
+        const uint32_t* src_vals = vals_in + tile_base + warp_base + lane;
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) asm volatile("prefetch.global.L2 [%0];" :: "l"(src_vals + i * 32));
     }
 
     // every key is requested before the first one is used (the ranking below is short enough that the scheduler
@@ -541,6 +548,8 @@ const OnesweepConfig& config() {
         // 110.6 KB of shared memory per CTA (two still fit an SM), status words twice as many
         make_config<512, 12, 2, false, 0, 9>(),  // 11: as 0, 9-bit digits                        (untested on hardware yet)
         make_config<512, 12, 2, false, 3, 9>(),  // 12: as 10, 9-bit digits                       (untested on hardware yet)
+        make_config<512, 12, 2, false, 4>(),     // 13: as 0, values prefetched to L2 during the ranking (untested on hardware yet)
+        make_config<512, 12, 2, false, 4, 9>(),  // 14: as 11, the same                             (untested on hardware yet)
     };
     static const int pick = [] {
         const char* e = getenv("GCZ_SORT_VARIANT");

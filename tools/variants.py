@@ -29,6 +29,8 @@ VARIANTS = {
     "sort10_both": {"GCZ_SORT_VARIANT": "10"},
     "sort11_9bit": {"GCZ_SORT_VARIANT": "11"},
     "sort12_9bit_both": {"GCZ_SORT_VARIANT": "12"},
+    "sort13_prefetch_values": {"GCZ_SORT_VARIANT": "13"},
+    "sort14_9bit_prefetch": {"GCZ_SORT_VARIANT": "14"},
     "emit_lut": {"GCZ_EMIT_VARIANT": "1"},
     "text_hist_uniform": {"GCZ_TEXT_HIST_VARIANT": "1"},
     "bwt_packed": {"GCZ_BWT_VARIANT": "1"},
@@ -129,11 +131,14 @@ def main() -> None:
     with open(out, "w") as f:
         for name in names:
             env = dict(os.environ, **VARIANTS[name])
-            r = subprocess.run([sys.executable, __file__, "--child", name, "--length", str(args.length), "--steps", str(args.steps),
-                                "--ref", args.ref], env=env, capture_output=True, text=True, timeout=900)
-            line = next((l[7:] for l in r.stdout.splitlines() if l.startswith("RESULT ")), None)
-            rec = json.loads(line) if line else {"variant": name, "env": VARIANTS[name], "failed": r.returncode,
-                                                 "stderr": r.stderr[-1500:]}
+            try:                                  # a variant that hangs (a look-back that never resolves) must not hold the box
+                r = subprocess.run([sys.executable, __file__, "--child", name, "--length", str(args.length), "--steps", str(args.steps),
+                                    "--ref", args.ref], env=env, capture_output=True, text=True, timeout=240)
+                line = next((l[7:] for l in r.stdout.splitlines() if l.startswith("RESULT ")), None)
+                rec = json.loads(line) if line else {"variant": name, "env": VARIANTS[name], "failed": r.returncode,
+                                                     "stderr": r.stderr[-1500:]}
+            except subprocess.TimeoutExpired:
+                line, rec = None, {"variant": name, "env": VARIANTS[name], "failed": "timeout after 240 s"}
             if name == "default" and line:
                 base_digest = rec["cfg2_digest"]
             elif line:
