@@ -294,12 +294,14 @@ static int build_block(int device, const uint8_t* text, int64_t n, int32_t sampl
     int carry_shift = std::getenv("GCZ_BWT_GATHER") ? 0 : 1;
     GCZ_TRY(suffix_sort(ctx, st, d_text, n, counts, d_sa, arena, &ss, &carry_shift));
     WaveletStats ws;
+    int64_t gcx_done = 0;                     // leading bytes of the .gcx body that are already on their way (GCZ_EARLY_MARKER=1)
     GCZ_TRY(build_wavelet_structures(ctx, st, d_text, d_sa, carry_shift, sa_out != nullptr, n, shape, sf, d_bwt, d_gcz, d_gcx, arena, &ws,
-                                     gcz_dev ? nullptr : gcz_body, ctx->copy_stream, ctx->copy_event));
+                                     gcz_dev ? nullptr : gcz_body, ctx->copy_stream, ctx->copy_event,
+                                     (gcx_dev || gcz_dev) ? nullptr : gcx_body, &gcx_done));
     GCZ_CUDA(cudaEventRecord(ev[2], st));
 
     if (!gcz_dev) GCZ_CUDA(cudaStreamWaitEvent(st, ctx->copy_event, 0));         // the .gcz body went out while the index was built
-    if (!gcx_dev) GCZ_CUDA(cudaMemcpyAsync(gcx_body, d_gcx, (size_t)gcx_body_len, cudaMemcpyDeviceToHost, st));
+    if (!gcx_dev) GCZ_CUDA(cudaMemcpyAsync(gcx_body + gcx_done, d_gcx + gcx_done, (size_t)(gcx_body_len - gcx_done), cudaMemcpyDeviceToHost, st));
     if (sa_out && !sa_dev) GCZ_CUDA(cudaMemcpyAsync(sa_out, d_sa, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     if (bwt_out && !bwt_dev) GCZ_CUDA(cudaMemcpyAsync(bwt_out, d_bwt, (size_t)n, cudaMemcpyDeviceToHost, st));
     GCZ_CUDA(cudaEventRecord(ev[3], st));

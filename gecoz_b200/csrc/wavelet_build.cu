@@ -697,8 +697,10 @@ size_t wavelet_workspace_bytes(int64_t n, int sampling_factor) {
 int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, uint32_t* d_sa, int carry_shift, bool clean_sa,
                              int64_t n, const gcz_shape* shape, int sampling_factor, uint8_t* d_bwt,
                              uint8_t* d_gcz_body, uint8_t* d_gcx_body, Arena& arena, WaveletStats* stats,
-                             uint8_t* h_gcz_out, cudaStream_t copy_stream, cudaEvent_t gcz_copied) {
+                             uint8_t* h_gcz_out, cudaStream_t copy_stream, cudaEvent_t gcz_copied,
+                             uint8_t* h_gcx_out, int64_t* gcx_bytes_copied) {
     const size_t mark0 = arena.mark();
+    if (gcx_bytes_copied) *gcx_bytes_copied = 0;
     // ---- host tables -------------------------------------------------------------------------------
     SymbolTables h_tab;
     std::memset(&h_tab, 0, sizeof(h_tab));
@@ -858,6 +860,21 @@ int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_t
         GCZ_CUDA(cudaMemcpyAsync(h_gcz_out, d_gcz_body, (size_t)shape->size, cudaMemcpyDeviceToHost, copy_stream));
         GCZ_CUDA(cudaEventRecord(gcz_copied, copy_stream));
     }
+    // experimental (GCZ_EARLY_MARKER=1): the marker vector (n bits + counters, the larger part of the .gcx body) is final
+    // after bwt_count_kernel; laid out now, it follows the .gcz body to the host while the IndexWaveletTree is built
+    int tail_vec0 = marker_vec;
+    int64_t tail_sb0 = sb_nodes;
+    const char* early_env = std::getenv("GCZ_EARLY_MARKER");
+    if (early_env && early_env[0] == '1' && h_gcx_out && h_gcz_out && gcx_bytes_copied) {
+        tail_vec0 = level_vec0;
+        tail_sb0 = sb_nodes + vecs[marker_vec].sb_count;
+        GCZ_TRY(layout_vectors(ctx, st, d_raw, d_vecs, (int)vecs.size(), marker_vec, level_vec0, sb_nodes, tail_sb0, d_sb));
+        GCZ_CUDA(cudaEventRecord(gcz_copied, st));
+        GCZ_CUDA(cudaStreamWaitEvent(copy_stream, gcz_copied, 0));
+        GCZ_CUDA(cudaMemcpyAsync(h_gcx_out, d_gcx_body, (size_t)rank_bytes, cudaMemcpyDeviceToHost, copy_stream));
+        GCZ_CUDA(cudaEventRecord(gcz_copied, copy_stream));          // the caller's wait now covers both copies
+        *gcx_bytes_copied = rank_bytes;
+    }
     if (stats) GCZ_CUDA(cudaEventRecord(ev1, st));
 
     // ---- sampled SA + IndexWaveletTree ---------------------------------------------------------------------
@@ -867,7 +884,7 @@ int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_t
     GCZ_TRY(iwt_levels(ctx, st, d_ssa, m, levels, d_raw, vecs, level_vec0, d_zeros, d_block_zeros, d_level_raw));
 
     // ---- counters + final byte layout of every vector ---------------------------------------------------------
-    GCZ_TRY(layout_vectors(ctx, st, d_raw, d_vecs, (int)vecs.size(), marker_vec, (int)vecs.size(), sb_nodes, total_sb, d_sb));
+    GCZ_TRY(layout_vectors(ctx, st, d_raw, d_vecs, (int)vecs.size(), tail_vec0, (int)vecs.size(), tail_sb0, total_sb, d_sb));
 
     if (stats) {
         GCZ_CUDA(cudaEventRecord(ev2, st));
