@@ -29,6 +29,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #define GCZ_TRY_HOST(expr)                  \
@@ -70,6 +71,9 @@ struct FastaRecord {
     int64_t position = 0, length = 0;
     int64_t span_end = 0;        // the sequence's characters are the non-CR/LF bytes of [position, span_end)
     bool multiline = false;
+    // long sequences: (file offset, CR/LF bytes of [position, offset)) at the slice starts of the threaded scan, ascending —
+    // the assembly threads start there without counting again
+    std::vector<std::pair<int64_t, int64_t>> marks;
 };
 
 // first byte of [p, end) that is one of the two, or end
@@ -192,12 +196,13 @@ SliceScan scan_slice(const uint8_t* buf, int64_t a, int64_t b) {
     return r;
 }
 
-struct Region { int64_t end, length, lines; };
+struct Region { int64_t end, length, lines; std::vector<std::pair<int64_t, int64_t>> marks; };
 
 // slice: bytes per thread and step; the first step is a short one on the calling thread
 Region scan_region(const uint8_t* buf, int64_t from, int64_t size, int64_t slice, int threads) {
     int64_t eol = 0, runs = 0, at = from, hit = -1;
     bool first = true;
+    std::vector<std::pair<int64_t, int64_t>> marks;
     while (at < size && hit < 0) {
         const int64_t step = first || threads <= 1 ? std::min<int64_t>(slice / 8 + 1, size - at) : std::min<int64_t>(slice * threads, size - at);
         if (first || threads <= 1) {                         // short sequences (reads, contigs) never leave this branch
@@ -209,13 +214,17 @@ Region scan_region(const uint8_t* buf, int64_t from, int64_t size, int64_t slice
             for (int t = 0; t < threads; t++)
                 pool.emplace_back([&, t] { part[(size_t)t] = scan_slice(buf, at + step * t / threads, at + step * (t + 1) / threads); });
             for (std::thread& th : pool) th.join();
-            for (int t = 0; t < threads && hit < 0; t++) { eol += part[(size_t)t].eol; runs += part[(size_t)t].runs; hit = part[(size_t)t].hit; }
+            for (int t = 0; t < threads && hit < 0; t++) {
+                marks.emplace_back(at + step * t / threads, eol);
+                eol += part[(size_t)t].eol; runs += part[(size_t)t].runs; hit = part[(size_t)t].hit;
+            }
         }
         first = false;
         at += step;
     }
     const int64_t end = hit >= 0 ? hit : size;
-    return Region{ end, (end - from) - eol, runs };
+    while (!marks.empty() && marks.back().first >= end) marks.pop_back();
+    return Region{ end, (end - from) - eol, runs, std::move(marks) };
 }
 
 void scan_fasta(const uint8_t* buf, int64_t size, std::vector<FastaRecord>& out) {
@@ -255,6 +264,7 @@ void scan_fasta(const uint8_t* buf, int64_t size, std::vector<FastaRecord>& out)
         rec.span_end = seq.end;
         rec.length = seq.length;
         rec.multiline = seq.lines > 1;
+        rec.marks = seq.marks;
         int64_t posnew = seq.end + 1;                                                  // == p after the ending byte was read
         run_to(buf + seq.end, ch);
         if (ch == '+') {                                                               // skip qualities :98-113
@@ -341,7 +351,31 @@ int64_t read_sequence(const gcz_fasta* f, const FastaRecord& r, uint8_t* out, in
         std::memcpy(out, f->data + r.position, (size_t)avail);
         return avail;
     }
-    return strip_eol_parallel(f->data + r.position, f->data + r.span_end, out, want, host_threads());
+    const int threads = host_threads();
+    if (want == r.length && threads > 1 && r.marks.size() >= 2) {
+        // pieces: [position, marks[0]) and one per mark; piece i starts at out[(offset - position) - CR/LF bytes before it]
+        const int64_t pieces = (int64_t)r.marks.size() + 1;
+        auto piece = [&](int64_t i, int64_t* begin, int64_t* end, int64_t* out_at) {
+            *begin = i == 0 ? r.position : r.marks[(size_t)i - 1].first;
+            *end = i + 1 < pieces ? r.marks[(size_t)i].first : r.span_end;
+            *out_at = i == 0 ? 0 : (*begin - r.position) - r.marks[(size_t)i - 1].second;
+        };
+        std::vector<std::thread> pool;
+        const int workers = (int)std::min<int64_t>(threads, pieces);
+        for (int t = 0; t < workers; t++)
+            pool.emplace_back([&, t] {
+                for (int64_t i = t; i < pieces; i += workers) {
+                    int64_t b, e, o, nb, ne, no;
+                    piece(i, &b, &e, &o);
+                    int64_t stop = r.length;
+                    if (i + 1 < pieces) { piece(i + 1, &nb, &ne, &no); stop = no; }
+                    strip_eol(f->data + b, f->data + e, out + o, stop - o);
+                }
+            });
+        for (std::thread& th : pool) th.join();
+        return want;
+    }
+    return strip_eol_parallel(f->data + r.position, f->data + r.span_end, out, want, threads);
 }
 
 // ---- GecoIndex: one block per sequence, greedy merge, file order  tools/GecoIndex.java:57-98 ------------------------
