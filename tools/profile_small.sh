@@ -15,6 +15,7 @@ ncu --set full --clock-control none --import-source on \
     -k 'regex:bwt_count|hswt_emit|text_hist|group_flags|group_apply|group_finish|refine_keys|sample_kernel|run_keys|iwt_low_levels' \
     -s 19 -c 19 -o "$OUT" python tools/build_once.py 2 > gpurun_out/build_once_ncu.log 2>&1 || { tail -20 gpurun_out/build_once_ncu.log; exit 1; }
 # and the launch list of one whole step for the shares
-ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 120 --csv --log-file gpurun_out/launches_small_r02.csv \
-    python tools/build_once.py 2 > gpurun_out/build_once_list.log 2>&1 || true
+# (94 launches per build with the default kernels: any window of 94 consecutive launches after the first build is one whole step)
+ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 94 --csv --log-file gpurun_out/launches_small_r02.csv \
+    python tools/build_once.py 3 > gpurun_out/build_once_list.log 2>&1 || true
 ls -la gpurun_out | tail -8
