@@ -198,14 +198,15 @@ SliceScan scan_slice(const uint8_t* buf, int64_t a, int64_t b) {
 
 struct Region { int64_t end, length, lines; std::vector<std::pair<int64_t, int64_t>> marks; };
 
-// slice: bytes per thread and step; the first step is a short one on the calling thread
+// slice: bytes per thread and step; the first `slice` bytes of a region are scanned on the calling thread, so that reads and
+// contigs (a file may hold millions) never start a thread
 Region scan_region(const uint8_t* buf, int64_t from, int64_t size, int64_t slice, int threads) {
     int64_t eol = 0, runs = 0, at = from, hit = -1;
-    bool first = true;
     std::vector<std::pair<int64_t, int64_t>> marks;
     while (at < size && hit < 0) {
+        const bool first = at - from < slice;
         const int64_t step = first || threads <= 1 ? std::min<int64_t>(slice / 8 + 1, size - at) : std::min<int64_t>(slice * threads, size - at);
-        if (first || threads <= 1) {                         // short sequences (reads, contigs) never leave this branch
+        if (first || threads <= 1) {
             const SliceScan r = scan_slice(buf, at, at + step);
             eol += r.eol; runs += r.runs; hit = r.hit;
         } else {
@@ -219,7 +220,6 @@ Region scan_region(const uint8_t* buf, int64_t from, int64_t size, int64_t slice
                 eol += part[(size_t)t].eol; runs += part[(size_t)t].runs; hit = part[(size_t)t].hit;
             }
         }
-        first = false;
         at += step;
     }
     const int64_t end = hit >= 0 ? hit : size;
