@@ -25,6 +25,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -735,7 +736,8 @@ int gcz_index_fasta(const gcz_fasta* fasta, const char* gcz_path, const char* gc
     const size_t all_tokens = free_tokens.size();
     int first_error = GCZ_OK;
     std::string first_message;
-    std::vector<std::thread> workers;
+    std::deque<std::thread> workers;                 // oldest first; joined as new ones start, so that a file of many small
+    int64_t n_blocks = 0;                            // blocks does not leave a finished thread per block behind
     int64_t ref_pos = 0, ssa_pos = 0, symbols = 0, sequences = 0;
 
     // One text buffer per token, sized for the largest block.  The bodies come back into buffers of a second pool and go
@@ -808,6 +810,8 @@ int gcz_index_fasta(const gcz_fasta* fasta, const char* gcz_path, const char* gc
                          t_alloc * 1e3, t_read * 1e3, t_count * 1e3);
         // BlockWriter.run (:256-284) on its own thread; GCZ_E_NOMEM: once more when nothing else is in flight
         // (WriterPoolExecutor.afterExecute :203-226)
+        n_blocks++;
+        while (workers.size() >= 4 * all_tokens) { workers.front().join(); workers.pop_front(); }
         workers.emplace_back([&, device, text, shape, n, my_ref, my_ssa, hlen, idx_size, hb, sb]() mutable {
             const auto b0 = std::chrono::steady_clock::now();
             // one buffer: [.. ref header | .gcz body .. ssa header | .gcx body], both bodies on a 4 KiB boundary, so that each
@@ -844,7 +848,7 @@ int gcz_index_fasta(const gcz_fasta* fasta, const char* gcz_path, const char* gc
     ::close(ref_fd);
     ::close(ssa_fd);
     if (report) {
-        report->blocks = (int64_t)workers.size();
+        report->blocks = n_blocks;
         report->sequences = sequences;
         report->symbols = symbols;
         report->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
