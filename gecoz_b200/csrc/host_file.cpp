@@ -26,6 +26,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <exception>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -812,37 +813,43 @@ int gcz_index_fasta(const gcz_fasta* fasta, const char* gcz_path, const char* gc
         // (WriterPoolExecutor.afterExecute :203-226)
         n_blocks++;
         while (workers.size() >= 4 * all_tokens) { workers.front().join(); workers.pop_front(); }
-        workers.emplace_back([&, device, text, shape, n, my_ref, my_ssa, hlen, idx_size, hb, sb]() mutable {
-            const auto b0 = std::chrono::steady_clock::now();
-            // one buffer: [.. ref header | .gcz body .. ssa header | .gcx body], both bodies on a 4 KiB boundary, so that each
-            // file gets its header and body with one write
-            const int64_t ref_at = (hlen + 4095) & ~(int64_t)4095;
-            const int64_t ssa_at = ((ref_at + shape->size + 4095) & ~(int64_t)4095) + 4096;
-            std::unique_ptr<HostBuffer> out = bodies.take((size_t)(ssa_at + idx_size));
-            int rc2 = out->data ? GCZ_OK : fail(GCZ_E_NOMEM, "host buffer of %lld bytes", (long long)(ssa_at + idx_size));
-            for (int attempts = 0; rc2 == GCZ_OK; ) {
-                rc2 = eng.build_block(device, text->data, n, sampling_rate, shape.get(), out->data + ref_at, shape->size, out->data + ssa_at,
-                                      idx_size, nullptr, nullptr);
-                if (rc2 != GCZ_E_NOMEM || attempts++ > 0) break;
-                std::unique_lock<std::mutex> l(mu);
-                cv.wait(l, [&] { return free_tokens.size() == all_tokens - 1; });
-                rc2 = GCZ_OK;
-            }
-            if (rc2 != GCZ_OK) record_error(rc2);
-            text.reset();                                                            // the text buffer goes back with the token
+        try {
+            workers.emplace_back([&, device, text, shape, n, my_ref, my_ssa, hlen, idx_size, hb, sb]() mutable {
+                const auto b0 = std::chrono::steady_clock::now();
+                // one buffer: [.. ref header | .gcz body .. ssa header | .gcx body], both bodies on a 4 KiB boundary, so that each
+                // file gets its header and body with one write
+                const int64_t ref_at = (hlen + 4095) & ~(int64_t)4095;
+                const int64_t ssa_at = ((ref_at + shape->size + 4095) & ~(int64_t)4095) + 4096;
+                std::unique_ptr<HostBuffer> out = bodies.take((size_t)(ssa_at + idx_size));
+                int rc2 = out->data ? GCZ_OK : fail(GCZ_E_NOMEM, "host buffer of %lld bytes", (long long)(ssa_at + idx_size));
+                for (int attempts = 0; rc2 == GCZ_OK; ) {
+                    rc2 = eng.build_block(device, text->data, n, sampling_rate, shape.get(), out->data + ref_at, shape->size, out->data + ssa_at,
+                                          idx_size, nullptr, nullptr);
+                    if (rc2 != GCZ_E_NOMEM || attempts++ > 0) break;
+                    std::unique_lock<std::mutex> l(mu);
+                    cv.wait(l, [&] { return free_tokens.size() == all_tokens - 1; });
+                    rc2 = GCZ_OK;
+                }
+                if (rc2 != GCZ_OK) record_error(rc2);
+                text.reset();                                                            // the text buffer goes back with the token
+                release(device);
+                const double t_build = seconds_since(b0);
+                if (rc2 == GCZ_OK) {
+                    std::memcpy(out->data + ref_at - hlen, hb.data(), (size_t)hlen);
+                    std::memcpy(out->data + ssa_at - 25, sb.data(), 25);
+                    if (!write_fully(ref_fd, out->data + ref_at - hlen, hlen + shape->size, my_ref) ||
+                        !write_fully(ssa_fd, out->data + ssa_at - 25, 25 + idx_size, my_ssa))
+                        record_error(fail(GCZ_E_ARG, "cannot write %s / %s", ref_path.c_str(), ssa_path.c_str()));
+                }
+                bodies.give(std::move(out));
+                if (host_trace()) std::fprintf(stderr, "[gcz host] block n=%lld: build %.1f ms, write %.1f ms\n", (long long)n, t_build * 1e3,
+                                               (seconds_since(b0) - t_build) * 1e3);
+            });
+        } catch (const std::exception& ex) {                  // no thread could be started
             release(device);
-            const double t_build = seconds_since(b0);
-            if (rc2 == GCZ_OK) {
-                std::memcpy(out->data + ref_at - hlen, hb.data(), (size_t)hlen);
-                std::memcpy(out->data + ssa_at - 25, sb.data(), 25);
-                if (!write_fully(ref_fd, out->data + ref_at - hlen, hlen + shape->size, my_ref) ||
-                    !write_fully(ssa_fd, out->data + ssa_at - 25, 25 + idx_size, my_ssa))
-                    record_error(fail(GCZ_E_ARG, "cannot write %s / %s", ref_path.c_str(), ssa_path.c_str()));
-            }
-            bodies.give(std::move(out));
-            if (host_trace()) std::fprintf(stderr, "[gcz host] block n=%lld: build %.1f ms, write %.1f ms\n", (long long)n, t_build * 1e3,
-                                           (seconds_since(b0) - t_build) * 1e3);
-        });
+            record_error(fail(GCZ_E_NOMEM, "cannot start a block worker: %s", ex.what()));
+            break;
+        }
     }
     for (std::thread& t : workers) t.join();
     ::close(ref_fd);
