@@ -29,6 +29,7 @@
 #include <exception>
 #include <memory>
 #include <mutex>
+#include <new>
 #include <string>
 #include <thread>
 #include <utility>
@@ -581,12 +582,24 @@ using namespace gcz;
 namespace {
 bool host_trace() { static const bool on = [] { const char* e = std::getenv("GCZ_HOST_TRACE"); return e && e[0] == '1'; }(); return on; }
 double seconds_since(std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); }
+
+// no C++ exception leaves the library: memory exhaustion and anything else unexpected become status codes
+template <class F>
+int guarded(F&& body) {
+    try {
+        return body();
+    } catch (const std::bad_alloc&) {
+        return fail(GCZ_E_NOMEM, "out of host memory");
+    } catch (const std::exception& ex) {
+        return fail(GCZ_E_INTERNAL, "unexpected: %s", ex.what());
+    }
+}
 }  // namespace
 
 // =====================================================================================================================
 extern "C" {
 
-int gcz_fasta_open(const char* path, gcz_fasta** out) {
+static int fasta_open_impl(const char* path, gcz_fasta** out) {
     clear_error();
     if (!path || !out) return fail(GCZ_E_ARG, "null argument");
     std::unique_ptr<gcz_fasta> f(new gcz_fasta());
@@ -621,7 +634,7 @@ int gcz_fasta_open(const char* path, gcz_fasta** out) {
     return GCZ_OK;
 }
 
-int gcz_fasta_open_buffer(const uint8_t* data, int64_t size, gcz_fasta** out) {
+static int fasta_open_buffer_impl(const uint8_t* data, int64_t size, gcz_fasta** out) {
     clear_error();
     if ((!data && size > 0) || size < 0 || !out) return fail(GCZ_E_ARG, "null argument");
     std::unique_ptr<gcz_fasta> f(new gcz_fasta());
@@ -700,7 +713,7 @@ int64_t gcz_ssa_header_write(const char* const* headers, int32_t n, int64_t inde
 }
 
 // ---- writer -------------------------------------------------------------------------------------------------------------
-int gcz_index_fasta(const gcz_fasta* fasta, const char* gcz_path, const char* gcx_path, int32_t sampling_rate,
+static int index_fasta_impl(const gcz_fasta* fasta, const char* gcz_path, const char* gcx_path, int32_t sampling_rate,
                     int32_t n_devices, const int* devices, const gcz_engine* engine, gcz_index_report* report) {
     clear_error();
     if (!fasta || !gcz_path) return fail(GCZ_E_ARG, "null argument");
@@ -761,6 +774,8 @@ int gcz_index_fasta(const gcz_fasta* fasta, const char* gcz_path, const char* gc
         if (first_error == GCZ_OK) { first_error = rc; first_message = gcz_last_error(); }
     };
 
+    bool aborting = false;                           // set under mu when the submitting loop dies of an exception
+    try {
     for (const Block& block : blocks) {
         {
             std::lock_guard<std::mutex> l(mu);
@@ -827,7 +842,8 @@ int gcz_index_fasta(const gcz_fasta* fasta, const char* gcz_path, const char* gc
                                           idx_size, nullptr, nullptr);
                     if (rc2 != GCZ_E_NOMEM || attempts++ > 0) break;
                     std::unique_lock<std::mutex> l(mu);
-                    cv.wait(l, [&] { return free_tokens.size() == all_tokens - 1; });
+                    cv.wait(l, [&] { return aborting || free_tokens.size() == all_tokens - 1; });
+                    if (aborting) break;
                     rc2 = GCZ_OK;
                 }
                 if (rc2 != GCZ_OK) record_error(rc2);
@@ -850,6 +866,12 @@ int gcz_index_fasta(const gcz_fasta* fasta, const char* gcz_path, const char* gc
             record_error(fail(GCZ_E_NOMEM, "cannot start a block worker: %s", ex.what()));
             break;
         }
+    }
+    } catch (const std::exception& ex) {                  // the workers that are running must still be joined
+        record_error(fail(dynamic_cast<const std::bad_alloc*>(&ex) ? GCZ_E_NOMEM : GCZ_E_INTERNAL, "index writer: %s", ex.what()));
+        std::lock_guard<std::mutex> l(mu);
+        aborting = true;
+        cv.notify_all();
     }
     for (std::thread& t : workers) t.join();
     ::close(ref_fd);
@@ -880,7 +902,7 @@ struct gcz_reader {
 
 extern "C" {
 
-int gcz_reader_open(const char* gcz_path, gcz_reader** out) {
+static int reader_open_impl(const char* gcz_path, gcz_reader** out) {
     clear_error();
     if (!gcz_path || !out) return fail(GCZ_E_ARG, "null argument");
     std::unique_ptr<gcz_reader> r(new gcz_reader());
@@ -1143,7 +1165,7 @@ uint8_t complement(uint8_t b) {                                                 
 
 }  // namespace
 
-int gcz_match(const gcz_reader* r, int device, const char* header, const uint8_t* pattern, int64_t pattern_len,
+static int match_impl(const gcz_reader* r, int device, const char* header, const uint8_t* pattern, int64_t pattern_len,
               int32_t with_positions, const gcz_query_engine* engine, char** out_text, int64_t* out_len) {
     clear_error();
     if (!r || !pattern || pattern_len <= 0 || !out_text) return fail(GCZ_E_ARG, "match arguments");
@@ -1178,7 +1200,7 @@ int gcz_match(const gcz_reader* r, int device, const char* header, const uint8_t
     return give_text(text, out_text, out_len);
 }
 
-int gcz_gff_search(const gcz_reader* r, int device, const uint8_t* patterns, int64_t patterns_len,
+static int gff_search_impl(const gcz_reader* r, int device, const uint8_t* patterns, int64_t patterns_len,
                    const gcz_query_engine* engine, char** out_text, int64_t* out_len) {
     clear_error();
     if (!r || (!patterns && patterns_len > 0) || patterns_len < 0 || !out_text) return fail(GCZ_E_ARG, "gff arguments");
@@ -1233,7 +1255,7 @@ int gcz_gff_search(const gcz_reader* r, int device, const uint8_t* patterns, int
     return give_text(text, out_text, out_len);
 }
 
-int gcz_extract_fasta(const gcz_reader* r, int device, const char* fasta_path, const gcz_query_engine* engine, int64_t* n_sequences) {
+static int extract_fasta_impl(const gcz_reader* r, int device, const char* fasta_path, const gcz_query_engine* engine, int64_t* n_sequences) {
     clear_error();
     if (!r || !fasta_path) return fail(GCZ_E_ARG, "extract arguments");
     const gcz_query_engine q = resolve(engine);
@@ -1287,7 +1309,7 @@ int gcz_extract_fasta(const gcz_reader* r, int device, const char* fasta_path, c
 
 // GecoRead.sequence  tools/GecoRead.java:33-81: the raw symbols [from, min(to, length)) of one sequence into `path`, one
 // GSSA.extract call (ssa.extract(buf, nstr, from) :72 with a buffer of to - from bytes)
-int gcz_extract_sequence(const gcz_reader* r, int device, const char* header, int64_t from, int64_t to, const char* path,
+static int extract_sequence_impl(const gcz_reader* r, int device, const char* header, int64_t from, int64_t to, const char* path,
                          const gcz_query_engine* engine, int64_t* written) {
     clear_error();
     if (!r || !header || !path) return fail(GCZ_E_ARG, "extract arguments");
@@ -1312,6 +1334,39 @@ int gcz_extract_sequence(const gcz_reader* r, int device, const char* header, in
     if (!ok) return fail(GCZ_E_ARG, "cannot write %s", path);
     if (written) *written = w;
     return GCZ_OK;
+}
+
+// ---- the entry points above, behind the exception guard -----------------------------------------------------------------------
+int gcz_fasta_open(const char* path, gcz_fasta** out) {
+    return guarded([&] { return fasta_open_impl(path, out); });
+}
+
+int gcz_fasta_open_buffer(const uint8_t* data, int64_t size, gcz_fasta** out) {
+    return guarded([&] { return fasta_open_buffer_impl(data, size, out); });
+}
+
+int gcz_index_fasta(const gcz_fasta* fasta, const char* gcz_path, const char* gcx_path, int32_t sampling_rate, int32_t n_devices, const int* devices, const gcz_engine* engine, gcz_index_report* report) {
+    return guarded([&] { return index_fasta_impl(fasta, gcz_path, gcx_path, sampling_rate, n_devices, devices, engine, report); });
+}
+
+int gcz_reader_open(const char* gcz_path, gcz_reader** out) {
+    return guarded([&] { return reader_open_impl(gcz_path, out); });
+}
+
+int gcz_match(const gcz_reader* r, int device, const char* header, const uint8_t* pattern, int64_t pattern_len, int32_t with_positions, const gcz_query_engine* engine, char** out_text, int64_t* out_len) {
+    return guarded([&] { return match_impl(r, device, header, pattern, pattern_len, with_positions, engine, out_text, out_len); });
+}
+
+int gcz_gff_search(const gcz_reader* r, int device, const uint8_t* patterns, int64_t patterns_len, const gcz_query_engine* engine, char** out_text, int64_t* out_len) {
+    return guarded([&] { return gff_search_impl(r, device, patterns, patterns_len, engine, out_text, out_len); });
+}
+
+int gcz_extract_fasta(const gcz_reader* r, int device, const char* fasta_path, const gcz_query_engine* engine, int64_t* n_sequences) {
+    return guarded([&] { return extract_fasta_impl(r, device, fasta_path, engine, n_sequences); });
+}
+
+int gcz_extract_sequence(const gcz_reader* r, int device, const char* header, int64_t from, int64_t to, const char* path, const gcz_query_engine* engine, int64_t* written) {
+    return guarded([&] { return extract_sequence_impl(r, device, header, from, to, path, engine, written); });
 }
 
 }  // extern "C"
