@@ -373,7 +373,7 @@ int gcz_set_stream(int device, void* cuda_stream) {
 int gcz_shape_from_counts(const int64_t counts[256], gcz_shape* out) {
     clear_error();
     if (!counts || !out) return fail(GCZ_E_ARG, "null argument");
-    return shape_from_counts(counts, out);
+    return guarded([&] { return shape_from_counts(counts, out); });
 }
 int64_t gcz_shape_write(const gcz_shape* shape, uint8_t* out, int64_t cap) {
     clear_error();
@@ -390,14 +390,14 @@ int64_t gcz_index_size(int64_t n, int32_t sampling_factor) { return index_size(n
 
 int gcz_count_symbols(int device, const uint8_t* text, int64_t n, int64_t counts[256]) {
     clear_error();
-    return count_symbols(device, text, n, counts);
+    return guarded([&] { return count_symbols(device, text, n, counts); });
 }
 
 int gcz_build_block(int device, const uint8_t* text, int64_t n, int32_t sampling_rate, const gcz_shape* shape,
                     uint8_t* gcz_body, int64_t gcz_body_len, uint8_t* gcx_body, int64_t gcx_body_len,
                     int32_t* sa_out, uint8_t* bwt_out) {
     clear_error();
-    return build_block(device, text, n, sampling_rate, shape, gcz_body, gcz_body_len, gcx_body, gcx_body_len, sa_out, bwt_out);
+    return guarded([&] { return build_block(device, text, n, sampling_rate, shape, gcz_body, gcz_body_len, gcx_body, gcx_body_len, sa_out, bwt_out); });
 }
 
 int gcz_last_build_timing(gcz_build_timing* out) {
@@ -411,7 +411,7 @@ int gcz_open_block(int device, const uint8_t* gcz_body, int64_t body_len, int64_
     clear_error();
     DeviceCtx* ctx = nullptr;
     GCZ_TRY(get_ctx(device, &ctx));
-    return open_block(ctx, gcz_body, body_len, text_len, gcx_body, gcx_len, out);
+    return guarded([&] { return open_block(ctx, gcz_body, body_len, text_len, gcx_body, gcx_len, out); });
 }
 void gcz_close_block(gcz_index* idx) { close_block(idx); }
 
@@ -431,20 +431,20 @@ int gcz_c_array(const gcz_index* idx, int64_t c[256]) {
 
 int gcz_count_batch(gcz_index* idx, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats, int64_t* sp, int64_t* ep) {
     clear_error();
-    return count_batch(idx, pats, pat_off, n_pats, sp, ep);
+    return guarded([&] { return count_batch(idx, pats, pat_off, n_pats, sp, ep); });
 }
 int gcz_locate_rows(gcz_index* idx, const int64_t* rows, int64_t n_rows, int64_t* positions) {
     clear_error();
-    return locate_rows(idx, rows, n_rows, positions);
+    return guarded([&] { return locate_rows(idx, rows, n_rows, positions); });
 }
 int gcz_find_batch(gcz_index* idx, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats,
                    int64_t* per_string_counts, int64_t** positions, int64_t** pos_off) {
     clear_error();
-    return find_batch(idx, pats, pat_off, n_pats, per_string_counts, positions, pos_off);
+    return guarded([&] { return find_batch(idx, pats, pat_off, n_pats, per_string_counts, positions, pos_off); });
 }
 int gcz_extract(gcz_index* idx, int32_t nstr, int64_t from, uint8_t* out, int64_t cap, int64_t* written) {
     clear_error();
-    return extract(idx, nstr, from, out, cap, written);
+    return guarded([&] { return extract(idx, nstr, from, out, cap, written); });
 }
 void gcz_free(void* p) { std::free(p); }
 

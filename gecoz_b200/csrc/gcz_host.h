@@ -4,6 +4,8 @@
 #include "../../include/gcz.h"
 
 #include <cstdint>
+#include <exception>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -12,6 +14,18 @@ namespace gcz {
 // error reporting: sets the thread-local message behind gcz_last_error() and returns `code`
 int fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
 void clear_error();
+
+// no C++ exception leaves the library: memory exhaustion and anything else unexpected become status codes
+template <class F>
+auto guarded(F&& body) -> decltype(body()) {
+    try {
+        return body();
+    } catch (const std::bad_alloc&) {
+        return fail(GCZ_E_NOMEM, "out of host memory");
+    } catch (const std::exception& ex) {
+        return fail(GCZ_E_INTERNAL, "unexpected: %s", ex.what());
+    }
+}
 
 // shape.cpp — byte-defining host code (no CUDA)
 bool    deflate_code(const std::vector<int64_t>& weights, int max_bits, std::vector<int>& len, std::vector<int>& code);

@@ -582,18 +582,6 @@ using namespace gcz;
 namespace {
 bool host_trace() { static const bool on = [] { const char* e = std::getenv("GCZ_HOST_TRACE"); return e && e[0] == '1'; }(); return on; }
 double seconds_since(std::chrono::steady_clock::time_point t) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); }
-
-// no C++ exception leaves the library: memory exhaustion and anything else unexpected become status codes
-template <class F>
-int guarded(F&& body) {
-    try {
-        return body();
-    } catch (const std::bad_alloc&) {
-        return fail(GCZ_E_NOMEM, "out of host memory");
-    } catch (const std::exception& ex) {
-        return fail(GCZ_E_INTERNAL, "unexpected: %s", ex.what());
-    }
-}
 }  // namespace
 
 // =====================================================================================================================
