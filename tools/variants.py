@@ -90,8 +90,6 @@ def child(args) -> None:
             if ref is not None and ref.get(f"{name}/{rate}") != d:
                 what = [w for w, x, y in zip(("gcz", "gcx", "sa", "bwt"), ref.get(f"{name}/{rate}", [None] * 4), d) if x != y]
                 mismatches.append(f"{name}/{rate}: {','.join(what)}")
-    if ref is None:
-        ref_path.write_text(json.dumps(digests))
     # the sorter on its own: pairs and keys only (the query path sorts keys only), odd sizes and bit widths
     from gecoz_b200 import _native as N
     rng = np.random.default_rng(7)
@@ -108,6 +106,21 @@ def child(args) -> None:
         order = np.argsort(keys, kind="stable")
         if not np.array_equal(k2, keys[order]) or (with_vals and not np.array_equal(v2, vals[order])):
             mismatches.append(f"sort n={n_keys} bits={bits} vals={with_vals}")
+    # queries on a merged block (the locate post-processing sorts keys only): intervals, positions, per-string split
+    seqs = [synth.iid_acgtn(500_000, 31), synth.iid_acgtn(300_000, 32), synth.iid_acgtn(7, 33)]
+    qtext = synth.block_of(seqs)
+    gcz, gcx, _, _, _ = build(G, qtext, 32)
+    g = G.GSSA.open(0, gcz, len(qtext), gcx)
+    data, off = synth.patterns(qtext, 50_000, 6, 40, seed=8)
+    sp, ep = g.count_batch(packed=(data, off))
+    per, pos, poff = g.find_batch_raw(packed=(data, off))
+    g.close()
+    qd = [hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest() for a in (sp, ep, per, pos, poff)]
+    digests["queries"] = qd
+    if ref is not None and ref.get("queries") != qd:
+        mismatches.append("queries: " + ",".join(w for w, x, y in zip(("sp", "ep", "per", "pos", "off"), ref.get("queries", [None] * 5), qd) if x != y))
+    if ref is None:
+        ref_path.write_text(json.dumps(digests))
     # timing: device-resident builds of the chr1-shaped block
     text = synth.cfg2_text(args.length, seed=3)
     n = len(text)
