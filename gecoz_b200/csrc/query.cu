@@ -13,6 +13,7 @@
 #include "query.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -446,6 +447,94 @@ locate_occurrences_kernel(const QueryTables* __restrict__ tables, const uint32_t
     }
 }
 
+// Experimental (GCZ_LOCATE_VARIANT=1, default off; written without hardware): the same work in two launches.
+//  walk:   LF walks end after 0 .. 2^sf - 1 steps, so in locate_occurrences_kernel a warp waits for its longest one.  Here a
+//          lane that has reached a marked row takes the next occurrence from a grid-wide counter (one atomic per warp and
+//          refill) and the warp keeps stepping; the walk leaves (steps << 32 | sampled index) behind.
+//  finish: the IndexWaveletTree descent (one node per level for every occurrence) runs with all lanes in step.
+__global__ void __launch_bounds__(256)
+locate_walk_refill_kernel(const QueryTables* __restrict__ tables, const uint32_t* __restrict__ sectors,
+                          const int64_t* __restrict__ sp, const int64_t* __restrict__ occ_excl /* per pattern, exclusive */,
+                          int64_t first_pat, int64_t n_chunk_pats, int64_t base_occ, int64_t n_occ,
+                          uint64_t* __restrict__ keys, uint64_t* __restrict__ walked, unsigned long long* __restrict__ next) {
+    __shared__ QueryTables t;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&t);
+        for (int i = threadIdx.x; i < (int)(sizeof(QueryTables) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u, lt = lanemask_lt();
+    long long o = 0, idx = 0, steps = 0;
+    bool have = false, exhausted = false;                    // exhausted: the counter has passed n_occ (same for the whole warp)
+    while (true) {
+        const unsigned need = __ballot_sync(0xffffffffu, !have);
+        if (need && !exhausted) {
+            const int leader = __ffs(need) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(next, (unsigned long long)__popc(need));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (!have) {
+                o = (long long)base + __popc(need & lt);
+                if (o < n_occ) {
+                    const int64_t target = base_occ + o;
+                    int64_t lo = first_pat, hi = first_pat + n_chunk_pats;       // invariant: occ_excl[lo] <= target < occ_excl[hi]
+                    while (hi - lo > 1) {
+                        const int64_t mid = (lo + hi) >> 1;
+                        if (occ_excl[mid] <= target) lo = mid; else hi = mid;
+                    }
+                    idx = sp[lo] + (target - occ_excl[lo]);
+                    steps = 0;
+                    have = true;
+                    keys[o] = (uint64_t)(lo - first_pat) << 32;
+                }
+            }
+            exhausted = (long long)base + __popc(need) > n_occ;
+        }
+        if (!__any_sync(0xffffffffu, have)) break;
+        if (have) {
+            const BitRank mk = sector_bit_rank(sectors, t.marker_sector0, (uint32_t)idx);
+            if (mk.bit) {
+                walked[o] = ((uint64_t)steps << 32) | (uint64_t)(uint32_t)(mk.rank - 1);
+                have = false;
+            } else if (steps > t.n) {                        // the reference would never return here
+                walked[o] = ((uint64_t)steps << 32) | 0xFFFFFFFFull;
+                have = false;
+            } else {                                         // one LF step, as in locate_row
+                long long pos = idx;
+                int v = 0;
+                while (v >= 0) {
+                    const BitRank br = sector_bit_rank(sectors, t.node_sector0[v], (uint32_t)pos);
+                    pos = br.bit ? (long long)br.rank - 1 : pos - (long long)br.rank;
+                    v = t.child[v][br.bit];
+                }
+                idx = (long long)(int)(t.c[~v] + pos);
+                steps++;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+locate_finish_kernel(const QueryTables* __restrict__ tables, const uint32_t* __restrict__ sectors,
+                     const uint64_t* __restrict__ walked, int64_t n_occ, uint64_t* __restrict__ keys) {
+    __shared__ QueryTables t;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&t);
+        for (int i = threadIdx.x; i < (int)(sizeof(QueryTables) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n_occ; o += stride) {
+        const uint64_t w = walked[o];
+        const uint32_t sampled = (uint32_t)w;
+        const long long steps = (long long)(w >> 32);
+        const long long pos = sampled == 0xFFFFFFFFu ? -1 : (iwt_get(&t, sectors, (long long)sampled) << t.sampling_factor) + steps;
+        keys[o] |= (uint64_t)(uint32_t)pos;
+    }
+}
+
 // symbol counts through occ(i, n - 1), the way GSSA.index derives C[]  algo/ssa/GSSA.java:215-226
 __global__ void symbol_occ_kernel(const QueryTables* __restrict__ tables, const uint32_t* __restrict__ sectors, long long* __restrict__ out) {
     const int s = threadIdx.x;
@@ -764,8 +853,19 @@ int find_batch(gcz_index* idx, const uint8_t* pats, const int64_t* pat_off, int6
             if (!d_sp || !d_ex || !d_k0 || !d_k1 || !d_tmp) { std::free(h_pos); std::free(h_off); return fail(GCZ_E_NOMEM, "find_batch workspace"); }
             GCZ_CUDA(cudaMemcpyAsync(d_sp, sp.data() + p0, (size_t)np * 8, cudaMemcpyHostToDevice, st));
             GCZ_CUDA(cudaMemcpyAsync(d_ex, occ_excl.data() + p0, ((size_t)np + 1) * 8, cudaMemcpyHostToDevice, st));
-            GCZ_LAUNCH(ctx, locate_occurrences_kernel, launch_grid(ctx, n_occ, 256), 256, 0, st, idx->d_tables, idx->d_sectors,
-                       d_sp, d_ex, (int64_t)0, np, occ_excl[(size_t)p0], n_occ, d_k0);
+            const char* locate_env = std::getenv("GCZ_LOCATE_VARIANT");
+            if (locate_env && locate_env[0] == '1') {
+                unsigned long long* d_next = ctx->arena.get<unsigned long long>(2);
+                if (!d_next) { std::free(h_pos); std::free(h_off); return fail(GCZ_E_NOMEM, "find_batch workspace"); }
+                GCZ_CUDA(cudaMemsetAsync(d_next, 0, 16, st));
+                const int walk_grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_occ + 255) / 256, (int64_t)ctx->sm_count * 8));
+                GCZ_LAUNCH(ctx, locate_walk_refill_kernel, walk_grid, 256, 0, st, idx->d_tables, idx->d_sectors, d_sp, d_ex, (int64_t)0, np,
+                           occ_excl[(size_t)p0], n_occ, d_k0, d_k1, d_next);
+                GCZ_LAUNCH(ctx, locate_finish_kernel, launch_grid(ctx, n_occ, 256), 256, 0, st, idx->d_tables, idx->d_sectors, d_k1, n_occ, d_k0);
+            } else {
+                GCZ_LAUNCH(ctx, locate_occurrences_kernel, launch_grid(ctx, n_occ, 256), 256, 0, st, idx->d_tables, idx->d_sectors,
+                           d_sp, d_ex, (int64_t)0, np, occ_excl[(size_t)p0], n_occ, d_k0);
+            }
             RadixBuffers rb;
             rb.keys[0] = d_k0; rb.keys[1] = d_k1;
             int pat_bits = 1;

@@ -34,6 +34,7 @@ VARIANTS = {
     "emit_lut": {"GCZ_EMIT_VARIANT": "1"},
     "text_hist_uniform": {"GCZ_TEXT_HIST_VARIANT": "1"},
     "bwt_packed": {"GCZ_BWT_VARIANT": "1"},
+    "locate_refill": {"GCZ_LOCATE_VARIANT": "1"},   # queries only: the digest check here; time it with tools/run_configs.py (cfg5)
     "early_marker": {"GCZ_EARLY_MARKER": "1"},      # host outputs only: parity here, timing through `GCZ_EARLY_MARKER=1 python bench.py` (e2e)
     "all_small": {"GCZ_EMIT_VARIANT": "1", "GCZ_TEXT_HIST_VARIANT": "1", "GCZ_BWT_VARIANT": "1"},
     "all_small_9bit": {"GCZ_EMIT_VARIANT": "1", "GCZ_TEXT_HIST_VARIANT": "1", "GCZ_BWT_VARIANT": "1", "GCZ_SORT_VARIANT": "11"},
