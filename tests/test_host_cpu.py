@@ -234,3 +234,14 @@ def test_native_host_layer_under_thread_sanitizer(tmp_path):
     r = subprocess.run([str(exe), str(tmp_path / "o.gcz")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr, r.stderr[-4000:]
     assert r.stdout.count("rc 0 blocks") == 2
+
+
+def test_synthetic_workloads_are_pinned():
+    """bench.py, tools/ and the committed profiles quote numbers on these generators: a change of their output (a numpy
+    upgrade, an edit of synth.py) must be noticed, not silently move the workload."""
+    import hashlib
+    from gecoz_b200 import synth
+    text = synth.cfg2_text(3_000_000, seed=3)
+    data, off = synth.patterns(text, 10_000, 15, 100, seed=5)
+    digest = lambda a: hashlib.sha256(a.tobytes()).hexdigest()[:16]
+    assert (digest(text), digest(data), digest(off)) == ("165caa614f83a843", "61a4ceecdc0a6e7d", "0584b6814f516ac9")
