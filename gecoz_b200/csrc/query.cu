@@ -176,10 +176,14 @@ __device__ __forceinline__ void hswt_occ2(const QueryTables* __restrict__ t, con
 // would idle most of the time.  Lanes are refilled instead: a lane that finishes its pattern takes the next one from its
 // warp's reservation (64 patterns per atomic on the global counter), and every trip of the loop is one backward-search
 // step for all 32 lanes.
+// ORDERED (experimental, GCZ_COUNT_SORT=1): patterns are taken in the order of `order` (sorted by their last symbols, see
+// pattern_suffix_keys_kernel), so that the lanes of a warp walk the same rows for the first steps of the backward search.
+template <bool ORDERED>
 __global__ void __launch_bounds__(256)
 count_kernel(const QueryTables* __restrict__ tables, const uint32_t* __restrict__ sectors,
              const uint8_t* __restrict__ pats, const int64_t* __restrict__ pat_off, int64_t n_pats,
-             int64_t* __restrict__ sp_out, int64_t* __restrict__ ep_out, unsigned long long* __restrict__ next_pattern) {
+             int64_t* __restrict__ sp_out, int64_t* __restrict__ ep_out, unsigned long long* __restrict__ next_pattern,
+             const uint32_t* __restrict__ order) {
     __shared__ QueryTables t;
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
@@ -206,7 +210,7 @@ count_kernel(const QueryTables* __restrict__ tables, const uint32_t* __restrict_
             }
             const long long mine = wnext + __popc(idle & lt);
             if (q < 0 && mine < wend) {
-                q = mine;
+                q = ORDERED ? (long long)order[mine] : mine;
                 b = pat_off[q];
                 const long long e = pat_off[q + 1];
                 sp = 0; ep = -1; i = b - 1;              // empty pattern / byte >= 0x80: reported as not found
@@ -241,6 +245,25 @@ count_kernel(const QueryTables* __restrict__ tables, const uint32_t* __restrict_
                 q = -1;
             }
         }
+    }
+}
+
+// Sort key of a pattern for GCZ_COUNT_SORT=1: its last 12 symbols, the last one most significant, 5 bits each (the id of the
+// byte among the symbols of the block, modulo 32) — the order in which the backward search consumes them.
+struct SymbolIds { uint8_t id[256]; };
+
+__global__ void pattern_suffix_keys_kernel(const uint8_t* __restrict__ pats, const int64_t* __restrict__ pat_off, int64_t n_pats,
+                                           SymbolIds ids, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_pats; q += stride) {
+        const int64_t b = pat_off[q], e = pat_off[q + 1];
+        uint64_t key = 0;
+        for (int j = 0; j < 12; j++) {
+            const int64_t at = e - 1 - j;
+            key = (key << 5) | (at >= b ? (uint64_t)(ids.id[pats[at]] & 31u) : 0ull);
+        }
+        keys[q] = key;
+        vals[q] = (uint32_t)q;
     }
 }
 
@@ -748,7 +771,9 @@ int count_batch(gcz_index* idx, const uint8_t* pats, const int64_t* pat_off, int
     const bool off_dev = is_device_ptr(pat_off);
     if (off_dev) GCZ_CUDA(cudaMemcpy(&total_bytes, pat_off + n_pats, 8, cudaMemcpyDeviceToHost));
     else total_bytes = pat_off[n_pats];
-    const size_t need = (size_t)total_bytes + (size_t)n_pats * 24 + (1 << 20);
+    const char* sort_env0 = std::getenv("GCZ_COUNT_SORT");
+    const size_t sort_bytes = (sort_env0 && sort_env0[0] == '1') ? (size_t)n_pats * 24 + radix_sort_temp_bytes(n_pats) + (1 << 20) : 0;
+    const size_t need = (size_t)total_bytes + (size_t)n_pats * 24 + (1 << 20) + sort_bytes;
     if (ctx->arena.capacity < need) GCZ_TRY(ctx->arena.reserve(need));
 
     const uint8_t* d_pats = nullptr; const int64_t* d_off = nullptr;
@@ -764,7 +789,28 @@ int count_batch(gcz_index* idx, const uint8_t* pats, const int64_t* pat_off, int
     if (!d_next) return fail(GCZ_E_NOMEM, "query staging");
     GCZ_CUDA(cudaMemsetAsync(d_next, 0, 8, st));
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_pats + 255) / 256, (int64_t)ctx->sm_count * 8));
-    GCZ_LAUNCH(ctx, count_kernel, grid, 256, 0, st, idx->d_tables, idx->d_sectors, d_pats, d_off, n_pats, d_sp, d_ep, d_next);
+    const char* sort_env = std::getenv("GCZ_COUNT_SORT");
+    if (sort_env && sort_env[0] == '1' && n_pats >= 1024 && n_pats < ((int64_t)1 << 31)) {
+        const size_t more = (size_t)n_pats * 24 + radix_sort_temp_bytes(n_pats) + (1 << 20);
+        RadixBuffers rb;
+        rb.keys[0] = ctx->arena.get<uint64_t>((size_t)n_pats); rb.keys[1] = ctx->arena.get<uint64_t>((size_t)n_pats);
+        rb.vals[0] = ctx->arena.get<uint32_t>((size_t)n_pats); rb.vals[1] = ctx->arena.get<uint32_t>((size_t)n_pats);
+        void* d_tmp = ctx->arena.raw(radix_sort_temp_bytes(n_pats));
+        if (!rb.keys[0] || !rb.keys[1] || !rb.vals[0] || !rb.vals[1] || !d_tmp) return fail(GCZ_E_NOMEM, "query staging (%zu more bytes)", more);
+        SymbolIds ids;
+        int next_id = 1;
+        for (int ch = 0; ch < 256; ch++) {
+            const int64_t here = (ch < 255 ? idx->c[ch + 1] : idx->n) - idx->c[ch];
+            ids.id[ch] = here > 0 ? (uint8_t)(next_id++ & 31) : 0;
+        }
+        GCZ_LAUNCH(ctx, pattern_suffix_keys_kernel, launch_grid(ctx, n_pats, 256), 256, 0, st, d_pats, d_off, n_pats, ids, rb.keys[0], rb.vals[0]);
+        GCZ_TRY(radix_sort_pairs(ctx, st, rb, n_pats, 0, 60, d_tmp, nullptr));
+        GCZ_LAUNCH(ctx, count_kernel<true>, grid, 256, 0, st, idx->d_tables, idx->d_sectors, d_pats, d_off, n_pats, d_sp, d_ep, d_next,
+                   (const uint32_t*)rb.vals[rb.cur]);
+    } else {
+        GCZ_LAUNCH(ctx, count_kernel<false>, grid, 256, 0, st, idx->d_tables, idx->d_sectors, d_pats, d_off, n_pats, d_sp, d_ep, d_next,
+                   (const uint32_t*)nullptr);
+    }
     if (!out_dev) {
         GCZ_CUDA(cudaMemcpyAsync(sp, d_sp, (size_t)n_pats * 8, cudaMemcpyDeviceToHost, st));
         GCZ_CUDA(cudaMemcpyAsync(ep, d_ep, (size_t)n_pats * 8, cudaMemcpyDeviceToHost, st));

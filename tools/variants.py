@@ -34,6 +34,7 @@ VARIANTS = {
     "emit_lut": {"GCZ_EMIT_VARIANT": "1"},
     "text_hist_uniform": {"GCZ_TEXT_HIST_VARIANT": "1"},
     "bwt_packed": {"GCZ_BWT_VARIANT": "1"},
+    "count_sorted": {"GCZ_COUNT_SORT": "1"},        # queries only: digests + count_ms below
     "locate_refill": {"GCZ_LOCATE_VARIANT": "1"},   # queries only: the digest check here; time it with tools/run_configs.py (cfg5)
     "early_marker": {"GCZ_EARLY_MARKER": "1"},      # host outputs only: parity here, timing through `GCZ_EARLY_MARKER=1 python bench.py` (e2e)
     "all_small": {"GCZ_EMIT_VARIANT": "1", "GCZ_TEXT_HIST_VARIANT": "1", "GCZ_BWT_VARIANT": "1"},
@@ -138,6 +139,27 @@ def child(args) -> None:
             "radix_launches", "radix_full_launches", "kernel_launches")
     mean = {k: float(np.mean([t[k] for t in infos])) for k in keys}
     big = hashlib.sha256(d_gcz.cpu().numpy().tobytes()).hexdigest()[:16] + hashlib.sha256(d_gcx.cpu().numpy().tobytes()).hexdigest()[:16]
+    # count and find on that index: 1 M patterns resident on the device (wall clock around the call, best of three)
+    import time
+    g = G.GSSA.open(0, d_gcz, n, d_gcx)
+    pdata, poff = synth.patterns(text, 1_000_000, 15, 100, seed=5)
+    dp, do = torch.from_numpy(pdata).cuda(), torch.from_numpy(poff).cuda()
+    d_sp = torch.empty(len(poff) - 1, dtype=torch.int64, device="cuda")
+    d_ep = torch.empty_like(d_sp)
+    count_ms, find_ms = [], []
+    for _ in range(4):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        g.count_batch(packed=(dp, do), out=(d_sp, d_ep))
+        torch.cuda.synchronize()
+        count_ms.append((time.perf_counter() - t0) * 1e3)
+    small = (pdata[:int(poff[100_000])], poff[:100_001])
+    for _ in range(3):
+        t0 = time.perf_counter()
+        g.find_batch_raw(packed=small)
+        find_ms.append((time.perf_counter() - t0) * 1e3)
+    g.close()
+    mean["count_1M_ms"], mean["find_100k_ms"] = float(min(count_ms[1:])), float(min(find_ms[1:]))
     print("RESULT " + json.dumps({"variant": args.child, "env": VARIANTS[args.child], "parity_vs_default": ("stored" if ref is None else "ok") if not mismatches
                                   else mismatches, "cfg2_digest": big, "n": n, **mean}), flush=True)
 
@@ -177,7 +199,7 @@ def main() -> None:
             f.write(json.dumps(rec) + "\n")
             f.flush()
             print(json.dumps({k: rec.get(k) for k in ("variant", "parity_vs_default", "cfg2_same_as_default", "total_ms", "sort_initial_ms",
-                                                      "bwt_hswt_ms", "radix_full_ms", "radix_text_ms", "failed")}), flush=True)
+                                                      "bwt_hswt_ms", "radix_full_ms", "radix_text_ms", "count_1M_ms", "find_100k_ms", "failed")}), flush=True)
 
 
 if __name__ == "__main__":
