@@ -7,9 +7,9 @@ mkdir -p gpurun_out
 L=gpurun_out/r2_first
 {
 echo "== 1. the GPU test suite (default kernels; includes the rewritten writers and the native host layer)"
-timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -15
+timeout 900 python -m pytest tests -q -m gpu -x > gpurun_out/r2_pytest_gpu.log 2>&1; tail -40 gpurun_out/r2_pytest_gpu.log
 echo "== 2. the test that was waiting for hardware"
-GCZ_TEST_PENDING=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -k native_callers 2>&1 | tail -5
+GCZ_TEST_PENDING=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -k native_callers > gpurun_out/r2_pytest_pending.log 2>&1; tail -30 gpurun_out/r2_pytest_pending.log
 echo "== 3. bench, default kernels"
 timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err; tail -c 600 gpurun_out/r2_bench_default.json; tail -3 gpurun_out/r2_bench_default.err
 echo "== 4. every prepared variant: parity against the default kernels, then time"
