@@ -75,6 +75,7 @@ EXPORTS = [
     "gcz_count_symbols", "gcz_build_block", "gcz_last_build_timing",
     "gcz_open_block", "gcz_close_block", "gcz_text_length", "gcz_sampling_factor", "gcz_num_strings",
     "gcz_string_ends", "gcz_c_array", "gcz_count_batch", "gcz_locate_rows", "gcz_find_batch", "gcz_extract", "gcz_free",
+    "gcz_count_multi", "gcz_count_stats", "gcz_last_query_stats", "gcz_find_multi", "gcz_hits_free",
     "gcz_dbg_sort_pairs", "gcz_dbg_suffix_array", "gcz_dbg_ranked_vector", "gcz_dbg_index_wavelet_tree",
 ]
 
@@ -91,6 +92,21 @@ FILE_EXPORTS = [
 COUNT_SYMBOLS_FN = C.CFUNCTYPE(C.c_int, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64))
 BUILD_BLOCK_FN = C.CFUNCTYPE(C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(Shape), C.c_void_p, C.c_int64,
                              C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p)
+
+
+class Hits(C.Structure):
+    """struct gcz_hits (include/gcz.h)."""
+    _fields_ = [("n_hits", C.c_int64), ("block_off", C.POINTER(C.c_int64)), ("pattern", C.POINTER(C.c_int64)),
+                ("string", C.POINTER(C.c_int32)), ("position", C.POINTER(C.c_int64))]
+
+
+class QueryStats(C.Structure):
+    """struct gcz_query_stats (include/gcz.h)."""
+    _fields_ = [("patterns", C.c_int64), ("blocks", C.c_int64), ("steps", C.c_int64), ("rank_sectors", C.c_int64),
+                ("reference_rank_calls", C.c_int64), ("index_bytes", C.c_int64), ("kernel_ms", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 class Engine(C.Structure):
@@ -166,6 +182,11 @@ def lib() -> C.CDLL:
         "gcz_find_batch": (C.c_int, [P, P, P, i64, P, C.POINTER(P), C.POINTER(P)]),
         "gcz_extract": (C.c_int, [P, i32, i64, P, i64, C.POINTER(i64)]),
         "gcz_free": (None, [P]),
+        "gcz_count_multi": (C.c_int, [P, i32, P, P, i64, P]),
+        "gcz_count_stats": (C.c_int, [P, i32, P, P, i64, C.POINTER(QueryStats)]),
+        "gcz_last_query_stats": (C.c_int, [C.POINTER(QueryStats)]),
+        "gcz_find_multi": (C.c_int, [P, i32, P, P, i64, C.POINTER(Hits)]),
+        "gcz_hits_free": (None, [C.POINTER(Hits)]),
         "gcz_dbg_sort_pairs": (C.c_int, [C.c_int, P, P, i64, i32, i32]),
         "gcz_dbg_suffix_array": (C.c_int, [C.c_int, P, i64, P]),
         "gcz_dbg_ranked_vector": (C.c_int, [C.c_int, P, i64, P]),

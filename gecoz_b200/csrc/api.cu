@@ -448,6 +448,25 @@ int gcz_extract(gcz_index* idx, int32_t nstr, int64_t from, uint8_t* out, int64_
 }
 void gcz_free(void* p) { std::free(p); }
 
+int gcz_count_multi(gcz_index* const* blocks, int32_t n_blocks, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats, int64_t* totals) {
+    clear_error();
+    return guarded([&] { return count_multi(blocks, n_blocks, pats, pat_off, n_pats, totals); });
+}
+int gcz_count_stats(gcz_index* const* blocks, int32_t n_blocks, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats, gcz_query_stats* out) {
+    clear_error();
+    return guarded([&] { return count_stats(blocks, n_blocks, pats, pat_off, n_pats, out); });
+}
+int gcz_last_query_stats(gcz_query_stats* out) { return last_query_stats(out); }
+int gcz_find_multi(gcz_index* const* blocks, int32_t n_blocks, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats, gcz_hits* out) {
+    clear_error();
+    return guarded([&] { return find_multi(blocks, n_blocks, pats, pat_off, n_pats, out); });
+}
+void gcz_hits_free(gcz_hits* hits) {
+    if (!hits) return;
+    std::free(hits->block_off); std::free(hits->pattern); std::free(hits->string); std::free(hits->position);
+    std::memset(hits, 0, sizeof(*hits));
+}
+
 // ---- stage hooks ---------------------------------------------------------------------------------------------------
 int gcz_dbg_sort_pairs(int device, uint64_t* keys, uint32_t* vals, int64_t n, int32_t begin_bit, int32_t end_bit) {
     clear_error();

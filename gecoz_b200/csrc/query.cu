@@ -137,11 +137,17 @@ __device__ __forceinline__ uint32_t sector_rank_at(const uint32_t (&w)[8], uint3
     return r + __popc(cur << (31 - bi));
 }
 
+// What a batch of backward searches touches (gcz_count_stats): rank sectors of 32 bytes actually loaded, and the
+// RankedWTNode.count calls the reference's loop makes for the same patterns (2 per character and code bit while the
+// position is >= 0, algo/tree/HuffmanShapedWaveletTree.java:247-267) — 74 bytes each in the file layout.
+struct OccStats { unsigned long long sectors = 0, ref_calls = 0, steps = 0; };
+
 // The two occ() of one backward-search step, occ(symbol, p1) and occ(symbol, p2) with p1 <= p2, walking the
 // symbol's path once: on every node the two positions usually fall into the same rank sector (always, once the
 // interval has shrunk to a few suffixes), and that sector is loaded once.
+template <bool STATS>
 __device__ __forceinline__ void hswt_occ2(const QueryTables* __restrict__ t, const uint32_t* __restrict__ sectors,
-                                          int symbol, long long& p1, long long& p2) {
+                                          int symbol, long long& p1, long long& p2, OccStats* stats) {
     const int len = t->len[symbol];
     if (len == 0) { p1 = -1; p2 = -1; return; }
     const unsigned code = t->code[symbol];
@@ -155,6 +161,7 @@ __device__ __forceinline__ void hswt_occ2(const QueryTables* __restrict__ t, con
             const uint4 a = __ldg(p), b = __ldg(p + 1);
             w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
         }
+        if (STATS) { stats->sectors++; stats->ref_calls += p1 >= 0 ? 2 : 1; }
         const uint32_t r2 = sector_rank_at(w, q2 - sec2 * kSectorBits);
         if (p1 >= 0) {
             const uint32_t q1 = (uint32_t)p1, sec1 = q1 / kSectorBits;
@@ -163,6 +170,7 @@ __device__ __forceinline__ void hswt_occ2(const QueryTables* __restrict__ t, con
                 r1 = sector_rank_at(w, q1 - sec1 * kSectorBits);
             } else {
                 r1 = sector_bit_rank(sectors, s0, q1).rank;
+                if (STATS) stats->sectors++;
             }
             p1 = one ? (long long)r1 - 1 : p1 - (long long)r1;
         }
@@ -176,14 +184,14 @@ __device__ __forceinline__ void hswt_occ2(const QueryTables* __restrict__ t, con
 // would idle most of the time.  Lanes are refilled instead: a lane that finishes its pattern takes the next one from its
 // warp's reservation (64 patterns per atomic on the global counter), and every trip of the loop is one backward-search
 // step for all 32 lanes.
-// ORDERED (experimental, GCZ_COUNT_SORT=1): patterns are taken in the order of `order` (sorted by their last symbols, see
-// pattern_suffix_keys_kernel), so that the lanes of a warp walk the same rows for the first steps of the backward search.
-template <bool ORDERED>
+// MODE 0: (sp, ep) per pattern.  MODE 1: totals[q] += max(0, ep - sp + 1) — one block after the other of a multi-block
+// index into the same array (gcz_count_multi).  MODE 2: as 0, and the OccStats of the whole launch (gcz_count_stats).
+template <int MODE>
 __global__ void __launch_bounds__(256)
 count_kernel(const QueryTables* __restrict__ tables, const uint32_t* __restrict__ sectors,
              const uint8_t* __restrict__ pats, const int64_t* __restrict__ pat_off, int64_t n_pats,
              int64_t* __restrict__ sp_out, int64_t* __restrict__ ep_out, unsigned long long* __restrict__ next_pattern,
-             const uint32_t* __restrict__ order) {
+             unsigned long long* __restrict__ stats_out) {
     __shared__ QueryTables t;
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
@@ -196,6 +204,7 @@ count_kernel(const QueryTables* __restrict__ tables, const uint32_t* __restrict_
     long long wnext = 0, wend = 0;                       // the warp's reservation [wnext, wend), uniform across lanes
     long long q = -1, i = 0, b = 0, sp = 0, ep = -1;     // q: my pattern, -1 = none
     bool drained = false;                                // the global counter ran past n_pats
+    OccStats stats;
     while (true) {
         // hand patterns to the idle lanes
         unsigned idle = __ballot_sync(0xffffffffu, q < 0);
@@ -210,7 +219,7 @@ count_kernel(const QueryTables* __restrict__ tables, const uint32_t* __restrict_
             }
             const long long mine = wnext + __popc(idle & lt);
             if (q < 0 && mine < wend) {
-                q = ORDERED ? (long long)order[mine] : mine;
+                q = mine;
                 b = pat_off[q];
                 const long long e = pat_off[q + 1];
                 sp = 0; ep = -1; i = b - 1;              // empty pattern / byte >= 0x80: reported as not found
@@ -234,36 +243,30 @@ count_kernel(const QueryTables* __restrict__ tables, const uint32_t* __restrict_
                     sp = 0; ep = -1;
                 } else {
                     long long o1 = sp - 1, o2 = ep;
-                    hswt_occ2(&t, sectors, ch, o1, o2);
+                    hswt_occ2<MODE == 2>(&t, sectors, ch, o1, o2, &stats);
+                    if (MODE == 2) stats.steps++;
                     sp = t.c[ch] + o1 + 1;
                     ep = t.c[ch] + o2;
                 }
                 i--;
             } else {
-                sp_out[q] = sp;
-                ep_out[q] = ep;
+                if (MODE == 1) {
+                    if (ep >= sp) sp_out[q] += ep - sp + 1;
+                } else {
+                    sp_out[q] = sp;
+                    ep_out[q] = ep;
+                }
                 q = -1;
             }
         }
     }
-}
-
-// Sort key of a pattern for GCZ_COUNT_SORT=1: its last 12 symbols, the last one most significant, 5 bits each (the id of the
-// byte among the symbols of the block, modulo 32) — the order in which the backward search consumes them.
-struct SymbolIds { uint8_t id[256]; };
-
-__global__ void pattern_suffix_keys_kernel(const uint8_t* __restrict__ pats, const int64_t* __restrict__ pat_off, int64_t n_pats,
-                                           SymbolIds ids, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_pats; q += stride) {
-        const int64_t b = pat_off[q], e = pat_off[q + 1];
-        uint64_t key = 0;
-        for (int j = 0; j < 12; j++) {
-            const int64_t at = e - 1 - j;
-            key = (key << 5) | (at >= b ? (uint64_t)(ids.id[pats[at]] & 31u) : 0ull);
+    if (MODE == 2) {
+        unsigned long long v[3] = { stats.sectors, stats.ref_calls, stats.steps };
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+            if (lane == 0 && v[k]) atomicAdd(&stats_out[k], v[k]);
         }
-        keys[q] = key;
-        vals[q] = (uint32_t)q;
     }
 }
 
@@ -470,94 +473,6 @@ locate_occurrences_kernel(const QueryTables* __restrict__ tables, const uint32_t
     }
 }
 
-// Experimental (GCZ_LOCATE_VARIANT=1, default off; written without hardware): the same work in two launches.
-//  walk:   LF walks end after 0 .. 2^sf - 1 steps, so in locate_occurrences_kernel a warp waits for its longest one.  Here a
-//          lane that has reached a marked row takes the next occurrence from a grid-wide counter (one atomic per warp and
-//          refill) and the warp keeps stepping; the walk leaves (steps << 32 | sampled index) behind.
-//  finish: the IndexWaveletTree descent (one node per level for every occurrence) runs with all lanes in step.
-__global__ void __launch_bounds__(256)
-locate_walk_refill_kernel(const QueryTables* __restrict__ tables, const uint32_t* __restrict__ sectors,
-                          const int64_t* __restrict__ sp, const int64_t* __restrict__ occ_excl /* per pattern, exclusive */,
-                          int64_t first_pat, int64_t n_chunk_pats, int64_t base_occ, int64_t n_occ,
-                          uint64_t* __restrict__ keys, uint64_t* __restrict__ walked, unsigned long long* __restrict__ next) {
-    __shared__ QueryTables t;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&t);
-        for (int i = threadIdx.x; i < (int)(sizeof(QueryTables) / 4); i += blockDim.x) dst[i] = src[i];
-    }
-    __syncthreads();
-    const unsigned lane = threadIdx.x & 31u, lt = lanemask_lt();
-    long long o = 0, idx = 0, steps = 0;
-    bool have = false, exhausted = false;                    // exhausted: the counter has passed n_occ (same for the whole warp)
-    while (true) {
-        const unsigned need = __ballot_sync(0xffffffffu, !have);
-        if (need && !exhausted) {
-            const int leader = __ffs(need) - 1;
-            unsigned long long base = 0;
-            if ((int)lane == leader) base = atomicAdd(next, (unsigned long long)__popc(need));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (!have) {
-                o = (long long)base + __popc(need & lt);
-                if (o < n_occ) {
-                    const int64_t target = base_occ + o;
-                    int64_t lo = first_pat, hi = first_pat + n_chunk_pats;       // invariant: occ_excl[lo] <= target < occ_excl[hi]
-                    while (hi - lo > 1) {
-                        const int64_t mid = (lo + hi) >> 1;
-                        if (occ_excl[mid] <= target) lo = mid; else hi = mid;
-                    }
-                    idx = sp[lo] + (target - occ_excl[lo]);
-                    steps = 0;
-                    have = true;
-                    keys[o] = (uint64_t)(lo - first_pat) << 32;
-                }
-            }
-            exhausted = (long long)base + __popc(need) > n_occ;
-        }
-        if (!__any_sync(0xffffffffu, have)) break;
-        if (have) {
-            const BitRank mk = sector_bit_rank(sectors, t.marker_sector0, (uint32_t)idx);
-            if (mk.bit) {
-                walked[o] = ((uint64_t)steps << 32) | (uint64_t)(uint32_t)(mk.rank - 1);
-                have = false;
-            } else if (steps > t.n) {                        // the reference would never return here
-                walked[o] = ((uint64_t)steps << 32) | 0xFFFFFFFFull;
-                have = false;
-            } else {                                         // one LF step, as in locate_row
-                long long pos = idx;
-                int v = 0;
-                while (v >= 0) {
-                    const BitRank br = sector_bit_rank(sectors, t.node_sector0[v], (uint32_t)pos);
-                    pos = br.bit ? (long long)br.rank - 1 : pos - (long long)br.rank;
-                    v = t.child[v][br.bit];
-                }
-                idx = (long long)(int)(t.c[~v] + pos);
-                steps++;
-            }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256)
-locate_finish_kernel(const QueryTables* __restrict__ tables, const uint32_t* __restrict__ sectors,
-                     const uint64_t* __restrict__ walked, int64_t n_occ, uint64_t* __restrict__ keys) {
-    __shared__ QueryTables t;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&t);
-        for (int i = threadIdx.x; i < (int)(sizeof(QueryTables) / 4); i += blockDim.x) dst[i] = src[i];
-    }
-    __syncthreads();
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n_occ; o += stride) {
-        const uint64_t w = walked[o];
-        const uint32_t sampled = (uint32_t)w;
-        const long long steps = (long long)(w >> 32);
-        const long long pos = sampled == 0xFFFFFFFFu ? -1 : (iwt_get(&t, sectors, (long long)sampled) << t.sampling_factor) + steps;
-        keys[o] |= (uint64_t)(uint32_t)pos;
-    }
-}
-
 // symbol counts through occ(i, n - 1), the way GSSA.index derives C[]  algo/ssa/GSSA.java:215-226
 __global__ void symbol_occ_kernel(const QueryTables* __restrict__ tables, const uint32_t* __restrict__ sectors, long long* __restrict__ out) {
     const int s = threadIdx.x;
@@ -757,6 +672,302 @@ static int stage_in(cudaStream_t st, Arena& arena, const T* src, size_t count, c
     return GCZ_OK;
 }
 
+// ---- batched queries: host side ------------------------------------------------------------------------------------
+namespace {
+
+// A pattern batch on the device (uploaded once, whatever the number of blocks it is searched in).
+struct DeviceBatch {
+    const uint8_t* pats = nullptr;
+    const int64_t* off = nullptr;
+    int64_t n = 0, bytes = 0;
+};
+
+int stage_batch(cudaStream_t st, Arena& arena, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats, DeviceBatch* out) {
+    int64_t total_bytes = 0;
+    if (is_device_ptr(pat_off)) GCZ_CUDA(cudaMemcpy(&total_bytes, pat_off + n_pats, 8, cudaMemcpyDeviceToHost));
+    else total_bytes = pat_off[n_pats];
+    if (total_bytes < 0) return fail(GCZ_E_ARG, "pattern offsets");
+    out->n = n_pats; out->bytes = total_bytes;
+    GCZ_TRY(stage_in(st, arena, pats, (size_t)total_bytes, &out->pats));
+    GCZ_TRY(stage_in(st, arena, pat_off, (size_t)n_pats + 1, &out->off));
+    return GCZ_OK;
+}
+
+size_t batch_bytes(const uint8_t* pats, const int64_t* pat_off, int64_t n_pats) {
+    // staging space when the batch lives on the host (the byte count of a device-resident batch needs no staging)
+    if (is_device_ptr(pats) && is_device_ptr(pat_off)) return 0;
+    const int64_t bytes = is_device_ptr(pat_off) ? 0 : pat_off[n_pats];
+    return (size_t)std::max<int64_t>(bytes, 0) + (size_t)(n_pats + 3) * 8 + 4096;
+}
+
+int count_grid(DeviceCtx* ctx, int64_t n_pats) {
+    return (int)std::max<int64_t>(1, std::min<int64_t>((n_pats + 255) / 256, (int64_t)ctx->sm_count * 8));
+}
+
+int same_device(gcz_index* const* blocks, int32_t n_blocks, DeviceCtx** ctx) {
+    if (!blocks || n_blocks <= 0) return fail(GCZ_E_ARG, "no blocks");
+    for (int32_t b = 0; b < n_blocks; b++) {
+        if (!blocks[b]) return fail(GCZ_E_ARG, "null block %d", b);
+        if (blocks[b]->ctx != blocks[0]->ctx) return fail(GCZ_E_ARG, "the blocks of one call must be open on one device");
+    }
+    *ctx = blocks[0]->ctx;
+    return GCZ_OK;
+}
+
+thread_local gcz_query_stats t_query_stats = {};
+thread_local size_t t_find_want = 0;            // arena bytes a find_block that ran out of workspace asks for
+
+// exclusive prefix sums of n int64 values (out has n + 1 entries): chunk sums, one CTA over the chunk sums, chunk scans
+constexpr int kScanThreads = 256, kScanItems = 8, kScanChunk = kScanThreads * kScanItems;
+
+__global__ void __launch_bounds__(kScanThreads)
+occ_chunk_sums_kernel(const int64_t* __restrict__ sp, const int64_t* __restrict__ ep, int64_t n, int64_t* __restrict__ chunk_sums) {
+    __shared__ long long s_w[kScanThreads / 32];
+    const int64_t base = (int64_t)blockIdx.x * kScanChunk;
+    long long v = 0;
+    for (int i = threadIdx.x; i < kScanChunk; i += kScanThreads) {
+        const int64_t q = base + i;
+        if (q < n) v += max((long long)0, (long long)(ep[q] - sp[q] + 1));
+    }
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane_id() == 0) s_w[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        for (int w = 0; w < kScanThreads / 32; w++) t += s_w[w];
+        chunk_sums[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+scan_chunk_sums_kernel(int64_t* __restrict__ chunk_sums, int64_t chunks, int64_t* __restrict__ total) {
+    __shared__ long long s_w[32];
+    __shared__ long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int64_t c0 = 0; c0 < chunks; c0 += 1024) {
+        const int64_t c = c0 + threadIdx.x;
+        const long long v = c < chunks ? chunk_sums[c] : 0;
+        long long incl = v;
+        for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane_id() >= o) incl += t; }
+        if (lane_id() == 31) s_w[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        long long before = s_carry;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); w++) before += s_w[w];
+        if (c < chunks) chunk_sums[c] = before + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = before + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = s_carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+occ_scan_kernel(const int64_t* __restrict__ sp, const int64_t* __restrict__ ep, int64_t n, const int64_t* __restrict__ chunk_excl,
+                const int64_t* __restrict__ total, int64_t* __restrict__ occ_excl /* n + 1 */) {
+    __shared__ long long s_w[kScanThreads / 32];
+    const int64_t base = (int64_t)blockIdx.x * kScanChunk + (int64_t)threadIdx.x * kScanItems;
+    long long v[kScanItems], sum = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        const int64_t q = base + i;
+        v[i] = q < n ? max((long long)0, (long long)(ep[q] - sp[q] + 1)) : 0;
+        sum += v[i];
+    }
+    long long incl = sum;
+    for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane_id() >= o) incl += t; }
+    if (lane_id() == 31) s_w[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    long long before = chunk_excl[blockIdx.x] + incl - sum;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); w++) before += s_w[w];
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        const int64_t q = base + i;
+        if (q < n) occ_excl[q] = before;
+        before += v[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) occ_excl[n] = *total;
+}
+
+// GSSA.find :170-184 for occurrences sorted by (pattern, position): the string of an occurrence at text position x is
+// the first one whose end e[i] lies above x, its position there x - start.  flags[0] is raised when a position equals a
+// string end (the reference's binarySearch then FINDS the key and takes its other branch) and flags[1] when a position
+// lies behind the last string end (the reference drops it): such chunks are redone by the literal loop on the host.
+__global__ void __launch_bounds__(256)
+split_by_string_kernel(const uint64_t* __restrict__ keys, int64_t n_occ, const int64_t* __restrict__ e, int32_t ns,
+                       int32_t* __restrict__ out_string, int64_t* __restrict__ out_pos, unsigned* __restrict__ flags) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n_occ; o += stride) {
+        const long long x = (long long)(int32_t)(uint32_t)(keys[o] & 0xFFFFFFFFull);
+        int lo = 0, hi = ns;                               // first i with e[i] >= x
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (e[mid] < x) lo = mid + 1; else hi = mid;
+        }
+        if (lo < ns && e[lo] == x) atomicOr(&flags[0], 1u);
+        if (lo >= ns) { atomicOr(&flags[1], 1u); out_string[o] = -1; out_pos[o] = x; continue; }
+        out_string[o] = lo;
+        out_pos[o] = x - (lo > 0 ? e[lo - 1] + 1 : 0);
+    }
+}
+
+// java.util.Arrays.binarySearch(long[] a, int from, int to, long key)
+int64_t java_binary_search(const int64_t* a, int64_t from, int64_t to, int64_t key) {
+    int64_t low = from, high = to - 1;
+    while (low <= high) {
+        const int64_t mid = (int64_t)(((uint64_t)low + (uint64_t)high) >> 1);
+        if (a[mid] < key) low = mid + 1;
+        else if (a[mid] > key) high = mid - 1;
+        else return mid;
+    }
+    return -(low + 1);
+}
+
+// Hits of one block in the order GSSA.find returns them: pattern after pattern, string after string, ascending.
+struct BlockHits {
+    std::vector<int64_t> off;        // n_pats + 1
+    std::vector<int32_t> string;
+    std::vector<int64_t> pos;
+};
+
+// The whole of GSSA.find for a device-resident batch against one block.  Intervals, occurrence offsets, locate, the sort
+// by (pattern, position) and the split by string ends all run on the device; what comes back is 12 bytes per hit and
+// 8 per pattern.  A chunk whose split met one of the reference's corner cases is redone literally on the host.
+int find_block(gcz_index* idx, cudaStream_t st, const DeviceBatch& batch, BlockHits* out) {
+    DeviceCtx* ctx = idx->ctx;
+    Arena& arena = ctx->arena;
+    const size_t mark0 = arena.mark();
+    const int64_t n_pats = batch.n;
+    const int32_t ns = (int32_t)idx->e.size();
+    out->off.assign((size_t)n_pats + 1, 0);
+    out->string.clear(); out->pos.clear();
+    if (n_pats == 0) return GCZ_OK;
+
+    const int64_t chunks = (n_pats + kScanChunk - 1) / kScanChunk;
+    int64_t* d_sp = arena.get<int64_t>((size_t)n_pats);
+    int64_t* d_ep = arena.get<int64_t>((size_t)n_pats);
+    int64_t* d_excl = arena.get<int64_t>((size_t)n_pats + 1);
+    int64_t* d_chunk = arena.get<int64_t>((size_t)chunks + 1);
+    int64_t* d_e = arena.get<int64_t>((size_t)ns + 1);
+    unsigned long long* d_next = arena.get<unsigned long long>(4);      // [0] pattern counter, [1] total, [2] flags
+    if (!d_sp || !d_ep || !d_excl || !d_chunk || !d_e || !d_next) return fail(GCZ_E_NOMEM, "find workspace");
+    GCZ_CUDA(cudaMemsetAsync(d_next, 0, 32, st));
+    if (ns > 0) GCZ_CUDA(cudaMemcpyAsync(d_e, idx->e.data(), (size_t)ns * 8, cudaMemcpyHostToDevice, st));
+    GCZ_LAUNCH(ctx, count_kernel<0>, count_grid(ctx, n_pats), 256, 0, st, idx->d_tables, idx->d_sectors, batch.pats, batch.off, n_pats,
+               d_sp, d_ep, d_next, (unsigned long long*)nullptr);
+    int64_t* d_total = reinterpret_cast<int64_t*>(d_next + 1);
+    GCZ_LAUNCH(ctx, occ_chunk_sums_kernel, (unsigned)chunks, kScanThreads, 0, st, d_sp, d_ep, n_pats, d_chunk);
+    GCZ_LAUNCH(ctx, scan_chunk_sums_kernel, 1, 1024, 0, st, d_chunk, chunks, d_total);
+    GCZ_LAUNCH(ctx, occ_scan_kernel, (unsigned)chunks, kScanThreads, 0, st, d_sp, d_ep, n_pats, d_chunk, d_total, d_excl);
+    int64_t total_occ = 0;
+    GCZ_CUDA(cudaMemcpyAsync(&total_occ, d_total, 8, cudaMemcpyDeviceToHost, st));
+    GCZ_CUDA(cudaStreamSynchronize(st));
+    if (total_occ == 0) { arena.release(mark0); return GCZ_OK; }
+
+    // pattern ranges of at most kChunk occurrences (a single pattern may exceed it); one range in the common case
+    const int64_t kChunk = (int64_t)1 << 26;
+    std::vector<int64_t> h_excl;
+    std::vector<int64_t> cuts = { 0, n_pats };
+    if (total_occ > kChunk) {
+        h_excl.resize((size_t)n_pats + 1);
+        GCZ_CUDA(cudaMemcpyAsync(h_excl.data(), d_excl, ((size_t)n_pats + 1) * 8, cudaMemcpyDeviceToHost, st));
+        GCZ_CUDA(cudaStreamSynchronize(st));
+        cuts.assign(1, 0);
+        int64_t p0 = 0;
+        while (p0 < n_pats) {
+            int64_t p1 = p0 + 1;
+            while (p1 < n_pats && h_excl[(size_t)p1 + 1] - h_excl[(size_t)p0] <= kChunk) p1++;
+            cuts.push_back(p1);
+            p0 = p1;
+        }
+    }
+    out->string.resize((size_t)total_occ);
+    out->pos.resize((size_t)total_occ);
+    GCZ_CUDA(cudaMemcpyAsync(out->off.data(), d_excl, ((size_t)n_pats + 1) * 8, cudaMemcpyDeviceToHost, st));
+
+    bool literal = false;                                 // some chunk needs the reference's loop as written
+    const size_t mark1 = arena.mark();
+    std::vector<uint64_t> h_keys;
+    std::vector<std::pair<int64_t, int64_t>> redo;        // pattern ranges to redo literally
+    int64_t occ_base = 0;
+    for (size_t c = 0; c + 1 < cuts.size(); c++) {
+        const int64_t p0 = cuts[c], p1 = cuts[c + 1], np = p1 - p0;
+        int64_t n_occ = total_occ;
+        if (cuts.size() > 2) n_occ = h_excl[(size_t)p1] - h_excl[(size_t)p0];
+        if (n_occ == 0) continue;
+        arena.release(mark1);
+        t_find_want = arena.mark() + (size_t)n_occ * 28 + radix_sort_temp_bytes(n_occ) + ((size_t)8 << 20);
+        uint64_t* d_k0 = arena.get<uint64_t>((size_t)n_occ);
+        uint64_t* d_k1 = arena.get<uint64_t>((size_t)n_occ);
+        void* d_tmp = arena.raw(radix_sort_temp_bytes(n_occ));
+        int32_t* d_str = arena.get<int32_t>((size_t)n_occ);
+        int64_t* d_pos = arena.get<int64_t>((size_t)n_occ);
+        if (!d_k0 || !d_k1 || !d_tmp || !d_str || !d_pos) return fail(GCZ_E_NOMEM, "find workspace for %lld occurrences", (long long)n_occ);
+        GCZ_LAUNCH(ctx, locate_occurrences_kernel, launch_grid(ctx, n_occ, 256), 256, 0, st, idx->d_tables, idx->d_sectors,
+                   d_sp, d_excl, p0, np, occ_base, n_occ, d_k0);
+        RadixBuffers rb;
+        rb.keys[0] = d_k0; rb.keys[1] = d_k1;
+        int pat_bits = 1;
+        while (((int64_t)1 << pat_bits) < np) pat_bits++;
+        GCZ_TRY(radix_sort_pairs(ctx, st, rb, n_occ, 0, 32 + pat_bits, d_tmp, nullptr));
+        unsigned* d_flags = reinterpret_cast<unsigned*>(d_next + 2);
+        GCZ_CUDA(cudaMemsetAsync(d_flags, 0, 8, st));
+        GCZ_LAUNCH(ctx, split_by_string_kernel, launch_grid(ctx, n_occ, 256), 256, 0, st, rb.keys[rb.cur], n_occ, d_e, ns, d_str, d_pos, d_flags);
+        unsigned h_flags[2] = { 0, 0 };
+        GCZ_CUDA(cudaMemcpyAsync(h_flags, d_flags, 8, cudaMemcpyDeviceToHost, st));
+        GCZ_CUDA(cudaMemcpyAsync(out->string.data() + occ_base, d_str, (size_t)n_occ * 4, cudaMemcpyDeviceToHost, st));
+        GCZ_CUDA(cudaMemcpyAsync(out->pos.data() + occ_base, d_pos, (size_t)n_occ * 8, cudaMemcpyDeviceToHost, st));
+        GCZ_CUDA(cudaStreamSynchronize(st));
+        if (h_flags[0] || h_flags[1]) {
+            // keep the sorted text positions of this chunk in out->pos (sign-extended, as the reference's long[] holds them)
+            literal = true;
+            h_keys.resize((size_t)n_occ);
+            GCZ_CUDA(cudaMemcpyAsync(h_keys.data(), rb.keys[rb.cur], (size_t)n_occ * 8, cudaMemcpyDeviceToHost, st));
+            GCZ_CUDA(cudaStreamSynchronize(st));
+            for (int64_t o = 0; o < n_occ; o++) {
+                out->pos[(size_t)(occ_base + o)] = (int64_t)(int32_t)(uint32_t)(h_keys[(size_t)o] & 0xFFFFFFFFull);
+                out->string[(size_t)(occ_base + o)] = -2;                 // marks "not split yet"
+            }
+            redo.emplace_back(p0, p1);
+        }
+        occ_base += n_occ;
+    }
+    arena.release(mark0);
+    if (!literal) return GCZ_OK;
+
+    // GSSA.find :170-184 as written, for the chunks that asked for it; hits may be fewer than occurrences afterwards
+    BlockHits fixed;
+    fixed.off.assign((size_t)n_pats + 1, 0);
+    fixed.string.reserve(out->string.size());
+    fixed.pos.reserve(out->pos.size());
+    size_t r = 0;
+    for (int64_t p = 0; p < n_pats; p++) {
+        while (r < redo.size() && p >= redo[r].second) r++;
+        const bool lit = r < redo.size() && p >= redo[r].first && p < redo[r].second;
+        const int64_t first = out->off[(size_t)p], k = out->off[(size_t)p + 1] - first;
+        if (!lit) {
+            fixed.string.insert(fixed.string.end(), out->string.begin() + first, out->string.begin() + first + k);
+            fixed.pos.insert(fixed.pos.end(), out->pos.begin() + first, out->pos.begin() + first + k);
+        } else {
+            const int64_t* sa = out->pos.data() + first;
+            int64_t idx1 = 0;
+            for (int64_t i = 0; i < ns && k > 0; i++) {
+                const int64_t idx2 = -java_binary_search(sa, idx1, k, idx->e[(size_t)i]) - 1;
+                if (idx2 > idx1) {
+                    const int64_t start = i > 0 ? idx->e[(size_t)i - 1] + 1 : 0;
+                    for (int64_t j = idx1; j < idx2; j++) { fixed.string.push_back((int32_t)i); fixed.pos.push_back(sa[j] - start); }
+                    idx1 = idx2;
+                }
+            }
+        }
+        fixed.off[(size_t)p + 1] = (int64_t)fixed.pos.size();
+    }
+    *out = std::move(fixed);
+    return GCZ_OK;
+}
+
+}  // namespace
+
 int count_batch(gcz_index* idx, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats, int64_t* sp, int64_t* ep) {
     if (!idx || !pats || !pat_off || !sp || !ep || n_pats < 0) return fail(GCZ_E_ARG, "count_batch arguments");
     if (n_pats == 0) return GCZ_OK;
@@ -765,57 +976,109 @@ int count_batch(gcz_index* idx, const uint8_t* pats, const int64_t* pat_off, int
     GCZ_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = stream_of(ctx);
     ctx->arena.reset();
-
-    // pattern bytes: the offsets say how many
-    int64_t total_bytes = 0;
-    const bool off_dev = is_device_ptr(pat_off);
-    if (off_dev) GCZ_CUDA(cudaMemcpy(&total_bytes, pat_off + n_pats, 8, cudaMemcpyDeviceToHost));
-    else total_bytes = pat_off[n_pats];
-    const char* sort_env0 = std::getenv("GCZ_COUNT_SORT");
-    const size_t sort_bytes = (sort_env0 && sort_env0[0] == '1') ? (size_t)n_pats * 24 + radix_sort_temp_bytes(n_pats) + (1 << 20) : 0;
-    const size_t need = (size_t)total_bytes + (size_t)n_pats * 24 + (1 << 20) + sort_bytes;
+    const size_t need = batch_bytes(pats, pat_off, n_pats) + (size_t)n_pats * 16 + (1 << 20);
     if (ctx->arena.capacity < need) GCZ_TRY(ctx->arena.reserve(need));
-
-    const uint8_t* d_pats = nullptr; const int64_t* d_off = nullptr;
-    GCZ_TRY(stage_in(st, ctx->arena, pats, (size_t)total_bytes, &d_pats));
-    GCZ_TRY(stage_in(st, ctx->arena, pat_off, (size_t)n_pats + 1, &d_off));
+    DeviceBatch batch;
+    GCZ_TRY(stage_batch(st, ctx->arena, pats, pat_off, n_pats, &batch));
     const bool out_dev = is_device_ptr(sp);
     if (out_dev != is_device_ptr(ep)) return fail(GCZ_E_ARG, "sp and ep must live on the same side");
     int64_t* d_sp = out_dev ? sp : ctx->arena.get<int64_t>((size_t)n_pats);
     int64_t* d_ep = out_dev ? ep : ctx->arena.get<int64_t>((size_t)n_pats);
-    if (!d_sp || !d_ep) return fail(GCZ_E_NOMEM, "query staging");
-
     unsigned long long* d_next = ctx->arena.get<unsigned long long>(1);
-    if (!d_next) return fail(GCZ_E_NOMEM, "query staging");
+    if (!d_sp || !d_ep || !d_next) return fail(GCZ_E_NOMEM, "query staging");
     GCZ_CUDA(cudaMemsetAsync(d_next, 0, 8, st));
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_pats + 255) / 256, (int64_t)ctx->sm_count * 8));
-    const char* sort_env = std::getenv("GCZ_COUNT_SORT");
-    if (sort_env && sort_env[0] == '1' && n_pats >= 1024 && n_pats < ((int64_t)1 << 31)) {
-        const size_t more = (size_t)n_pats * 24 + radix_sort_temp_bytes(n_pats) + (1 << 20);
-        RadixBuffers rb;
-        rb.keys[0] = ctx->arena.get<uint64_t>((size_t)n_pats); rb.keys[1] = ctx->arena.get<uint64_t>((size_t)n_pats);
-        rb.vals[0] = ctx->arena.get<uint32_t>((size_t)n_pats); rb.vals[1] = ctx->arena.get<uint32_t>((size_t)n_pats);
-        void* d_tmp = ctx->arena.raw(radix_sort_temp_bytes(n_pats));
-        if (!rb.keys[0] || !rb.keys[1] || !rb.vals[0] || !rb.vals[1] || !d_tmp) return fail(GCZ_E_NOMEM, "query staging (%zu more bytes)", more);
-        SymbolIds ids;
-        int next_id = 1;
-        for (int ch = 0; ch < 256; ch++) {
-            const int64_t here = (ch < 255 ? idx->c[ch + 1] : idx->n) - idx->c[ch];
-            ids.id[ch] = here > 0 ? (uint8_t)(next_id++ & 31) : 0;
-        }
-        GCZ_LAUNCH(ctx, pattern_suffix_keys_kernel, launch_grid(ctx, n_pats, 256), 256, 0, st, d_pats, d_off, n_pats, ids, rb.keys[0], rb.vals[0]);
-        GCZ_TRY(radix_sort_pairs(ctx, st, rb, n_pats, 0, 60, d_tmp, nullptr));
-        GCZ_LAUNCH(ctx, count_kernel<true>, grid, 256, 0, st, idx->d_tables, idx->d_sectors, d_pats, d_off, n_pats, d_sp, d_ep, d_next,
-                   (const uint32_t*)rb.vals[rb.cur]);
-    } else {
-        GCZ_LAUNCH(ctx, count_kernel<false>, grid, 256, 0, st, idx->d_tables, idx->d_sectors, d_pats, d_off, n_pats, d_sp, d_ep, d_next,
-                   (const uint32_t*)nullptr);
-    }
+    GCZ_LAUNCH(ctx, count_kernel<0>, count_grid(ctx, n_pats), 256, 0, st, idx->d_tables, idx->d_sectors, batch.pats, batch.off, n_pats,
+               d_sp, d_ep, d_next, (unsigned long long*)nullptr);
     if (!out_dev) {
         GCZ_CUDA(cudaMemcpyAsync(sp, d_sp, (size_t)n_pats * 8, cudaMemcpyDeviceToHost, st));
         GCZ_CUDA(cudaMemcpyAsync(ep, d_ep, (size_t)n_pats * 8, cudaMemcpyDeviceToHost, st));
     }
     GCZ_CUDA(cudaStreamSynchronize(st));
+    return GCZ_OK;
+}
+
+// The loop of GecoMatch over the blocks of a file (tools/GecoMatch.java:114-131) for a whole batch: the batch is uploaded
+// once, every block is searched on the device, the occurrences of a pattern are summed there; 8 bytes per pattern come back.
+int count_multi(gcz_index* const* blocks, int32_t n_blocks, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats, int64_t* totals) {
+    if (!pats || !pat_off || !totals || n_pats < 0) return fail(GCZ_E_ARG, "count_multi arguments");
+    DeviceCtx* ctx = nullptr;
+    GCZ_TRY(same_device(blocks, n_blocks, &ctx));
+    if (n_pats == 0) return GCZ_OK;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    GCZ_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream_of(ctx);
+    ctx->arena.reset();
+    const size_t need = batch_bytes(pats, pat_off, n_pats) + (size_t)n_pats * 8 + (size_t)n_blocks * 8 + (1 << 20);
+    if (ctx->arena.capacity < need) GCZ_TRY(ctx->arena.reserve(need));
+    DeviceBatch batch;
+    GCZ_TRY(stage_batch(st, ctx->arena, pats, pat_off, n_pats, &batch));
+    const bool out_dev = is_device_ptr(totals);
+    int64_t* d_tot = out_dev ? totals : ctx->arena.get<int64_t>((size_t)n_pats);
+    unsigned long long* d_next = ctx->arena.get<unsigned long long>((size_t)n_blocks);
+    if (!d_tot || !d_next) return fail(GCZ_E_NOMEM, "query staging");
+    GCZ_CUDA(cudaMemsetAsync(d_tot, 0, (size_t)n_pats * 8, st));
+    GCZ_CUDA(cudaMemsetAsync(d_next, 0, (size_t)n_blocks * 8, st));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    GCZ_CUDA(cudaEventCreate(&e0)); GCZ_CUDA(cudaEventCreate(&e1));
+    GCZ_CUDA(cudaEventRecord(e0, st));
+    for (int32_t b = 0; b < n_blocks; b++) {
+        GCZ_LAUNCH(ctx, count_kernel<1>, count_grid(ctx, n_pats), 256, 0, st, blocks[b]->d_tables, blocks[b]->d_sectors, batch.pats, batch.off,
+                   n_pats, d_tot, (int64_t*)nullptr, d_next + b, (unsigned long long*)nullptr);
+    }
+    GCZ_CUDA(cudaEventRecord(e1, st));
+    if (!out_dev) GCZ_CUDA(cudaMemcpyAsync(totals, d_tot, (size_t)n_pats * 8, cudaMemcpyDeviceToHost, st));
+    GCZ_CUDA(cudaStreamSynchronize(st));
+    t_query_stats = gcz_query_stats{};
+    t_query_stats.patterns = n_pats;
+    t_query_stats.blocks = n_blocks;
+    cudaEventElapsedTime(&t_query_stats.kernel_ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return GCZ_OK;
+}
+
+// The same searches with counters: rank sectors loaded, backward-search steps, and the RankedWTNode.count calls of the
+// reference's loop for these patterns.  Not a timed path (the counters cost registers); kernel_ms is of this launch.
+int count_stats(gcz_index* const* blocks, int32_t n_blocks, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats, gcz_query_stats* out) {
+    if (!pats || !pat_off || !out || n_pats < 0) return fail(GCZ_E_ARG, "count_stats arguments");
+    DeviceCtx* ctx = nullptr;
+    GCZ_TRY(same_device(blocks, n_blocks, &ctx));
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    GCZ_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream_of(ctx);
+    ctx->arena.reset();
+    const size_t need = batch_bytes(pats, pat_off, n_pats) + (size_t)n_pats * 16 + (size_t)n_blocks * 8 + (1 << 20);
+    if (ctx->arena.capacity < need) GCZ_TRY(ctx->arena.reserve(need));
+    DeviceBatch batch;
+    GCZ_TRY(stage_batch(st, ctx->arena, pats, pat_off, n_pats, &batch));
+    int64_t* d_sp = ctx->arena.get<int64_t>((size_t)n_pats + 1);
+    int64_t* d_ep = ctx->arena.get<int64_t>((size_t)n_pats + 1);
+    unsigned long long* d_next = ctx->arena.get<unsigned long long>((size_t)n_blocks + 4);
+    if (!d_sp || !d_ep || !d_next) return fail(GCZ_E_NOMEM, "query staging");
+    GCZ_CUDA(cudaMemsetAsync(d_next, 0, ((size_t)n_blocks + 4) * 8, st));
+    unsigned long long* d_stats = d_next + n_blocks;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    GCZ_CUDA(cudaEventCreate(&e0)); GCZ_CUDA(cudaEventCreate(&e1));
+    GCZ_CUDA(cudaEventRecord(e0, st));
+    for (int32_t b = 0; b < n_blocks && n_pats > 0; b++) {
+        GCZ_LAUNCH(ctx, count_kernel<2>, count_grid(ctx, n_pats), 256, 0, st, blocks[b]->d_tables, blocks[b]->d_sectors, batch.pats, batch.off,
+                   n_pats, d_sp, d_ep, d_next + b, d_stats);
+    }
+    GCZ_CUDA(cudaEventRecord(e1, st));
+    unsigned long long h[3] = { 0, 0, 0 };
+    GCZ_CUDA(cudaMemcpyAsync(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost, st));
+    GCZ_CUDA(cudaStreamSynchronize(st));
+    *out = gcz_query_stats{};
+    out->patterns = n_pats; out->blocks = n_blocks;
+    out->rank_sectors = (int64_t)h[0]; out->reference_rank_calls = (int64_t)h[1]; out->steps = (int64_t)h[2];
+    for (int32_t b = 0; b < n_blocks; b++) out->index_bytes += (int64_t)blocks[b]->sector_bytes;
+    cudaEventElapsedTime(&out->kernel_ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return GCZ_OK;
+}
+
+int last_query_stats(gcz_query_stats* out) {
+    if (!out) return fail(GCZ_E_ARG, "null argument");
+    *out = t_query_stats;
     return GCZ_OK;
 }
 
@@ -840,111 +1103,92 @@ int locate_rows(gcz_index* idx, const int64_t* rows, int64_t n_rows, int64_t* po
     return GCZ_OK;
 }
 
-// java.util.Arrays.binarySearch(long[] a, int from, int to, long key)
-static int64_t java_binary_search(const int64_t* a, int64_t from, int64_t to, int64_t key) {
-    int64_t low = from, high = to - 1;
-    while (low <= high) {
-        const int64_t mid = (int64_t)(((uint64_t)low + (uint64_t)high) >> 1);
-        if (a[mid] < key) low = mid + 1;
-        else if (a[mid] > key) high = mid - 1;
-        else return mid;
-    }
-    return -(low + 1);
-}
 
-int find_batch(gcz_index* idx, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats,
-               int64_t* per_string_counts, int64_t** positions, int64_t** pos_off) {
-    if (!idx || !pats || !pat_off || !positions || !pos_off || n_pats < 0) return fail(GCZ_E_ARG, "find_batch arguments");
-    if (is_device_ptr(pats) || is_device_ptr(pat_off)) return fail(GCZ_E_ARG, "find_batch takes host pattern buffers");
-    DeviceCtx* ctx = idx->ctx;
-    const int64_t ns = (int64_t)idx->e.size();
-    *positions = nullptr; *pos_off = nullptr;
-
-    // 1. intervals
-    std::vector<int64_t> sp((size_t)n_pats), ep((size_t)n_pats);
-    if (n_pats > 0) GCZ_TRY(count_batch(idx, pats, pat_off, n_pats, sp.data(), ep.data()));
-    std::vector<int64_t> occ_excl((size_t)n_pats + 1, 0);
-    for (int64_t i = 0; i < n_pats; i++) occ_excl[(size_t)i + 1] = occ_excl[(size_t)i] + std::max<int64_t>(0, ep[(size_t)i] - sp[(size_t)i] + 1);
-    const int64_t total_occ = occ_excl[(size_t)n_pats];
-
-    int64_t* h_pos = static_cast<int64_t*>(std::malloc(sizeof(int64_t) * (size_t)std::max<int64_t>(total_occ, 1)));
-    int64_t* h_off = static_cast<int64_t*>(std::malloc(sizeof(int64_t) * ((size_t)n_pats + 1)));
-    if (!h_pos || !h_off) { std::free(h_pos); std::free(h_off); return fail(GCZ_E_NOMEM, "find_batch results"); }
-    if (per_string_counts) std::memset(per_string_counts, 0, sizeof(int64_t) * (size_t)(n_pats * ns));
-
+// GSSA.find for a batch against every block of a file (the loops of GecoMatch / SimpleGFFGenerator over the blocks): the
+// batch is uploaded once; per block the hits come back as sparse records sorted by (pattern, string, position).
+int find_multi(gcz_index* const* blocks, int32_t n_blocks, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats, gcz_hits* out) {
+    if (!pats || !pat_off || !out || n_pats < 0) return fail(GCZ_E_ARG, "find_multi arguments");
+    std::memset(out, 0, sizeof(*out));
+    DeviceCtx* ctx = nullptr;
+    GCZ_TRY(same_device(blocks, n_blocks, &ctx));
     std::lock_guard<std::mutex> lock(ctx->mu);
     GCZ_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = stream_of(ctx);
+    ctx->arena.reset();
+    // the batch, the intervals and offsets of one block, and room for the occurrence keys of a typical batch up front
+    const size_t need = batch_bytes(pats, pat_off, n_pats) + (size_t)n_pats * 40 + ((size_t)64 << 20);
+    if (ctx->arena.capacity < need) GCZ_TRY(ctx->arena.reserve(need));
+    DeviceBatch batch;
+    if (n_pats > 0) GCZ_TRY(stage_batch(st, ctx->arena, pats, pat_off, n_pats, &batch));
+    const size_t mark = ctx->arena.mark();
 
-    // 2. locate + sort in chunks of at most kChunk occurrences (a single pattern may exceed it)
-    const int64_t kChunk = (int64_t)1 << 26;
-    std::vector<uint64_t> h_keys;
-    int64_t written = 0;
-    h_off[0] = 0;
-    int64_t p0 = 0;
-    while (p0 < n_pats) {
-        int64_t p1 = p0 + 1;
-        while (p1 < n_pats && occ_excl[(size_t)p1 + 1] - occ_excl[(size_t)p0] <= kChunk) p1++;
-        const int64_t n_occ = occ_excl[(size_t)p1] - occ_excl[(size_t)p0];
-        const int64_t np = p1 - p0;
-        if (n_occ > 0) {
-            ctx->arena.reset();
-            const size_t need = (size_t)n_occ * 16 + (size_t)np * 16 + radix_sort_temp_bytes(n_occ) + (1 << 20);
-            if (ctx->arena.capacity < need) { int rc = ctx->arena.reserve(need); if (rc) { std::free(h_pos); std::free(h_off); return rc; } }
-            int64_t* d_sp = ctx->arena.get<int64_t>((size_t)np);
-            int64_t* d_ex = ctx->arena.get<int64_t>((size_t)np + 1);
-            uint64_t* d_k0 = ctx->arena.get<uint64_t>((size_t)n_occ);
-            uint64_t* d_k1 = ctx->arena.get<uint64_t>((size_t)n_occ);
-            void* d_tmp = ctx->arena.raw(radix_sort_temp_bytes(n_occ));
-            if (!d_sp || !d_ex || !d_k0 || !d_k1 || !d_tmp) { std::free(h_pos); std::free(h_off); return fail(GCZ_E_NOMEM, "find_batch workspace"); }
-            GCZ_CUDA(cudaMemcpyAsync(d_sp, sp.data() + p0, (size_t)np * 8, cudaMemcpyHostToDevice, st));
-            GCZ_CUDA(cudaMemcpyAsync(d_ex, occ_excl.data() + p0, ((size_t)np + 1) * 8, cudaMemcpyHostToDevice, st));
-            const char* locate_env = std::getenv("GCZ_LOCATE_VARIANT");
-            if (locate_env && locate_env[0] == '1') {
-                unsigned long long* d_next = ctx->arena.get<unsigned long long>(2);
-                if (!d_next) { std::free(h_pos); std::free(h_off); return fail(GCZ_E_NOMEM, "find_batch workspace"); }
-                GCZ_CUDA(cudaMemsetAsync(d_next, 0, 16, st));
-                const int walk_grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_occ + 255) / 256, (int64_t)ctx->sm_count * 8));
-                GCZ_LAUNCH(ctx, locate_walk_refill_kernel, walk_grid, 256, 0, st, idx->d_tables, idx->d_sectors, d_sp, d_ex, (int64_t)0, np,
-                           occ_excl[(size_t)p0], n_occ, d_k0, d_k1, d_next);
-                GCZ_LAUNCH(ctx, locate_finish_kernel, launch_grid(ctx, n_occ, 256), 256, 0, st, idx->d_tables, idx->d_sectors, d_k1, n_occ, d_k0);
-            } else {
-                GCZ_LAUNCH(ctx, locate_occurrences_kernel, launch_grid(ctx, n_occ, 256), 256, 0, st, idx->d_tables, idx->d_sectors,
-                           d_sp, d_ex, (int64_t)0, np, occ_excl[(size_t)p0], n_occ, d_k0);
-            }
-            RadixBuffers rb;
-            rb.keys[0] = d_k0; rb.keys[1] = d_k1;
-            int pat_bits = 1;
-            while (((int64_t)1 << pat_bits) < np) pat_bits++;
-            int rc = radix_sort_pairs(ctx, st, rb, n_occ, 0, 32 + pat_bits, d_tmp, nullptr);
-            if (rc) { std::free(h_pos); std::free(h_off); return rc; }
-            h_keys.resize((size_t)n_occ);
-            GCZ_CUDA(cudaMemcpyAsync(h_keys.data(), rb.keys[rb.cur], (size_t)n_occ * 8, cudaMemcpyDeviceToHost, st));
+    std::vector<BlockHits> per((size_t)n_blocks);
+    int64_t total = 0;
+    for (int32_t b = 0; b < n_blocks; b++) {
+        ctx->arena.release(mark);
+        t_find_want = 0;
+        int rc = find_block(blocks[b], st, batch, &per[(size_t)b]);
+        if (rc == GCZ_E_NOMEM) {
+            // the occurrence workspace did not fit: grow the arena (the staged batch is lost with it) and redo this block
             GCZ_CUDA(cudaStreamSynchronize(st));
+            const size_t more = std::max(t_find_want, ctx->arena.capacity) + ((size_t)64 << 20);
+            ctx->arena.reset();
+            GCZ_TRY(ctx->arena.reserve(more));
+            if (n_pats > 0) GCZ_TRY(stage_batch(st, ctx->arena, pats, pat_off, n_pats, &batch));
+            if (ctx->arena.mark() != mark) return fail(GCZ_E_INTERNAL, "arena layout changed");
+            rc = find_block(blocks[b], st, batch, &per[(size_t)b]);
         }
-        // 3. GSSA.find :170-184 per pattern: split the ascending positions by the string ends
-        std::vector<int64_t> sa;
-        for (int64_t p = p0; p < p1; p++) {
-            const int64_t k = occ_excl[(size_t)p + 1] - occ_excl[(size_t)p];
-            const int64_t first = occ_excl[(size_t)p] - occ_excl[(size_t)p0];
-            sa.resize((size_t)k);
-            for (int64_t j = 0; j < k; j++) sa[(size_t)j] = (int64_t)(int32_t)(uint32_t)(h_keys[(size_t)(first + j)] & 0xFFFFFFFFull);
-            int64_t idx1 = 0;
-            for (int64_t i = 0; i < ns && k > 0; i++) {
-                const int64_t idx2 = -java_binary_search(sa.data(), idx1, k, idx->e[(size_t)i]) - 1;
-                if (idx2 > idx1) {
-                    const int64_t start = i > 0 ? idx->e[(size_t)i - 1] + 1 : 0;
-                    if (per_string_counts) per_string_counts[p * ns + i] = idx2 - idx1;
-                    for (int64_t j = idx1; j < idx2; j++) h_pos[written++] = sa[(size_t)j] - start;
-                    idx1 = idx2;
-                }
-            }
-            h_off[p + 1] = written;
-        }
-        p0 = p1;
+        GCZ_TRY(rc);
+        total += (int64_t)per[(size_t)b].pos.size();
     }
-    *positions = h_pos;
+    out->n_hits = total;
+    out->block_off = static_cast<int64_t*>(std::malloc(sizeof(int64_t) * ((size_t)n_blocks + 1)));
+    out->pattern = static_cast<int64_t*>(std::malloc(sizeof(int64_t) * (size_t)std::max<int64_t>(total, 1)));
+    out->string = static_cast<int32_t*>(std::malloc(sizeof(int32_t) * (size_t)std::max<int64_t>(total, 1)));
+    out->position = static_cast<int64_t*>(std::malloc(sizeof(int64_t) * (size_t)std::max<int64_t>(total, 1)));
+    if (!out->block_off || !out->pattern || !out->string || !out->position) {
+        std::free(out->block_off); std::free(out->pattern); std::free(out->string); std::free(out->position);
+        std::memset(out, 0, sizeof(*out));
+        return fail(GCZ_E_NOMEM, "find_multi results");
+    }
+    int64_t at = 0;
+    for (int32_t b = 0; b < n_blocks; b++) {
+        const BlockHits& h = per[(size_t)b];
+        out->block_off[b] = at;
+        for (int64_t p = 0; p < n_pats; p++) {
+            for (int64_t j = h.off[(size_t)p]; j < h.off[(size_t)p + 1]; j++) out->pattern[at + j] = p;
+        }
+        if (!h.pos.empty()) {
+            std::memcpy(out->string + at, h.string.data(), h.string.size() * 4);
+            std::memcpy(out->position + at, h.pos.data(), h.pos.size() * 8);
+        }
+        at += (int64_t)h.pos.size();
+    }
+    out->block_off[n_blocks] = at;
+    return GCZ_OK;
+}
+
+// GSSA.find  :160-185 for a batch against one block, in the dense form of the C ABI
+int find_batch(gcz_index* idx, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats,
+               int64_t* per_string_counts, int64_t** positions, int64_t** pos_off) {
+    if (!idx || !pats || !pat_off || !positions || !pos_off || n_pats < 0) return fail(GCZ_E_ARG, "find_batch arguments");
+    *positions = nullptr; *pos_off = nullptr;
+    gcz_hits hits;
+    gcz_index* one[1] = { idx };
+    GCZ_TRY(find_multi(one, 1, pats, pat_off, n_pats, &hits));
+    const int64_t ns = (int64_t)idx->e.size();
+    int64_t* h_off = static_cast<int64_t*>(std::malloc(sizeof(int64_t) * ((size_t)n_pats + 1)));
+    if (!h_off) { std::free(hits.block_off); std::free(hits.pattern); std::free(hits.string); std::free(hits.position); return fail(GCZ_E_NOMEM, "find_batch results"); }
+    if (per_string_counts) std::memset(per_string_counts, 0, sizeof(int64_t) * (size_t)(n_pats * ns));
+    std::memset(h_off, 0, sizeof(int64_t) * ((size_t)n_pats + 1));
+    for (int64_t j = 0; j < hits.n_hits; j++) {
+        h_off[hits.pattern[j] + 1]++;
+        if (per_string_counts) per_string_counts[hits.pattern[j] * ns + hits.string[j]]++;
+    }
+    for (int64_t p = 0; p < n_pats; p++) h_off[p + 1] += h_off[p];
+    *positions = hits.position;                            // already pattern after pattern, string after string
     *pos_off = h_off;
+    std::free(hits.block_off); std::free(hits.pattern); std::free(hits.string);
     return GCZ_OK;
 }
 

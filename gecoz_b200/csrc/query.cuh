@@ -50,5 +50,9 @@ int  locate_rows(gcz_index* idx, const int64_t* rows, int64_t n_rows, int64_t* p
 int  extract(gcz_index* idx, int32_t nstr, int64_t from, uint8_t* out, int64_t cap, int64_t* written);
 int  find_batch(gcz_index* idx, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats,
                 int64_t* per_string_counts, int64_t** positions, int64_t** pos_off);
+int  count_multi(gcz_index* const* blocks, int32_t n_blocks, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats, int64_t* totals);
+int  count_stats(gcz_index* const* blocks, int32_t n_blocks, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats, gcz_query_stats* out);
+int  last_query_stats(gcz_query_stats* out);
+int  find_multi(gcz_index* const* blocks, int32_t n_blocks, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats, gcz_hits* out);
 
 }  // namespace gcz

@@ -1,14 +1,16 @@
-// LSD radix sort of (u64 key, u32 value) pairs, 8-bit digits (9-bit in the experimental variants), one HBM round trip per digit.
+// LSD radix sort of (u64 key, u32 value) pairs, 8-bit digits, one HBM round trip per digit.
 //
 // This is the workhorse of the suffix sorter (replaces the induced-sorting loops of
 // algo/string/SAIS.java:103-137 by a data-parallel sort; only the resulting order is shared).
 //
 // Per sort:   one histogram launch (all digits at once, 8 B/key read),
 //             one tiny scan launch (digit bases),
-// per digit:  one "onesweep" launch: every CTA takes the next tile by ticket, ranks its keys with
-//             warp match/ballot into per-warp digit counters, learns the tile's global offsets through a
-//             decoupled look-back over 64-bit status words (aggregate | inclusive-prefix flags), reorders
-//             the tile in shared memory and writes digit runs out coalesced.
+// per digit:  one "onesweep" launch: every CTA takes tiles by ticket, ranks their keys with warp ballots into
+//             per-warp digit counters, learns a tile's global offsets through a decoupled look-back over
+//             64-bit status words (aggregate | inclusive-prefix flags), reorders the tile in shared memory
+//             and writes digit runs out coalesced.  Pairs take the persistent kernel whose tiles arrive by
+//             TMA bulk copies (onesweep_pairs_kernel); keys only and the pass that reads the text take the
+//             one-tile-per-CTA kernel (onesweep_kernel).
 // Algorithmic traffic per digit pass: read 12 B + write 12 B per pair (8 + 8 for keys only).
 #include "radix_sort.cuh"
 
@@ -19,7 +21,8 @@ namespace gcz {
 
 namespace {
 
-// digits are RB bits wide (template parameter of every kernel below; 8 unless a GCZ_SORT_VARIANT says otherwise)
+constexpr int RB = 8;                   // digit width
+constexpr int kRadix = 1 << RB;
 constexpr int kHistThreads = 512;
 constexpr int kLookWindow = 8;
 
@@ -28,11 +31,9 @@ constexpr unsigned long long kFlagPrefix = 2ull << 62;
 constexpr unsigned long long kValueMask = (1ull << 62) - 1;
 
 // ---- histogram of every digit in one pass -------------------------------------------------------
-template <int RB>
 __global__ void __launch_bounds__(kHistThreads)
 radix_hist_kernel(const uint64_t* __restrict__ keys, int64_t n, int begin_bit, int npass,
                   unsigned long long* __restrict__ hist /* [npass][radix] */) {
-    constexpr int kRadix = 1 << RB;
     __shared__ unsigned s_hist[8 * kRadix];
     for (int i = threadIdx.x; i < npass * kRadix; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
@@ -62,12 +63,8 @@ __device__ __forceinline__ uint64_t slide_key(uint64_t key, uint32_t c_out, uint
     return key * radix + c_in;
 }
 
-// UNIFORM (experimental, GCZ_TEXT_HIST_VARIANT=1): inside a long run of one symbol all 32 lanes of a warp hold the same key
-// and their six shared-memory atomics hit one counter each; such a warp lets lane 0 add 32 instead.
-template <int RB, bool UNIFORM = false>
 __global__ void __launch_bounds__(kTextThreads)
 text_hist_kernel(TextKeySource src, int npass, unsigned long long* __restrict__ hist /* [npass][radix] */, int64_t tiles) {
-    constexpr int kRadix = 1 << RB;
     __shared__ unsigned s_hist[8 * kRadix];
     __shared__ uint8_t s_code_of[256];
     __shared__ __align__(16) uint8_t s_codes[16 + kTextTile + kMaxKeySymbols + 16];    // index 16 = first position of the tile
@@ -116,21 +113,10 @@ text_hist_kernel(TextKeySource src, int npass, unsigned long long* __restrict__ 
         for (int i = 0; i < kTextItems; i++) {
             key = slide_key(key, i > 0 ? s_codes[first + i - 1] : 0u, s_codes[first + i + k - 1], radix, top);
             const int64_t p = base + first - 16 + i;
-            bool counted = false;
-            if (UNIFORM) {
-                const uint64_t key0 = __shfl_sync(0xffffffffu, key, 0);
-                counted = __all_sync(0xffffffffu, p < n && key == key0);
-                if (counted && (threadIdx.x & 31) == 0) {
-#pragma unroll
-                    for (int d = 0; d < 8; d++) {
-                        if (d < npass) atomicAdd(&s_hist[d * kRadix + (int)((key >> (RB * d)) & (kRadix - 1))], 32u);
-                    }
-                }
-            }
             if (p < n) {
 #pragma unroll
                 for (int d = 0; d < 8; d++) {
-                    if (d < npass && !counted) atomicAdd(&s_hist[d * kRadix + (int)((key >> (RB * d)) & (kRadix - 1))], 1u);
+                    if (d < npass) atomicAdd(&s_hist[d * kRadix + (int)((key >> (RB * d)) & (kRadix - 1))], 1u);
                 }
                 const uint32_t c = s_codes[first + i];
                 if (src.run_marks && key == (uint64_t)c * unit) {
@@ -154,9 +140,7 @@ text_hist_kernel(TextKeySource src, int npass, unsigned long long* __restrict__ 
 }
 
 // exclusive scan of each pass's bins, in place (one thread per bin)
-template <int RB>
 __global__ void radix_scan_kernel(unsigned long long* hist, int npass) {
-    constexpr int kRadix = 1 << RB;
     __shared__ unsigned long long s_warp[kRadix / 32];
     for (int p = 0; p < npass; p++) {
         unsigned long long v = hist[p * kRadix + threadIdx.x];
@@ -175,11 +159,9 @@ __global__ void radix_scan_kernel(unsigned long long* hist, int npass) {
     }
 }
 
-// Lanes of the warp whose RB-bit digit equals mine: one ballot per bit, each folded in with two logic ops
+// Lanes of the warp whose 8-bit digit equals mine: one ballot per bit, each folded in with two logic ops
 // (written in PTX: the compiler's own expansion of the C form spends six instructions per bit).
-template <int RB>
 __device__ __forceinline__ unsigned peers_with_same_digit(unsigned d) {
-    static_assert(RB == 8 || RB == 9, "digit widths the ballot chain is written for");
     unsigned acc;
     asm(
         "{\n"
@@ -196,23 +178,36 @@ __device__ __forceinline__ unsigned peers_with_same_digit(unsigned d) {
         "and.b32 t, %1, 128; setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; selp.b32 m, 0, 0xffffffff, p; lop3.b32 %0, %0, v, m, 0x60;\n"
         "}\n"
         : "=&r"(acc) : "r"(d));
-    if (RB == 9) {
-        asm(
-            "{\n"
-            ".reg .pred p;\n"
-            ".reg .b32 t, v, m;\n"
-            "and.b32 t, %1, 256; setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; selp.b32 m, 0, 0xffffffff, p; lop3.b32 %0, %0, v, m, 0x60;\n"
-            "}\n"
-            : "+r"(acc) : "r"(d));
-    }
     return acc;
 }
 
-// ---- one digit pass --------------------------------------------------------------------------------
-// Phases of one CTA (tile of THREADS x ITEMS pairs):
+// Ranks of a thread's ITEMS keys among the keys of its warp with the same digit, in element order (item, then lane),
+// two to a register; the warp's digit counters (my_hist, shared memory, zero on entry) end up holding the warp's counts.
+template <int ITEMS>
+__device__ __forceinline__ void rank_in_warp(const uint64_t (&key)[ITEMS], int shift, unsigned* my_hist, unsigned lt,
+                                             unsigned (&rank2)[ITEMS / 2]) {
+    static_assert(ITEMS % 2 == 0, "ranks are kept two to a register");
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+        const unsigned d = (unsigned)(key[i] >> shift) & (unsigned)(kRadix - 1);
+        const unsigned peers = peers_with_same_digit(d);
+        const unsigned below = __popc(peers & lt);
+        unsigned base = 0;
+        if (below == 0) {
+            base = my_hist[d];
+            my_hist[d] = base + __popc(peers);
+        }
+        base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
+        if (i & 1) rank2[i >> 1] |= (base + below) << 16; else rank2[i >> 1] = base + below;
+        __syncwarp();
+    }
+}
+
+// ---- one digit pass, one tile per CTA (keys only, and the pass that computes its keys from the text) ------------
+// Phases of one CTA (tile of THREADS x ITEMS elements):
 //   1 load keys (warp-striped)
-//   2 rank keys inside each warp: peers with the same digit (8 ballots, or one match.any) get consecutive
-//     ranks in element order; per-warp digit counters live in shared memory
+//   2 rank keys inside each warp: peers with the same digit (8 ballots) get consecutive ranks in element order;
+//     per-warp digit counters live in shared memory
 //   3 values are requested from global memory only now (they are not live during the ranking)
 //   4 threads 0..255: per-warp counts -> exclusive warp offsets and the tile histogram; publish the tile
 //     aggregate for the look-back; scan -> digit starts inside the tile
@@ -221,10 +216,7 @@ __device__ __forceinline__ unsigned peers_with_same_digit(unsigned d) {
 //   7 write digit runs out, coalesced
 //   1' (FROM_TEXT) the tile's keys are computed from the text instead: codes to shared memory, a k-symbol window
 //      slid over ITEMS consecutive positions per thread, transposed to the warp-striped order through shared memory
-// OPT (tuning variants, GCZ_SORT_VARIANT; 0 = what the benchmarks use): bit 0 = 32-bit destination offsets and no
-// bounds test in the write-out of a full tile; bit 1 = the first look-back window is requested before the shared-memory
-// reorder, so that its latency overlaps the scatter; bit 2 = the tile's values are prefetched into L2 while the keys are ranked.
-template <int THREADS, int ITEMS, bool HAS_VALS, int MIN_BLOCKS, bool USE_MATCH, bool FROM_TEXT, int OPT = 0, int RB = 8>
+template <int THREADS, int ITEMS, bool HAS_VALS, int MIN_BLOCKS, bool FROM_TEXT>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
                 const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
@@ -232,7 +224,6 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
                 unsigned long long* __restrict__ status, unsigned* __restrict__ ticket, TextKeySource src) {
     constexpr int TILE = THREADS * ITEMS;
     constexpr int WARPS = THREADS / 32;
-    constexpr int kRadix = 1 << RB;
     static_assert(THREADS >= kRadix, "one thread per digit is needed for the look-back");
     static_assert(!FROM_TEXT || HAS_VALS, "text input produces (key, position) pairs");
     static_assert(TILE * 4 >= TILE + kMaxKeySymbols + 8 + 256, "the value staging area holds the tile's symbol codes");
@@ -316,41 +307,15 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
         }
     }
 
-    // OPT bit 2: the values are not wanted in registers before the ranking is done, but their lines can be on their way to L2
-    if ((OPT & 4) && HAS_VALS && !FROM_TEXT && count == TILE) {
-        const uint32_t* src_vals = vals_in + tile_base + warp_base + lane;
-#pragma unroll
-        for (int i = 0; i < ITEMS; i++) asm volatile("prefetch.global.L2 [%0];" :: "l"(src_vals + i * 32));
-    }
-
     // every key is requested before the first one is used (the ranking below is short enough that the scheduler
     // would otherwise sink each load next to its use and wait for it there)
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) asm volatile("" : "+l"(key[i]));
 
     // 2. rank inside the warp
-    static_assert(ITEMS % 2 == 0, "ranks are kept two to a register");
     unsigned rank2[ITEMS / 2];                  // ranks of items 2j (low half) and 2j + 1 (high half)
     unsigned* my_hist = s_warp_hist + warp * kRadix;
-#pragma unroll
-    for (int i = 0; i < ITEMS; i++) {
-        const unsigned d = (unsigned)(key[i] >> shift) & (unsigned)(kRadix - 1);
-        unsigned peers;
-        if (USE_MATCH) {
-            peers = __match_any_sync(0xffffffffu, d);
-        } else {
-            peers = peers_with_same_digit<RB>(d);
-        }
-        const unsigned below = __popc(peers & lt);
-        unsigned base = 0;
-        if (below == 0) {
-            base = my_hist[d];
-            my_hist[d] = base + __popc(peers);
-        }
-        base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
-        if (i & 1) rank2[i >> 1] |= (base + below) << 16; else rank2[i >> 1] = base + below;
-        __syncwarp();
-    }
+    rank_in_warp<ITEMS>(key, shift, my_hist, lt, rank2);
 
     // 3. values
     uint32_t val[ITEMS];
@@ -399,16 +364,6 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
     }
     __syncthreads();
 
-    constexpr int kEarly = 4;
-    unsigned long long early[kEarly];
-    if ((OPT & 2) && threadIdx.x < kRadix) {
-#pragma unroll
-        for (int j = 0; j < kEarly; j++) {
-            const long long t = (long long)tile - 1 - j;
-            early[j] = t >= 0 ? ld_relaxed_u64(&status[(size_t)t * kRadix + threadIdx.x]) : kFlagPrefix;
-        }
-    }
-
     // 5. reorder the tile in shared memory (padding keys are the last digit and rank last: they land at >= count)
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
@@ -424,19 +379,6 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
         unsigned long long excl = 0;
         long long t = (long long)tile - 1;
         bool done = tile == 0;
-        if (OPT & 2) {                                   // the window requested before the reorder
-            int used = 0;
-#pragma unroll
-            for (int j = 0; j < kEarly; j++) {
-                const unsigned long long flag = early[j] & ~kValueMask;
-                if (!done && used == j && flag != 0) {
-                    excl += early[j] & kValueMask;
-                    used = j + 1;
-                    done = flag == kFlagPrefix;
-                }
-            }
-            t -= used;
-        }
         while (!done) {
             unsigned long long v[kLookWindow];
 #pragma unroll
@@ -456,148 +398,355 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
             t -= used;                                   // a status word that was not ready yet is polled again
         }
         if (tile > 0) st_relaxed_u64(&status[(size_t)tile * kRadix + threadIdx.x], (excl + total) | kFlagPrefix);
-        if (OPT & 1) {                                   // destinations are below 2^32: unsigned wrap-around arithmetic
-            reinterpret_cast<unsigned*>(s_gofs)[threadIdx.x] = (unsigned)(digit_base[threadIdx.x] + excl) - s_digit_start[threadIdx.x];
-        } else {
-            s_gofs[threadIdx.x] = (long long)(digit_base[threadIdx.x] + excl) - (long long)s_digit_start[threadIdx.x];
-        }
+        s_gofs[threadIdx.x] = (long long)(digit_base[threadIdx.x] + excl) - (long long)s_digit_start[threadIdx.x];
     }
     __syncthreads();
 
     // 7. digit runs are contiguous both in shared memory and at their destination
-    if ((OPT & 1) && count == TILE) {
-        const unsigned* gofs32 = reinterpret_cast<const unsigned*>(s_gofs);
-#pragma unroll
-        for (int i = 0; i < ITEMS; i++) {
-            const unsigned j = i * THREADS + threadIdx.x;
-            const uint64_t k = s_keys[j];
-            const unsigned dst = gofs32[(unsigned)(k >> shift) & (unsigned)(kRadix - 1)] + j;
-            keys_out[dst] = k;
-            if (HAS_VALS) vals_out[dst] = s_vals[j];
-        }
-        return;
-    }
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) {
         const int j = i * THREADS + threadIdx.x;
         if (j < count) {
             const uint64_t k = s_keys[j];
-            const long long dst = (OPT & 1) ? (long long)(reinterpret_cast<const unsigned*>(s_gofs)[(unsigned)(k >> shift) & (unsigned)(kRadix - 1)] + (unsigned)j)
-                                            : s_gofs[(unsigned)(k >> shift) & (unsigned)(kRadix - 1)] + j;
+            const long long dst = s_gofs[(unsigned)(k >> shift) & (unsigned)(kRadix - 1)] + j;
             keys_out[dst] = k;
             if (HAS_VALS) vals_out[dst] = s_vals[j];
         }
     }
 }
 
-typedef void (*OnesweepFn)(const uint64_t*, uint64_t*, const uint32_t*, uint32_t*, int64_t, int, const unsigned long long*,
-                           unsigned long long*, unsigned*, TextKeySource);
-typedef void (*HistFn)(const uint64_t*, int64_t, int, int, unsigned long long*);
-typedef void (*TextHistFn)(TextKeySource, int, unsigned long long*, int64_t);
-typedef void (*ScanFn)(unsigned long long*, int);
+// ---- one digit pass over (key, value) pairs: persistent CTAs, tiles delivered by TMA -----------------------------
+// Two CTAs of 512 threads per SM stay resident for the whole pass and take tiles of 6144 pairs by ticket (the ticket of
+// the NEXT tile is drawn at the top of the current one, so its address is known when shared memory frees up).  The tile
+// lives in ONE shared-memory image (48 KB keys + 24 KB values) that is both the landing zone of the bulk copies
+// (cp.async.bulk.shared::cluster.global + mbarrier complete_tx) and the buffer the tile is reordered in:
+//
+//   wait(keys)  -> keys to registers, rank inside each warp (as above)
+//   wait(values)-> values to registers                       | barrier: every element of the image is in a register
+//   scan of the warp counters, tile aggregate published      | barrier x2
+//   reorder in place (registers -> image)
+//   look-back: ALL 512 threads, 2 x kLook predecessors per round trip (thread = digit x half; the halves meet in shared
+//   memory) — at 25 tiles per microsecond a window of 8 needs 2.7 round trips per tile (measured, profiles/), 24 needs one
+//                                                             | barrier
+//   keys out (destinations stay in registers)                 | barrier: key image drained -> bulk copy of the next tile's keys
+//   values out, warp counters zeroed                          | barrier: value image drained -> bulk copy of the next values
+//
+// so the DRAM latency of a tile's keys hides behind the value write-out of the tile before, and that of its values
+// behind its own ranking.  The last, partial tile takes plain guarded loads.
+constexpr int kPThreads = 512, kPItems = 12, kPTile = kPThreads * kPItems, kPWarps = kPThreads / 32;
+constexpr int kLook = 12;                          // predecessors per thread and round trip (two halves: 24 per round)
 
-struct OnesweepConfig {
-    int threads, items, bits;
-    OnesweepFn pairs, keys_only, from_text;
-    HistFn hist;
-    TextHistFn text_hist;
-    ScanFn scan;
-    size_t smem_pairs, smem_keys;
-    int tile() const { return threads * items; }
-    int radix() const { return 1 << bits; }
+struct PairsSmem {
+    uint64_t keys[kPTile];
+    uint32_t vals[kPTile];
+    unsigned warp_hist[kPWarps * kRadix];
+    long long gofs[kRadix];
+    unsigned digit_start[kRadix];
+    unsigned long long look_sum[2][2][kRadix];     // [round parity][half][digit]
+    unsigned look_state[2][2][kRadix];             // (entries used << 2) | 0 found the prefix, 1 all ready, 2 met an unpublished tile
+    unsigned scan[8];
+    unsigned long long bar_keys, bar_vals;         // mbarriers
+    unsigned next_tile;
 };
 
-bool text_hist_uniform() {
-    const char* e = getenv("GCZ_TEXT_HIST_VARIANT");
-    return e && e[0] == '1';
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (TMA, no tensor map): bytes a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// generic-proxy accesses to shared memory before this point are ordered before async-proxy (TMA) writes after it
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kPThreads, 2)
+onesweep_pairs_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
+                      const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
+                      int64_t n, int shift, const unsigned long long* __restrict__ digit_base,
+                      unsigned long long* __restrict__ status, unsigned* __restrict__ ticket) {
+    constexpr int TILE = kPTile, ITEMS = kPItems, THREADS = kPThreads, WARPS = kPWarps;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    PairsSmem& sm = *reinterpret_cast<PairsSmem*>(smem_raw);
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned lt = lanemask_lt();
+    const unsigned digit = threadIdx.x & (kRadix - 1), half = threadIdx.x >> RB;        // look-back role
+    const long long tiles = (n + TILE - 1) / TILE;
+    const int warp_base = warp * ITEMS * 32;
+    unsigned* my_hist = sm.warp_hist + warp * kRadix;
+    const unsigned long long my_base = digit_base[digit];
+
+    auto is_full = [&](long long t) { return (t + 1) * (long long)TILE <= n; };
+
+    if (threadIdx.x == 0) {
+        mbar_init(&sm.bar_keys, 1);
+        mbar_init(&sm.bar_vals, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const unsigned first = atomicAdd(ticket, 1u);
+        sm.next_tile = first;
+        if ((long long)first < tiles && is_full(first)) {
+            fence_proxy_async();
+            mbar_expect_tx(&sm.bar_keys, TILE * 8);
+            bulk_load(sm.keys, keys_in + (size_t)first * TILE, TILE * 8, &sm.bar_keys);
+            mbar_expect_tx(&sm.bar_vals, TILE * 4);
+            bulk_load(sm.vals, vals_in + (size_t)first * TILE, TILE * 4, &sm.bar_vals);
+        }
+    }
+    for (int i = threadIdx.x; i < WARPS * kRadix; i += THREADS) sm.warp_hist[i] = 0;
+    __syncthreads();
+    unsigned phase = 0;                              // parity of both mbarriers: they complete once per full tile
+    long long tile = sm.next_tile;
+
+    while (tile < tiles) {
+        const int64_t tile_base = (int64_t)tile * TILE;
+        const int count = (int)min((int64_t)TILE, n - tile_base);
+        const bool full = count == TILE;
+        unsigned drawn = 0;
+        if (threadIdx.x == 0) drawn = atomicAdd(ticket, 1u);          // the tile after this one (used ~10 us from now)
+
+        // 1. keys
+        uint64_t key[ITEMS];
+        if (full) {
+            mbar_wait(&sm.bar_keys, phase);
+#pragma unroll
+            for (int i = 0; i < ITEMS; i++) key[i] = sm.keys[warp_base + i * 32 + lane];
+        } else {
+#pragma unroll
+            for (int i = 0; i < ITEMS; i++) {
+                const int e = warp_base + i * 32 + lane;
+                key[i] = e < count ? keys_in[tile_base + e] : ~0ull;
+            }
+        }
+
+        // 2. rank inside the warp
+        unsigned rank2[ITEMS / 2];
+        rank_in_warp<ITEMS>(key, shift, my_hist, lt, rank2);
+
+        // 3. values
+        uint32_t val[ITEMS];
+        if (full) {
+            mbar_wait(&sm.bar_vals, phase);
+#pragma unroll
+            for (int i = 0; i < ITEMS; i++) val[i] = sm.vals[warp_base + i * 32 + lane];
+        } else {
+#pragma unroll
+            for (int i = 0; i < ITEMS; i++) {
+                const int e = warp_base + i * 32 + lane;
+                val[i] = e < count ? vals_in[tile_base + e] : 0u;
+            }
+        }
+        if (full) phase ^= 1u;
+        __syncthreads();                              // the whole image is in registers; the warp counters are complete
+
+        // 4. per-warp counts -> exclusive warp offsets, tile histogram, aggregate, digit starts
+        unsigned total = 0;
+        if (threadIdx.x < kRadix) {
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) {
+                const unsigned c = sm.warp_hist[w * kRadix + threadIdx.x];
+                sm.warp_hist[w * kRadix + threadIdx.x] = total;
+                total += c;
+            }
+            if (threadIdx.x == kRadix - 1) total -= (unsigned)(TILE - count);     // padding keys are all the last digit
+            st_relaxed_u64(&status[(size_t)tile * kRadix + threadIdx.x],
+                           (unsigned long long)total | (tile == 0 ? kFlagPrefix : kFlagAgg));
+            const unsigned incl = warp_incl_sum(total);
+            if (lane == 31) sm.scan[warp] = incl;
+            sm.digit_start[threadIdx.x] = incl - total;
+        }
+        if (threadIdx.x == 0) sm.next_tile = drawn;
+        __syncthreads();
+        if (threadIdx.x < kRadix) {
+            unsigned base = 0;
+            for (unsigned w = 0; w < warp; w++) base += sm.scan[w];
+            sm.digit_start[threadIdx.x] += base;
+        }
+        __syncthreads();
+
+        // 5. reorder in place (padding keys are the last digit and rank last: they land at >= count)
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            const unsigned d = (unsigned)(key[i] >> shift) & (unsigned)(kRadix - 1);
+            const unsigned pos = sm.digit_start[d] + my_hist[d] + ((i & 1) ? rank2[i >> 1] >> 16 : rank2[i >> 1] & 0xffffu);
+            sm.keys[pos] = key[i];
+            sm.vals[pos] = val[i];
+        }
+
+        // 6. decoupled look-back by all threads: (digit, half) looks at predecessors t - half * kLook - j, j < kLook
+        {
+            unsigned long long excl = 0;
+            long long t = tile - 1;
+            bool done = tile == 0;
+            unsigned par = 0;
+            while (true) {
+                if (__syncthreads_and(done)) break;               // also: the slots of two rounds ago are free again
+                if (!done) {
+                    unsigned long long v[kLook];
+                    const long long first = t - (long long)half * kLook;
+#pragma unroll
+                    for (int j = 0; j < kLook; j++) {
+                        v[j] = first - j >= 0 ? ld_relaxed_u64(&status[(size_t)(first - j) * kRadix + digit]) : kFlagPrefix;
+                    }
+                    unsigned long long sum = 0;
+                    unsigned used = 0, state = 1;
+#pragma unroll
+                    for (int j = 0; j < kLook; j++) {
+                        const unsigned long long flag = v[j] & ~kValueMask;
+                        if (state == 1 && used == (unsigned)j) {
+                            if (flag == 0) {
+                                state = 2;
+                            } else {
+                                sum += v[j] & kValueMask;
+                                used = j + 1;
+                                if (flag == kFlagPrefix) state = 0;
+                            }
+                        }
+                    }
+                    sm.look_sum[par][half][digit] = sum;
+                    sm.look_state[par][half][digit] = (used << 2) | state;
+                }
+                __syncthreads();
+                if (!done) {
+                    const unsigned s0 = sm.look_state[par][0][digit], s1 = sm.look_state[par][1][digit];
+                    excl += sm.look_sum[par][0][digit];
+                    if ((s0 & 3u) == 0) {
+                        done = true;
+                    } else if ((s0 & 3u) == 2) {
+                        t -= (long long)(s0 >> 2);                 // an unpublished tile in the near half: poll it again
+                    } else {
+                        excl += sm.look_sum[par][1][digit];
+                        if ((s1 & 3u) == 0) done = true;
+                        else t -= (long long)kLook + (long long)(s1 >> 2);
+                    }
+                }
+                par ^= 1u;
+            }
+            if (threadIdx.x < kRadix) {
+                if (tile > 0) st_relaxed_u64(&status[(size_t)tile * kRadix + threadIdx.x], (excl + total) | kFlagPrefix);
+                sm.gofs[threadIdx.x] = (long long)(my_base + excl) - (long long)sm.digit_start[threadIdx.x];
+            }
+        }
+        __syncthreads();
+
+        const long long next = sm.next_tile;
+        const bool next_full = next < tiles && is_full(next);
+
+        // 7a. keys out; destinations (below 2^31) stay in registers for the values
+        unsigned dst[ITEMS];
+        if (full) {
+#pragma unroll
+            for (int i = 0; i < ITEMS; i++) {
+                const unsigned j = i * THREADS + threadIdx.x;
+                const uint64_t k = sm.keys[j];
+                dst[i] = (unsigned)(sm.gofs[(unsigned)(k >> shift) & (unsigned)(kRadix - 1)] + (long long)j);
+                keys_out[dst[i]] = k;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < ITEMS; i++) {
+                const int j = i * THREADS + threadIdx.x;
+                dst[i] = 0;
+                if (j < count) {
+                    const uint64_t k = sm.keys[j];
+                    dst[i] = (unsigned)(sm.gofs[(unsigned)(k >> shift) & (unsigned)(kRadix - 1)] + (long long)j);
+                    keys_out[dst[i]] = k;
+                }
+            }
+        }
+        __syncthreads();                              // the key image is drained
+        if (threadIdx.x == 0 && next_full) {
+            fence_proxy_async();
+            mbar_expect_tx(&sm.bar_keys, TILE * 8);
+            bulk_load(sm.keys, keys_in + (size_t)next * TILE, TILE * 8, &sm.bar_keys);
+        }
+
+        // 7b. values out; warp counters zeroed for the next tile
+        if (full) {
+#pragma unroll
+            for (int i = 0; i < ITEMS; i++) vals_out[dst[i]] = sm.vals[i * THREADS + threadIdx.x];
+        } else {
+#pragma unroll
+            for (int i = 0; i < ITEMS; i++) {
+                const int j = i * THREADS + threadIdx.x;
+                if (j < count) vals_out[dst[i]] = sm.vals[j];
+            }
+        }
+        {
+            uint4* z = reinterpret_cast<uint4*>(sm.warp_hist);
+#pragma unroll
+            for (int i = 0; i < WARPS * kRadix / 4 / THREADS; i++) z[i * THREADS + threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();                              // the value image is drained
+        if (threadIdx.x == 0 && next_full) {
+            fence_proxy_async();
+            mbar_expect_tx(&sm.bar_vals, TILE * 4);
+            bulk_load(sm.vals, vals_in + (size_t)next * TILE, TILE * 4, &sm.bar_vals);
+        }
+        tile = next;
+    }
 }
 
-template <int THREADS, int ITEMS, int MIN_BLOCKS, bool USE_MATCH, int OPT = 0, int RB = 8>
-OnesweepConfig make_config() {
-    constexpr int kRadix = 1 << RB;
-    const size_t fixed = (size_t)(THREADS / 32) * kRadix * 4 + kRadix * 8 + kRadix * 4 + 64;
-    OnesweepConfig c;
-    c.threads = THREADS; c.items = ITEMS; c.bits = RB;
-    c.pairs = onesweep_kernel<THREADS, ITEMS, true, MIN_BLOCKS, USE_MATCH, false, OPT, RB>;
-    c.keys_only = onesweep_kernel<THREADS, ITEMS, false, MIN_BLOCKS, USE_MATCH, false, OPT, RB>;
-    c.from_text = onesweep_kernel<THREADS, ITEMS, true, MIN_BLOCKS, USE_MATCH, true, OPT, RB>;
-    c.hist = radix_hist_kernel<RB>;
-    c.text_hist = text_hist_uniform() ? text_hist_kernel<RB, true> : text_hist_kernel<RB, false>;
-    c.scan = radix_scan_kernel<RB>;
-    c.smem_pairs = (size_t)THREADS * ITEMS * 12 + fixed;
-    c.smem_keys = (size_t)THREADS * ITEMS * 8 + fixed;
-    return c;
-}
+typedef void (*OnesweepFn)(const uint64_t*, uint64_t*, const uint32_t*, uint32_t*, int64_t, int, const unsigned long long*,
+                           unsigned long long*, unsigned*, TextKeySource);
 
-// GCZ_SORT_VARIANT selects the tile shape / ranking primitive / digit width (tuning knob; 0 is what the benchmarks use).
-// profiles/sort_variants_r01.md holds the sweep these were picked from.
-const OnesweepConfig& config() {
-    static const OnesweepConfig table[] = {
-        make_config<512, 12, 2, false>(),     // 0: 6144 pairs, 2 CTAs/SM (32 warps), ballots   <- measured best on B200
-        make_config<512, 12, 2, true>(),      // 1: same, match.any
-        make_config<384, 16, 2, false>(),     // 2: 6144 pairs, 24 warps/SM
-        make_config<256, 16, 3, false>(),     // 3: 4096 pairs, 3 CTAs/SM
-        make_config<384, 12, 3, false>(),     // 4: 4608 pairs, 3 CTAs/SM
-        make_config<512, 8, 3, false>(),      // 5: 4096 pairs, 3 CTAs/SM (48 warps, 40 regs)
-        make_config<1024, 6, 1, false>(),     // 6: 6144 pairs, 1 CTA/SM
-        make_config<512, 16, 1, false>(),     // 7: 8192 pairs, 1 CTA/SM
-        make_config<512, 12, 2, false, 1>(),  // 8: as 0, 32-bit destination offsets              (untested on hardware yet)
-        make_config<512, 12, 2, false, 2>(),  // 9: as 0, early look-back window                  (untested on hardware yet)
-        make_config<512, 12, 2, false, 3>(),  // 10: both                                         (untested on hardware yet)
-        // 9-bit digits: a 44-bit key (17 symbols of ACGTN + separator) takes 5 passes instead of 6; 512 bins, one per thread,
-        // 110.6 KB of shared memory per CTA (two still fit an SM), status words twice as many
-        make_config<512, 12, 2, false, 0, 9>(),  // 11: as 0, 9-bit digits                        (untested on hardware yet)
-        make_config<512, 12, 2, false, 3, 9>(),  // 12: as 10, 9-bit digits                       (untested on hardware yet)
-        make_config<512, 12, 2, false, 4>(),     // 13: as 0, values prefetched to L2 during the ranking (untested on hardware yet)
-        make_config<512, 12, 2, false, 4, 9>(),  // 14: as 11, the same                             (untested on hardware yet)
-    };
-    static const int pick = [] {
-        const char* e = getenv("GCZ_SORT_VARIANT");
-        const int v = e ? atoi(e) : 0;
-        return (v >= 0 && v < (int)(sizeof(table) / sizeof(table[0]))) ? v : 0;
-    }();
-    return table[pick];
-}
+// one-tile-per-CTA kernels: 512 threads x 12 elements, two CTAs per SM (the shape profiles/sort_variants_r01.md picked)
+constexpr int kThreads = 512, kItems = 12, kTile = kThreads * kItems;
+constexpr size_t kFixedSmem = (size_t)(kThreads / 32) * kRadix * 4 + kRadix * 8 + kRadix * 4 + 64;
+constexpr size_t kSmemPairs = (size_t)kTile * 12 + kFixedSmem, kSmemKeys = (size_t)kTile * 8 + kFixedSmem;
+static_assert(kPTile == kTile, "both kernels cut the array into the same tiles (one status array)");
 
-constexpr int kMinTile = 4096;          // smallest tile of any variant: sizes the status array
+// GCZ_SORT_PERSISTENT=0 sends pairs through the one-tile-per-CTA kernel as well (A/B timing, tools/sortbench.py)
+bool use_persistent() {
+    static const bool on = [] { const char* e = getenv("GCZ_SORT_PERSISTENT"); return !(e && e[0] == '0'); }();
+    return on;
+}
 
 }  // namespace
 
-int radix_sort_passes(int bits) { return (bits + config().bits - 1) / config().bits; }
+int radix_sort_passes(int bits) { return (bits + RB - 1) / RB; }
 
 size_t radix_sort_temp_bytes(int64_t n) {
-    const int64_t tiles = (n + kMinTile - 1) / kMinTile;
-    const size_t radix = (size_t)config().radix();
+    const int64_t tiles = (n + kTile - 1) / kTile;
     // [8][radix] histogram + per-pass (status[tiles][radix] + ticket)
-    return 8 * radix * 8 + 256 + ((size_t)tiles * radix * 8 + 256);
+    return 8 * (size_t)kRadix * 8 + 256 + ((size_t)tiles * kRadix * 8 + 256);
 }
 
 int radix_sort_pairs(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n, int begin_bit, int end_bit,
                      void* temp, SortStats* stats, const TextKeySource* src) {
     if (n <= 0 || end_bit <= begin_bit) return GCZ_OK;
     if (end_bit - begin_bit > 64 || begin_bit < 0) return fail(GCZ_E_ARG, "radix sort bit range");
-    const OnesweepConfig& cfg = config();
     const int npass = radix_sort_passes(end_bit - begin_bit);
-    const int kRadix = cfg.radix();
     const bool has_vals = b.vals[0] != nullptr;
     if (src && (!has_vals || begin_bit != 0 || src->n != n)) return fail(GCZ_E_ARG, "radix sort from text: arguments");
-    // two CTAs of the 9-bit variants need 221 KB of an SM's 228: ask for the largest shared-memory carve-out
-    const bool wide = cfg.bits > 8;
-    if (!ctx->sort_attr[has_vals ? 1 : 0]) {
-        GCZ_CUDA(cudaFuncSetAttribute(has_vals ? cfg.pairs : cfg.keys_only, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(has_vals ? cfg.smem_pairs : cfg.smem_keys)));
-        if (wide) GCZ_CUDA(cudaFuncSetAttribute(has_vals ? cfg.pairs : cfg.keys_only, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                (int)cudaSharedmemCarveoutMaxShared));
-        ctx->sort_attr[has_vals ? 1 : 0] = true;
-    }
-    if (src && !ctx->sort_attr[2]) {
-        GCZ_CUDA(cudaFuncSetAttribute(cfg.from_text, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_pairs));
-        if (wide) GCZ_CUDA(cudaFuncSetAttribute(cfg.from_text, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-        ctx->sort_attr[2] = true;
+    const OnesweepFn pairs = onesweep_kernel<kThreads, kItems, true, 2, false>;
+    const OnesweepFn keys_only = onesweep_kernel<kThreads, kItems, false, 2, false>;
+    const OnesweepFn from_text = onesweep_kernel<kThreads, kItems, true, 2, true>;
+    if (!ctx->sort_attr[0]) {
+        GCZ_CUDA(cudaFuncSetAttribute(pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPairs));
+        GCZ_CUDA(cudaFuncSetAttribute(keys_only, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemKeys));
+        GCZ_CUDA(cudaFuncSetAttribute(from_text, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPairs));
+        GCZ_CUDA(cudaFuncSetAttribute(onesweep_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairsSmem)));
+        ctx->sort_attr[0] = true;
     }
     auto* hist = static_cast<unsigned long long*>(temp);
     auto* status = hist + 8 * kRadix + 32;
-    const int64_t tiles = (n + cfg.tile() - 1) / cfg.tile();
+    const int64_t tiles = (n + kTile - 1) / kTile;
     auto* ticket = reinterpret_cast<unsigned*>(status + (size_t)tiles * kRadix);
     const TextKeySource none;
 
@@ -605,31 +754,38 @@ int radix_sort_pairs(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n
     if (src) {
         const int64_t ttiles = (n + kTextTile - 1) / kTextTile;
         const int grid = (int)std::min<int64_t>(ttiles, (int64_t)ctx->sm_count * 8);
-        GCZ_LAUNCH(ctx, cfg.text_hist, grid, kTextThreads, 0, st, *src, npass, hist, ttiles);
+        GCZ_LAUNCH(ctx, text_hist_kernel, grid, kTextThreads, 0, st, *src, npass, hist, ttiles);
     } else {
         const int hist_grid = (int)std::min<int64_t>((n + kHistThreads * 8 - 1) / (kHistThreads * 8), (int64_t)ctx->sm_count * 4);
-        GCZ_LAUNCH(ctx, cfg.hist, hist_grid, kHistThreads, 0, st, b.keys[b.cur], n, begin_bit, npass, hist);
+        GCZ_LAUNCH(ctx, radix_hist_kernel, hist_grid, kHistThreads, 0, st, b.keys[b.cur], n, begin_bit, npass, hist);
     }
-    GCZ_LAUNCH(ctx, cfg.scan, 1, kRadix, 0, st, hist, npass);
+    GCZ_LAUNCH(ctx, radix_scan_kernel, 1, kRadix, 0, st, hist, npass);
 
+    // bulk copies need 16-byte aligned sources: arena buffers are; anything else takes the one-tile-per-CTA kernel
+    const bool aligned = ((reinterpret_cast<uintptr_t>(b.keys[0]) | reinterpret_cast<uintptr_t>(b.keys[1]) |
+                           reinterpret_cast<uintptr_t>(b.vals[0]) | reinterpret_cast<uintptr_t>(b.vals[1])) & 15) == 0;
     for (int p = 0; p < npass; p++) {
         GCZ_CUDA(cudaMemsetAsync(status, 0, (size_t)tiles * kRadix * 8 + 64, st));
         const int in = b.cur, out = b.cur ^ 1;
-        const int shift = begin_bit + cfg.bits * p;
+        const int shift = begin_bit + RB * p;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (stats) {
             GCZ_CUDA(cudaEventCreate(&e0)); GCZ_CUDA(cudaEventCreate(&e1));
             GCZ_CUDA(cudaEventRecord(e0, st));
         }
         if (src && p == 0) {
-            cfg.from_text<<<(unsigned)tiles, cfg.threads, cfg.smem_pairs, st>>>(nullptr, b.keys[out], nullptr, b.vals[out], n, shift,
-                                                                                hist + p * kRadix, status, ticket, *src);
+            from_text<<<(unsigned)tiles, kThreads, kSmemPairs, st>>>(nullptr, b.keys[out], nullptr, b.vals[out], n, shift,
+                                                                     hist + p * kRadix, status, ticket, *src);
+        } else if (has_vals && aligned && use_persistent()) {
+            const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * 2);
+            onesweep_pairs_kernel<<<grid, kPThreads, sizeof(PairsSmem), st>>>(b.keys[in], b.keys[out], b.vals[in], b.vals[out], n, shift,
+                                                                              hist + p * kRadix, status, ticket);
         } else if (has_vals) {
-            cfg.pairs<<<(unsigned)tiles, cfg.threads, cfg.smem_pairs, st>>>(b.keys[in], b.keys[out], b.vals[in], b.vals[out], n, shift,
-                                                                            hist + p * kRadix, status, ticket, none);
+            pairs<<<(unsigned)tiles, kThreads, kSmemPairs, st>>>(b.keys[in], b.keys[out], b.vals[in], b.vals[out], n, shift,
+                                                                 hist + p * kRadix, status, ticket, none);
         } else {
-            cfg.keys_only<<<(unsigned)tiles, cfg.threads, cfg.smem_keys, st>>>(b.keys[in], b.keys[out], nullptr, nullptr, n, shift,
-                                                                               hist + p * kRadix, status, ticket, none);
+            keys_only<<<(unsigned)tiles, kThreads, kSmemKeys, st>>>(b.keys[in], b.keys[out], nullptr, nullptr, n, shift,
+                                                                    hist + p * kRadix, status, ticket, none);
         }
         ctx->launches++;
         GCZ_CUDA(cudaPeekAtLastError());

@@ -436,7 +436,10 @@ KeyCoder choose_key(const int64_t counts[256], int64_t n, int sigma) {
 size_t suffix_sort_workspace_bytes(int64_t n) {
     // rank 4n + keys 16n + vals(other) 4n + refinement worst case (lists 24n, sort 12n, run list 8n) + run marks + sort temp
     const size_t tiles = (size_t)(n / kGrpTile + 2);
-    return (size_t)n * (4 + 16 + 4 + 44 + 2) + radix_sort_temp_bytes(n) + tiles * kAggs * 8 + (size_t)n / 4 + (size_t)n / 8 + (8 << 20);
+    // run marks: two arrays of n/8 + 1024 u64 (2 x n bytes) and the run list of half as many 8-byte entries (n/2 bytes);
+    // every allocation below is rounded up to 256 bytes (the 8 MB at the end covers those)
+    const size_t marks = ((size_t)n / 8 + 1024) * 8 * 2 + ((size_t)n / 16 + 513) * sizeof(Run);
+    return (size_t)n * (4 + 16 + 4 + 44) + marks + radix_sort_temp_bytes(n) + tiles * kAggs * 8 + (size_t)n / 4 + (size_t)n / 8 + (8 << 20);
 }
 
 int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t n, const int64_t counts[256],

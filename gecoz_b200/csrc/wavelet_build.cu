@@ -42,7 +42,7 @@ struct SymbolTables {
 // ---- BWT gather + per-tile symbol counts + marker bits -----------------------------------------------
 // carry_shift != 0: SA entries hold the dense code (1..sigma) of the preceding text symbol above bit carry_shift
 // (suffix_sort.cuh) — the BWT is read off the entries and, when sa_clean is set, plain positions are written back.
-// PACKED (experimental, GCZ_BWT_VARIANT=1, alphabets of up to 8 symbols): every lane counts its own symbols in eight 8-bit
+// PACKED (alphabets of up to 8 symbols): every lane counts its own symbols in eight 8-bit
 // fields of one register (32 symbols per lane and tile, so no field overflows) and the warp adds the fields up once per
 // tile, instead of one ballot round per distinct symbol of every 32-symbol chunk.
 template <bool PACKED>
@@ -287,7 +287,7 @@ hswt_emit_small_kernel(const uint8_t* __restrict__ bwt, int64_t n, const SymbolT
     if (fill > 0 && (uint32_t)acc != 0) atomicOr(&raw[word], (uint32_t)acc);
 }
 
-// Experimental (GCZ_EMIT_VARIANT=1; the build uses hswt_emit_small_kernel unless asked): trees of at most kLutNodes nodes,
+// Trees of at most kLutNodes nodes (alphabets of up to 8 symbols: the path every DNA block takes),
 // i.e. alphabets of up to 8 symbols.  Every lane takes 32 consecutive BWT symbols and appends to its own per-node
 // accumulators, four symbols at a time through a table indexed by the four dense codes (entry: for every node one byte,
 // the branch bits of those of the four symbols that pass the node, low bit first, and how many they are above bit 4).
@@ -789,9 +789,9 @@ int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_t
     GCZ_CUDA(cudaMemcpyAsync(d_vecs, vecs.data(), sizeof(VectorDesc) * vecs.size(), cudaMemcpyHostToDevice, st));
     GCZ_CUDA(cudaMemsetAsync(d_raw, 0, ((size_t)raw_words + 16) * 4, st));
 
-    // experimental table-driven node emission (GCZ_EMIT_VARIANT=1): alphabets of up to 8 symbols
-    const char* emit_env = std::getenv("GCZ_EMIT_VARIANT");
-    const bool emit_lut = emit_env && emit_env[0] == '1' && sigma <= 8 && n_nodes <= kLutNodes;
+    // table-driven node emission for alphabets of up to 8 symbols (every DNA block): 1.6 ms -> 0.55 ms on the chr1-shaped block
+    // (profiles/variants_r02.md); larger alphabets take the ballot kernels below
+    const bool emit_lut = sigma <= 8 && n_nodes <= kLutNodes;
     std::vector<uint2> h_lut;
     uint2* d_lut = nullptr;
     if (emit_lut) {
@@ -827,8 +827,7 @@ int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_t
     const unsigned wt_grid = (unsigned)((tiles + kWtThreads / 32 - 1) / (kWtThreads / 32));
     const uint32_t sample_mask = (1u << sampling_factor) - 1u;
     uint32_t* d_marker_raw = d_raw + vecs[marker_vec].raw_word;
-    const char* bwt_env = std::getenv("GCZ_BWT_VARIANT");
-    if (bwt_env && bwt_env[0] == '1' && sigma <= 8) {
+    if (sigma <= 8) {                      // packed per-lane counters (0.95 ms -> 0.47 ms on the chr1-shaped block)
         GCZ_LAUNCH(ctx, bwt_count_kernel<true>, wt_grid, kWtThreads, 0, st, d_text, d_sa, n, d_tab, sample_mask, carry_shift,
                    (carry_shift && clean_sa) ? d_sa : (uint32_t*)nullptr, d_bwt, d_marker_raw, d_tile_counts, tiles);
     } else {
@@ -860,21 +859,8 @@ int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_t
         GCZ_CUDA(cudaMemcpyAsync(h_gcz_out, d_gcz_body, (size_t)shape->size, cudaMemcpyDeviceToHost, copy_stream));
         GCZ_CUDA(cudaEventRecord(gcz_copied, copy_stream));
     }
-    // experimental (GCZ_EARLY_MARKER=1): the marker vector (n bits + counters, the larger part of the .gcx body) is final
-    // after bwt_count_kernel; laid out now, it follows the .gcz body to the host while the IndexWaveletTree is built
-    int tail_vec0 = marker_vec;
-    int64_t tail_sb0 = sb_nodes;
-    const char* early_env = std::getenv("GCZ_EARLY_MARKER");
-    if (early_env && early_env[0] == '1' && h_gcx_out && h_gcz_out && gcx_bytes_copied) {
-        tail_vec0 = level_vec0;
-        tail_sb0 = sb_nodes + vecs[marker_vec].sb_count;
-        GCZ_TRY(layout_vectors(ctx, st, d_raw, d_vecs, (int)vecs.size(), marker_vec, level_vec0, sb_nodes, tail_sb0, d_sb));
-        GCZ_CUDA(cudaEventRecord(gcz_copied, st));
-        GCZ_CUDA(cudaStreamWaitEvent(copy_stream, gcz_copied, 0));
-        GCZ_CUDA(cudaMemcpyAsync(h_gcx_out, d_gcx_body, (size_t)rank_bytes, cudaMemcpyDeviceToHost, copy_stream));
-        GCZ_CUDA(cudaEventRecord(gcz_copied, copy_stream));          // the caller's wait now covers both copies
-        *gcx_bytes_copied = rank_bytes;
-    }
+    const int tail_vec0 = marker_vec;
+    const int64_t tail_sb0 = sb_nodes;
     if (stats) GCZ_CUDA(cudaEventRecord(ev1, st));
 
     // ---- sampled SA + IndexWaveletTree ---------------------------------------------------------------------

@@ -149,3 +149,63 @@ class GSSA:
         if sa is None or len(sa) == 0:
             return None
         return [len(x) if x is not None and len(x) > 0 else 0 for x in sa]
+
+
+# ---- a batch against every block of a file (include/gcz.h: gcz_count_multi / gcz_find_multi) -------------------------------
+def _handles(gssas):
+    arr = (C.c_void_p * len(gssas))(*[g._h for g in gssas])
+    return arr, len(gssas)
+
+
+def _count(n_or_off):
+    return (n_or_off.numel() if hasattr(n_or_off, "numel") else len(n_or_off)) - 1
+
+
+def count_totals(gssas: Sequence[GSSA], data, off, out=None):
+    """Occurrences of every pattern summed over the blocks (GecoMatch's "total found", tools/GecoMatch.java:114-131): the
+    batch (host or device arrays) is uploaded once and searched against every block on the device.  `out`: int64[n]
+    (numpy, pinned or CUDA tensor); a numpy array is returned when it is omitted."""
+    n = _count(off)
+    if out is None:
+        out = np.zeros(n, np.int64)
+    arr, k = _handles(gssas)
+    N.check(N.lib().gcz_count_multi(arr, k, N.ptr(data), N.ptr(off), n, N.ptr(out)))
+    return out
+
+
+def count_stats(gssas: Sequence[GSSA], data, off) -> dict:
+    """Rank sectors read / backward-search steps / reference rank calls of a batch (gcz_count_stats; measurement only)."""
+    st = N.QueryStats()
+    arr, k = _handles(gssas)
+    N.check(N.lib().gcz_count_stats(arr, k, N.ptr(data), N.ptr(off), _count(off), C.byref(st)))
+    return st.as_dict()
+
+
+def last_query_stats() -> dict:
+    st = N.QueryStats()
+    N.check(N.lib().gcz_last_query_stats(C.byref(st)))
+    return st.as_dict()
+
+
+def find_multi(gssas: Sequence[GSSA], data, off, copy: bool = True):
+    """GSSA.find of a batch against every block: (block_off[k + 1], pattern, string, position) — the hits of block b are
+    rows block_off[b] .. block_off[b + 1], sorted by (pattern, string, position)."""
+    hits = N.Hits()
+    arr, k = _handles(gssas)
+    N.check(N.lib().gcz_find_multi(arr, k, N.ptr(data), N.ptr(off), _count(off), C.byref(hits)))
+    try:
+        n = int(hits.n_hits)
+        block_off = np.ctypeslib.as_array(hits.block_off, shape=(k + 1,)).copy()
+        if not copy:
+            return block_off, n
+        if n == 0:
+            return block_off, np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(0, np.int64)
+        return (block_off, np.ctypeslib.as_array(hits.pattern, shape=(n,)).copy(), np.ctypeslib.as_array(hits.string, shape=(n,)).copy(),
+                np.ctypeslib.as_array(hits.position, shape=(n,)).copy())
+    finally:
+        N.lib().gcz_hits_free(C.byref(hits))
+
+
+def find_total(gssas: Sequence[GSSA], data, off) -> int:
+    """Number of hits of a batch over all blocks (the arrays are produced and dropped: what a caller that streams them out pays)."""
+    return int(find_multi(gssas, data, off, copy=False)[1])

@@ -151,6 +151,45 @@ int  gcz_find_batch(gcz_index* idx, const uint8_t* pats, const int64_t* pat_off,
 int  gcz_extract(gcz_index* idx, int32_t nstr, int64_t from, uint8_t* out, int64_t cap, int64_t* written);
 void gcz_free(void* p);
 
+/* ---- a batch against every block of a file -------------------------------------------------------
+ * The callers of the reference loop over the blocks for every pattern (GecoMatch.match  tools/GecoMatch.java:114-131,
+ * SimpleGFFGenerator.search  tools/SimpleGFFGenerator.java:52-56,128).  For a batch the loops are swapped: the batch is
+ * uploaded ONCE (or already lives on the device: `pats` / `pat_off` may be device pointers), every block is searched
+ * there, and only results come back.  All blocks of one call must be open on the same device. */
+
+/* "total found" of GecoMatch for every pattern: totals[i] = sum over the blocks of max(0, ep - sp + 1) of pattern i
+ * (host or device array of n_pats). */
+int  gcz_count_multi(gcz_index* const* blocks, int32_t n_blocks, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats,
+                     int64_t* totals);
+
+/* GSSA.find :160-185 of every pattern in every block, as sparse records: the hits of block b are
+ * [block_off[b], block_off[b + 1]), sorted by (pattern, string, position) — for one pattern that is the order in which
+ * find returns them (string after string, positions ascending, 0-based inside the string).  Intervals, locate
+ * (:241-251), the sort and the split by string ends all run on the device.  The arrays are callee-allocated host
+ * memory: release them with gcz_hits_free. */
+typedef struct gcz_hits {
+    int64_t  n_hits;
+    int64_t* block_off;    /* n_blocks + 1 */
+    int64_t* pattern;      /* index of the pattern in the batch */
+    int32_t* string;       /* string ordinal inside its block (= index into the block header's list) */
+    int64_t* position;
+} gcz_hits;
+int  gcz_find_multi(gcz_index* const* blocks, int32_t n_blocks, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats,
+                    gcz_hits* out);
+void gcz_hits_free(gcz_hits* hits);
+
+/* What a batch of backward searches reads (measurement, not a timed path): rank sectors of 32 bytes loaded by the
+ * kernel, its backward-search steps, and the RankedWTNode.count calls (algo/tree/RankedWTNode.java:98-122) the
+ * reference's own loop makes for the same patterns — 2 per character and code bit while the position is >= 0
+ * (algo/tree/HuffmanShapedWaveletTree.java:247-267), 74 bytes each in the file layout. */
+typedef struct gcz_query_stats {
+    int64_t patterns, blocks, steps, rank_sectors, reference_rank_calls, index_bytes;
+    float   kernel_ms;       /* device time of the search kernels of the call */
+} gcz_query_stats;
+int  gcz_count_stats(gcz_index* const* blocks, int32_t n_blocks, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats,
+                     gcz_query_stats* out);
+int  gcz_last_query_stats(gcz_query_stats* out);   /* of the calling thread's last gcz_count_multi: patterns, blocks, kernel_ms */
+
 /* ---- stage-level hooks used by the parity tests (each one is a stage of gcz_build_block) ------- */
 int gcz_dbg_sort_pairs(int device, uint64_t* keys, uint32_t* vals, int64_t n, int32_t begin_bit, int32_t end_bit);
 int gcz_dbg_suffix_array(int device, const uint8_t* text, int64_t n, int32_t* sa);

@@ -117,3 +117,110 @@ def test_cfg2_full_properties(G):
     # determinism: a second build writes the same bytes
     shape2, gcz2, gcx2, _, _, _ = _build(G, text, want_sa=False)
     assert np.array_equal(gcz, gcz2) and np.array_equal(gcx, gcx2)
+
+
+# ---- byte parity at the benchmarked sizes: sha256 against the oracle's digests --------------------------------------
+# tests/golden/full_size_digests.json is written by tools/make_digests.py from the CPU oracle alone (5 minutes on 8
+# cores); nothing here runs the oracle, so the comparison costs one build and one hash per block on the GPU box.
+import hashlib
+import json
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+GOLD = json.loads((Path(__file__).parent / "golden" / "full_size_digests.json").read_text())
+
+
+def _sha(a) -> str:
+    return hashlib.sha256(memoryview(np.ascontiguousarray(a)).cast("B")).hexdigest()
+
+
+def test_cfg2_digests_equal_the_oracles(G):
+    from gecoz_b200 import synth
+    text = synth.cfg2_text()
+    g2 = GOLD["cfg2"]
+    assert len(text) == g2["n"] and _sha(text) == g2["text"], "the generator no longer produces the text the digests were made from"
+    shape, gcz, gcx, sa, bwt, _ = _build(G, text)
+    assert (len(gcz), len(gcx)) == (g2["gcz_body_len"], g2["gcx_body_len"])
+    assert _sha(gcz) == g2["gcz_body"], ".gcz body of the full cfg2 block differs from the oracle's"
+    assert _sha(gcx) == g2["gcx_body"], ".gcx body of the full cfg2 block differs from the oracle's"
+    assert _sha(sa) == g2["sa"], "suffix array of the full cfg2 block differs from the oracle's"
+    assert _sha(bwt) == g2["bwt"], "BWT of the full cfg2 block differs from the oracle's"
+
+
+@pytest.fixture(scope="module")
+def genome():
+    """The hg38-shaped genome as the product blocks it (GecoIndex merge) and its synthetic block texts (made on demand)."""
+    from gecoz_b200 import synth
+    from gecoz_b200.geco_index import FastaSequence, merge_blocks
+    seqs = [FastaSequence(h, ln, None, i) for i, (h, ln) in enumerate(zip(synth.HG38_NAMES, synth.HG38_LENGTHS))]
+    plan = [([s.header for s in b.sequences], [s.id for s in b.sequences], int(b.size)) for b in merge_blocks(seqs)]
+
+    def text_of(b):
+        return synth.block_of([synth.chromosome_shaped(synth.HG38_LENGTHS[i], 4 + i) for i in plan[b][1]])
+    return plan, text_of
+
+
+def test_cfg3_block_plan_equals_the_oracles(genome):
+    plan, _ = genome
+    gold = GOLD["cfg3"]["blocks"]
+    assert [p[0] for p in plan] == [b["headers"] for b in gold]
+    assert [p[2] for p in plan] == [b["n"] for b in gold]
+    assert sum(p[2] for p in plan) == GOLD["cfg3"]["symbols"] == 3_088_286_426
+
+
+def test_cfg3_every_block_equals_the_oracles_digests(G, genome):
+    """All 18 blocks of the 3.1 Gbp genome: .gcz and .gcx bodies (and SA + BWT on the merged blocks) byte for byte, and the two
+    whole files (headers + bodies in file order) against the digests of the files the oracle writes."""
+    from gecoz_b200.gecoz_file import GecozRefBlockHeader, GecozSSABlockHeader
+    plan, text_of = genome
+    gold = GOLD["cfg3"]
+    hz, hx = hashlib.sha256(), hashlib.sha256()
+    with ThreadPoolExecutor(3) as pool:                       # synthesis of the next blocks overlaps build + hashing
+        texts = [pool.submit(text_of, b) for b in range(len(plan))]
+        for b, (headers, ids, n) in enumerate(plan):
+            text = texts[b].result()
+            texts[b] = None
+            gb = gold["blocks"][b]
+            assert len(text) == n and _sha(text) == gb["text"], f"block {b}: synthetic text differs from the one the digests were made from"
+            merged = len(ids) > 1
+            shape, gcz, gcx, sa, bwt, _ = _build(G, text, want_sa=merged)
+            assert _sha(gcz) == gb["gcz_body"], f"block {b} {headers}: .gcz body differs from the oracle's"
+            assert _sha(gcx) == gb["gcx_body"], f"block {b} {headers}: .gcx body differs from the oracle's"
+            if merged:
+                assert _sha(sa) == gb["sa"] and _sha(bwt) == gb["bwt"], f"block {b} {headers}: SA / BWT differ from the oracle's"
+            hz.update(GecozRefBlockHeader(headers, GecozRefBlockHeader.block_header_length(headers) + len(gcz), n).to_bytes())
+            hz.update(memoryview(gcz))
+            hx.update(GecozSSABlockHeader(headers, len(gcx)).to_bytes())
+            hx.update(memoryview(gcx))
+            del text, gcz, gcx, sa, bwt
+    assert hz.hexdigest() == gold["gcz_file"] and hx.hexdigest() == gold["gcx_file"]
+
+
+@pytest.mark.parametrize("first", ["chr13", "chr15", "chr11"])
+def test_cfg4_cfg5_results_equal_the_oracles_digests(G, genome, first):
+    """count (cfg4) and find (cfg5) at full size on the merged blocks chr13+chr14 and chr15+chr22+chr21+chrM — where per-string
+    results are more than intervals — and on the chr11 block of the `-s chr11` filter: 100 000 patterns of 15..100 symbols."""
+    from gecoz_b200 import synth
+    import gecoz_b200 as GG
+    plan, text_of = genome
+    b = [p[0][0] for p in plan].index(first)
+    q = GOLD["cfg3"]["blocks"][b]["queries"]
+    text = text_of(b)
+    shape, gcz, gcx, _, _, _ = _build(G, text, want_sa=False)
+    g = G.GSSA.open(0, gcz, len(text), gcx, plan[b][0])
+    assert g.n_strings == q["n_strings"] and g.e.tolist() == q["string_ends"]
+    data, off = synth.patterns(text, q["patterns"], 15, 100, seed=q["seed"])
+    assert _sha(data) == q["pattern_bytes"]
+    sp, ep = g.count_batch(packed=(data, off))
+    assert _sha(sp) == q["sp"] and _sha(ep) == q["ep"] and int((ep >= sp).sum()) == q["found"]
+    # the rank calls the reference's loop makes for this batch, counted by the kernel, equal the instrumented oracle's
+    st = GG.count_stats([g], data, off)
+    assert st["reference_rank_calls"] == q["rank_calls"]
+    assert 0 < st["rank_sectors"] <= st["reference_rank_calls"]
+    # totals over "all blocks" of a one-block index
+    tot = GG.count_totals([g], data, off)
+    assert np.array_equal(tot, np.maximum(ep - sp + 1, 0))
+    k = q["find_patterns"]
+    per, pos, poff = g.find_batch_raw(packed=(data[:off[k]], off[:k + 1]))
+    assert _sha(per) == q["per_string_counts"] and _sha(pos) == q["positions"] and len(pos) == q["occurrences"]
+    g.close()

@@ -621,9 +621,6 @@ def test_native_writer_and_reader_on_the_gpu(G, O, tmp_path):
         g.close()
 
 
-@pytest.mark.skipif(os.environ.get("GCZ_TEST_PENDING") != "1",
-                    reason="written after the round's GPU budget was spent: the same code passes on CPU with the oracle as the query "
-                           "engine (tests/test_native_host_cpu.py); set GCZ_TEST_PENDING=1 for its first hardware run")
 def test_native_callers_on_the_gpu(G, O, tmp_path):
     """gcz_match / gcz_gff_search / gcz_extract_fasta with the library's own CUDA entry points as the engine."""
     from gecoz_b200 import geco_match, geco_read, native_file as NF
@@ -638,3 +635,108 @@ def test_native_callers_on_the_gpu(G, O, tmp_path):
         assert r.extract_fasta(tmp_path / "native.fa") == len(recs)
     geco_read.fasta(tmp_path / "g.gcz", tmp_path / "python.fa")
     assert (tmp_path / "native.fa").read_bytes() == (tmp_path / "python.fa").read_bytes()
+
+
+# ---- a batch against every block of a file: gcz_count_multi / gcz_find_multi ------------------------------------------------
+@pytest.fixture(scope="module")
+def three_blocks(G, O):
+    """Three blocks as GecoIndex would write them: one single-string block, one merged block whose later strings sort before the
+    first one (the LF-across-separator quirk) and one tiny block."""
+    from gecoz_b200 import synth
+    blocks = [[synth.iid_acgtn(200_000, 41)],
+              [synth.iid_acgtn(5000, 31), synth.iid_acgtn(3000, 32), synth.iid_acgtn(2987, 33), synth.iid_acgtn(19, 34)],
+              [synth.iid_acgtn(300, 51), synth.iid_acgtn(41, 52)]]
+    blocks[1][0][:4] = np.frombuffer(b"TTTT", np.uint8)
+    out = []
+    for seqs in blocks:
+        text = synth.block_of(seqs)
+        ref = O.build_block(text, 32)
+        out.append((text, ref, G.GSSA.open(0, ref["gcz_body"], len(text), ref["gcx_body"]), O.GSSA(ref["gcz_body"], len(text), ref["gcx_body"])))
+    yield out
+    for _, _, g, og in out:
+        g.close()
+        og.close()
+
+
+def _mixed_patterns(three_blocks, count=4000, seed=3):
+    from gecoz_b200 import synth
+    rng = np.random.default_rng(seed)
+    pats = []
+    for text, _, _, _ in three_blocks:
+        for _ in range(count // 3):
+            ln = int(rng.integers(1, 24))
+            a = int(rng.integers(0, max(1, len(text) - ln)))
+            pats.append(text[a:a + ln].tobytes())              # may span a separator: patterns holding '\0' hit string ends exactly
+    pats += [b"A", b"N", b"\0", b"T\0", b"\0A", b"ZZ", bytes([200, 65]), b"ACGT" * 30]
+    return pats
+
+
+def test_count_multi_equals_the_sum_over_blocks(G, three_blocks):
+    import torch
+    pats = _mixed_patterns(three_blocks)
+    data, off = G.pack_patterns(pats)
+    gssas = [g for _, _, g, _ in three_blocks]
+    exp = np.zeros(len(pats), np.int64)
+    for g in gssas:
+        sp, ep = g.count_batch(packed=(data, off))
+        exp += np.maximum(ep - sp + 1, 0)
+    assert np.array_equal(G.count_totals(gssas, data, off), exp)
+    # device-resident batch and result, and a pinned host batch
+    d_data, d_off = torch.from_numpy(data).cuda(), torch.from_numpy(off).cuda()
+    d_out = torch.full((len(pats),), -7, dtype=torch.int64, device="cuda")
+    G.count_totals(gssas, d_data, d_off, d_out)
+    assert np.array_equal(d_out.cpu().numpy(), exp)
+    h_out = torch.empty(len(pats), dtype=torch.int64).pin_memory()
+    G.count_totals(gssas, torch.from_numpy(data).pin_memory(), torch.from_numpy(off).pin_memory(), h_out)
+    assert np.array_equal(h_out.numpy(), exp)
+    st = G.last_query_stats()
+    assert st["patterns"] == len(pats) and st["blocks"] == 3 and st["kernel_ms"] > 0
+
+
+def test_count_stats_equal_the_instrumented_oracle(G, three_blocks):
+    pats = _mixed_patterns(three_blocks, count=1500, seed=5)
+    data, off = G.pack_patterns(pats)
+    calls = 0
+    for _, _, g, og in three_blocks:
+        calls += og.search_batch(data, off)[2]
+    st = G.count_stats([g for _, _, g, _ in three_blocks], data, off)
+    assert st["reference_rank_calls"] == calls
+    assert 0 < st["rank_sectors"] <= calls and st["steps"] > 0 and st["index_bytes"] > 0
+
+
+def test_find_multi_equals_the_oracles_find_per_block(G, three_blocks):
+    """Sparse hit records of a batch over three blocks == GSSA.find of the oracle, pattern by pattern and block by block —
+    including patterns that hold a separator (their positions ARE string ends: the reference's binarySearch finds the key
+    and takes its other branch) and the merged block whose LF walk crosses separators."""
+    import torch
+    pats = _mixed_patterns(three_blocks)
+    data, off = G.pack_patterns(pats)
+    gssas = [g for _, _, g, _ in three_blocks]
+    for src in ((data, off), (torch.from_numpy(data).cuda(), torch.from_numpy(off).cuda())):
+        block_off, pattern, string, position = G.find_multi(gssas, *src)
+        assert block_off[0] == 0 and block_off[-1] == len(pattern) == len(string) == len(position)
+        for b, (_, _, g, og) in enumerate(three_blocks):
+            lo, hi = int(block_off[b]), int(block_off[b + 1])
+            pb, sb, xb = pattern[lo:hi], string[lo:hi], position[lo:hi]
+            assert (np.diff(pb) >= 0).all()
+            starts = np.searchsorted(pb, np.arange(len(pats) + 1))
+            for i, p in enumerate(pats):
+                if len(p) == 0 or max(p) >= 128:
+                    exp = None
+                else:
+                    exp = og.find(p)
+                got = [[] for _ in range(g.n_strings)]
+                for j in range(starts[i], starts[i + 1]):
+                    got[int(sb[j])].append(int(xb[j]))
+                want = [[] if (exp is None or x is None) else x.tolist() for x in (exp or [None] * g.n_strings)]
+                assert got == want, (b, p)
+
+
+def test_find_batch_dense_form_still_matches(G, three_blocks):
+    pats = _mixed_patterns(three_blocks, count=900, seed=9)
+    for _, _, g, og in three_blocks:
+        got = g.find_batch(pats)
+        for p, r in zip(pats, got):
+            if max(p) >= 128:
+                continue
+            assert _as_lists(r) == _as_lists(og.find(p)), p

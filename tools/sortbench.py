@@ -1,4 +1,5 @@
-"""Tuning aid: device time of the onesweep digit passes for one tile-shape variant (GCZ_SORT_VARIANT)."""
+"""Tuning aid: device time of the onesweep digit passes over (u64, u32) pairs.  GCZ_SORT_PERSISTENT=0 sends pairs through the
+one-tile-per-CTA kernel instead of the persistent TMA one (A/B):  python tools/sortbench.py [n] [bits]"""
 import ctypes as C
 import os
 import sys
@@ -25,5 +26,5 @@ for it in range(3):
     res.append((t.radix_ms, t.radix_launches))
 ok = bool((keys[1:] >= keys[:-1]).all())
 ms, passes = res[-1]
-print(f"variant={os.environ.get('GCZ_SORT_VARIANT', '0')} n={n} bits={bits} passes={passes} ms={ms:.3f} "
+print(f"persistent={os.environ.get('GCZ_SORT_PERSISTENT', '1')} n={n} bits={bits} passes={passes} ms={ms:.3f} "
       f"per_pass={ms / passes:.3f} GB/s={24 * n * passes / ms / 1e6:.0f} sorted={ok}")
