@@ -181,6 +181,37 @@ __device__ __forceinline__ unsigned peers_with_same_digit(unsigned d) {
     return acc;
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (TMA, no tensor map): bytes a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// generic-proxy accesses to shared memory before this point are ordered before async-proxy (TMA) writes after it
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// shared-memory reduction without a return value (and without the match-based aggregation ptxas wraps atomicAdd in)
+__device__ __forceinline__ void red_shared_inc(unsigned* p) {
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(smem_u32(p)) : "memory");
+}
+
 // Ranks of a thread's ITEMS keys among the keys of its warp with the same digit, in element order (item, then lane),
 // two to a register; the warp's digit counters (my_hist, shared memory, zero on entry) end up holding the warp's counts.
 template <int ITEMS>
@@ -216,7 +247,7 @@ __device__ __forceinline__ void rank_in_warp(const uint64_t (&key)[ITEMS], int s
 //   7 write digit runs out, coalesced
 //   1' (FROM_TEXT) the tile's keys are computed from the text instead: codes to shared memory, a k-symbol window
 //      slid over ITEMS consecutive positions per thread, transposed to the warp-striped order through shared memory
-template <int THREADS, int ITEMS, bool HAS_VALS, int MIN_BLOCKS, bool FROM_TEXT>
+template <int THREADS, int ITEMS, bool HAS_VALS, int MIN_BLOCKS, bool FROM_TEXT, bool EARLY>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
                 const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
@@ -312,65 +343,112 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
 #pragma unroll
     for (int i = 0; i < ITEMS; i++) asm volatile("" : "+l"(key[i]));
 
-    // 2. rank inside the warp
     unsigned rank2[ITEMS / 2];                  // ranks of items 2j (low half) and 2j + 1 (high half)
     unsigned* my_hist = s_warp_hist + warp * kRadix;
-    rank_in_warp<ITEMS>(key, shift, my_hist, lt, rank2);
-
-    // 3. values
     uint32_t val[ITEMS];
-    if (FROM_TEXT) {
-#pragma unroll
-        for (int i = 0; i < ITEMS; i++) {
-            const int e = warp_base + i * 32 + lane;
-            val[i] = (uint32_t)(tile_base + e) | (src.carry_shift ? (uint32_t)s_codes[e] << src.carry_shift : 0u);
-        }
-    } else if (HAS_VALS) {
-        if (count == TILE) {
-            const uint32_t* src_vals = vals_in + tile_base + warp_base + lane;
-#pragma unroll
-            for (int i = 0; i < ITEMS; i++) val[i] = src_vals[i * 32];
-        } else {
+    unsigned total = 0;
+    auto load_values = [&]() {
+        if (FROM_TEXT) {
 #pragma unroll
             for (int i = 0; i < ITEMS; i++) {
                 const int e = warp_base + i * 32 + lane;
-                val[i] = e < count ? vals_in[tile_base + e] : 0u;
+                val[i] = (uint32_t)(tile_base + e) | (src.carry_shift ? (uint32_t)s_codes[e] << src.carry_shift : 0u);
+            }
+        } else if (HAS_VALS) {
+            if (count == TILE) {
+                const uint32_t* src_vals = vals_in + tile_base + warp_base + lane;
+#pragma unroll
+                for (int i = 0; i < ITEMS; i++) val[i] = src_vals[i * 32];
+            } else {
+#pragma unroll
+                for (int i = 0; i < ITEMS; i++) {
+                    const int e = warp_base + i * 32 + lane;
+                    val[i] = e < count ? vals_in[tile_base + e] : 0u;
+                }
             }
         }
-    }
-    __syncthreads();
-
-    // 4. per-warp counts -> exclusive warp offsets, tile histogram, aggregate, digit starts
-    unsigned total = 0;
-    if (threadIdx.x < kRadix) {
+    };
+    if (EARLY) {
+        // 2e. digit counts of every warp first (one shared-memory reduction per key), so that the tile's aggregate is
+        //     published BEFORE the ranking: by the time the tiles behind this one look back, it is microseconds old
 #pragma unroll
-        for (int w = 0; w < WARPS; w++) {
-            const unsigned c = s_warp_hist[w * kRadix + threadIdx.x];
-            s_warp_hist[w * kRadix + threadIdx.x] = total;
-            total += c;
+        for (int i = 0; i < ITEMS; i++) red_shared_inc(&my_hist[(unsigned)(key[i] >> shift) & (unsigned)(kRadix - 1)]);
+        __syncthreads();
+        if (threadIdx.x < kRadix) {
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) total += s_warp_hist[w * kRadix + threadIdx.x];
+            const unsigned with_padding = total;
+            if (threadIdx.x == kRadix - 1) total -= (unsigned)(TILE - count);     // padding keys are all the last digit
+            st_relaxed_u64(&status[(size_t)tile * kRadix + threadIdx.x],
+                           (unsigned long long)total | (tile == 0 ? kFlagPrefix : kFlagAgg));
+            const unsigned incl = warp_incl_sum(with_padding);
+            if (lane == 31) s_scan[warp] = incl;
+            s_digit_start[threadIdx.x] = incl - with_padding;
         }
-        if (threadIdx.x == kRadix - 1) total -= (unsigned)(TILE - count);     // padding keys are all the last digit
-        st_relaxed_u64(&status[(size_t)tile * kRadix + threadIdx.x],
-                       (unsigned long long)total | (tile == 0 ? kFlagPrefix : kFlagAgg));
-        const unsigned incl = warp_incl_sum(total);
-        if (lane == 31) s_scan[warp] = incl;
-        s_digit_start[threadIdx.x] = incl - total;
-    }
-    __syncthreads();
-    if (threadIdx.x < kRadix) {
-        unsigned base = 0;
-        for (unsigned w = 0; w < warp; w++) base += s_scan[w];
-        s_digit_start[threadIdx.x] += base;
-    }
-    __syncthreads();
-
-    // 5. reorder the tile in shared memory (padding keys are the last digit and rank last: they land at >= count)
+        __syncthreads();
+        if (threadIdx.x < kRadix) {
+            unsigned at = s_digit_start[threadIdx.x];
+            for (unsigned w = 0; w < warp; w++) at += s_scan[w];
+            s_digit_start[threadIdx.x] = at;
+            // where the first key of digit d in warp w lands: digit start + keys of d in the warps before w
 #pragma unroll
-    for (int i = 0; i < ITEMS; i++) {
-        const unsigned d = (unsigned)(key[i] >> shift) & (unsigned)(kRadix - 1);
-        const unsigned pos = s_digit_start[d] + my_hist[d] + ((i & 1) ? rank2[i >> 1] >> 16 : rank2[i >> 1] & 0xffffu);
-        s_keys[pos] = key[i];
-        if (HAS_VALS) s_vals[pos] = val[i];
+            for (int w = 0; w < WARPS; w++) {
+                const unsigned c = s_warp_hist[w * kRadix + threadIdx.x];
+                s_warp_hist[w * kRadix + threadIdx.x] = at;
+                at += c;
+            }
+        }
+        __syncthreads();
+        // 3e. rank inside the warp: my_hist[d] is the next free position of digit d for this warp, so the rank IS the position
+        rank_in_warp<ITEMS>(key, shift, my_hist, lt, rank2);
+        load_values();
+        if (FROM_TEXT) __syncthreads();           // the symbol codes share their shared memory with the reordered values
+        // 5e. reorder the tile in shared memory (padding keys are the last digit and rank last: they land at >= count)
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            const unsigned pos = (i & 1) ? rank2[i >> 1] >> 16 : rank2[i >> 1] & 0xffffu;
+            s_keys[pos] = key[i];
+            if (HAS_VALS) s_vals[pos] = val[i];
+        }
+    } else {
+        // 2. rank inside the warp
+        rank_in_warp<ITEMS>(key, shift, my_hist, lt, rank2);
+
+        // 3. values
+        load_values();
+        __syncthreads();
+
+        // 4. per-warp counts -> exclusive warp offsets, tile histogram, aggregate, digit starts
+        if (threadIdx.x < kRadix) {
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) {
+                const unsigned c = s_warp_hist[w * kRadix + threadIdx.x];
+                s_warp_hist[w * kRadix + threadIdx.x] = total;
+                total += c;
+            }
+            if (threadIdx.x == kRadix - 1) total -= (unsigned)(TILE - count);     // padding keys are all the last digit
+            st_relaxed_u64(&status[(size_t)tile * kRadix + threadIdx.x],
+                           (unsigned long long)total | (tile == 0 ? kFlagPrefix : kFlagAgg));
+            const unsigned incl = warp_incl_sum(total);
+            if (lane == 31) s_scan[warp] = incl;
+            s_digit_start[threadIdx.x] = incl - total;
+        }
+        __syncthreads();
+        if (threadIdx.x < kRadix) {
+            unsigned base = 0;
+            for (unsigned w = 0; w < warp; w++) base += s_scan[w];
+            s_digit_start[threadIdx.x] += base;
+        }
+        __syncthreads();
+
+        // 5. reorder the tile in shared memory (padding keys are the last digit and rank last: they land at >= count)
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) {
+            const unsigned d = (unsigned)(key[i] >> shift) & (unsigned)(kRadix - 1);
+            const unsigned pos = s_digit_start[d] + my_hist[d] + ((i & 1) ? rank2[i >> 1] >> 16 : rank2[i >> 1] & 0xffffu);
+            s_keys[pos] = key[i];
+            if (HAS_VALS) s_vals[pos] = val[i];
+        }
     }
 
     // 6. decoupled look-back, kLookWindow predecessors per step: their status words are loaded together so the
@@ -379,15 +457,16 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
         unsigned long long excl = 0;
         long long t = (long long)tile - 1;
         bool done = tile == 0;
+        constexpr int kWindow = EARLY ? 16 : kLookWindow;
         while (!done) {
-            unsigned long long v[kLookWindow];
+            unsigned long long v[kWindow];
 #pragma unroll
-            for (int j = 0; j < kLookWindow; j++) {
+            for (int j = 0; j < kWindow; j++) {
                 v[j] = t - j >= 0 ? ld_relaxed_u64(&status[(size_t)(t - j) * kRadix + threadIdx.x]) : kFlagPrefix;
             }
             int used = 0;
 #pragma unroll
-            for (int j = 0; j < kLookWindow; j++) {
+            for (int j = 0; j < kWindow; j++) {
                 const unsigned long long flag = v[j] & ~kValueMask;
                 if (!done && used == j && flag != 0) {
                     excl += v[j] & kValueMask;
@@ -421,20 +500,24 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
 // lives in ONE shared-memory image (48 KB keys + 24 KB values) that is both the landing zone of the bulk copies
 // (cp.async.bulk.shared::cluster.global + mbarrier complete_tx) and the buffer the tile is reordered in:
 //
-//   wait(keys)  -> keys to registers, rank inside each warp (as above)
-//   wait(values)-> values to registers                       | barrier: every element of the image is in a register
-//   scan of the warp counters, tile aggregate published      | barrier x2
+//   wait(keys)   -> keys to registers; digit counts of every warp (one shared-memory reduction per key)   | barrier
+//   counts -> tile histogram, PUBLISHED NOW for the look-back of the tiles behind this one; digit starts   | barrier
+//   per-warp starting positions (digit start + keys of the digit in earlier warps)                         | barrier
+//   rank inside each warp: the rank IS the position in the reordered tile
+//   wait(values) -> values to registers                       | barrier: every element of the image is in a register
 //   reorder in place (registers -> image)
-//   look-back: ALL 512 threads, 2 x kLook predecessors per round trip (thread = digit x half; the halves meet in shared
-//   memory) — at 25 tiles per microsecond a window of 8 needs 2.7 round trips per tile (measured, profiles/), 24 needs one
-//                                                             | barrier
-//   keys out (destinations stay in registers)                 | barrier: key image drained -> bulk copy of the next tile's keys
-//   values out, warp counters zeroed                          | barrier: value image drained -> bulk copy of the next values
+//   look-back over windows of kLookWindowP predecessors                                                    | barrier
+//   key image + destinations to registers                     | barrier: key image drained -> bulk copy of the next tile's keys
+//   keys and values out, warp counters zeroed                 | barrier: value image drained -> bulk copy of the next values
 //
-// so the DRAM latency of a tile's keys hides behind the value write-out of the tile before, and that of its values
-// behind its own ranking.  The last, partial tile takes plain guarded loads.
+// Why the histogram comes before the ranking: at 25 tiles per microsecond (249 M pairs in 1.6 ms) a tile's predecessors
+// are all in flight at once, and a look-back that starts one scatter phase (~1 us) after the aggregates were published
+// finds the nearest ones unpublished and polls: 2.7 round trips per tile, 10 % of all warp samples waiting behind it
+// (profiles/onesweep_512x12_full_r01.*, profiles/onesweep_persistent_first_r02.*).  Published before the ranking, an
+// aggregate is ~5 us old when it is needed.  The DRAM latency of a tile's keys hides behind the value write-out of the
+// tile before, that of its values behind its own ranking.  The last, partial tile takes plain guarded loads.
 constexpr int kPThreads = 512, kPItems = 12, kPTile = kPThreads * kPItems, kPWarps = kPThreads / 32;
-constexpr int kLook = 12;                          // predecessors per thread and round trip (two halves: 24 per round)
+constexpr int kLookWindowP = 16;
 
 struct PairsSmem {
     uint64_t keys[kPTile];
@@ -442,39 +525,10 @@ struct PairsSmem {
     unsigned warp_hist[kPWarps * kRadix];
     long long gofs[kRadix];
     unsigned digit_start[kRadix];
-    unsigned long long look_sum[2][2][kRadix];     // [round parity][half][digit]
-    unsigned look_state[2][2][kRadix];             // (entries used << 2) | 0 found the prefix, 1 all ready, 2 met an unpublished tile
     unsigned scan[8];
     unsigned long long bar_keys, bar_vals;         // mbarriers
     unsigned next_tile;
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// global -> shared bulk copy (TMA, no tensor map): bytes a multiple of 16, both addresses 16-byte aligned
-__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-// generic-proxy accesses to shared memory before this point are ordered before async-proxy (TMA) writes after it
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __global__ void __launch_bounds__(kPThreads, 2)
 onesweep_pairs_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
@@ -486,11 +540,10 @@ onesweep_pairs_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict
     PairsSmem& sm = *reinterpret_cast<PairsSmem*>(smem_raw);
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned lt = lanemask_lt();
-    const unsigned digit = threadIdx.x & (kRadix - 1), half = threadIdx.x >> RB;        // look-back role
     const long long tiles = (n + TILE - 1) / TILE;
     const int warp_base = warp * ITEMS * 32;
     unsigned* my_hist = sm.warp_hist + warp * kRadix;
-    const unsigned long long my_base = digit_base[digit];
+    const unsigned long long my_base = threadIdx.x < kRadix ? digit_base[threadIdx.x] : 0ull;
 
     auto is_full = [&](long long t) { return (t + 1) * (long long)TILE <= n; };
 
@@ -520,7 +573,7 @@ onesweep_pairs_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict
         unsigned drawn = 0;
         if (threadIdx.x == 0) drawn = atomicAdd(ticket, 1u);          // the tile after this one (used ~10 us from now)
 
-        // 1. keys
+        // 1. keys, and the digit counts of this warp
         uint64_t key[ITEMS];
         if (full) {
             mbar_wait(&sm.bar_keys, phase);
@@ -533,12 +586,45 @@ onesweep_pairs_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict
                 key[i] = e < count ? keys_in[tile_base + e] : ~0ull;
             }
         }
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) red_shared_inc(&my_hist[(unsigned)(key[i] >> shift) & (unsigned)(kRadix - 1)]);
+        __syncthreads();
 
-        // 2. rank inside the warp
+        // 2. tile histogram -> aggregate for the look-back (published before the ranking), digit starts
+        unsigned total = 0;
+        if (threadIdx.x < kRadix) {
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) total += sm.warp_hist[w * kRadix + threadIdx.x];
+            const unsigned with_padding = total;
+            if (threadIdx.x == kRadix - 1) total -= (unsigned)(TILE - count);     // padding keys are all the last digit
+            st_relaxed_u64(&status[(size_t)tile * kRadix + threadIdx.x],
+                           (unsigned long long)total | (tile == 0 ? kFlagPrefix : kFlagAgg));
+            const unsigned incl = warp_incl_sum(with_padding);
+            if (lane == 31) sm.scan[warp] = incl;
+            sm.digit_start[threadIdx.x] = incl - with_padding;
+        }
+        if (threadIdx.x == 0) sm.next_tile = drawn;
+        __syncthreads();
+        if (threadIdx.x < kRadix) {
+            unsigned at = sm.digit_start[threadIdx.x];
+            for (unsigned w = 0; w < warp; w++) at += sm.scan[w];
+            sm.digit_start[threadIdx.x] = at;
+            // where the first key of digit d in warp w lands: digit start + keys of d in the warps before w
+#pragma unroll
+            for (int w = 0; w < WARPS; w++) {
+                const unsigned c = sm.warp_hist[w * kRadix + threadIdx.x];
+                sm.warp_hist[w * kRadix + threadIdx.x] = at;
+                at += c;
+            }
+        }
+        __syncthreads();
+
+        // 3. rank inside the warp: my_hist[d] is the next free position of digit d for this warp, so the rank is the
+        //    position of the pair in the reordered tile (padding keys are the last digit and rank last: >= count)
         unsigned rank2[ITEMS / 2];
         rank_in_warp<ITEMS>(key, shift, my_hist, lt, rank2);
 
-        // 3. values
+        // 4. values
         uint32_t val[ITEMS];
         if (full) {
             mbar_wait(&sm.bar_vals, phase);
@@ -552,122 +638,56 @@ onesweep_pairs_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict
             }
         }
         if (full) phase ^= 1u;
-        __syncthreads();                              // the whole image is in registers; the warp counters are complete
+        __syncthreads();                              // the whole image is in registers
 
-        // 4. per-warp counts -> exclusive warp offsets, tile histogram, aggregate, digit starts
-        unsigned total = 0;
-        if (threadIdx.x < kRadix) {
-#pragma unroll
-            for (int w = 0; w < WARPS; w++) {
-                const unsigned c = sm.warp_hist[w * kRadix + threadIdx.x];
-                sm.warp_hist[w * kRadix + threadIdx.x] = total;
-                total += c;
-            }
-            if (threadIdx.x == kRadix - 1) total -= (unsigned)(TILE - count);     // padding keys are all the last digit
-            st_relaxed_u64(&status[(size_t)tile * kRadix + threadIdx.x],
-                           (unsigned long long)total | (tile == 0 ? kFlagPrefix : kFlagAgg));
-            const unsigned incl = warp_incl_sum(total);
-            if (lane == 31) sm.scan[warp] = incl;
-            sm.digit_start[threadIdx.x] = incl - total;
-        }
-        if (threadIdx.x == 0) sm.next_tile = drawn;
-        __syncthreads();
-        if (threadIdx.x < kRadix) {
-            unsigned base = 0;
-            for (unsigned w = 0; w < warp; w++) base += sm.scan[w];
-            sm.digit_start[threadIdx.x] += base;
-        }
-        __syncthreads();
-
-        // 5. reorder in place (padding keys are the last digit and rank last: they land at >= count)
+        // 5. reorder in place
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
-            const unsigned d = (unsigned)(key[i] >> shift) & (unsigned)(kRadix - 1);
-            const unsigned pos = sm.digit_start[d] + my_hist[d] + ((i & 1) ? rank2[i >> 1] >> 16 : rank2[i >> 1] & 0xffffu);
+            const unsigned pos = (i & 1) ? rank2[i >> 1] >> 16 : rank2[i >> 1] & 0xffffu;
             sm.keys[pos] = key[i];
             sm.vals[pos] = val[i];
         }
 
-        // 6. decoupled look-back by all threads: (digit, half) looks at predecessors t - half * kLook - j, j < kLook
-        {
+        // 6. decoupled look-back, kLookWindowP predecessors per round trip (their aggregates are microseconds old by now)
+        if (threadIdx.x < kRadix) {
             unsigned long long excl = 0;
             long long t = tile - 1;
             bool done = tile == 0;
-            unsigned par = 0;
-            while (true) {
-                if (__syncthreads_and(done)) break;               // also: the slots of two rounds ago are free again
-                if (!done) {
-                    unsigned long long v[kLook];
-                    const long long first = t - (long long)half * kLook;
+            while (!done) {
+                unsigned long long v[kLookWindowP];
 #pragma unroll
-                    for (int j = 0; j < kLook; j++) {
-                        v[j] = first - j >= 0 ? ld_relaxed_u64(&status[(size_t)(first - j) * kRadix + digit]) : kFlagPrefix;
-                    }
-                    unsigned long long sum = 0;
-                    unsigned used = 0, state = 1;
-#pragma unroll
-                    for (int j = 0; j < kLook; j++) {
-                        const unsigned long long flag = v[j] & ~kValueMask;
-                        if (state == 1 && used == (unsigned)j) {
-                            if (flag == 0) {
-                                state = 2;
-                            } else {
-                                sum += v[j] & kValueMask;
-                                used = j + 1;
-                                if (flag == kFlagPrefix) state = 0;
-                            }
-                        }
-                    }
-                    sm.look_sum[par][half][digit] = sum;
-                    sm.look_state[par][half][digit] = (used << 2) | state;
+                for (int j = 0; j < kLookWindowP; j++) {
+                    v[j] = t - j >= 0 ? ld_relaxed_u64(&status[(size_t)(t - j) * kRadix + threadIdx.x]) : kFlagPrefix;
                 }
-                __syncthreads();
-                if (!done) {
-                    const unsigned s0 = sm.look_state[par][0][digit], s1 = sm.look_state[par][1][digit];
-                    excl += sm.look_sum[par][0][digit];
-                    if ((s0 & 3u) == 0) {
-                        done = true;
-                    } else if ((s0 & 3u) == 2) {
-                        t -= (long long)(s0 >> 2);                 // an unpublished tile in the near half: poll it again
-                    } else {
-                        excl += sm.look_sum[par][1][digit];
-                        if ((s1 & 3u) == 0) done = true;
-                        else t -= (long long)kLook + (long long)(s1 >> 2);
+                int used = 0;
+#pragma unroll
+                for (int j = 0; j < kLookWindowP; j++) {
+                    const unsigned long long flag = v[j] & ~kValueMask;
+                    if (!done && used == j && flag != 0) {
+                        excl += v[j] & kValueMask;
+                        used = j + 1;
+                        done = flag == kFlagPrefix;
                     }
                 }
-                par ^= 1u;
+                t -= used;                                   // a status word that was not ready yet is polled again
             }
-            if (threadIdx.x < kRadix) {
-                if (tile > 0) st_relaxed_u64(&status[(size_t)tile * kRadix + threadIdx.x], (excl + total) | kFlagPrefix);
-                sm.gofs[threadIdx.x] = (long long)(my_base + excl) - (long long)sm.digit_start[threadIdx.x];
-            }
+            if (tile > 0) st_relaxed_u64(&status[(size_t)tile * kRadix + threadIdx.x], (excl + total) | kFlagPrefix);
+            sm.gofs[threadIdx.x] = (long long)(my_base + excl) - (long long)sm.digit_start[threadIdx.x];
         }
         __syncthreads();
 
         const long long next = sm.next_tile;
         const bool next_full = next < tiles && is_full(next);
 
-        // 7a. keys out; destinations (below 2^31) stay in registers for the values
+        // 7a. the key image goes to registers (with the destinations, which are below 2^31): it is drained early, so that the
+        //     bulk copy of the next tile's keys has the whole write-out to land
+        uint64_t kout[ITEMS];
         unsigned dst[ITEMS];
-        if (full) {
 #pragma unroll
-            for (int i = 0; i < ITEMS; i++) {
-                const unsigned j = i * THREADS + threadIdx.x;
-                const uint64_t k = sm.keys[j];
-                dst[i] = (unsigned)(sm.gofs[(unsigned)(k >> shift) & (unsigned)(kRadix - 1)] + (long long)j);
-                keys_out[dst[i]] = k;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < ITEMS; i++) {
-                const int j = i * THREADS + threadIdx.x;
-                dst[i] = 0;
-                if (j < count) {
-                    const uint64_t k = sm.keys[j];
-                    dst[i] = (unsigned)(sm.gofs[(unsigned)(k >> shift) & (unsigned)(kRadix - 1)] + (long long)j);
-                    keys_out[dst[i]] = k;
-                }
-            }
+        for (int i = 0; i < ITEMS; i++) {
+            const int j = i * THREADS + threadIdx.x;
+            kout[i] = sm.keys[j];
+            dst[i] = (unsigned)(sm.gofs[(unsigned)(kout[i] >> shift) & (unsigned)(kRadix - 1)] + (long long)j);
         }
         __syncthreads();                              // the key image is drained
         if (threadIdx.x == 0 && next_full) {
@@ -676,15 +696,21 @@ onesweep_pairs_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict
             bulk_load(sm.keys, keys_in + (size_t)next * TILE, TILE * 8, &sm.bar_keys);
         }
 
-        // 7b. values out; warp counters zeroed for the next tile
+        // 7b. keys and values out; warp counters zeroed for the next tile
         if (full) {
 #pragma unroll
-            for (int i = 0; i < ITEMS; i++) vals_out[dst[i]] = sm.vals[i * THREADS + threadIdx.x];
+            for (int i = 0; i < ITEMS; i++) {
+                keys_out[dst[i]] = kout[i];
+                vals_out[dst[i]] = sm.vals[i * THREADS + threadIdx.x];
+            }
         } else {
 #pragma unroll
             for (int i = 0; i < ITEMS; i++) {
                 const int j = i * THREADS + threadIdx.x;
-                if (j < count) vals_out[dst[i]] = sm.vals[j];
+                if (j < count) {
+                    keys_out[dst[i]] = kout[i];
+                    vals_out[dst[i]] = sm.vals[j];
+                }
             }
         }
         {
@@ -717,6 +743,12 @@ bool use_persistent() {
     return on;
 }
 
+// GCZ_SORT_EARLY=1: the one-tile-per-CTA kernels publish their aggregates before the ranking too (A/B timing)
+bool use_early() {
+    static const bool on = [] { const char* e = getenv("GCZ_SORT_EARLY"); return e && e[0] == '1'; }();
+    return on;
+}
+
 }  // namespace
 
 int radix_sort_passes(int bits) { return (bits + RB - 1) / RB; }
@@ -734,9 +766,10 @@ int radix_sort_pairs(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n
     const int npass = radix_sort_passes(end_bit - begin_bit);
     const bool has_vals = b.vals[0] != nullptr;
     if (src && (!has_vals || begin_bit != 0 || src->n != n)) return fail(GCZ_E_ARG, "radix sort from text: arguments");
-    const OnesweepFn pairs = onesweep_kernel<kThreads, kItems, true, 2, false>;
-    const OnesweepFn keys_only = onesweep_kernel<kThreads, kItems, false, 2, false>;
-    const OnesweepFn from_text = onesweep_kernel<kThreads, kItems, true, 2, true>;
+    const bool early = use_early();
+    const OnesweepFn pairs = early ? onesweep_kernel<kThreads, kItems, true, 2, false, true> : onesweep_kernel<kThreads, kItems, true, 2, false, false>;
+    const OnesweepFn keys_only = early ? onesweep_kernel<kThreads, kItems, false, 2, false, true> : onesweep_kernel<kThreads, kItems, false, 2, false, false>;
+    const OnesweepFn from_text = early ? onesweep_kernel<kThreads, kItems, true, 2, true, true> : onesweep_kernel<kThreads, kItems, true, 2, true, false>;
     if (!ctx->sort_attr[0]) {
         GCZ_CUDA(cudaFuncSetAttribute(pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPairs));
         GCZ_CUDA(cudaFuncSetAttribute(keys_only, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemKeys));

@@ -201,30 +201,51 @@ def _shard_patterns(data, off, lo: int, hi: int):
     return sdata, np.ascontiguousarray(off[lo:hi + 1] - b)
 
 
+def _gather_device(t, *, rank: int, world: int, group=None):
+    """One device tensor per rank (equal dtype, any lengths) to rank 0 without leaving the device: lengths first, then one
+    padded gather.  Returns the list of tensors on rank 0, None elsewhere."""
+    import torch
+    dist = _dist()
+    mine = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
+    each = [torch.zeros(1, dtype=torch.int64, device=t.device) for _ in range(world)]
+    dist.all_gather(each, mine, group=group)
+    lens = [int(x.item()) for x in each]
+    width = max(lens)
+    if width == 0:
+        return [t[:0] for _ in range(world)] if rank == 0 else None
+    padded = t.reshape(-1) if t.numel() == width else torch.cat([t.reshape(-1), torch.zeros(width - t.numel(), dtype=t.dtype, device=t.device)])
+    parts = [torch.empty(width, dtype=t.dtype, device=t.device) for _ in range(world)] if rank == 0 else None
+    dist.gather(padded, parts, dst=0, group=group)
+    return [p[:n] for p, n in zip(parts, lens)] if rank == 0 else None
+
+
+def _is_cuda(device) -> bool:
+    return device is not None and str(device).startswith("cuda")
+
+
 def count_totals_sharded(gssas: Sequence, data, off, *, rank: int = 0, world: int = 1, group=None, device=None):
     """Occurrences of every pattern summed over all blocks (what `gecotools -c PATTERN` logs as "total found",
     tools/GecoMatch.java:110-133), query-sharded: int64[n_patterns] on rank 0, None elsewhere.  On a CUDA `device`
-    the shard is uploaded once, searched against every block there, reduced there, and 8 bytes per pattern come
-    back."""
+    the shard is uploaded once, searched against every block and summed there (gcz_count_multi), the shards meet on
+    rank 0's device through ONE gather, and 8 bytes per pattern come back to the host."""
     n = len(off) - 1
     lo, hi = shard_bounds(n, world)[rank]
     sdata, soff = _shard_patterns(data, off, lo, hi)
-    if device is not None and str(device).startswith("cuda") and hi > lo:
+    if _is_cuda(device):
         import torch
-        t_data, t_off = torch.from_numpy(sdata).to(device), torch.from_numpy(soff).to(device)
-        sp = torch.empty(hi - lo, dtype=torch.int64, device=device)
-        ep = torch.empty(hi - lo, dtype=torch.int64, device=device)
+        from .gssa import count_totals
         tot = torch.zeros(hi - lo, dtype=torch.int64, device=device)
-        for g in gssas:
-            g.count_batch(packed=(t_data, t_off), out=(sp, ep))
-            tot += (ep - sp + 1).clamp_(min=0)
-        local = tot.cpu().numpy()
-    else:
-        local = np.zeros(hi - lo, dtype=np.int64)
-        for g in gssas:
-            if hi > lo:
-                sp, ep = g.count_batch(packed=(sdata, soff))
-                local += np.maximum(np.asarray(ep) - np.asarray(sp) + 1, 0)
+        if hi > lo:
+            count_totals(gssas, torch.from_numpy(sdata).to(device), torch.from_numpy(soff).to(device), tot)
+        if world == 1:
+            return tot.cpu().numpy()
+        parts = _gather_device(tot, rank=rank, world=world, group=group)
+        return None if parts is None else torch.cat(parts).cpu().numpy()
+    local = np.zeros(hi - lo, dtype=np.int64)
+    for g in gssas:
+        if hi > lo:
+            sp, ep = g.count_batch(packed=(sdata, soff))
+            local += np.maximum(np.asarray(ep) - np.asarray(sp) + 1, 0)
     parts = gather_varlen(local, rank=rank, world=world, group=group, device=device)
     return None if parts is None else np.concatenate(parts)
 
@@ -240,20 +261,28 @@ def count_sharded(gssas: Sequence, data, off, *, rank: int = 0, world: int = 1, 
     lo, hi = shard_bounds(n, world)[rank]
     sdata, soff = _shard_patterns(data, off, lo, hi)
     k = len(gssas)
-    if device is not None and str(device).startswith("cuda") and hi > lo:
-        # the shard goes to the device once and is searched there against every block
+    if _is_cuda(device):
+        # the shard goes to the device once, is searched there against every block, and the intervals of all ranks meet
+        # on rank 0's device before anything is copied to the host
         import torch
-        t_data, t_off = torch.from_numpy(sdata).to(device), torch.from_numpy(soff).to(device)
         t_out = torch.empty((k, 2, hi - lo), dtype=torch.int64, device=device)
-        for b, g in enumerate(gssas):
-            g.count_batch(packed=(t_data, t_off), out=(t_out[b, 0], t_out[b, 1]))
-        local = t_out.cpu().numpy()
-    else:
-        local = np.zeros((k, 2, hi - lo), dtype=np.int64)
-        for b, g in enumerate(gssas):
-            if hi > lo:
-                sp, ep = g.count_batch(packed=(sdata, soff))
-                local[b, 0], local[b, 1] = np.asarray(sp), np.asarray(ep)
+        if hi > lo:
+            t_data, t_off = torch.from_numpy(sdata).to(device), torch.from_numpy(soff).to(device)
+            for b, g in enumerate(gssas):
+                g.count_batch(packed=(t_data, t_off), out=(t_out[b, 0], t_out[b, 1]))
+        if world == 1:
+            full = t_out.cpu().numpy()
+            return full[:, 0, :], full[:, 1, :]
+        parts = _gather_device(t_out.reshape(-1), rank=rank, world=world, group=group)
+        if parts is None:
+            return None
+        full = torch.cat([p.reshape(k, 2, -1) for p in parts], dim=2).cpu().numpy()
+        return full[:, 0, :], full[:, 1, :]
+    local = np.zeros((k, 2, hi - lo), dtype=np.int64)
+    for b, g in enumerate(gssas):
+        if hi > lo:
+            sp, ep = g.count_batch(packed=(sdata, soff))
+            local[b, 0], local[b, 1] = np.asarray(sp), np.asarray(ep)
     parts = gather_varlen(local, rank=rank, world=world, group=group, device=device)
     if parts is None:
         return None
