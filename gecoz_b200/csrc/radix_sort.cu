@@ -212,6 +212,49 @@ __device__ __forceinline__ void red_shared_inc(unsigned* p) {
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(smem_u32(p)) : "memory");
 }
 
+// ---- scan-ahead ---------------------------------------------------------------------------------------------------
+// At 25 tiles per microsecond (249 M pairs in 1.6 ms) and ~1 us for a word to travel from one SM to another through L2,
+// a decoupled look-back has ~40 unfinished predecessors to walk over, every tile, in every one of its 256 digit threads:
+// 2 - 3 dependent round trips that the whole CTA waits for (profiles/onesweep_*_r02.summary.txt).  Instead, tiles
+// publish their digit counts BEFORE they rank their keys (agg32: count | kAggReady), and ONE extra CTA does nothing but
+// follow that stream: thread d adds up the counts of digit d tile after tile (a window of kScanWindow loads in flight)
+// and writes the inclusive prefix of every tile (status: sum | kFlagPrefix).  When a tile CTA needs its global offsets,
+// ~5 us after it published, the prefix of its predecessor is one load away.
+constexpr unsigned kAggReady = 1u << 31;
+constexpr int kScanWindow = 40;
+
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(unsigned* p, unsigned v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __noinline__ void scan_ahead(long long tiles, unsigned long long* __restrict__ status) {
+    if (threadIdx.x >= kRadix) return;
+    const unsigned* agg32 = reinterpret_cast<const unsigned*>(status + (size_t)tiles * kRadix) + threadIdx.x;
+    unsigned long long* prefix = status + threadIdx.x;
+    unsigned long long run = 0;
+    long long t0 = 0;
+    while (t0 < tiles) {
+        unsigned a[kScanWindow];
+#pragma unroll
+        for (int i = 0; i < kScanWindow; i++) a[i] = t0 + i < tiles ? ld_relaxed_u32(agg32 + (size_t)(t0 + i) * kRadix) : 0u;
+        int used = 0;
+#pragma unroll
+        for (int i = 0; i < kScanWindow; i++) {
+            if (used == i && (a[i] & kAggReady)) {
+                run += a[i] & ~kAggReady;
+                st_relaxed_u64(prefix + (size_t)(t0 + i) * kRadix, run | kFlagPrefix);
+                used = i + 1;
+            }
+        }
+        t0 += used;                                      // counts that were not there yet are asked for again
+    }
+}
+
 // Ranks of a thread's ITEMS keys among the keys of its warp with the same digit, in element order (item, then lane),
 // two to a register; the warp's digit counters (my_hist, shared memory, zero on entry) end up holding the warp's counts.
 template <int ITEMS>
@@ -247,7 +290,7 @@ __device__ __forceinline__ void rank_in_warp(const uint64_t (&key)[ITEMS], int s
 //   7 write digit runs out, coalesced
 //   1' (FROM_TEXT) the tile's keys are computed from the text instead: codes to shared memory, a k-symbol window
 //      slid over ITEMS consecutive positions per thread, transposed to the warp-striped order through shared memory
-template <int THREADS, int ITEMS, bool HAS_VALS, int MIN_BLOCKS, bool FROM_TEXT, bool EARLY>
+template <int THREADS, int ITEMS, bool HAS_VALS, int MIN_BLOCKS, bool FROM_TEXT, int MODE>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
                 const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
@@ -255,8 +298,15 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
                 unsigned long long* __restrict__ status, unsigned* __restrict__ ticket, TextKeySource src) {
     constexpr int TILE = THREADS * ITEMS;
     constexpr int WARPS = THREADS / 32;
+    constexpr bool EARLY = MODE >= 1, SCAN = MODE == 2;
     static_assert(THREADS >= kRadix, "one thread per digit is needed for the look-back");
     static_assert(!FROM_TEXT || HAS_VALS, "text input produces (key, position) pairs");
+    if (SCAN) {
+        if (blockIdx.x == 0) {                        // the scanner CTA: aggregates -> inclusive prefixes, for the whole pass
+            scan_ahead((n + TILE - 1) / TILE, status);
+            return;
+        }
+    }
     static_assert(TILE * 4 >= TILE + kMaxKeySymbols + 8 + 256, "the value staging area holds the tile's symbol codes");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -347,6 +397,7 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
     unsigned* my_hist = s_warp_hist + warp * kRadix;
     uint32_t val[ITEMS];
     unsigned total = 0;
+    unsigned long long ahead = 0;                 // SCAN: the predecessor's inclusive prefix, requested before the reorder
     auto load_values = [&]() {
         if (FROM_TEXT) {
 #pragma unroll
@@ -379,8 +430,13 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
             for (int w = 0; w < WARPS; w++) total += s_warp_hist[w * kRadix + threadIdx.x];
             const unsigned with_padding = total;
             if (threadIdx.x == kRadix - 1) total -= (unsigned)(TILE - count);     // padding keys are all the last digit
-            st_relaxed_u64(&status[(size_t)tile * kRadix + threadIdx.x],
-                           (unsigned long long)total | (tile == 0 ? kFlagPrefix : kFlagAgg));
+            if (SCAN) {
+                unsigned* agg32 = reinterpret_cast<unsigned*>(status + (size_t)((n + TILE - 1) / TILE) * kRadix);
+                st_relaxed_u32(&agg32[(size_t)tile * kRadix + threadIdx.x], total | kAggReady);
+            } else {
+                st_relaxed_u64(&status[(size_t)tile * kRadix + threadIdx.x],
+                               (unsigned long long)total | (tile == 0 ? kFlagPrefix : kFlagAgg));
+            }
             const unsigned incl = warp_incl_sum(with_padding);
             if (lane == 31) s_scan[warp] = incl;
             s_digit_start[threadIdx.x] = incl - with_padding;
@@ -403,6 +459,7 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
         rank_in_warp<ITEMS>(key, shift, my_hist, lt, rank2);
         load_values();
         if (FROM_TEXT) __syncthreads();           // the symbol codes share their shared memory with the reordered values
+        if (SCAN && threadIdx.x < kRadix && tile > 0) ahead = ld_relaxed_u64(&status[(size_t)(tile - 1) * kRadix + threadIdx.x]);
         // 5e. reorder the tile in shared memory (padding keys are the last digit and rank last: they land at >= count)
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
@@ -451,9 +508,17 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
         }
     }
 
-    // 6. decoupled look-back, kLookWindow predecessors per step: their status words are loaded together so the
-    //    walk back to the nearest inclusive prefix costs one memory latency per window, not one per tile
-    if (threadIdx.x < kRadix) {
+    // 6. global offsets of the tile's digit runs
+    if (SCAN) {
+        // the scanner CTA has turned the aggregates of all earlier tiles into the inclusive prefix of tile - 1 (requested
+        // before the reorder; polled again only if it had not been written yet)
+        if (threadIdx.x < kRadix) {
+            while (tile > 0 && (ahead & ~kValueMask) == 0) ahead = ld_relaxed_u64(&status[(size_t)(tile - 1) * kRadix + threadIdx.x]);
+            s_gofs[threadIdx.x] = (long long)(digit_base[threadIdx.x] + (ahead & kValueMask)) - (long long)s_digit_start[threadIdx.x];
+        }
+    } else if (threadIdx.x < kRadix) {
+        // decoupled look-back, kWindow predecessors per step: their status words are loaded together so the walk back
+        // to the nearest inclusive prefix costs one memory latency per window, not one per tile
         unsigned long long excl = 0;
         long long t = (long long)tile - 1;
         bool done = tile == 0;
@@ -739,14 +804,15 @@ static_assert(kPTile == kTile, "both kernels cut the array into the same tiles (
 
 // GCZ_SORT_PERSISTENT=0 sends pairs through the one-tile-per-CTA kernel as well (A/B timing, tools/sortbench.py)
 bool use_persistent() {
-    static const bool on = [] { const char* e = getenv("GCZ_SORT_PERSISTENT"); return !(e && e[0] == '0'); }();
+    static const bool on = [] { const char* e = getenv("GCZ_SORT_PERSISTENT"); return e && e[0] == '1'; }();
     return on;
 }
 
-// GCZ_SORT_EARLY=1: the one-tile-per-CTA kernels publish their aggregates before the ranking too (A/B timing)
-bool use_early() {
-    static const bool on = [] { const char* e = getenv("GCZ_SORT_EARLY"); return e && e[0] == '1'; }();
-    return on;
+// GCZ_SORT_MODE (A/B timing): 0 = decoupled look-back after the ranking, 1 = aggregates published before the ranking,
+// 2 = as 1 with the scan-ahead CTA instead of the look-back
+int sort_mode() {
+    static const int mode = [] { const char* e = getenv("GCZ_SORT_MODE"); return e ? std::max(0, std::min(2, atoi(e))) : 2; }();
+    return mode;
 }
 
 }  // namespace
@@ -755,8 +821,8 @@ int radix_sort_passes(int bits) { return (bits + RB - 1) / RB; }
 
 size_t radix_sort_temp_bytes(int64_t n) {
     const int64_t tiles = (n + kTile - 1) / kTile;
-    // [8][radix] histogram + per-pass (status[tiles][radix] + ticket)
-    return 8 * (size_t)kRadix * 8 + 256 + ((size_t)tiles * kRadix * 8 + 256);
+    // [8][radix] histogram + per-pass (status[tiles][radix] u64 + agg32[tiles][radix] u32 + ticket)
+    return 8 * (size_t)kRadix * 8 + 256 + ((size_t)tiles * kRadix * 12 + 256);
 }
 
 int radix_sort_pairs(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n, int begin_bit, int end_bit,
@@ -766,10 +832,11 @@ int radix_sort_pairs(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n
     const int npass = radix_sort_passes(end_bit - begin_bit);
     const bool has_vals = b.vals[0] != nullptr;
     if (src && (!has_vals || begin_bit != 0 || src->n != n)) return fail(GCZ_E_ARG, "radix sort from text: arguments");
-    const bool early = use_early();
-    const OnesweepFn pairs = early ? onesweep_kernel<kThreads, kItems, true, 2, false, true> : onesweep_kernel<kThreads, kItems, true, 2, false, false>;
-    const OnesweepFn keys_only = early ? onesweep_kernel<kThreads, kItems, false, 2, false, true> : onesweep_kernel<kThreads, kItems, false, 2, false, false>;
-    const OnesweepFn from_text = early ? onesweep_kernel<kThreads, kItems, true, 2, true, true> : onesweep_kernel<kThreads, kItems, true, 2, true, false>;
+    const int mode = sort_mode();
+    const OnesweepFn pairs = mode == 2 ? onesweep_kernel<kThreads, kItems, true, 2, false, 2> : mode == 1 ? onesweep_kernel<kThreads, kItems, true, 2, false, 1> : onesweep_kernel<kThreads, kItems, true, 2, false, 0>;
+    const OnesweepFn keys_only = mode == 2 ? onesweep_kernel<kThreads, kItems, false, 2, false, 2> : mode == 1 ? onesweep_kernel<kThreads, kItems, false, 2, false, 1> : onesweep_kernel<kThreads, kItems, false, 2, false, 0>;
+    const OnesweepFn from_text = mode == 2 ? onesweep_kernel<kThreads, kItems, true, 2, true, 2> : mode == 1 ? onesweep_kernel<kThreads, kItems, true, 2, true, 1> : onesweep_kernel<kThreads, kItems, true, 2, true, 0>;
+    const unsigned extra = mode == 2 ? 1u : 0u;             // the scanner CTA
     if (!ctx->sort_attr[0]) {
         GCZ_CUDA(cudaFuncSetAttribute(pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPairs));
         GCZ_CUDA(cudaFuncSetAttribute(keys_only, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemKeys));
@@ -780,7 +847,7 @@ int radix_sort_pairs(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n
     auto* hist = static_cast<unsigned long long*>(temp);
     auto* status = hist + 8 * kRadix + 32;
     const int64_t tiles = (n + kTile - 1) / kTile;
-    auto* ticket = reinterpret_cast<unsigned*>(status + (size_t)tiles * kRadix);
+    auto* ticket = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned*>(status + (size_t)tiles * kRadix) + (size_t)tiles * kRadix);
     const TextKeySource none;
 
     GCZ_CUDA(cudaMemsetAsync(hist, 0, (size_t)8 * kRadix * 8, st));
@@ -798,7 +865,7 @@ int radix_sort_pairs(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n
     const bool aligned = ((reinterpret_cast<uintptr_t>(b.keys[0]) | reinterpret_cast<uintptr_t>(b.keys[1]) |
                            reinterpret_cast<uintptr_t>(b.vals[0]) | reinterpret_cast<uintptr_t>(b.vals[1])) & 15) == 0;
     for (int p = 0; p < npass; p++) {
-        GCZ_CUDA(cudaMemsetAsync(status, 0, (size_t)tiles * kRadix * 8 + 64, st));
+        GCZ_CUDA(cudaMemsetAsync(status, 0, (size_t)tiles * kRadix * 12 + 64, st));
         const int in = b.cur, out = b.cur ^ 1;
         const int shift = begin_bit + RB * p;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -807,17 +874,17 @@ int radix_sort_pairs(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n
             GCZ_CUDA(cudaEventRecord(e0, st));
         }
         if (src && p == 0) {
-            from_text<<<(unsigned)tiles, kThreads, kSmemPairs, st>>>(nullptr, b.keys[out], nullptr, b.vals[out], n, shift,
+            from_text<<<(unsigned)tiles + extra, kThreads, kSmemPairs, st>>>(nullptr, b.keys[out], nullptr, b.vals[out], n, shift,
                                                                      hist + p * kRadix, status, ticket, *src);
         } else if (has_vals && aligned && use_persistent()) {
             const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * 2);
             onesweep_pairs_kernel<<<grid, kPThreads, sizeof(PairsSmem), st>>>(b.keys[in], b.keys[out], b.vals[in], b.vals[out], n, shift,
                                                                               hist + p * kRadix, status, ticket);
         } else if (has_vals) {
-            pairs<<<(unsigned)tiles, kThreads, kSmemPairs, st>>>(b.keys[in], b.keys[out], b.vals[in], b.vals[out], n, shift,
+            pairs<<<(unsigned)tiles + extra, kThreads, kSmemPairs, st>>>(b.keys[in], b.keys[out], b.vals[in], b.vals[out], n, shift,
                                                                  hist + p * kRadix, status, ticket, none);
         } else {
-            keys_only<<<(unsigned)tiles, kThreads, kSmemKeys, st>>>(b.keys[in], b.keys[out], nullptr, nullptr, n, shift,
+            keys_only<<<(unsigned)tiles + extra, kThreads, kSmemKeys, st>>>(b.keys[in], b.keys[out], nullptr, nullptr, n, shift,
                                                                     hist + p * kRadix, status, ticket, none);
         }
         ctx->launches++;
