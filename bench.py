@@ -383,6 +383,8 @@ class Bench:
         def e2e_step():
             return G.build_block(lr, h_text, n, 32, stage(), h_gcz, h_gcx)
 
+        e2e_infos = []
+
         def e2e_pipelined(k: int):
             # what GecozFileWriter does with its two blocks in flight per GPU: block i + 1 is counted / uploaded (the
             # library's staging stream) while block i is being built; every step still moves its own text in and its
@@ -392,7 +394,7 @@ class Bench:
                 shp = nxt.result()
                 if i + 1 < k:
                     nxt = self.stager.submit(stage)
-                G.build_block(lr, h_text, n, 32, shp, h_gcz, h_gcx)
+                e2e_infos.append(G.build_block(lr, h_text, n, 32, shp, h_gcz, h_gcx))
 
         self.wd.enter("cfg2: device-resident steps", 300)
         clocks = ClockSampler(lr)
@@ -433,7 +435,9 @@ class Bench:
                     "pipelining": "the upload + histogram of step i + 1 overlaps the build of step i (two text slots per device), as in "
                                   "GecozFileWriter; K steps timed as one region",
                     "serial": {"value": bases / 1e6 / (ms_serial_total / self.steps / 1e3), "ms_per_step": ms_serial_total / self.steps,
-                               "what": "the same calls strictly one after the other"}},
+                               "what": "the same calls strictly one after the other"},
+                    "build_call_phases_ms": {k: float(np.mean([i[k] for i in e2e_infos[-self.steps:]])) for k in
+                                             ("h2d_ms", "sort_initial_ms", "sort_refine_ms", "bwt_hswt_ms", "ssa_ms", "d2h_ms", "total_ms")}},
             "gpu_launches": int(sum(i["kernel_launches"] for i in infos)),
             "roofline": self.roofline_of(infos, n, ms_step, step_alg_bytes, self.steps),
             "parity": parity,
