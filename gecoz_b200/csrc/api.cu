@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -140,12 +141,10 @@ static int histogram_device(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_te
     return GCZ_OK;
 }
 
-// 64 bytes of a host text at fixed places: a staged copy is only used for a buffer that still shows the same bytes
-// (a buffer freed and reallocated at the same address with the same length must not find the old text)
 constexpr int64_t kStageChunk = 4 << 20;
 
-static void text_probe(const uint8_t* text, int64_t n, uint8_t out[64]) {
-    for (int i = 0; i < 64; i++) out[i] = text[(int64_t)((__int128)(n - 1) * i / 63)];
+static void text_probe(const uint8_t* text, int64_t n, uint8_t out[kProbeBytes]) {
+    for (int i = 0; i < kProbeBytes; i++) out[i] = text[(int64_t)((__int128)(n - 1) * i / (kProbeBytes - 1))];
 }
 
 static int count_symbols(int device, const uint8_t* text, int64_t n, int64_t counts[256]) {
@@ -196,8 +195,9 @@ static int count_symbols(int device, const uint8_t* text, int64_t n, int64_t cou
     cudaStream_t st = ctx->stage_stream;
     // in pieces: the small uploads of a build running on the other stream share the copy engine and must not
     // queue behind one transfer of the whole text
-    for (int64_t off = 0; off < n; off += kStageChunk) {
-        GCZ_CUDA(cudaMemcpyAsync(slot->dev + off, text + off, (size_t)std::min<int64_t>(kStageChunk, n - off), cudaMemcpyHostToDevice, st));
+    static const int64_t chunk = [] { const char* e = std::getenv("GCZ_STAGE_CHUNK_MB"); return e ? std::max<int64_t>(1, std::atol(e)) << 20 : kStageChunk; }();
+    for (int64_t off = 0; off < n; off += chunk) {
+        GCZ_CUDA(cudaMemcpyAsync(slot->dev + off, text + off, (size_t)std::min<int64_t>(chunk, n - off), cudaMemcpyHostToDevice, st));
     }
     GCZ_TRY(histogram_device(ctx, st, slot->dev, n, ctx->stage_counts));
     GCZ_CUDA(cudaMemcpyAsync(counts, ctx->stage_counts, 256 * 8, cudaMemcpyDeviceToHost, st));
@@ -238,12 +238,12 @@ static int build_block(int device, const uint8_t* text, int64_t n, int32_t sampl
     } claim{ctx};
     {
         std::lock_guard<std::mutex> l(ctx->stage_mu);
-        uint8_t probe[64];
+        uint8_t probe[kProbeBytes];
         bool probed = false;
         for (auto& c : ctx->staged) {
             if (c.state != 1 || c.host != text || c.n != n) continue;
             if (!probed) { text_probe(text, n, probe); probed = true; }
-            if (std::memcmp(probe, c.probe, 64) != 0) { c.state = 0; c.host = nullptr; continue; }     // stale
+            if (std::memcmp(probe, c.probe, kProbeBytes) != 0) { c.state = 0; c.host = nullptr; continue; }     // stale
             if (!claim.slot || c.stamp < claim.slot->stamp) claim.slot = &c;
         }
         if (claim.slot) claim.slot->state = 2;
@@ -262,6 +262,11 @@ static int build_block(int device, const uint8_t* text, int64_t n, int32_t sampl
     cudaEvent_t ev[4];
     for (auto& e : ev) GCZ_CUDA(cudaEventCreate(&e));
     GCZ_CUDA(cudaEventRecord(ev[0], st));
+    // GCZ_BUILD_TRACE=1: host wall clock at the stage boundaries of every call, one line on stderr
+    static const bool trace = [] { const char* e = std::getenv("GCZ_BUILD_TRACE"); return e && e[0] == '1'; }();
+    const auto w0 = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
+    double w_hist = 0, w_sort = 0, w_wave = 0;
 
     const uint8_t* d_text = text_staged ? claim.slot->dev : text;
     if (!text_dev) {
@@ -287,26 +292,32 @@ static int build_block(int device, const uint8_t* text, int64_t n, int32_t sampl
     for (int c = 0; c < 256; c++) {
         if ((counts[c] > 0) != (shape->bit_lengths[c] > 0)) return fail(GCZ_E_ARG, "shape does not match the text (symbol %d)", c);
     }
+    w_hist = since(w0);
 
     SuffixSortStats ss;
     // SA entries may carry their BWT symbol (no text gather afterwards); GCZ_BWT_GATHER=1 forces the gather path
     // that blocks too large for the carry take (tests)
     int carry_shift = std::getenv("GCZ_BWT_GATHER") ? 0 : 1;
     GCZ_TRY(suffix_sort(ctx, st, d_text, n, counts, d_sa, arena, &ss, &carry_shift));
+    w_sort = since(w0);
     WaveletStats ws;
-    int64_t gcx_done = 0;                     // leading bytes of the .gcx body that are already on their way (GCZ_EARLY_MARKER=1)
     GCZ_TRY(build_wavelet_structures(ctx, st, d_text, d_sa, carry_shift, sa_out != nullptr, n, shape, sf, d_bwt, d_gcz, d_gcx, arena, &ws,
-                                     gcz_dev ? nullptr : gcz_body, ctx->copy_stream, ctx->copy_event,
-                                     (gcx_dev || gcz_dev) ? nullptr : gcx_body, &gcx_done));
+                                     gcz_dev ? nullptr : gcz_body, ctx->copy_stream, ctx->copy_event));
+    w_wave = since(w0);
     GCZ_CUDA(cudaEventRecord(ev[2], st));
 
     if (!gcz_dev) GCZ_CUDA(cudaStreamWaitEvent(st, ctx->copy_event, 0));         // the .gcz body went out while the index was built
-    if (!gcx_dev) GCZ_CUDA(cudaMemcpyAsync(gcx_body + gcx_done, d_gcx + gcx_done, (size_t)(gcx_body_len - gcx_done), cudaMemcpyDeviceToHost, st));
+    if (!gcx_dev) GCZ_CUDA(cudaMemcpyAsync(gcx_body, d_gcx, (size_t)gcx_body_len, cudaMemcpyDeviceToHost, st));
     if (sa_out && !sa_dev) GCZ_CUDA(cudaMemcpyAsync(sa_out, d_sa, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     if (bwt_out && !bwt_dev) GCZ_CUDA(cudaMemcpyAsync(bwt_out, d_bwt, (size_t)n, cudaMemcpyDeviceToHost, st));
     GCZ_CUDA(cudaEventRecord(ev[3], st));
     GCZ_CUDA(cudaEventSynchronize(ev[3]));
 
+    if (trace) {
+        std::fprintf(stderr, "[gcz build] n=%lld host wall ms: histogram %.3f, suffix sort %.3f (device: initial %.3f refine %.3f), wavelet %.3f "
+                             "(device: bwt+hswt %.3f ssa %.3f), copies out %.3f; text %s\n", (long long)n, w_hist, w_sort - w_hist, ss.initial_ms,
+                     ss.refine_ms, w_wave - w_sort, ws.bwt_hswt_ms, ws.ssa_ms, since(w0) - w_wave, text_staged ? "staged" : text_dev ? "device" : "host");
+    }
     cudaEventElapsedTime(&t_timing.h2d_ms, ev[0], ev[1]);
     cudaEventElapsedTime(&t_timing.d2h_ms, ev[2], ev[3]);
     cudaEventElapsedTime(&t_timing.total_ms, ev[0], ev[3]);

@@ -45,6 +45,11 @@ struct Arena {
     void destroy();
 };
 
+// A staged text is only used for a host buffer that still shows the same bytes at kProbeBytes evenly spaced places (a buffer
+// freed and reallocated at the same address must not find the old text).  The contract of gcz_count_symbols is that the
+// buffer does not change before gcz_build_block; the probe catches the accidents, not an adversary.
+constexpr int kProbeBytes = 2048;
+
 struct DeviceCtx {
     int          device = -1;
     int          sm_count = 0;
@@ -61,7 +66,7 @@ struct DeviceCtx {
         size_t      cap = 0;
         int         state = 0;                // 0 free, 1 staged, 2 in use by a build, 3 being filled
         uint64_t    stamp = 0;                // staging order (the older staged text is overwritten first)
-        uint8_t     probe[64] = {};           // bytes of the host buffer at fixed places, compared again at build time
+        uint8_t     probe[kProbeBytes] = {};  // bytes of the host buffer at fixed places, compared again at build time
     };
     std::mutex   stage_mu;                   // slot bookkeeping (short critical sections only)
     std::mutex   stage_io_mu;                // one staging at a time

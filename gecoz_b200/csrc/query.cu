@@ -186,8 +186,8 @@ __device__ __forceinline__ void hswt_occ2(const QueryTables* __restrict__ t, con
 // step for all 32 lanes.
 // MODE 0: (sp, ep) per pattern.  MODE 1: totals[q] += max(0, ep - sp + 1) — one block after the other of a multi-block
 // index into the same array (gcz_count_multi).  MODE 2: as 0, and the OccStats of the whole launch (gcz_count_stats).
-template <int MODE>
-__global__ void __launch_bounds__(256)
+template <int MODE, int MINB = 5>
+__global__ void __launch_bounds__(256, MINB)
 count_kernel(const QueryTables* __restrict__ tables, const uint32_t* __restrict__ sectors,
              const uint8_t* __restrict__ pats, const int64_t* __restrict__ pat_off, int64_t n_pats,
              int64_t* __restrict__ sp_out, int64_t* __restrict__ ep_out, unsigned long long* __restrict__ next_pattern,
@@ -794,11 +794,13 @@ occ_scan_kernel(const int64_t* __restrict__ sp, const int64_t* __restrict__ ep, 
 // string end (the reference's binarySearch then FINDS the key and takes its other branch) and flags[1] when a position
 // lies behind the last string end (the reference drops it): such chunks are redone by the literal loop on the host.
 __global__ void __launch_bounds__(256)
-split_by_string_kernel(const uint64_t* __restrict__ keys, int64_t n_occ, const int64_t* __restrict__ e, int32_t ns,
-                       int32_t* __restrict__ out_string, int64_t* __restrict__ out_pos, unsigned* __restrict__ flags) {
+split_by_string_kernel(const uint64_t* __restrict__ keys, int64_t n_occ, const int64_t* __restrict__ e, int32_t ns, int64_t first_pat,
+                       int64_t* __restrict__ out_pattern, int32_t* __restrict__ out_string, int64_t* __restrict__ out_pos,
+                       unsigned* __restrict__ flags) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n_occ; o += stride) {
         const long long x = (long long)(int32_t)(uint32_t)(keys[o] & 0xFFFFFFFFull);
+        out_pattern[o] = first_pat + (int64_t)(keys[o] >> 32);
         int lo = 0, hi = ns;                               // first i with e[i] >= x
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
@@ -825,22 +827,21 @@ int64_t java_binary_search(const int64_t* a, int64_t from, int64_t to, int64_t k
 
 // Hits of one block in the order GSSA.find returns them: pattern after pattern, string after string, ascending.
 struct BlockHits {
-    std::vector<int64_t> off;        // n_pats + 1
+    std::vector<int64_t> pattern;
     std::vector<int32_t> string;
     std::vector<int64_t> pos;
 };
 
 // The whole of GSSA.find for a device-resident batch against one block.  Intervals, occurrence offsets, locate, the sort
-// by (pattern, position) and the split by string ends all run on the device; what comes back is 12 bytes per hit and
-// 8 per pattern.  A chunk whose split met one of the reference's corner cases is redone literally on the host.
+// by (pattern, position) and the split by string ends all run on the device; what comes back is 20 bytes per hit and
+// nothing per pattern.  A chunk whose split met one of the reference's corner cases is redone literally on the host.
 int find_block(gcz_index* idx, cudaStream_t st, const DeviceBatch& batch, BlockHits* out) {
     DeviceCtx* ctx = idx->ctx;
     Arena& arena = ctx->arena;
     const size_t mark0 = arena.mark();
     const int64_t n_pats = batch.n;
     const int32_t ns = (int32_t)idx->e.size();
-    out->off.assign((size_t)n_pats + 1, 0);
-    out->string.clear(); out->pos.clear();
+    out->pattern.clear(); out->string.clear(); out->pos.clear();
     if (n_pats == 0) return GCZ_OK;
 
     const int64_t chunks = (n_pats + kScanChunk - 1) / kScanChunk;
@@ -881,14 +882,13 @@ int find_block(gcz_index* idx, cudaStream_t st, const DeviceBatch& batch, BlockH
             p0 = p1;
         }
     }
+    out->pattern.resize((size_t)total_occ);
     out->string.resize((size_t)total_occ);
     out->pos.resize((size_t)total_occ);
-    GCZ_CUDA(cudaMemcpyAsync(out->off.data(), d_excl, ((size_t)n_pats + 1) * 8, cudaMemcpyDeviceToHost, st));
 
-    bool literal = false;                                 // some chunk needs the reference's loop as written
     const size_t mark1 = arena.mark();
     std::vector<uint64_t> h_keys;
-    std::vector<std::pair<int64_t, int64_t>> redo;        // pattern ranges to redo literally
+    std::vector<std::pair<int64_t, int64_t>> redo;        // occurrence ranges whose split has to be redone literally
     int64_t occ_base = 0;
     for (size_t c = 0; c + 1 < cuts.size(); c++) {
         const int64_t p0 = cuts[c], p1 = cuts[c + 1], np = p1 - p0;
@@ -896,13 +896,14 @@ int find_block(gcz_index* idx, cudaStream_t st, const DeviceBatch& batch, BlockH
         if (cuts.size() > 2) n_occ = h_excl[(size_t)p1] - h_excl[(size_t)p0];
         if (n_occ == 0) continue;
         arena.release(mark1);
-        t_find_want = arena.mark() + (size_t)n_occ * 28 + radix_sort_temp_bytes(n_occ) + ((size_t)8 << 20);
+        t_find_want = arena.mark() + (size_t)n_occ * 36 + radix_sort_temp_bytes(n_occ) + ((size_t)8 << 20);
         uint64_t* d_k0 = arena.get<uint64_t>((size_t)n_occ);
         uint64_t* d_k1 = arena.get<uint64_t>((size_t)n_occ);
         void* d_tmp = arena.raw(radix_sort_temp_bytes(n_occ));
+        int64_t* d_pat = arena.get<int64_t>((size_t)n_occ);
         int32_t* d_str = arena.get<int32_t>((size_t)n_occ);
         int64_t* d_pos = arena.get<int64_t>((size_t)n_occ);
-        if (!d_k0 || !d_k1 || !d_tmp || !d_str || !d_pos) return fail(GCZ_E_NOMEM, "find workspace for %lld occurrences", (long long)n_occ);
+        if (!d_k0 || !d_k1 || !d_tmp || !d_pat || !d_str || !d_pos) return fail(GCZ_E_NOMEM, "find workspace for %lld occurrences", (long long)n_occ);
         GCZ_LAUNCH(ctx, locate_occurrences_kernel, launch_grid(ctx, n_occ, 256), 256, 0, st, idx->d_tables, idx->d_sectors,
                    d_sp, d_excl, p0, np, occ_base, n_occ, d_k0);
         RadixBuffers rb;
@@ -912,55 +913,57 @@ int find_block(gcz_index* idx, cudaStream_t st, const DeviceBatch& batch, BlockH
         GCZ_TRY(radix_sort_pairs(ctx, st, rb, n_occ, 0, 32 + pat_bits, d_tmp, nullptr));
         unsigned* d_flags = reinterpret_cast<unsigned*>(d_next + 2);
         GCZ_CUDA(cudaMemsetAsync(d_flags, 0, 8, st));
-        GCZ_LAUNCH(ctx, split_by_string_kernel, launch_grid(ctx, n_occ, 256), 256, 0, st, rb.keys[rb.cur], n_occ, d_e, ns, d_str, d_pos, d_flags);
+        GCZ_LAUNCH(ctx, split_by_string_kernel, launch_grid(ctx, n_occ, 256), 256, 0, st, rb.keys[rb.cur], n_occ, d_e, ns, p0, d_pat, d_str, d_pos, d_flags);
         unsigned h_flags[2] = { 0, 0 };
         GCZ_CUDA(cudaMemcpyAsync(h_flags, d_flags, 8, cudaMemcpyDeviceToHost, st));
+        GCZ_CUDA(cudaMemcpyAsync(out->pattern.data() + occ_base, d_pat, (size_t)n_occ * 8, cudaMemcpyDeviceToHost, st));
         GCZ_CUDA(cudaMemcpyAsync(out->string.data() + occ_base, d_str, (size_t)n_occ * 4, cudaMemcpyDeviceToHost, st));
         GCZ_CUDA(cudaMemcpyAsync(out->pos.data() + occ_base, d_pos, (size_t)n_occ * 8, cudaMemcpyDeviceToHost, st));
         GCZ_CUDA(cudaStreamSynchronize(st));
         if (h_flags[0] || h_flags[1]) {
             // keep the sorted text positions of this chunk in out->pos (sign-extended, as the reference's long[] holds them)
-            literal = true;
             h_keys.resize((size_t)n_occ);
             GCZ_CUDA(cudaMemcpyAsync(h_keys.data(), rb.keys[rb.cur], (size_t)n_occ * 8, cudaMemcpyDeviceToHost, st));
             GCZ_CUDA(cudaStreamSynchronize(st));
-            for (int64_t o = 0; o < n_occ; o++) {
-                out->pos[(size_t)(occ_base + o)] = (int64_t)(int32_t)(uint32_t)(h_keys[(size_t)o] & 0xFFFFFFFFull);
-                out->string[(size_t)(occ_base + o)] = -2;                 // marks "not split yet"
-            }
-            redo.emplace_back(p0, p1);
+            for (int64_t o = 0; o < n_occ; o++) out->pos[(size_t)(occ_base + o)] = (int64_t)(int32_t)(uint32_t)(h_keys[(size_t)o] & 0xFFFFFFFFull);
+            redo.emplace_back(occ_base, occ_base + n_occ);
         }
         occ_base += n_occ;
     }
     arena.release(mark0);
-    if (!literal) return GCZ_OK;
+    if (redo.empty()) return GCZ_OK;
 
     // GSSA.find :170-184 as written, for the chunks that asked for it; hits may be fewer than occurrences afterwards
     BlockHits fixed;
-    fixed.off.assign((size_t)n_pats + 1, 0);
-    fixed.string.reserve(out->string.size());
-    fixed.pos.reserve(out->pos.size());
+    fixed.pattern.reserve(out->pos.size()); fixed.string.reserve(out->pos.size()); fixed.pos.reserve(out->pos.size());
     size_t r = 0;
-    for (int64_t p = 0; p < n_pats; p++) {
-        while (r < redo.size() && p >= redo[r].second) r++;
-        const bool lit = r < redo.size() && p >= redo[r].first && p < redo[r].second;
-        const int64_t first = out->off[(size_t)p], k = out->off[(size_t)p + 1] - first;
-        if (!lit) {
-            fixed.string.insert(fixed.string.end(), out->string.begin() + first, out->string.begin() + first + k);
-            fixed.pos.insert(fixed.pos.end(), out->pos.begin() + first, out->pos.begin() + first + k);
-        } else {
-            const int64_t* sa = out->pos.data() + first;
-            int64_t idx1 = 0;
-            for (int64_t i = 0; i < ns && k > 0; i++) {
-                const int64_t idx2 = -java_binary_search(sa, idx1, k, idx->e[(size_t)i]) - 1;
-                if (idx2 > idx1) {
-                    const int64_t start = i > 0 ? idx->e[(size_t)i - 1] + 1 : 0;
-                    for (int64_t j = idx1; j < idx2; j++) { fixed.string.push_back((int32_t)i); fixed.pos.push_back(sa[j] - start); }
-                    idx1 = idx2;
-                }
+    const int64_t total = (int64_t)out->pos.size();
+    int64_t o = 0;
+    while (o < total) {
+        while (r < redo.size() && o >= redo[r].second) r++;
+        if (!(r < redo.size() && o >= redo[r].first)) {                  // a chunk the device split completely
+            const int64_t end = r < redo.size() ? redo[r].first : total;
+            fixed.pattern.insert(fixed.pattern.end(), out->pattern.begin() + o, out->pattern.begin() + end);
+            fixed.string.insert(fixed.string.end(), out->string.begin() + o, out->string.begin() + end);
+            fixed.pos.insert(fixed.pos.end(), out->pos.begin() + o, out->pos.begin() + end);
+            o = end;
+            continue;
+        }
+        // the occurrences of one pattern: out->pos holds their sorted text positions
+        const int64_t p = out->pattern[(size_t)o];
+        int64_t k = 1;
+        while (o + k < redo[r].second && out->pattern[(size_t)(o + k)] == p) k++;
+        const int64_t* sa = out->pos.data() + o;
+        int64_t idx1 = 0;
+        for (int64_t i = 0; i < ns; i++) {
+            const int64_t idx2 = -java_binary_search(sa, idx1, k, idx->e[(size_t)i]) - 1;
+            if (idx2 > idx1) {
+                const int64_t start = i > 0 ? idx->e[(size_t)i - 1] + 1 : 0;
+                for (int64_t j = idx1; j < idx2; j++) { fixed.pattern.push_back(p); fixed.string.push_back((int32_t)i); fixed.pos.push_back(sa[j] - start); }
+                idx1 = idx2;
             }
         }
-        fixed.off[(size_t)p + 1] = (int64_t)fixed.pos.size();
+        o += k;
     }
     *out = std::move(fixed);
     return GCZ_OK;
@@ -1036,8 +1039,14 @@ int count_multi(gcz_index* const* blocks, int32_t n_blocks, const uint8_t* pats,
             attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
             GCZ_CUDA(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
         }
-        GCZ_LAUNCH(ctx, count_kernel<1>, count_grid(ctx, n_pats), 256, 0, st, blocks[b]->d_tables, blocks[b]->d_sectors, batch.pats, batch.off,
-                   n_pats, d_tot, (int64_t*)nullptr, d_next + b, (unsigned long long*)nullptr);
+        static const bool dense = [] { const char* e = std::getenv("GCZ_COUNT_OCC6"); return e && e[0] == '1'; }();
+        if (dense) {
+            GCZ_LAUNCH(ctx, (count_kernel<1, 6>), count_grid(ctx, n_pats), 256, 0, st, blocks[b]->d_tables, blocks[b]->d_sectors, batch.pats, batch.off,
+                       n_pats, d_tot, (int64_t*)nullptr, d_next + b, (unsigned long long*)nullptr);
+        } else {
+            GCZ_LAUNCH(ctx, count_kernel<1>, count_grid(ctx, n_pats), 256, 0, st, blocks[b]->d_tables, blocks[b]->d_sectors, batch.pats, batch.off,
+                       n_pats, d_tot, (int64_t*)nullptr, d_next + b, (unsigned long long*)nullptr);
+        }
     }
     if (window_mb > 0) {
         cudaStreamAttrValue attr;
@@ -1136,7 +1145,7 @@ int find_multi(gcz_index* const* blocks, int32_t n_blocks, const uint8_t* pats, 
     cudaStream_t st = stream_of(ctx);
     ctx->arena.reset();
     // the batch, the intervals and offsets of one block, and room for the occurrence keys of a typical batch up front
-    const size_t need = batch_bytes(pats, pat_off, n_pats) + (size_t)n_pats * 40 + ((size_t)64 << 20);
+    const size_t need = batch_bytes(pats, pat_off, n_pats) + (size_t)n_pats * 40 + ((size_t)96 << 20);
     if (ctx->arena.capacity < need) GCZ_TRY(ctx->arena.reserve(need));
     DeviceBatch batch;
     if (n_pats > 0) GCZ_TRY(stage_batch(st, ctx->arena, pats, pat_off, n_pats, &batch));
@@ -1175,10 +1184,8 @@ int find_multi(gcz_index* const* blocks, int32_t n_blocks, const uint8_t* pats, 
     for (int32_t b = 0; b < n_blocks; b++) {
         const BlockHits& h = per[(size_t)b];
         out->block_off[b] = at;
-        for (int64_t p = 0; p < n_pats; p++) {
-            for (int64_t j = h.off[(size_t)p]; j < h.off[(size_t)p + 1]; j++) out->pattern[at + j] = p;
-        }
         if (!h.pos.empty()) {
+            std::memcpy(out->pattern + at, h.pattern.data(), h.pattern.size() * 8);
             std::memcpy(out->string + at, h.string.data(), h.string.size() * 4);
             std::memcpy(out->position + at, h.pos.data(), h.pos.size() * 8);
         }

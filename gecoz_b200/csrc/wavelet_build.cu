@@ -697,10 +697,8 @@ size_t wavelet_workspace_bytes(int64_t n, int sampling_factor) {
 int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, uint32_t* d_sa, int carry_shift, bool clean_sa,
                              int64_t n, const gcz_shape* shape, int sampling_factor, uint8_t* d_bwt,
                              uint8_t* d_gcz_body, uint8_t* d_gcx_body, Arena& arena, WaveletStats* stats,
-                             uint8_t* h_gcz_out, cudaStream_t copy_stream, cudaEvent_t gcz_copied,
-                             uint8_t* h_gcx_out, int64_t* gcx_bytes_copied) {
+                             uint8_t* h_gcz_out, cudaStream_t copy_stream, cudaEvent_t gcz_copied) {
     const size_t mark0 = arena.mark();
-    if (gcx_bytes_copied) *gcx_bytes_copied = 0;
     // ---- host tables -------------------------------------------------------------------------------
     SymbolTables h_tab;
     std::memset(&h_tab, 0, sizeof(h_tab));

@@ -18,11 +18,9 @@ size_t wavelet_workspace_bytes(int64_t n, int sampling_factor);
 int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, uint32_t* d_sa, int carry_shift, bool clean_sa,
                              int64_t n, const gcz_shape* shape, int sampling_factor, uint8_t* d_bwt,
                              uint8_t* d_gcz_body, uint8_t* d_gcx_body, Arena& arena, WaveletStats* stats,
-                             uint8_t* h_gcz_out = nullptr, cudaStream_t copy_stream = nullptr, cudaEvent_t gcz_copied = nullptr,
-                             uint8_t* h_gcx_out = nullptr, int64_t* gcx_bytes_copied = nullptr);
+                             uint8_t* h_gcz_out = nullptr, cudaStream_t copy_stream = nullptr, cudaEvent_t gcz_copied = nullptr);
 // h_gcz_out (optional, host): the finished .gcz body is copied there on copy_stream while the index is still being
-// built; gcz_copied is recorded on copy_stream after that copy (the caller waits for it).  h_gcx_out (optional, host,
-// with GCZ_EARLY_MARKER=1 only): the leading *gcx_bytes_copied bytes of the .gcx body (the marker vector) go the same way.
+// built; gcz_copied is recorded on copy_stream after that copy (the caller waits for it).
 
 // stage hooks (parity tests)
 int ranked_vector_from_bits(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_bits, int64_t len, uint8_t* d_out, Arena& arena);
