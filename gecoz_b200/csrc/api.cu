@@ -193,11 +193,22 @@ static int count_symbols(int device, const uint8_t* text, int64_t n, int64_t cou
         slot->cap = want;
     }
     cudaStream_t st = ctx->stage_stream;
-    // in pieces: the small uploads of a build running on the other stream share the copy engine and must not
-    // queue behind one transfer of the whole text
-    static const int64_t chunk = [] { const char* e = std::getenv("GCZ_STAGE_CHUNK_MB"); return e ? std::max<int64_t>(1, std::atol(e)) << 20 : kStageChunk; }();
-    for (int64_t off = 0; off < n; off += chunk) {
-        GCZ_CUDA(cudaMemcpyAsync(slot->dev + off, text + off, (size_t)std::min<int64_t>(chunk, n - off), cudaMemcpyHostToDevice, st));
+    // In pieces, and never more than two of them queued: the small uploads of a build running on the other stream share
+    // the copy engine, which serves its queue in order — with the whole text queued at once, a 256-byte table of the build
+    // waited 4.5 ms for it (every other build of a pipelined writer: GCZ_BUILD_TRACE=1, profiles/e2e_staging_r02.md).
+    {
+        cudaEvent_t piece[2] = { nullptr, nullptr };
+        GCZ_CUDA(cudaEventCreateWithFlags(&piece[0], cudaEventDisableTiming));
+        GCZ_CUDA(cudaEventCreateWithFlags(&piece[1], cudaEventDisableTiming));
+        int k = 0;
+        cudaError_t err = cudaSuccess;
+        for (int64_t off = 0; off < n && err == cudaSuccess; off += kStageChunk, k++) {
+            if (k >= 2) err = cudaEventSynchronize(piece[k & 1]);          // the piece before the previous one has landed
+            if (err == cudaSuccess) err = cudaMemcpyAsync(slot->dev + off, text + off, (size_t)std::min<int64_t>(kStageChunk, n - off), cudaMemcpyHostToDevice, st);
+            if (err == cudaSuccess) err = cudaEventRecord(piece[k & 1], st);
+        }
+        cudaEventDestroy(piece[0]); cudaEventDestroy(piece[1]);
+        GCZ_CUDA(err);
     }
     GCZ_TRY(histogram_device(ctx, st, slot->dev, n, ctx->stage_counts));
     GCZ_CUDA(cudaMemcpyAsync(counts, ctx->stage_counts, 256 * 8, cudaMemcpyDeviceToHost, st));

@@ -114,6 +114,14 @@ def main():
             c = sharding.count_sharded(gssas, data, off, rank=rank, world=world)
             f = sharding.find_sharded(gssas, data, off, rank=rank, world=world)
             tot = sharding.count_totals_sharded(gssas, data, off, rank=rank, world=world)
+            # the gather the CUDA paths use (tensors stay where they are: here on the CPU), shards of unequal and of zero length
+            import torch
+            for lens in ([3, 5], [0, 4], [2, 0], [0, 0]):
+                parts = sharding._gather_device(torch.arange(lens[rank], dtype=torch.int64) + 100 * rank, rank=rank, world=world)
+                if rank == 0:
+                    assert [p.tolist() for p in parts] == [list(range(100 * r, 100 * r + lens[r])) for r in range(world)]
+                else:
+                    assert parts is None
             if rank == 0:
                 assert np.array_equal(tot, np.maximum(c[1] - c[0] + 1, 0).sum(axis=0))
                 np.savez(out_dir / "query.npz", sp=c[0], ep=c[1],
