@@ -93,6 +93,7 @@ void destroy_all_ctx() {
         if (kv.second->stage_stream) cudaStreamDestroy(kv.second->stage_stream);
         if (kv.second->stage_counts) cudaFree(kv.second->stage_counts);
         for (auto& slot : kv.second->staged) if (slot.dev) cudaFree(slot.dev);
+        for (auto& slot : kv.second->out_slot) { if (slot.dev) cudaFree(slot.dev); if (slot.done) cudaEventDestroy(slot.done); }
     }
     g_ctx.clear();
 }
@@ -217,6 +218,7 @@ static int count_symbols(int device, const uint8_t* text, int64_t n, int64_t cou
         std::lock_guard<std::mutex> l(ctx->stage_mu);
         slot->host = text; slot->n = n; slot->state = 1; slot->stamp = ++ctx->stage_clock;
         text_probe(text, n, slot->probe);
+        std::memcpy(slot->counts, counts, sizeof(slot->counts));
         fill.done = true;
     }
     return GCZ_OK;
@@ -236,8 +238,32 @@ static int build_block(int device, const uint8_t* text, int64_t n, int32_t sampl
 
     DeviceCtx* ctx = nullptr;
     GCZ_TRY(get_ctx(device, &ctx));
-    std::lock_guard<std::mutex> lock(ctx->mu);
     GCZ_CUDA(cudaSetDevice(ctx->device));
+    // both bodies go to host buffers and no parity artefact is asked for: they are built in an output slot outside the
+    // arena, and the device is released before their copies have landed (see DeviceCtx::OutSlot)
+    const bool tail_overlap = !is_device_ptr(gcz_body) && !is_device_ptr(gcx_body) && !sa_out && !bwt_out;
+    struct SlotHold {
+        DeviceCtx* ctx; DeviceCtx::OutSlot* slot = nullptr;
+        ~SlotHold() { if (slot) { { std::lock_guard<std::mutex> l(ctx->out_mu); slot->busy = false; } ctx->out_cv.notify_all(); } }
+    } hold{ctx};
+    if (tail_overlap) {
+        std::unique_lock<std::mutex> l(ctx->out_mu);
+        ctx->out_cv.wait(l, [&] { return !ctx->out_slot[0].busy || !ctx->out_slot[1].busy; });
+        hold.slot = !ctx->out_slot[0].busy ? &ctx->out_slot[0] : &ctx->out_slot[1];
+        hold.slot->busy = true;
+        l.unlock();
+        const size_t want = (((size_t)gcz_body_len + 511) & ~size_t(255)) + (size_t)gcx_body_len + 512;
+        if (hold.slot->cap < want) {
+            if (hold.slot->dev) cudaFree(hold.slot->dev);
+            hold.slot->dev = nullptr; hold.slot->cap = 0;
+            const size_t rounded = (want + ((size_t)8 << 20)) & ~(((size_t)1 << 20) - 1);
+            cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&hold.slot->dev), rounded);
+            if (e != cudaSuccess) { cudaGetLastError(); hold.slot->dev = nullptr; return fail(GCZ_E_NOMEM, "output staging of %zu bytes", rounded); }
+            hold.slot->cap = rounded;
+        }
+        if (!hold.slot->done) GCZ_CUDA(cudaEventCreate(&hold.slot->done));
+    }
+    std::unique_lock<std::mutex> lock(ctx->mu);
     cudaStream_t st = stream_of(ctx);
     const int64_t launches0 = ctx->launches;
     std::memset(&t_timing, 0, sizeof(t_timing));
@@ -264,7 +290,7 @@ static int build_block(int device, const uint8_t* text, int64_t n, int32_t sampl
     const bool sa_dev = sa_out && is_device_ptr(sa_out), bwt_dev = bwt_out && is_device_ptr(bwt_out);
 
     const size_t fixed = (text_dev ? 0 : (size_t)n + 256) + (size_t)n * 4 + (size_t)n + 256 +
-                         (gcz_dev ? 0 : (size_t)gcz_body_len + 256) + (gcx_dev ? 0 : (size_t)gcx_body_len + 256) + 4096;
+                         ((gcz_dev || tail_overlap) ? 0 : (size_t)gcz_body_len + 256) + ((gcx_dev || tail_overlap) ? 0 : (size_t)gcx_body_len + 256) + 4096;
     const size_t need = fixed + std::max(suffix_sort_workspace_bytes(n), wavelet_workspace_bytes(n, sf)) + ((size_t)8 << 20);
     ctx->arena.reset();
     if (ctx->arena.capacity < need) GCZ_TRY(ctx->arena.reserve(need));
@@ -288,20 +314,34 @@ static int build_block(int device, const uint8_t* text, int64_t n, int32_t sampl
     }
     uint32_t* d_sa = (sa_dev) ? reinterpret_cast<uint32_t*>(sa_out) : arena.get<uint32_t>((size_t)n);
     uint8_t* d_bwt = (bwt_dev) ? bwt_out : arena.get<uint8_t>((size_t)n + 64);
-    uint8_t* d_gcz = gcz_dev ? gcz_body : arena.get<uint8_t>((size_t)gcz_body_len + 64);
-    uint8_t* d_gcx = gcx_dev ? gcx_body : arena.get<uint8_t>((size_t)gcx_body_len + 64);
+    uint8_t* d_gcz = gcz_dev ? gcz_body : tail_overlap ? hold.slot->dev : arena.get<uint8_t>((size_t)gcz_body_len + 64);
+    uint8_t* d_gcx = gcx_dev ? gcx_body : tail_overlap ? hold.slot->dev + (((size_t)gcz_body_len + 511) & ~size_t(255))
+                                                       : arena.get<uint8_t>((size_t)gcx_body_len + 64);
     unsigned long long* d_counts = arena.get<unsigned long long>(256);
     if (!d_sa || !d_bwt || !d_gcz || !d_gcx || !d_counts) return fail(GCZ_E_NOMEM, "block buffers for n=%lld", (long long)n);
     GCZ_CUDA(cudaEventRecord(ev[1], st));
 
-    // the histogram is recomputed on the device: it both drives the key packer and guards against a shape
-    // that belongs to another text (the reference trusts its caller; a mismatch there corrupts the file)
-    GCZ_TRY(histogram_device(ctx, st, d_text, n, d_counts));
+    // the histogram drives the key packer and guards against a shape that belongs to another text (the reference trusts
+    // its caller; a mismatch there corrupts the file).  A staged text brings the histogram gcz_count_symbols computed from
+    // the same device copy; anything else is counted here.
     int64_t counts[256];
-    GCZ_CUDA(cudaMemcpyAsync(counts, d_counts, sizeof(counts), cudaMemcpyDeviceToHost, st));
-    GCZ_CUDA(cudaStreamSynchronize(st));
+    if (text_staged) {
+        std::memcpy(counts, claim.slot->counts, sizeof(counts));
+    } else {
+        GCZ_TRY(histogram_device(ctx, st, d_text, n, d_counts));
+        GCZ_CUDA(cudaMemcpyAsync(counts, d_counts, sizeof(counts), cudaMemcpyDeviceToHost, st));
+        GCZ_CUDA(cudaStreamSynchronize(st));
+    }
     for (int c = 0; c < 256; c++) {
         if ((counts[c] > 0) != (shape->bit_lengths[c] > 0)) return fail(GCZ_E_ARG, "shape does not match the text (symbol %d)", c);
+    }
+    {
+        // the exact test: the shape this text's histogram gives must be the one the caller sized the file slices with
+        gcz_shape mine;
+        GCZ_TRY(shape_from_counts(counts, &mine));
+        if (mine.size != shape->size || std::memcmp(mine.bit_lengths, shape->bit_lengths, sizeof(mine.bit_lengths)) != 0 ||
+            mine.n_nodes != shape->n_nodes || std::memcmp(mine.node_bits, shape->node_bits, sizeof(int64_t) * (size_t)mine.n_nodes) != 0)
+            return fail(GCZ_E_ARG, "shape does not match the text (it was built from another histogram)");
     }
     w_hist = since(w0);
 
@@ -317,12 +357,23 @@ static int build_block(int device, const uint8_t* text, int64_t n, int32_t sampl
     w_wave = since(w0);
     GCZ_CUDA(cudaEventRecord(ev[2], st));
 
-    if (!gcz_dev) GCZ_CUDA(cudaStreamWaitEvent(st, ctx->copy_event, 0));         // the .gcz body went out while the index was built
-    if (!gcx_dev) GCZ_CUDA(cudaMemcpyAsync(gcx_body, d_gcx, (size_t)gcx_body_len, cudaMemcpyDeviceToHost, st));
-    if (sa_out && !sa_dev) GCZ_CUDA(cudaMemcpyAsync(sa_out, d_sa, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    if (bwt_out && !bwt_dev) GCZ_CUDA(cudaMemcpyAsync(bwt_out, d_bwt, (size_t)n, cudaMemcpyDeviceToHost, st));
-    GCZ_CUDA(cudaEventRecord(ev[3], st));
-    GCZ_CUDA(cudaEventSynchronize(ev[3]));
+    const int64_t launches = ctx->launches - launches0;
+    if (tail_overlap) {
+        // the kernels are done (build_wavelet_structures waits for them to read its stage times): the .gcx body follows the
+        // .gcz body on the copy stream, the device goes to the next block, and this call waits for its own copies only
+        GCZ_CUDA(cudaMemcpyAsync(gcx_body, d_gcx, (size_t)gcx_body_len, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        GCZ_CUDA(cudaEventRecord(ev[3], ctx->copy_stream));
+        GCZ_CUDA(cudaEventRecord(hold.slot->done, ctx->copy_stream));
+        lock.unlock();
+        GCZ_CUDA(cudaEventSynchronize(hold.slot->done));
+    } else {
+        if (!gcz_dev) GCZ_CUDA(cudaStreamWaitEvent(st, ctx->copy_event, 0));         // the .gcz body went out while the index was built
+        if (!gcx_dev) GCZ_CUDA(cudaMemcpyAsync(gcx_body, d_gcx, (size_t)gcx_body_len, cudaMemcpyDeviceToHost, st));
+        if (sa_out && !sa_dev) GCZ_CUDA(cudaMemcpyAsync(sa_out, d_sa, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        if (bwt_out && !bwt_dev) GCZ_CUDA(cudaMemcpyAsync(bwt_out, d_bwt, (size_t)n, cudaMemcpyDeviceToHost, st));
+        GCZ_CUDA(cudaEventRecord(ev[3], st));
+        GCZ_CUDA(cudaEventSynchronize(ev[3]));
+    }
 
     if (trace) {
         std::fprintf(stderr, "[gcz build] n=%lld host wall ms: histogram %.3f, suffix sort %.3f (device: initial %.3f refine %.3f), wavelet %.3f "
@@ -340,7 +391,7 @@ static int build_block(int device, const uint8_t* text, int64_t n, int32_t sampl
     t_timing.radix_launches = ss.radix_passes;
     t_timing.radix_elements = ss.radix_elements;
     t_timing.radix_ms = ss.radix_ms;
-    t_timing.kernel_launches = ctx->launches - launches0;
+    t_timing.kernel_launches = launches;
     t_timing.symbols_per_key = ss.symbols_per_key;
     t_timing.long_runs = ss.long_runs;
     t_timing.unresolved_after_first_sort = ss.unresolved_after_first_sort;

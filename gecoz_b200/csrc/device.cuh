@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <condition_variable>
 #include <mutex>
 
 namespace gcz {
@@ -67,6 +68,7 @@ struct DeviceCtx {
         int         state = 0;                // 0 free, 1 staged, 2 in use by a build, 3 being filled
         uint64_t    stamp = 0;                // staging order (the older staged text is overwritten first)
         uint8_t     probe[kProbeBytes] = {};  // bytes of the host buffer at fixed places, compared again at build time
+        int64_t     counts[256] = {};         // the histogram gcz_count_symbols returned for this text (the build reuses it)
     };
     std::mutex   stage_mu;                   // slot bookkeeping (short critical sections only)
     std::mutex   stage_io_mu;                // one staging at a time
@@ -74,6 +76,19 @@ struct DeviceCtx {
     StagedText   staged[2];
     uint64_t     stage_clock = 0;
     unsigned long long* stage_counts = nullptr;   // device, 256 counters
+    // Device copies of the two bodies of a block whose outputs are host buffers.  They live outside the arena, two of
+    // them: the call that built them releases the device (`mu`) as soon as its kernels are done and waits for its copies
+    // on its own, so that the next block's kernels run while the previous block's bodies are still on their way to the
+    // host — what a writer with two blocks in flight per device (fmt/GecozFileWriter.java:174-227) needs.
+    struct OutSlot {
+        uint8_t*    dev = nullptr;
+        size_t      cap = 0;
+        cudaEvent_t done = nullptr;            // recorded on copy_stream after the last copy of the block
+        bool        busy = false;
+    };
+    std::mutex              out_mu;
+    std::condition_variable out_cv;
+    OutSlot                 out_slot[2];
     std::mutex   mu;                          // one build / query batch at a time per device (shared arena)
     Arena        arena;
     void*        pinned = nullptr;            // small pinned scratch for read-backs

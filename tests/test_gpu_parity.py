@@ -740,3 +740,20 @@ def test_find_batch_dense_form_still_matches(G, three_blocks):
             if max(p) >= 128:
                 continue
             assert _as_lists(r) == _as_lists(og.find(p)), p
+
+
+def test_build_refuses_a_shape_from_another_histogram(G):
+    """Same alphabet, other counts: the file slices the caller reserved would not fit what the text needs (the reference
+    trusts its caller here and corrupts the file)."""
+    from gecoz_b200 import synth
+    a = synth.cfg2_text(100_000, seed=41)
+    b = a.copy()
+    b[1000:3000] = ord("A")                                   # same symbols present, other histogram
+    shape_b = G.shape_from_counts(np.bincount(b, minlength=256).astype(np.int64))
+    shape_a = G.shape_from_counts(np.bincount(a, minlength=256).astype(np.int64))
+    if shape_a.size == shape_b.size:
+        pytest.skip("the two histograms happen to give the same sizes")
+    gcz = np.zeros(shape_b.size, np.uint8)
+    gcx = np.zeros(G.index_size(len(a), 5), np.uint8)
+    with pytest.raises(G.GczError, match="shape does not match"):
+        G.build_block(0, a, len(a), 32, shape_b, gcz, gcx)

@@ -91,6 +91,8 @@ def main() -> None:
     ap.add_argument("--devices", type=int, default=1)
     ap.add_argument("--engine", default="standin", choices=["standin", "cuda"], help="cuda: the library's own entry points (needs a GPU); "
                     "the files are then real indexes and their sha256 is printed")
+    ap.add_argument("--repeat", type=int, default=1, help="index the same FASTA this many times in one process: the first run pays for the CUDA "
+                    "context, the module load and the device arena; the later ones are what a long-lived process sees")
     args = ap.parse_args()
     from gecoz_b200 import native_file as NF
     out = Path(args.out)
@@ -104,9 +106,12 @@ def main() -> None:
     f = NF.Fasta(fasta)
     t_scan = time.perf_counter() - t
     total = sum(f.record(i)[2] for i in range(len(f)))
-    t = time.perf_counter()
-    rep = NF.index(f, out / "hostbench.gcz", None, 32, tuple(range(args.devices)), eng)
-    t_index = time.perf_counter() - t
+    for r in range(max(1, args.repeat)):
+        t = time.perf_counter()
+        rep = NF.index(f, out / "hostbench.gcz", None, 32, tuple(range(args.devices)), eng)
+        t_index = time.perf_counter() - t
+        if args.repeat > 1:
+            print(f"run {r + 1}: index {t_index:7.3f} s = {total / 1e6 / t_index:.0f} Mbp/s")
     f.close()
     dev = total / (args.gpu_gbps * 1e9) / args.devices
     print(f"records {rep['sequences']}  blocks {rep['blocks']}  symbols {rep['symbols']}")
