@@ -76,7 +76,7 @@ EXPORTS = [
     "gcz_open_block", "gcz_close_block", "gcz_text_length", "gcz_sampling_factor", "gcz_num_strings",
     "gcz_string_ends", "gcz_c_array", "gcz_count_batch", "gcz_locate_rows", "gcz_find_batch", "gcz_extract", "gcz_free",
     "gcz_count_multi", "gcz_count_stats", "gcz_last_query_stats", "gcz_find_multi", "gcz_hits_free",
-    "gcz_dbg_sort_pairs", "gcz_dbg_suffix_array", "gcz_dbg_ranked_vector", "gcz_dbg_index_wavelet_tree",
+    "gcz_dbg_set_find_chunk", "gcz_dbg_sort_pairs", "gcz_dbg_suffix_array", "gcz_dbg_ranked_vector", "gcz_dbg_index_wavelet_tree",
 ]
 
 # include/gcz_file.h — the native host layer (FASTA records, block planning, .gcz/.gcx writer and reader)
@@ -187,6 +187,7 @@ def lib() -> C.CDLL:
         "gcz_last_query_stats": (C.c_int, [C.POINTER(QueryStats)]),
         "gcz_find_multi": (C.c_int, [P, i32, P, P, i64, C.POINTER(Hits)]),
         "gcz_hits_free": (None, [C.POINTER(Hits)]),
+        "gcz_dbg_set_find_chunk": (C.c_int, [i64]),
         "gcz_dbg_sort_pairs": (C.c_int, [C.c_int, P, P, i64, i32, i32]),
         "gcz_dbg_suffix_array": (C.c_int, [C.c_int, P, i64, P]),
         "gcz_dbg_ranked_vector": (C.c_int, [C.c_int, P, i64, P]),

@@ -541,6 +541,7 @@ void gcz_hits_free(gcz_hits* hits) {
 }
 
 // ---- stage hooks ---------------------------------------------------------------------------------------------------
+int gcz_dbg_set_find_chunk(int64_t occurrences) { set_find_chunk(occurrences); return GCZ_OK; }
 int gcz_dbg_sort_pairs(int device, uint64_t* keys, uint32_t* vals, int64_t n, int32_t begin_bit, int32_t end_bit) {
     clear_error();
     DeviceCtx* ctx = nullptr;

@@ -714,6 +714,7 @@ int same_device(gcz_index* const* blocks, int32_t n_blocks, DeviceCtx** ctx) {
     return GCZ_OK;
 }
 
+std::atomic<int64_t> g_find_chunk{(int64_t)1 << 26};   // occurrences located and sorted per launch (gcz_dbg_set_find_chunk)
 thread_local gcz_query_stats t_query_stats = {};
 thread_local size_t t_find_want = 0;            // arena bytes a find_block that ran out of workspace asks for
 
@@ -866,7 +867,7 @@ int find_block(gcz_index* idx, cudaStream_t st, const DeviceBatch& batch, BlockH
     if (total_occ == 0) { arena.release(mark0); return GCZ_OK; }
 
     // pattern ranges of at most kChunk occurrences (a single pattern may exceed it); one range in the common case
-    const int64_t kChunk = (int64_t)1 << 26;
+    const int64_t kChunk = g_find_chunk.load();
     std::vector<int64_t> h_excl;
     std::vector<int64_t> cuts = { 0, n_pats };
     if (total_occ > kChunk) {
@@ -1078,6 +1079,8 @@ int count_stats(gcz_index* const* blocks, int32_t n_blocks, const uint8_t* pats,
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return GCZ_OK;
 }
+
+void set_find_chunk(int64_t occurrences) { g_find_chunk.store(occurrences > 0 ? occurrences : (int64_t)1 << 26); }
 
 int last_query_stats(gcz_query_stats* out) {
     if (!out) return fail(GCZ_E_ARG, "null argument");

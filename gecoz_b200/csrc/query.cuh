@@ -53,6 +53,7 @@ int  find_batch(gcz_index* idx, const uint8_t* pats, const int64_t* pat_off, int
 int  count_multi(gcz_index* const* blocks, int32_t n_blocks, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats, int64_t* totals);
 int  count_stats(gcz_index* const* blocks, int32_t n_blocks, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats, gcz_query_stats* out);
 int  last_query_stats(gcz_query_stats* out);
+void set_find_chunk(int64_t occurrences);
 int  find_multi(gcz_index* const* blocks, int32_t n_blocks, const uint8_t* pats, const int64_t* pat_off, int64_t n_pats, gcz_hits* out);
 
 }  // namespace gcz

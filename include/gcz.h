@@ -191,6 +191,7 @@ int  gcz_count_stats(gcz_index* const* blocks, int32_t n_blocks, const uint8_t* 
 int  gcz_last_query_stats(gcz_query_stats* out);   /* of the calling thread's last gcz_count_multi: patterns, blocks, kernel_ms */
 
 /* ---- stage-level hooks used by the parity tests (each one is a stage of gcz_build_block) ------- */
+int gcz_dbg_set_find_chunk(int64_t occurrences);   /* occurrences located + sorted per launch inside find (default 2^26; <= 0 restores it) */
 int gcz_dbg_sort_pairs(int device, uint64_t* keys, uint32_t* vals, int64_t n, int32_t begin_bit, int32_t end_bit);
 int gcz_dbg_suffix_array(int device, const uint8_t* text, int64_t n, int32_t* sa);
 int gcz_dbg_ranked_vector(int device, const uint8_t* bits, int64_t len, uint8_t* out);   /* one bit per byte in */

@@ -757,3 +757,29 @@ def test_build_refuses_a_shape_from_another_histogram(G):
     gcx = np.zeros(G.index_size(len(a), 5), np.uint8)
     with pytest.raises(G.GczError, match="shape does not match"):
         G.build_block(0, a, len(a), 32, shape_b, gcz, gcx)
+
+
+def test_find_in_small_chunks_and_with_a_grown_workspace(G, three_blocks):
+    """The two paths of find that ordinary batches do not reach: occurrences cut into several locate / sort / split launches
+    (here 1000 per launch instead of 2^26; a pattern with more than that gets a launch of its own), and a batch whose occurrences
+    outgrow the workspace reserved up front (the block is redone after the arena has grown)."""
+    pats = _mixed_patterns(three_blocks, count=1500, seed=12)
+    data, off = G.pack_patterns(pats)
+    gssas = [g for _, _, g, _ in three_blocks]
+    whole = G.find_multi(gssas, data, off)
+    G._native.check(G.lib().gcz_dbg_set_find_chunk(1000))
+    try:
+        chunked = G.find_multi(gssas, data, off)
+    finally:
+        G._native.check(G.lib().gcz_dbg_set_find_chunk(0))
+    for a, b in zip(whole, chunked):
+        assert np.array_equal(a, b)
+    # 150 x "A": ~50 000 occurrences each in the first block, 7.5 M in all = 270 MB of occurrence workspace
+    text, _, g, og = three_blocks[0]
+    many = [b"A"] * 150
+    data, off = G.pack_patterns(many)
+    block_off, pattern, string, position = G.find_multi([g], data, off)
+    exp = og.find(b"A")[0]
+    assert len(position) == 150 * len(exp) and block_off.tolist() == [0, len(position)]
+    assert np.array_equal(pattern, np.repeat(np.arange(150), len(exp)))
+    assert np.array_equal(position.reshape(150, -1), np.tile(exp, (150, 1))) and not string.any()
