@@ -24,9 +24,28 @@ constexpr int kRadix = 1 << RB;
 constexpr int kHistThreads = 512;
 constexpr int kLookWindow = 16;
 
-constexpr unsigned long long kFlagAgg = 1ull << 62;
-constexpr unsigned long long kFlagPrefix = 2ull << 62;
-constexpr unsigned long long kValueMask = (1ull << 62) - 1;
+// Status word of (tile, digit): count in the low bits, two flag bits on top (aggregate = this tile's count, prefix = the
+// count of this and all earlier tiles).  32-bit words whenever a prefix fits 30 bits (any block below 2^30 pairs): half
+// the L2 traffic of the look-back and a third of its instructions.  The array starts with kLookWindow rows of "prefix 0"
+// (written once per sort by radix_scan_kernel), so a window of predecessors never needs a bounds test.
+template <typename S> struct Status;
+template <> struct Status<uint32_t> {
+    static constexpr uint32_t kAgg = 1u << 30, kPrefix = 2u << 30;
+    static __device__ __forceinline__ uint32_t ld(const uint32_t* p) {
+        uint32_t v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+    }
+    static __device__ __forceinline__ void st(uint32_t* p, uint32_t v) {
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    }
+};
+template <> struct Status<unsigned long long> {
+    static constexpr unsigned long long kAgg = 1ull << 62, kPrefix = 2ull << 62;
+    static __device__ __forceinline__ unsigned long long ld(const unsigned long long* p) { return ld_relaxed_u64(p); }
+    static __device__ __forceinline__ void st(unsigned long long* p, unsigned long long v) { st_relaxed_u64(p, v); }
+};
+constexpr int64_t kNarrowStatusLimit = (int64_t)1 << 30;    // pairs a sort may have for 32-bit status words
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ---- histogram of every digit in one pass -------------------------------------------------------
 __global__ void __launch_bounds__(kHistThreads)
@@ -52,21 +71,40 @@ radix_hist_kernel(const uint64_t* __restrict__ keys, int64_t n, int begin_bit, i
 // kTextItems consecutive symbols (one 16-byte load) to codes and slides a k-symbol window over them.
 // A key equal to c * (radix^k - 1) / (radix - 1) is k copies of symbol c: that is how the first and last
 // positions of runs of >= k equal symbols are found without walking the text.
+//
+// Counting: npass shared-memory reductions per position.  With one 256-bin table per digit the 32 lanes of a warp hit random
+// banks (3.5 wavefronts per reduction: the first version was bound by exactly that, 245 M wavefronts per chr1-sized text).
+// Here every LANE has a column of its own: counter (digit, bin) of lane l is a 16-bit field of word [digit][bin / 2][l], bank l —
+// one wavefront per reduction.  A field counts what the eight warps of the CTA add for one lane: at most 128 per tile, so the
+// table is summed into the global histogram every kTextFlushTiles tiles.  The text of the next tile is requested before the
+// current one is counted.
 constexpr int kTextThreads = 256;
 constexpr int kTextItems = 16;
 constexpr int kTextTile = kTextThreads * kTextItems;
+constexpr int kTextFlushTiles = 500;                       // 500 x 128 < 2^16
+constexpr int kTextCodes = 16 + kTextTile + kMaxKeySymbols + 16;
+inline size_t text_hist_smem(int npass) { return (size_t)npass * (kRadix / 2) * 32 * 4 + kTextCodes + 256; }
 
 __device__ __forceinline__ uint64_t slide_key(uint64_t key, uint32_t c_out, uint32_t c_in, uint32_t radix, uint64_t top) {
     key -= (uint64_t)c_out * top;                          // 8-bit x 64-bit and 64-bit x 9-bit products: two IMADs each
     return key * radix + c_in;
 }
 
+__device__ __forceinline__ uint32_t byte_of(const uint32_t (&w)[5], int i) { return (w[i >> 2] >> (8 * (i & 3))) & 255u; }
+
+__device__ __forceinline__ uint32_t translate4(const uint8_t* s_code_of, uint32_t w) {
+    return (uint32_t)s_code_of[w & 255] | (uint32_t)s_code_of[(w >> 8) & 255] << 8 |
+           (uint32_t)s_code_of[(w >> 16) & 255] << 16 | (uint32_t)s_code_of[w >> 24] << 24;
+}
+
 __global__ void __launch_bounds__(kTextThreads)
-text_hist_kernel(TextKeySource src, int npass, unsigned long long* __restrict__ hist /* [npass][radix] */, int64_t tiles) {
-    __shared__ unsigned s_hist[8 * kRadix];
-    __shared__ uint8_t s_code_of[256];
-    __shared__ __align__(16) uint8_t s_codes[16 + kTextTile + kMaxKeySymbols + 16];    // index 16 = first position of the tile
-    for (int i = threadIdx.x; i < 8 * kRadix; i += kTextThreads) s_hist[i] = 0;
+text_hist_kernel(TextKeySource src, int npass, unsigned long long* __restrict__ hist /* [npass][radix] */, int64_t tiles, int flush_tiles) {
+    extern __shared__ __align__(16) unsigned char text_smem[];
+    unsigned* s_cnt = reinterpret_cast<unsigned*>(text_smem);                       // [npass][128][32]
+    uint8_t* s_codes = text_smem + (size_t)npass * (kRadix / 2) * 32 * 4;           // index 16 = first position of the tile
+    uint8_t* s_code_of = s_codes + kTextCodes;
+    const int cnt_words = npass * (kRadix / 2) * 32;
+    for (int i = threadIdx.x; i < cnt_words; i += kTextThreads) s_cnt[i] = 0;
     s_code_of[threadIdx.x] = src.code_of[threadIdx.x];
     const int k = src.coder.k;
     const uint32_t radix = (uint32_t)src.coder.radix;
@@ -75,71 +113,127 @@ text_hist_kernel(TextKeySource src, int npass, unsigned long long* __restrict__ 
     for (int j = 0; j < k; j++) unit = unit * radix + 1;
     const int64_t n = src.n;
     const bool aligned = (reinterpret_cast<uintptr_t>(src.text) & 15) == 0;
+    const unsigned lane = threadIdx.x & 31u;
+    const int first = 16 + threadIdx.x * kTextItems;
+    const int in_at = first + k - 1;                       // s_codes index of the symbol that enters the window at my first position
+    const uint32_t in_sel = 0x3210u + 0x1111u * (uint32_t)(in_at & 3);
+
+    // what the tile needs from global memory, as raw text bytes: my 16 symbols, and (threads 0 .. k + 1) one symbol of the edges
+    auto fetch = [&](int64_t tile, uint4& q, uint32_t& edge) {
+        const int64_t base = tile * kTextTile;
+        const int64_t p0 = base + (int64_t)threadIdx.x * kTextItems;
+        q = make_uint4(0, 0, 0, 0);
+        if (tile < tiles) {
+            if (aligned && p0 + kTextItems <= n) {
+                q = *reinterpret_cast<const uint4*>(src.text + p0);
+            } else {
+                uint32_t w[4] = { 0, 0, 0, 0 };
+                for (int j = 0; j < kTextItems; j++) {
+                    if (p0 + j < n) w[j >> 2] |= (uint32_t)src.text[p0 + j] << (8 * (j & 3));
+                }
+                q = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        edge = 0x100u;                                     // 0x100: no symbol there (code 0 = past the end)
+        if (tile < tiles) {
+            if (threadIdx.x <= (unsigned)k) {              // right halo: k + 1 symbols
+                const int64_t p = base + kTextTile + threadIdx.x;
+                if (p < n) edge = src.text[p];
+            } else if (threadIdx.x == kTextThreads - 1 && base > 0) {
+                edge = src.text[base - 1];
+            }
+        }
+    };
+    uint4 q;
+    uint32_t edge;
+    fetch(blockIdx.x, q, edge);
+    int since_flush = 0;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int64_t base = tile * kTextTile;
-        __syncthreads();
+        __syncthreads();                                   // the previous tile's codes are no longer read (first trip: tables are set)
         {
             const int64_t p0 = base + (int64_t)threadIdx.x * kTextItems;
-            uint32_t packed[4] = { 0, 0, 0, 0 };
-            if (aligned && p0 + kTextItems <= n) {
-                const uint4 q = *reinterpret_cast<const uint4*>(src.text + p0);
-                const uint32_t w[4] = { q.x, q.y, q.z, q.w };
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    packed[j] = (uint32_t)s_code_of[w[j] & 255] | (uint32_t)s_code_of[(w[j] >> 8) & 255] << 8 |
-                                (uint32_t)s_code_of[(w[j] >> 16) & 255] << 16 | (uint32_t)s_code_of[w[j] >> 24] << 24;
-                }
-            } else {
+            uint32_t packed[4] = { translate4(s_code_of, q.x), translate4(s_code_of, q.y), translate4(s_code_of, q.z), translate4(s_code_of, q.w) };
+            if (p0 + kTextItems > n) {                     // positions past the end carry code 0 whatever byte 0 maps to
 #pragma unroll
                 for (int j = 0; j < kTextItems; j++) {
-                    const int64_t p = p0 + j;
-                    if (p < n) packed[j >> 2] |= (uint32_t)s_code_of[src.text[p]] << (8 * (j & 3));   // 0 = past the end
+                    if (p0 + j >= n) packed[j >> 2] &= ~(255u << (8 * (j & 3)));
                 }
             }
-            *reinterpret_cast<uint4*>(s_codes + 16 + threadIdx.x * kTextItems) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            if (threadIdx.x <= (unsigned)k) {                 // right halo: k + 1 symbols
-                const int64_t p = base + kTextTile + threadIdx.x;
-                s_codes[16 + kTextTile + threadIdx.x] = p < n ? s_code_of[src.text[p]] : 0;
-            }
-            if (threadIdx.x == kTextThreads - 1) s_codes[15] = base > 0 ? s_code_of[src.text[base - 1]] : 0;
+            *reinterpret_cast<uint4*>(s_codes + first) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            if (threadIdx.x <= (unsigned)k) s_codes[16 + kTextTile + threadIdx.x] = edge < 256u ? s_code_of[edge] : 0;
+            if (threadIdx.x == kTextThreads - 1) s_codes[15] = edge < 256u ? s_code_of[edge] : 0;
         }
         __syncthreads();
-        const int first = 16 + threadIdx.x * kTextItems;
+        fetch(tile + gridDim.x, q, edge);                  // in flight while this tile is counted
+
+        uint32_t own[5], in[5];                            // own: codes of my positions; in: codes k - 1 positions further (17 of them)
+        {
+            const uint4 o = *reinterpret_cast<const uint4*>(s_codes + first);
+            own[0] = o.x; own[1] = o.y; own[2] = o.z; own[3] = o.w; own[4] = 0;
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(s_codes + (in_at & ~3));
+            uint32_t raw[6];
+#pragma unroll
+            for (int j = 0; j < 6; j++) raw[j] = w[j];
+#pragma unroll
+            for (int j = 0; j < 5; j++) in[j] = __byte_perm(raw[j], raw[j + 1], in_sel);
+        }
+        const uint32_t before = s_codes[first - 1];
         uint64_t key = 0;
         for (int j = 0; j < k - 1; j++) key = key * radix + s_codes[first + j];
-#pragma unroll 4
+        const int64_t p_first = base + first - 16;
+        const bool whole = p_first + kTextItems <= n;
+#pragma unroll
         for (int i = 0; i < kTextItems; i++) {
-            key = slide_key(key, i > 0 ? s_codes[first + i - 1] : 0u, s_codes[first + i + k - 1], radix, top);
-            const int64_t p = base + first - 16 + i;
-            if (p < n) {
+            key = slide_key(key, i > 0 ? byte_of(own, i - 1) : 0u, byte_of(in, i), radix, top);
+            const int64_t p = p_first + i;
+            if (whole || p < n) {
 #pragma unroll
                 for (int d = 0; d < 8; d++) {
-                    if (d < npass) atomicAdd(&s_hist[d * kRadix + (int)((key >> (RB * d)) & (kRadix - 1))], 1u);
+                    if (d < npass) {
+                        const unsigned bin = (unsigned)(key >> (RB * d)) & (kRadix - 1);
+                        unsigned* word = s_cnt + ((d * (kRadix / 2) + (bin >> 1)) * 32 + lane);
+                        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_u32(word)), "r"(1u << (16 * (bin & 1))) : "memory");
+                    }
                 }
-                const uint32_t c = s_codes[first + i];
+                const uint32_t c = byte_of(own, i);
                 if (src.run_marks && key == (uint64_t)c * unit) {
-                    if (p == 0 || s_codes[first + i - 1] != c) {
+                    if (p == 0 || (i > 0 ? byte_of(own, i - 1) : before) != c) {
                         const unsigned at = atomicAdd(src.run_mark_count, 1u);
                         if (at < src.run_mark_cap) src.run_marks[at] = 2ull * (uint64_t)p;
                     }
-                    if (s_codes[first + i + k] != c) {
+                    if (byte_of(in, i + 1) != c) {
                         const unsigned at = atomicAdd(src.run_mark_count, 1u);
                         if (at < src.run_mark_cap) src.run_marks[at] = 2ull * (uint64_t)(p + k - 1) + 1;
                     }
                 }
             }
         }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < npass * kRadix; i += kTextThreads) {
-        const unsigned v = s_hist[i];
-        if (v) atomicAdd(&hist[i], (unsigned long long)v);
+        const bool last_trip = tile + gridDim.x >= tiles;
+        if (++since_flush == flush_tiles || last_trip) {
+            since_flush = 0;
+            __syncthreads();
+            for (int d = 0; d < npass; d++) {              // thread b sums bin b over the 32 lane columns (rotated: bank = (j + b) % 32)
+                const unsigned* row = s_cnt + (d * (kRadix / 2) + (threadIdx.x >> 1)) * 32;
+                const int sh = 16 * (threadIdx.x & 1);
+                unsigned sum = 0;
+#pragma unroll 8
+                for (int j = 0; j < 32; j++) sum += (row[(j + threadIdx.x) & 31] >> sh) & 0xffffu;
+                if (sum) atomicAdd(&hist[d * kRadix + threadIdx.x], (unsigned long long)sum);
+            }
+            if (!last_trip) {
+                __syncthreads();
+                for (int i = threadIdx.x; i < cnt_words; i += kTextThreads) s_cnt[i] = 0;
+            }
+        }
     }
 }
 
-// exclusive scan of each pass's bins, in place (one thread per bin)
-__global__ void radix_scan_kernel(unsigned long long* hist, int npass) {
+// exclusive scan of each pass's bins, in place (one thread per bin); also writes the "prefix 0" rows in front of the status array
+template <typename S>
+__global__ void radix_scan_kernel(unsigned long long* hist, int npass, S* status_pad) {
     __shared__ unsigned long long s_warp[kRadix / 32];
+    for (int j = 0; j < kLookWindow; j++) status_pad[j * kRadix + threadIdx.x] = Status<S>::kPrefix;
     for (int p = 0; p < npass; p++) {
         unsigned long long v = hist[p * kRadix + threadIdx.x];
         unsigned long long incl = v;
@@ -178,8 +272,6 @@ __device__ __forceinline__ unsigned peers_with_same_digit(unsigned d) {
         : "=&r"(acc) : "r"(d));
     return acc;
 }
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // shared-memory reduction without a return value (and without the match-based aggregation ptxas wraps atomicAdd in)
 __device__ __forceinline__ void red_shared_inc(unsigned* p) {
@@ -232,29 +324,34 @@ __device__ __forceinline__ void rank_in_warp(const uint64_t (&key)[ITEMS], int s
 // and dropped — profiles/onesweep_experiments_r02.md has their kernels' numbers: persistent CTAs fed by TMA bulk copies
 // (cp.async.bulk + mbarrier; 1.86 ms per pass against 1.69), and a scan-ahead CTA that turns aggregates into prefixes
 // (2.99 ms: one chain of dependent L2 round trips cannot follow 25 tiles per microsecond).
-template <int THREADS, int ITEMS, bool HAS_VALS, int MIN_BLOCKS, bool FROM_TEXT>
+template <int THREADS, int ITEMS, bool HAS_VALS, int MIN_BLOCKS, bool FROM_TEXT, typename S>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
                 const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
                 int64_t n, int shift, const unsigned long long* __restrict__ digit_base,
-                unsigned long long* __restrict__ status, unsigned* __restrict__ ticket, TextKeySource src) {
+                S* __restrict__ status /* first real row (kLookWindow pad rows in front) */, unsigned* __restrict__ ticket,
+                TextKeySource src) {
     constexpr int TILE = THREADS * ITEMS;
     constexpr int WARPS = THREADS / 32;
     static_assert(THREADS >= kRadix, "one thread per digit is needed for the look-back");
     static_assert(!FROM_TEXT || HAS_VALS, "text input produces (key, position) pairs");
     static_assert(TILE * 4 >= TILE + kMaxKeySymbols + 8 + 256, "the value staging area holds the tile's symbol codes");
+    static_assert((WARPS * kRadix) % (4 * THREADS) == 0, "the warp counters are cleared with 16-byte stores");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* s_keys = reinterpret_cast<uint64_t*>(smem_raw);                       // TILE
     uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_keys + TILE);                  // TILE (if HAS_VALS)
     unsigned* s_warp_hist = s_vals + (HAS_VALS ? TILE : 0);                         // WARPS x 256
-    long long* s_gofs = reinterpret_cast<long long*>(s_warp_hist + WARPS * kRadix); // 256: global base - tile start
-    unsigned* s_digit_start = reinterpret_cast<unsigned*>(s_gofs + kRadix);         // 256
+    S* s_gofs = reinterpret_cast<S*>(s_warp_hist + WARPS * kRadix);                 // 256: global base - tile start (mod 2^bits)
+    unsigned* s_digit_start = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned long long*>(s_gofs) + kRadix);   // 256
     unsigned* s_scan = s_digit_start + kRadix;                                      // 8 warp totals
     __shared__ unsigned s_tile;
 
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    for (int i = threadIdx.x; i < WARPS * kRadix; i += THREADS) s_warp_hist[i] = 0;
+#pragma unroll
+    for (int i = 0; i < WARPS * kRadix / (4 * THREADS); i++) {
+        reinterpret_cast<uint4*>(s_warp_hist)[i * THREADS + threadIdx.x] = make_uint4(0, 0, 0, 0);
+    }
     __syncthreads();
     const unsigned tile = s_tile;
     const int64_t tile_base = (int64_t)tile * TILE;
@@ -335,13 +432,13 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
 
     // 3. tile histogram -> aggregate for the look-back (published before the ranking), digit starts, warp starting positions
     unsigned total = 0;
+    S* const my_status = status + (size_t)tile * kRadix + threadIdx.x;
     if (threadIdx.x < kRadix) {
 #pragma unroll
         for (int w = 0; w < WARPS; w++) total += s_warp_hist[w * kRadix + threadIdx.x];
         const unsigned with_padding = total;
         if (threadIdx.x == kRadix - 1) total -= (unsigned)(TILE - count);
-        st_relaxed_u64(&status[(size_t)tile * kRadix + threadIdx.x],
-                       (unsigned long long)total | (tile == 0 ? kFlagPrefix : kFlagAgg));
+        Status<S>::st(my_status, (S)total | Status<S>::kAgg);
         const unsigned incl = warp_incl_sum(with_padding);
         if (lane == 31) s_scan[warp] = incl;
         s_digit_start[threadIdx.x] = incl - with_padding;
@@ -394,100 +491,84 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
     }
 
     // 6. decoupled look-back, kLookWindow predecessors per step: their status words are loaded together so the
-    //    walk back to the nearest inclusive prefix costs one memory latency per window, not one per tile
+    //    walk back to the nearest inclusive prefix costs one memory latency per window, not one per tile.  The words are
+    //    summed with their flag bits on; the flags of `taken` aggregates and one prefix are subtracted at the end.
     if (threadIdx.x < kRadix) {
-        unsigned long long excl = 0;
-        long long t = (long long)tile - 1;
-        bool done = tile == 0;
-        while (!done) {
-            unsigned long long v[kLookWindow];
+        S raw = 0;
+        unsigned taken = 0;
+        const S* p = my_status - kRadix;                   // tile - 1 (row -1 .. -kLookWindow: "prefix 0")
+        bool done = false;
+        do {
+            S v[kLookWindow];
+#pragma unroll
+            for (int j = 0; j < kLookWindow; j++) v[j] = Status<S>::ld(p - j * kRadix);
+            bool go = true;
+            unsigned used = 0;
 #pragma unroll
             for (int j = 0; j < kLookWindow; j++) {
-                v[j] = t - j >= 0 ? ld_relaxed_u64(&status[(size_t)(t - j) * kRadix + threadIdx.x]) : kFlagPrefix;
+                go = go && v[j] >= Status<S>::kAgg;          // a status word that is not there yet ends the step: polled again
+                if (go) { raw += v[j]; used = j + 1; }
+                if (v[j] >= Status<S>::kPrefix) { done = done || go; go = false; }
             }
-            int used = 0;
-#pragma unroll
-            for (int j = 0; j < kLookWindow; j++) {
-                const unsigned long long flag = v[j] & ~kValueMask;
-                if (!done && used == j && flag != 0) {
-                    excl += v[j] & kValueMask;
-                    used = j + 1;
-                    done = flag == kFlagPrefix;
-                }
-            }
-            t -= used;                                   // a status word that was not ready yet is polled again
-        }
-        if (tile > 0) st_relaxed_u64(&status[(size_t)tile * kRadix + threadIdx.x], (excl + total) | kFlagPrefix);
-        s_gofs[threadIdx.x] = (long long)(digit_base[threadIdx.x] + excl) - (long long)s_digit_start[threadIdx.x];
+            taken += used;
+            p -= used * kRadix;
+        } while (!done);
+        const S excl = raw - (S)(taken - 1) * Status<S>::kAgg - Status<S>::kPrefix;
+        Status<S>::st(my_status, ((excl + total) & (Status<S>::kAgg - 1)) | Status<S>::kPrefix);
+        s_gofs[threadIdx.x] = (S)digit_base[threadIdx.x] + excl - (S)s_digit_start[threadIdx.x];
     }
     __syncthreads();
 
-    // 7. digit runs are contiguous both in shared memory and at their destination
+    // 7. digit runs are contiguous both in shared memory and at their destination (destination index mod 2^32 or 2^64:
+    //    base - start may wrap below zero, base - start + j does not)
+    if (count == TILE) {
 #pragma unroll
-    for (int i = 0; i < ITEMS; i++) {
-        const int j = i * THREADS + threadIdx.x;
-        if (j < count) {
+        for (int i = 0; i < ITEMS; i++) {
+            const int j = i * THREADS + threadIdx.x;
             const uint64_t k = s_keys[j];
-            const long long dst = s_gofs[(unsigned)(k >> shift) & (unsigned)(kRadix - 1)] + j;
+            const S dst = s_gofs[(unsigned)(k >> shift) & (unsigned)(kRadix - 1)] + (S)j;
+            keys_out[dst] = k;
+            if (HAS_VALS) vals_out[dst] = s_vals[j];
+        }
+    } else {
+#pragma unroll 1
+        for (int j = threadIdx.x; j < count; j += THREADS) {
+            const uint64_t k = s_keys[j];
+            const S dst = s_gofs[(unsigned)(k >> shift) & (unsigned)(kRadix - 1)] + (S)j;
             keys_out[dst] = k;
             if (HAS_VALS) vals_out[dst] = s_vals[j];
         }
     }
 }
 
-typedef void (*OnesweepFn)(const uint64_t*, uint64_t*, const uint32_t*, uint32_t*, int64_t, int, const unsigned long long*,
-                           unsigned long long*, unsigned*, TextKeySource);
-
 // 512 threads x 12 elements, two CTAs per SM (the shape profiles/sort_variants_r01.md picked)
 constexpr int kThreads = 512, kItems = 12, kTile = kThreads * kItems;
 constexpr size_t kFixedSmem = (size_t)(kThreads / 32) * kRadix * 4 + kRadix * 8 + kRadix * 4 + 64;
 constexpr size_t kSmemPairs = (size_t)kTile * 12 + kFixedSmem, kSmemKeys = (size_t)kTile * 8 + kFixedSmem;
 
-}  // namespace
-
-int radix_sort_passes(int bits) { return (bits + RB - 1) / RB; }
-
-size_t radix_sort_temp_bytes(int64_t n) {
-    const int64_t tiles = (n + kTile - 1) / kTile;
-    // [8][radix] histogram + per-pass (status[tiles][radix] + ticket)
-    return 8 * (size_t)kRadix * 8 + 256 + ((size_t)tiles * kRadix * 8 + 256);
-}
-
-int radix_sort_pairs(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n, int begin_bit, int end_bit,
-                     void* temp, SortStats* stats, const TextKeySource* src) {
-    if (n <= 0 || end_bit <= begin_bit) return GCZ_OK;
-    if (end_bit - begin_bit > 64 || begin_bit < 0) return fail(GCZ_E_ARG, "radix sort bit range");
-    const int npass = radix_sort_passes(end_bit - begin_bit);
+template <typename S>
+int digit_passes(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n, int begin_bit, int npass, unsigned long long* hist,
+                 void* status_mem, SortStats* stats, const TextKeySource* src) {
     const bool has_vals = b.vals[0] != nullptr;
-    if (src && (!has_vals || begin_bit != 0 || src->n != n)) return fail(GCZ_E_ARG, "radix sort from text: arguments");
-    const OnesweepFn pairs = onesweep_kernel<kThreads, kItems, true, 2, false>;
-    const OnesweepFn keys_only = onesweep_kernel<kThreads, kItems, false, 2, false>;
-    const OnesweepFn from_text = onesweep_kernel<kThreads, kItems, true, 2, true>;
-    if (!ctx->sort_attr[0]) {
+    auto* pairs = onesweep_kernel<kThreads, kItems, true, 2, false, S>;
+    auto* keys_only = onesweep_kernel<kThreads, kItems, false, 2, false, S>;
+    auto* from_text = onesweep_kernel<kThreads, kItems, true, 2, true, S>;
+    bool& attr = ctx->sort_attr[sizeof(S) == 4 ? 0 : 1];
+    if (!attr) {
         GCZ_CUDA(cudaFuncSetAttribute(pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPairs));
         GCZ_CUDA(cudaFuncSetAttribute(keys_only, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemKeys));
         GCZ_CUDA(cudaFuncSetAttribute(from_text, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPairs));
-        ctx->sort_attr[0] = true;
+        attr = true;
     }
-    auto* hist = static_cast<unsigned long long*>(temp);
-    auto* status = hist + 8 * kRadix + 32;
     const int64_t tiles = (n + kTile - 1) / kTile;
+    S* pad = static_cast<S*>(status_mem);
+    S* status = pad + (size_t)kLookWindow * kRadix;
     auto* ticket = reinterpret_cast<unsigned*>(status + (size_t)tiles * kRadix);
     const TextKeySource none;
-
-    GCZ_CUDA(cudaMemsetAsync(hist, 0, (size_t)8 * kRadix * 8, st));
-    if (src) {
-        const int64_t ttiles = (n + kTextTile - 1) / kTextTile;
-        const int grid = (int)std::min<int64_t>(ttiles, (int64_t)ctx->sm_count * 8);
-        GCZ_LAUNCH(ctx, text_hist_kernel, grid, kTextThreads, 0, st, *src, npass, hist, ttiles);
-    } else {
-        const int hist_grid = (int)std::min<int64_t>((n + kHistThreads * 8 - 1) / (kHistThreads * 8), (int64_t)ctx->sm_count * 4);
-        GCZ_LAUNCH(ctx, radix_hist_kernel, hist_grid, kHistThreads, 0, st, b.keys[b.cur], n, begin_bit, npass, hist);
-    }
-    GCZ_LAUNCH(ctx, radix_scan_kernel, 1, kRadix, 0, st, hist, npass);
+    GCZ_LAUNCH(ctx, radix_scan_kernel<S>, 1, kRadix, 0, st, hist, npass, pad);
 
     for (int p = 0; p < npass; p++) {
-        GCZ_CUDA(cudaMemsetAsync(status, 0, (size_t)tiles * kRadix * 8 + 64, st));
+        GCZ_CUDA(cudaMemsetAsync(status, 0, (size_t)tiles * kRadix * sizeof(S) + 64, st));
         const int in = b.cur, out = b.cur ^ 1;
         const int shift = begin_bit + RB * p;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -516,6 +597,48 @@ int radix_sort_pairs(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n
         }
     }
     return GCZ_OK;
+}
+
+}  // namespace
+
+int radix_sort_passes(int bits) { return (bits + RB - 1) / RB; }
+
+size_t radix_sort_temp_bytes(int64_t n) {
+    const int64_t tiles = (n + kTile - 1) / kTile;
+    // [8][radix] histogram + status rows (kLookWindow "prefix 0" rows, then one per tile) + ticket
+    return 8 * (size_t)kRadix * 8 + 256 + ((size_t)(tiles + kLookWindow) * kRadix * 8 + 256);
+}
+
+int radix_sort_pairs(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n, int begin_bit, int end_bit,
+                     void* temp, SortStats* stats, const TextKeySource* src) {
+    if (n <= 0 || end_bit <= begin_bit) return GCZ_OK;
+    if (end_bit - begin_bit > 64 || begin_bit < 0) return fail(GCZ_E_ARG, "radix sort bit range");
+    const int npass = radix_sort_passes(end_bit - begin_bit);
+    const bool has_vals = b.vals[0] != nullptr;
+    if (src && (!has_vals || begin_bit != 0 || src->n != n)) return fail(GCZ_E_ARG, "radix sort from text: arguments");
+    auto* hist = static_cast<unsigned long long*>(temp);
+    void* status_mem = hist + 8 * kRadix + 32;
+
+    GCZ_CUDA(cudaMemsetAsync(hist, 0, (size_t)8 * kRadix * 8, st));
+    if (src) {
+        const int64_t ttiles = (n + kTextTile - 1) / kTextTile;
+        const size_t smem = text_hist_smem(npass);
+        if (!ctx->sort_attr[2]) {
+            GCZ_CUDA(cudaFuncSetAttribute(text_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)text_hist_smem(8)));
+            ctx->sort_attr[2] = true;
+        }
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)220 << 10) / (smem + 1024)));
+        const int grid = (int)std::min<int64_t>(ttiles, (int64_t)ctx->sm_count * per_sm);
+        const char* fe = std::getenv("GCZ_TEXT_FLUSH_TILES");            // tests: the mid-run flush of the 16-bit counters
+        const int flush_tiles = fe && std::atoi(fe) > 0 ? std::min(std::atoi(fe), kTextFlushTiles) : kTextFlushTiles;
+        GCZ_LAUNCH(ctx, text_hist_kernel, grid, kTextThreads, smem, st, *src, npass, hist, ttiles, flush_tiles);
+    } else {
+        const int hist_grid = (int)std::min<int64_t>((n + kHistThreads * 8 - 1) / (kHistThreads * 8), (int64_t)ctx->sm_count * 4);
+        GCZ_LAUNCH(ctx, radix_hist_kernel, hist_grid, kHistThreads, 0, st, b.keys[b.cur], n, begin_bit, npass, hist);
+    }
+    const bool force_wide = std::getenv("GCZ_SORT_WIDE_STATUS") != nullptr;    // tests: the 64-bit status words at any size
+    if (n < kNarrowStatusLimit && !force_wide) return digit_passes<uint32_t>(ctx, st, b, n, begin_bit, npass, hist, status_mem, stats, src);
+    return digit_passes<unsigned long long>(ctx, st, b, n, begin_bit, npass, hist, status_mem, stats, src);
 }
 
 void SortStats::resolve() {

@@ -117,60 +117,89 @@ struct GroupArgs {
     uint32_t*       run_suf_out;
 };
 
+// Every thread owns kGrpItems CONSECUTIVE slots (eight 16-byte loads), so a boundary is one 64-bit compare against the key in
+// the previous register and the 16 flag bits of a thread never leave it; the neighbours' edge keys come by shuffle.  (The first
+// version staged the tile in shared memory and balloted three flags per slot: 92 instructions per key, issue-bound at a third
+// of the HBM rate.)
 template <bool INITIAL>
 __global__ void __launch_bounds__(kGrpThreads)
 group_flags_kernel(GroupArgs a) {
-    __shared__ uint64_t s_keys[kGrpTile + 2];          // [0] = slot before the tile, [1 ..] the tile, then the slot after
+    static_assert(kGrpItems == 16, "two threads fill one 32-bit word of the bit arrays");
     __shared__ uint64_t s_allc[256];
     __shared__ unsigned s_agg[kAggs][kGrpThreads / 32];
     int sigma = 0;
     if (INITIAL) {
         sigma = (a.sigma > 0 && *a.run_mark_count <= a.run_mark_cap) ? a.sigma : 0;
         if ((int)threadIdx.x < sigma) s_allc[threadIdx.x] = a.allc[threadIdx.x];
+        __syncthreads();
     }
     const int64_t tile_base = (int64_t)blockIdx.x * kGrpTile;
+    const int64_t t0 = tile_base + (int64_t)threadIdx.x * kGrpItems;
+    const int cnt = (int)max((int64_t)0, min((int64_t)kGrpItems, a.m - t0));
+    uint64_t key[kGrpItems];
+    if (cnt == kGrpItems && (reinterpret_cast<uintptr_t>(a.keys) & 15) == 0) {
+        const ulonglong2* src = reinterpret_cast<const ulonglong2*>(a.keys + t0);
 #pragma unroll
-    for (int i = 0; i < kGrpItems; i++) {
-        const int e = i * kGrpThreads + threadIdx.x;
-        const int64_t t = tile_base + e;
-        s_keys[1 + e] = t < a.m ? a.keys[t] : 0;
+        for (int i = 0; i < kGrpItems / 2; i++) { const ulonglong2 q = src[i]; key[2 * i] = q.x; key[2 * i + 1] = q.y; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kGrpItems; i++) key[i] = i < cnt ? a.keys[t0 + i] : 0;
     }
-    if (threadIdx.x == 0) s_keys[0] = tile_base > 0 ? a.keys[tile_base - 1] : 0;
-    if (threadIdx.x == 32) s_keys[kGrpTile + 1] = tile_base + kGrpTile < a.m ? a.keys[tile_base + kGrpTile] : 0;
-    __syncthreads();
-    unsigned last1 = 0, keep = 0, groups = 0, keep_run = 0, groups_run = 0;     // last1 = in-tile slot of the last boundary + 1
+    // the key before my first slot and the key after my last one
+    uint64_t prev = __shfl_up_sync(0xffffffffu, key[kGrpItems - 1], 1);
+    uint64_t next = __shfl_down_sync(0xffffffffu, key[0], 1);
+    if (lane_id() == 0 && cnt > 0 && t0 > 0) prev = a.keys[t0 - 1];
+    if (lane_id() == 31 && t0 + kGrpItems < a.m) next = a.keys[t0 + kGrpItems];
+    const unsigned valid = (1u << cnt) - 1u;
+    // bit i of bnd: slot t0 + i starts a key group; bit kGrpItems: so does the slot after mine (the end of the keys closes the last group)
+    unsigned bnd = 0;
 #pragma unroll
-    for (int i = 0; i < kGrpItems; i++) {
-        const int e = i * kGrpThreads + threadIdx.x;
-        const int64_t t = tile_base + e;
-        const uint64_t key = s_keys[1 + e];
-        const bool valid = t < a.m;
-        if (INITIAL && valid && (t & (kSampleStep - 1)) == 0) a.sample[t >> kSampleShift] = key;
-        const bool b = valid && (t == 0 || key != s_keys[e]);
-        const bool open = valid && !(b && (t + 1 >= a.m || s_keys[2 + e] != key));   // shares its key with a neighbour
-        bool run = false;
-        if (INITIAL && sigma > 0 && open) run = allc_symbol(key, s_allc, sigma) != 0;
-        const unsigned wb = __ballot_sync(0xffffffffu, b), wr = __ballot_sync(0xffffffffu, run);
-        const unsigned wo = __ballot_sync(0xffffffffu, open);
-        if (lane_id() == 0 && tile_base + (e & ~31) < a.m) {
-            a.bnd_bits[t >> 5] = wb;
-            if (INITIAL) a.run_bits[t >> 5] = wr;
-            if (wb) last1 = (e & ~31) + 32 - __clz(wb);                           // items ascend: the latest word wins
-            keep += __popc(wo & ~wr); groups += __popc(wb & wo & ~wr);
-            keep_run += __popc(wr);   groups_run += __popc(wb & wr);
+    for (int i = 0; i < kGrpItems; i++) bnd |= (unsigned)(key[i] != (i == 0 ? prev : key[i - 1])) << i;
+    if (t0 == 0) bnd |= 1u;
+    bnd &= valid;
+    if (t0 + cnt >= a.m || key[kGrpItems - 1] != next) bnd |= 1u << cnt;          // cnt < kGrpItems only at the end of the keys
+    const unsigned b = bnd & valid;
+    const unsigned open = valid & ~(bnd & (bnd >> 1));                             // shares its key with a neighbour
+    unsigned run = 0;
+    if (INITIAL && sigma > 0 && open) {
+        bool r = false;
+#pragma unroll
+        for (int i = 0; i < kGrpItems; i++) {
+            if ((open >> i) & 1) {
+                if (i == 0 || ((b >> i) & 1)) r = allc_symbol(key[i], s_allc, sigma) != 0;   // one search per key group
+                run |= (unsigned)r << i;
+            }
+        }
+    }
+    if (INITIAL && cnt > 0 && (t0 & (kSampleStep - 1)) == 0) a.sample[t0 >> kSampleShift] = key[0];
+    // two threads to a word of the bit arrays
+    const unsigned hi_b = __shfl_down_sync(0xffffffffu, b, 1), hi_r = __shfl_down_sync(0xffffffffu, run, 1);
+    if ((lane_id() & 1) == 0 && cnt > 0) {
+        a.bnd_bits[t0 >> 5] = b | hi_b << 16;
+        if (INITIAL) a.run_bits[t0 >> 5] = run | hi_r << 16;
+    }
+    // tile aggregates: in-tile slot of the last boundary + 1 (max), kept slots / groups of the general and of the long-run kind
+    unsigned v[kAggs] = { b ? threadIdx.x * kGrpItems + 32 - __clz(b) : 0u, (unsigned)__popc(open & ~run), (unsigned)__popc(b & open & ~run),
+                          (unsigned)__popc(run), (unsigned)__popc(b & run) };
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int q = 0; q < kAggs; q++) {
+            const unsigned t = __shfl_xor_sync(0xffffffffu, v[q], o);
+            v[q] = q == 0 ? max(v[q], t) : v[q] + t;
         }
     }
     if (lane_id() == 0) {
-        const int w = threadIdx.x >> 5;
-        s_agg[0][w] = last1; s_agg[1][w] = keep; s_agg[2][w] = groups; s_agg[3][w] = keep_run; s_agg[4][w] = groups_run;
+#pragma unroll
+        for (int q = 0; q < kAggs; q++) s_agg[q][threadIdx.x >> 5] = v[q];
     }
     __syncthreads();
     if (threadIdx.x < kAggs) {
-        unsigned v = 0;
-        for (int w = 0; w < kGrpThreads / 32; w++) v = threadIdx.x == 0 ? max(v, s_agg[0][w]) : v + s_agg[threadIdx.x][w];
+        unsigned t = 0;
+        for (int w = 0; w < kGrpThreads / 32; w++) t = threadIdx.x == 0 ? max(t, s_agg[0][w]) : t + s_agg[threadIdx.x][w];
         // aggregate 0 travels as a global slot + 1 (0 = no boundary in the tile)
-        if (threadIdx.x == 0 && v) v += (unsigned)tile_base;
-        a.agg[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = v;
+        if (threadIdx.x == 0 && t) t += (unsigned)tile_base;
+        a.agg[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = t;
     }
 }
 
@@ -281,22 +310,31 @@ group_apply_kernel(GroupArgs a) {
     unsigned keep = cnt[0], groups = cnt[1], keep_run = cnt[2];
     unsigned last = last1 - 1;                                                         // group start of the slot before mine
 
+    // the suffixes of my slots, requested together (unresolved slots come in long stretches: the members of a big group)
+    uint32_t sv[kGrpItems];
+    if (valid == (1u << kGrpItems) - 1u && (reinterpret_cast<uintptr_t>(a.suf) & 15) == 0) {
+        const uint4* src = reinterpret_cast<const uint4*>(a.suf + t0);
+#pragma unroll
+        for (int i = 0; i < kGrpItems / 4; i++) { const uint4 q = src[i]; sv[4 * i] = q.x; sv[4 * i + 1] = q.y; sv[4 * i + 2] = q.z; sv[4 * i + 3] = q.w; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kGrpItems; i++) sv[i] = ((valid & ~single) >> i) & 1 ? a.suf[t0 + i] : 0u;
+    }
 #pragma unroll
     for (int i = 0; i < kGrpItems; i++) {
-        if (!((valid >> i) & 1)) break;
+        if (!((valid >> i) & 1)) continue;                                             // valid slots are the low bits
         const uint32_t t = (uint32_t)t0 + i;
         if ((boundary >> i) & 1) last = t;
         if ((single >> i) & 1) continue;
-        const uint32_t sv = a.suf[t];
-        a.rank[sv & a.pos_mask] = INITIAL ? last : a.pos[last];
+        a.rank[sv[i] & a.pos_mask] = INITIAL ? last : a.pos[last];
         if (INITIAL && ((run >> i) & 1)) {
             a.run_pos_out[keep_run] = t;
-            a.run_suf_out[keep_run] = sv;
+            a.run_suf_out[keep_run] = sv[i];
             keep_run++;
         } else {
             if ((boundary >> i) & 1) groups++;
             a.pos_out[keep] = INITIAL ? t : a.pos[t];
-            a.suf_out[keep] = sv;
+            a.suf_out[keep] = sv[i];
             a.gid_out[keep] = a.gid_base + groups - 1;
             keep++;
         }

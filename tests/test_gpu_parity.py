@@ -64,6 +64,16 @@ def test_sort_skewed_digits(G):
     assert np.array_equal(k2, keys[order]) and np.array_equal(v2, vals[order])
 
 
+@pytest.mark.parametrize("n,bits", [(5, 64), (6145, 64), (1_000_003, 64), (3_000_000, 24)])
+def test_sort_pairs_wide_status(G, monkeypatch, n, bits):
+    """Sorts of 2^30 pairs and more use 64-bit status words in the look-back (radix_sort.cu: Status<unsigned long long>); the switch
+    sends a small sort through that instantiation."""
+    monkeypatch.setenv("GCZ_SORT_WIDE_STATUS", "1")
+    test_sort_pairs(G, n, bits)
+    monkeypatch.delenv("GCZ_SORT_WIDE_STATUS")
+    test_sort_pairs(G, n, bits)
+
+
 # ---- ranked bit vector layout ---------------------------------------------------------------------
 @pytest.mark.parametrize("n", [1, 7, 64, 511, 512, 513, 65535, 65536, 65537, 70001, 131072, 1_000_001])
 def test_ranked_vector(G, O, n):
@@ -135,6 +145,20 @@ def test_suffix_array(G, O, name, text):
     sa = np.zeros(len(text), np.int32)
     G._native.check(G.lib().gcz_dbg_suffix_array(0, _p(text), len(text), _p(sa)))
     assert np.array_equal(sa, O.suffix_array(text))
+
+
+def test_suffix_array_with_counter_flushes_and_wide_status(G, O, monkeypatch):
+    """Two paths of the first sort that only very large blocks reach: the 16-bit lane counters of text_hist_kernel are summed
+    into the histogram in mid-run (here after every tile instead of every 500), and the look-back runs on 64-bit status words."""
+    from gecoz_b200 import synth
+    text = synth.cfg2_text(3_000_000, seed=4)
+    exp = O.suffix_array(text)
+    for env in ("GCZ_TEXT_FLUSH_TILES", "GCZ_SORT_WIDE_STATUS"):
+        monkeypatch.setenv(env, "1")
+        sa = np.zeros(len(text), np.int32)
+        G._native.check(G.lib().gcz_dbg_suffix_array(0, _p(text), len(text), _p(sa)))
+        monkeypatch.delenv(env)
+        assert np.array_equal(sa, exp), env
 
 
 # ---- whole block: SA, BWT, .gcz body, .gcx body ------------------------------------------------------------

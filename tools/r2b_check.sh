@@ -1,0 +1,25 @@
+#!/bin/bash
+# r2b_check.sh — one GPU call: sorter timing, the GPU suite, the block bench, the launch list of a build step.
+#   /usr/local/graft/bin/gpurun --timeout 1200 -- 'bash tools/r2b_check.sh [tag] [NCU=1]'
+T=${1:-r2b}
+mkdir -p gpurun_out
+{
+echo "== sorter"
+timeout -k 5 60 python tools/sortbench.py 3000000 48 || echo "sortbench small rc=$?"
+timeout -k 5 120 python tools/sortbench.py 248956423 48 || echo "sortbench rc=$?"
+echo "== GPU tests"
+timeout -k 10 1500 python -m pytest tests -q -m gpu -x --timeout 600 > gpurun_out/${T}_pytest.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/${T}_pytest.log
+echo "== block bench"
+timeout -k 10 300 python bench.py --steps 10 --warmup 3 --block-only --no-cpu-baseline > gpurun_out/${T}_bench_block.json 2> gpurun_out/${T}_bench_block.err; echo "bench rc=$?"; tail -5 gpurun_out/${T}_bench_block.err
+python -c "
+import json; d=json.load(open('gpurun_out/${T}_bench_block.json')); print('step ms', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'], 'roofline', d['roofline']['frac'], d['roofline']['avg_launch_ms'], d['phases_ms'], d['parity']['ok'])"
+echo "== launch list"
+python tools/build_once.py 2
+timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${T}_launches.csv python tools/build_once.py 3 > gpurun_out/${T}_launches.log 2>&1; tail -2 gpurun_out/${T}_launches.log
+python tools/launch_shares.py gpurun_out/${T}_launches.csv 1
+if [ -n "$2" ]; then
+echo "== ncu --set full: digit passes + text histogram + grouping of a real build"
+timeout -k 10 600 ncu --set full --clock-control none --import-source on -k 'regex:onesweep_kernel|text_hist_kernel|group_flags_kernel|group_apply_kernel' -s 35 -c 9 -f -o gpurun_out/${T}_build python tools/build_once.py 2 > gpurun_out/${T}_ncu.log 2>&1; tail -2 gpurun_out/${T}_ncu.log
+fi
+} > gpurun_out/${T}.log 2>&1
+tail -100 gpurun_out/${T}.log
