@@ -96,6 +96,8 @@ struct DeviceCtx {
     std::atomic<int64_t> launches{0};        // kernels launched by this library on this device
     bool         iwt_attr = false;             // dynamic-smem opt-in done for iwt_low_levels_kernel
     bool         sort_attr[3] = { false, false, false };   // dynamic-smem opt-in done for the onesweep kernels
+    unsigned     sort_attr_mask = 0;           // bit v: the same, per variant of the digit pass
+    unsigned     text_hist_attr = 0;           // bit p: the same for text_hist_kernel<p>
 };
 
 int          get_ctx(int device, DeviceCtx** out);   // creates on first use; fails with GCZ_E_NODEVICE

@@ -22,7 +22,7 @@ namespace {
 constexpr int RB = 8;                   // digit width
 constexpr int kRadix = 1 << RB;
 constexpr int kHistThreads = 512;
-constexpr int kLookWindow = 16;
+constexpr int kPadRows = 32;                // "prefix 0" rows in front of the status array: the widest look-back window
 
 // Status word of (tile, digit): count in the low bits, two flag bits on top (aggregate = this tile's count, prefix = the
 // count of this and all earlier tiles).  32-bit words whenever a prefix fits 30 bits (any block below 2^30 pairs): half
@@ -43,6 +43,7 @@ template <> struct Status<unsigned long long> {
     static __device__ __forceinline__ unsigned long long ld(const unsigned long long* p) { return ld_relaxed_u64(p); }
     static __device__ __forceinline__ void st(unsigned long long* p, unsigned long long v) { st_relaxed_u64(p, v); }
 };
+constexpr int kDefaultSortVariant = 0;
 constexpr int64_t kNarrowStatusLimit = (int64_t)1 << 30;    // pairs a sort may have for 32-bit status words
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -74,16 +75,19 @@ radix_hist_kernel(const uint64_t* __restrict__ keys, int64_t n, int begin_bit, i
 //
 // Counting: npass shared-memory reductions per position.  With one 256-bin table per digit the 32 lanes of a warp hit random
 // banks (3.5 wavefronts per reduction: the first version was bound by exactly that, 245 M wavefronts per chr1-sized text).
-// Here every LANE has a column of its own: counter (digit, bin) of lane l is a 16-bit field of word [digit][bin / 2][l], bank l —
-// one wavefront per reduction.  A field counts what the eight warps of the CTA add for one lane: at most 128 per tile, so the
-// table is summed into the global histogram every kTextFlushTiles tiles.  The text of the next tile is requested before the
-// current one is counted.
+// Here counter (digit, bin) has 16 words, one per PAIR of lanes, and each lane of the pair owns a 16-bit half of the word:
+// word [digit][bin][lane / 2], bank (16 bin + lane / 2) % 32 — lanes of different pairs never meet in a bank, the two of a pair
+// do when their bins have the same parity (1.5 wavefronts on average), and the increment is a per-thread constant, so a count
+// is three instructions (byte of the key, address, reduction).  A half-word counts what the eight warps of the CTA add for one
+// lane: at most 128 per tile, so the table is summed into the global histogram every kTextFlushTiles tiles.  The text of the
+// next tile is requested before the current one is counted.
 constexpr int kTextThreads = 256;
 constexpr int kTextItems = 16;
 constexpr int kTextTile = kTextThreads * kTextItems;
 constexpr int kTextFlushTiles = 500;                       // 500 x 128 < 2^16
 constexpr int kTextCodes = 16 + kTextTile + kMaxKeySymbols + 16;
-inline size_t text_hist_smem(int npass) { return (size_t)npass * (kRadix / 2) * 32 * 4 + kTextCodes + 256; }
+constexpr int kTextDigitWords = kRadix * 16;               // words of one digit's table
+inline size_t text_hist_smem(int npass) { return (size_t)npass * kTextDigitWords * 4 + kTextCodes + 256; }
 
 __device__ __forceinline__ uint64_t slide_key(uint64_t key, uint32_t c_out, uint32_t c_in, uint32_t radix, uint64_t top) {
     key -= (uint64_t)c_out * top;                          // 8-bit x 64-bit and 64-bit x 9-bit products: two IMADs each
@@ -97,13 +101,14 @@ __device__ __forceinline__ uint32_t translate4(const uint8_t* s_code_of, uint32_
            (uint32_t)s_code_of[(w >> 16) & 255] << 16 | (uint32_t)s_code_of[w >> 24] << 24;
 }
 
+template <int NPASS>
 __global__ void __launch_bounds__(kTextThreads)
-text_hist_kernel(TextKeySource src, int npass, unsigned long long* __restrict__ hist /* [npass][radix] */, int64_t tiles, int flush_tiles) {
+text_hist_kernel(TextKeySource src, unsigned long long* __restrict__ hist /* [NPASS][radix] */, int64_t tiles, int flush_tiles) {
     extern __shared__ __align__(16) unsigned char text_smem[];
-    unsigned* s_cnt = reinterpret_cast<unsigned*>(text_smem);                       // [npass][128][32]
-    uint8_t* s_codes = text_smem + (size_t)npass * (kRadix / 2) * 32 * 4;           // index 16 = first position of the tile
+    unsigned* s_cnt = reinterpret_cast<unsigned*>(text_smem);                       // [NPASS][256][16]
+    uint8_t* s_codes = text_smem + (size_t)NPASS * kTextDigitWords * 4;             // index 16 = first position of the tile
     uint8_t* s_code_of = s_codes + kTextCodes;
-    const int cnt_words = npass * (kRadix / 2) * 32;
+    constexpr int cnt_words = NPASS * kTextDigitWords;
     for (int i = threadIdx.x; i < cnt_words; i += kTextThreads) s_cnt[i] = 0;
     s_code_of[threadIdx.x] = src.code_of[threadIdx.x];
     const int k = src.coder.k;
@@ -114,34 +119,33 @@ text_hist_kernel(TextKeySource src, int npass, unsigned long long* __restrict__ 
     const int64_t n = src.n;
     const bool aligned = (reinterpret_cast<uintptr_t>(src.text) & 15) == 0;
     const unsigned lane = threadIdx.x & 31u;
+    const uint32_t my_column = smem_u32(s_cnt) + (lane >> 1) * 4;     // shared-memory address of word [0][0][lane / 2]
+    const uint32_t my_one = 1u << (16 * (lane & 1));
     const int first = 16 + threadIdx.x * kTextItems;
     const int in_at = first + k - 1;                       // s_codes index of the symbol that enters the window at my first position
     const uint32_t in_sel = 0x3210u + 0x1111u * (uint32_t)(in_at & 3);
 
-    // what the tile needs from global memory, as raw text bytes: my 16 symbols, and (threads 0 .. k + 1) one symbol of the edges
+    // what the tile needs from global memory, as raw text bytes: my 16 symbols, and (threads 0 .. k, and the last) one symbol of the edges
     auto fetch = [&](int64_t tile, uint4& q, uint32_t& edge) {
         const int64_t base = tile * kTextTile;
         const int64_t p0 = base + (int64_t)threadIdx.x * kTextItems;
         q = make_uint4(0, 0, 0, 0);
-        if (tile < tiles) {
-            if (aligned && p0 + kTextItems <= n) {
-                q = *reinterpret_cast<const uint4*>(src.text + p0);
-            } else {
-                uint32_t w[4] = { 0, 0, 0, 0 };
-                for (int j = 0; j < kTextItems; j++) {
-                    if (p0 + j < n) w[j >> 2] |= (uint32_t)src.text[p0 + j] << (8 * (j & 3));
-                }
-                q = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-        }
         edge = 0x100u;                                     // 0x100: no symbol there (code 0 = past the end)
-        if (tile < tiles) {
-            if (threadIdx.x <= (unsigned)k) {              // right halo: k + 1 symbols
-                const int64_t p = base + kTextTile + threadIdx.x;
-                if (p < n) edge = src.text[p];
-            } else if (threadIdx.x == kTextThreads - 1 && base > 0) {
-                edge = src.text[base - 1];
+        if (tile >= tiles) return;
+        if (aligned && p0 + kTextItems <= n) {
+            q = *reinterpret_cast<const uint4*>(src.text + p0);
+        } else {
+            uint32_t w[4] = { 0, 0, 0, 0 };
+            for (int j = 0; j < kTextItems; j++) {
+                if (p0 + j < n) w[j >> 2] |= (uint32_t)src.text[p0 + j] << (8 * (j & 3));
             }
+            q = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        if (threadIdx.x <= (unsigned)k) {                  // right halo: k + 1 symbols
+            const int64_t p = base + kTextTile + threadIdx.x;
+            if (p < n) edge = src.text[p];
+        } else if (threadIdx.x == kTextThreads - 1 && base > 0) {
+            edge = src.text[base - 1];
         }
     };
     uint4 q;
@@ -188,13 +192,11 @@ text_hist_kernel(TextKeySource src, int npass, unsigned long long* __restrict__ 
             key = slide_key(key, i > 0 ? byte_of(own, i - 1) : 0u, byte_of(in, i), radix, top);
             const int64_t p = p_first + i;
             if (whole || p < n) {
+                const uint32_t klo = (uint32_t)key, khi = (uint32_t)(key >> 32);
 #pragma unroll
-                for (int d = 0; d < 8; d++) {
-                    if (d < npass) {
-                        const unsigned bin = (unsigned)(key >> (RB * d)) & (kRadix - 1);
-                        unsigned* word = s_cnt + ((d * (kRadix / 2) + (bin >> 1)) * 32 + lane);
-                        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_u32(word)), "r"(1u << (16 * (bin & 1))) : "memory");
-                    }
+                for (int d = 0; d < NPASS; d++) {
+                    const uint32_t bin = __byte_perm(d < 4 ? klo : khi, 0, 0x4440 + (d & 3));
+                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(my_column + bin * 64 + d * (kTextDigitWords * 4)), "r"(my_one) : "memory");
                 }
                 const uint32_t c = byte_of(own, i);
                 if (src.run_marks && key == (uint64_t)c * unit) {
@@ -213,12 +215,12 @@ text_hist_kernel(TextKeySource src, int npass, unsigned long long* __restrict__ 
         if (++since_flush == flush_tiles || last_trip) {
             since_flush = 0;
             __syncthreads();
-            for (int d = 0; d < npass; d++) {              // thread b sums bin b over the 32 lane columns (rotated: bank = (j + b) % 32)
-                const unsigned* row = s_cnt + (d * (kRadix / 2) + (threadIdx.x >> 1)) * 32;
-                const int sh = 16 * (threadIdx.x & 1);
+#pragma unroll 1
+            for (int d = 0; d < NPASS; d++) {              // thread b sums the 32 half-words of bin b (rotated: one bank per thread)
+                const unsigned* row = s_cnt + d * kTextDigitWords + threadIdx.x * 16;
                 unsigned sum = 0;
-#pragma unroll 8
-                for (int j = 0; j < 32; j++) sum += (row[(j + threadIdx.x) & 31] >> sh) & 0xffffu;
+#pragma unroll
+                for (int j = 0; j < 16; j++) { const unsigned w = row[(j + (threadIdx.x >> 1)) & 15]; sum += (w & 0xffffu) + (w >> 16); }
                 if (sum) atomicAdd(&hist[d * kRadix + threadIdx.x], (unsigned long long)sum);
             }
             if (!last_trip) {
@@ -229,11 +231,20 @@ text_hist_kernel(TextKeySource src, int npass, unsigned long long* __restrict__ 
     }
 }
 
+typedef void (*TextHistFn)(TextKeySource, unsigned long long*, int64_t, int);
+inline TextHistFn text_hist_fn(int npass) {
+    switch (npass) {
+        case 1: return text_hist_kernel<1>; case 2: return text_hist_kernel<2>; case 3: return text_hist_kernel<3>;
+        case 4: return text_hist_kernel<4>; case 5: return text_hist_kernel<5>; case 6: return text_hist_kernel<6>;
+        case 7: return text_hist_kernel<7>; default: return text_hist_kernel<8>;
+    }
+}
+
 // exclusive scan of each pass's bins, in place (one thread per bin); also writes the "prefix 0" rows in front of the status array
 template <typename S>
 __global__ void radix_scan_kernel(unsigned long long* hist, int npass, S* status_pad) {
     __shared__ unsigned long long s_warp[kRadix / 32];
-    for (int j = 0; j < kLookWindow; j++) status_pad[j * kRadix + threadIdx.x] = Status<S>::kPrefix;
+    for (int j = 0; j < kPadRows; j++) status_pad[j * kRadix + threadIdx.x] = Status<S>::kPrefix;
     for (int p = 0; p < npass; p++) {
         unsigned long long v = hist[p * kRadix + threadIdx.x];
         unsigned long long incl = v;
@@ -277,6 +288,31 @@ __device__ __forceinline__ unsigned peers_with_same_digit(unsigned d) {
 __device__ __forceinline__ void red_shared_inc(unsigned* p) {
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(smem_u32(p)) : "memory");
 }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (TMA, no tensor map): bytes a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// generic-proxy accesses to shared memory before this point are ordered before async-proxy (TMA) writes after it
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Positions of a thread's ITEMS keys: keys of the warp with the same digit get consecutive positions in element order
 // (item, then lane), counted up from my_hist[digit] (shared memory: where the warp's first key of that digit goes);
@@ -324,12 +360,12 @@ __device__ __forceinline__ void rank_in_warp(const uint64_t (&key)[ITEMS], int s
 // and dropped — profiles/onesweep_experiments_r02.md has their kernels' numbers: persistent CTAs fed by TMA bulk copies
 // (cp.async.bulk + mbarrier; 1.86 ms per pass against 1.69), and a scan-ahead CTA that turns aggregates into prefixes
 // (2.99 ms: one chain of dependent L2 round trips cannot follow 25 tiles per microsecond).
-template <int THREADS, int ITEMS, bool HAS_VALS, int MIN_BLOCKS, bool FROM_TEXT, typename S>
+template <int THREADS, int ITEMS, bool HAS_VALS, int MIN_BLOCKS, bool FROM_TEXT, typename S, int LOOK, bool ASYNC>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
                 const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
                 int64_t n, int shift, const unsigned long long* __restrict__ digit_base,
-                S* __restrict__ status /* first real row (kLookWindow pad rows in front) */, unsigned* __restrict__ ticket,
+                S* __restrict__ status /* first real row (kPadRows pad rows in front) */, unsigned* __restrict__ ticket,
                 TextKeySource src) {
     constexpr int TILE = THREADS * ITEMS;
     constexpr int WARPS = THREADS / 32;
@@ -337,6 +373,8 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
     static_assert(!FROM_TEXT || HAS_VALS, "text input produces (key, position) pairs");
     static_assert(TILE * 4 >= TILE + kMaxKeySymbols + 8 + 256, "the value staging area holds the tile's symbol codes");
     static_assert((WARPS * kRadix) % (4 * THREADS) == 0, "the warp counters are cleared with 16-byte stores");
+    static_assert(LOOK <= kPadRows, "pad rows cover the look-back window");
+    static_assert(!ASYNC || (HAS_VALS && !FROM_TEXT), "only (key, value) array passes stage their values");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* s_keys = reinterpret_cast<uint64_t*>(smem_raw);                       // TILE
@@ -346,8 +384,21 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
     unsigned* s_digit_start = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned long long*>(s_gofs) + kRadix);   // 256
     unsigned* s_scan = s_digit_start + kRadix;                                      // 8 warp totals
     __shared__ unsigned s_tile;
+    __shared__ unsigned long long s_bar;
 
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    // ASYNC: the tile's values are not needed before the reorder; one bulk copy (TMA) brings them to where the reordered
+    // values will go, issued by the thread that learns the tile number, and they are picked up after the ranking
+    const bool vals_aligned = ASYNC && (reinterpret_cast<uintptr_t>(vals_in) & 15) == 0;
+    if (threadIdx.x == 0) {
+        if (ASYNC) { mbar_init(&s_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+        const unsigned t = atomicAdd(ticket, 1u);
+        s_tile = t;
+        if (ASYNC && vals_aligned && ((int64_t)t + 1) * TILE <= n) {
+            fence_proxy_async();
+            mbar_expect_tx(&s_bar, TILE * 4);
+            bulk_load(s_vals, vals_in + (size_t)t * TILE, TILE * 4, &s_bar);
+        }
+    }
 #pragma unroll
     for (int i = 0; i < WARPS * kRadix / (4 * THREADS); i++) {
         reinterpret_cast<uint4*>(s_warp_hist)[i * THREADS + threadIdx.x] = make_uint4(0, 0, 0, 0);
@@ -470,6 +521,11 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
             val[i] = (uint32_t)(tile_base + e) | (src.carry_shift ? (uint32_t)s_codes[e] << src.carry_shift : 0u);
         }
         __syncthreads();                      // the symbol codes share their shared memory with the reordered values
+    } else if (ASYNC && vals_aligned && count == TILE) {
+        mbar_wait(&s_bar, 0);
+#pragma unroll
+        for (int i = 0; i < ITEMS; i++) val[i] = s_vals[warp_base + i * 32 + lane];
+        __syncthreads();                      // every staged value is in a register before the reordered ones are stored
     } else if (HAS_VALS) {
         if (count == TILE) {
             const uint32_t* src_vals = vals_in + tile_base + warp_base + lane;
@@ -490,22 +546,22 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
         if (HAS_VALS) s_vals[pos] = val[i];
     }
 
-    // 6. decoupled look-back, kLookWindow predecessors per step: their status words are loaded together so the
+    // 6. decoupled look-back, LOOK predecessors per step: their status words are loaded together so the
     //    walk back to the nearest inclusive prefix costs one memory latency per window, not one per tile.  The words are
     //    summed with their flag bits on; the flags of `taken` aggregates and one prefix are subtracted at the end.
     if (threadIdx.x < kRadix) {
         S raw = 0;
         unsigned taken = 0;
-        const S* p = my_status - kRadix;                   // tile - 1 (row -1 .. -kLookWindow: "prefix 0")
+        const S* p = my_status - kRadix;                   // tile - 1 (rows -1 .. -kPadRows: "prefix 0")
         bool done = false;
         do {
-            S v[kLookWindow];
+            S v[LOOK];
 #pragma unroll
-            for (int j = 0; j < kLookWindow; j++) v[j] = Status<S>::ld(p - j * kRadix);
+            for (int j = 0; j < LOOK; j++) v[j] = Status<S>::ld(p - j * kRadix);
             bool go = true;
             unsigned used = 0;
 #pragma unroll
-            for (int j = 0; j < kLookWindow; j++) {
+            for (int j = 0; j < LOOK; j++) {
                 go = go && v[j] >= Status<S>::kAgg;          // a status word that is not there yet ends the step: polled again
                 if (go) { raw += v[j]; used = j + 1; }
                 if (v[j] >= Status<S>::kPrefix) { done = done || go; go = false; }
@@ -541,28 +597,30 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
     }
 }
 
-// 512 threads x 12 elements, two CTAs per SM (the shape profiles/sort_variants_r01.md picked)
-constexpr int kThreads = 512, kItems = 12, kTile = kThreads * kItems;
-constexpr size_t kFixedSmem = (size_t)(kThreads / 32) * kRadix * 4 + kRadix * 8 + kRadix * 4 + 64;
-constexpr size_t kSmemPairs = (size_t)kTile * 12 + kFixedSmem, kSmemKeys = (size_t)kTile * 8 + kFixedSmem;
+// Shape of the pass: 512 threads x 12 elements, two CTAs per SM (what profiles/sort_variants_r01.md picked), or 384 x 12, three per SM.
+constexpr size_t onesweep_smem(int threads, int items, bool vals) {
+    return (size_t)threads * items * (vals ? 12 : 8) + (size_t)(threads / 32) * kRadix * 4 + kRadix * 8 + kRadix * 4 + 64;
+}
+constexpr int kMinTile = 384 * 12;
 
-template <typename S>
+template <typename S, int THREADS, int ITEMS, int MINB, int LOOK, bool ASYNC>
 int digit_passes(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n, int begin_bit, int npass, unsigned long long* hist,
-                 void* status_mem, SortStats* stats, const TextKeySource* src) {
+                 void* status_mem, SortStats* stats, const TextKeySource* src, int attr_slot) {
+    constexpr int kTile = THREADS * ITEMS;
+    constexpr size_t kSmemPairs = onesweep_smem(THREADS, ITEMS, true), kSmemKeys = onesweep_smem(THREADS, ITEMS, false);
     const bool has_vals = b.vals[0] != nullptr;
-    auto* pairs = onesweep_kernel<kThreads, kItems, true, 2, false, S>;
-    auto* keys_only = onesweep_kernel<kThreads, kItems, false, 2, false, S>;
-    auto* from_text = onesweep_kernel<kThreads, kItems, true, 2, true, S>;
-    bool& attr = ctx->sort_attr[sizeof(S) == 4 ? 0 : 1];
-    if (!attr) {
+    auto* pairs = onesweep_kernel<THREADS, ITEMS, true, MINB, false, S, LOOK, ASYNC>;
+    auto* keys_only = onesweep_kernel<THREADS, ITEMS, false, MINB, false, S, LOOK, false>;
+    auto* from_text = onesweep_kernel<THREADS, ITEMS, true, MINB, true, S, LOOK, false>;
+    if (!(ctx->sort_attr_mask >> attr_slot & 1)) {
         GCZ_CUDA(cudaFuncSetAttribute(pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPairs));
         GCZ_CUDA(cudaFuncSetAttribute(keys_only, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemKeys));
         GCZ_CUDA(cudaFuncSetAttribute(from_text, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPairs));
-        attr = true;
+        ctx->sort_attr_mask |= 1u << attr_slot;
     }
     const int64_t tiles = (n + kTile - 1) / kTile;
     S* pad = static_cast<S*>(status_mem);
-    S* status = pad + (size_t)kLookWindow * kRadix;
+    S* status = pad + (size_t)kPadRows * kRadix;
     auto* ticket = reinterpret_cast<unsigned*>(status + (size_t)tiles * kRadix);
     const TextKeySource none;
     GCZ_LAUNCH(ctx, radix_scan_kernel<S>, 1, kRadix, 0, st, hist, npass, pad);
@@ -577,14 +635,14 @@ int digit_passes(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n, in
             GCZ_CUDA(cudaEventRecord(e0, st));
         }
         if (src && p == 0) {
-            from_text<<<(unsigned)tiles, kThreads, kSmemPairs, st>>>(nullptr, b.keys[out], nullptr, b.vals[out], n, shift,
-                                                                     hist + p * kRadix, status, ticket, *src);
+            from_text<<<(unsigned)tiles, THREADS, kSmemPairs, st>>>(nullptr, b.keys[out], nullptr, b.vals[out], n, shift,
+                                                                    hist + p * kRadix, status, ticket, *src);
         } else if (has_vals) {
-            pairs<<<(unsigned)tiles, kThreads, kSmemPairs, st>>>(b.keys[in], b.keys[out], b.vals[in], b.vals[out], n, shift,
-                                                                 hist + p * kRadix, status, ticket, none);
+            pairs<<<(unsigned)tiles, THREADS, kSmemPairs, st>>>(b.keys[in], b.keys[out], b.vals[in], b.vals[out], n, shift,
+                                                                hist + p * kRadix, status, ticket, none);
         } else {
-            keys_only<<<(unsigned)tiles, kThreads, kSmemKeys, st>>>(b.keys[in], b.keys[out], nullptr, nullptr, n, shift,
-                                                                    hist + p * kRadix, status, ticket, none);
+            keys_only<<<(unsigned)tiles, THREADS, kSmemKeys, st>>>(b.keys[in], b.keys[out], nullptr, nullptr, n, shift,
+                                                                   hist + p * kRadix, status, ticket, none);
         }
         ctx->launches++;
         GCZ_CUDA(cudaPeekAtLastError());
@@ -604,9 +662,9 @@ int digit_passes(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n, in
 int radix_sort_passes(int bits) { return (bits + RB - 1) / RB; }
 
 size_t radix_sort_temp_bytes(int64_t n) {
-    const int64_t tiles = (n + kTile - 1) / kTile;
-    // [8][radix] histogram + status rows (kLookWindow "prefix 0" rows, then one per tile) + ticket
-    return 8 * (size_t)kRadix * 8 + 256 + ((size_t)(tiles + kLookWindow) * kRadix * 8 + 256);
+    const int64_t tiles = (n + kMinTile - 1) / kMinTile;
+    // [8][radix] histogram + status rows (kPadRows "prefix 0" rows, then one per tile) + ticket
+    return 8 * (size_t)kRadix * 8 + 256 + ((size_t)(tiles + kPadRows) * kRadix * 8 + 256);
 }
 
 int radix_sort_pairs(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n, int begin_bit, int end_bit,
@@ -623,22 +681,32 @@ int radix_sort_pairs(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n
     if (src) {
         const int64_t ttiles = (n + kTextTile - 1) / kTextTile;
         const size_t smem = text_hist_smem(npass);
-        if (!ctx->sort_attr[2]) {
-            GCZ_CUDA(cudaFuncSetAttribute(text_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)text_hist_smem(8)));
-            ctx->sort_attr[2] = true;
+        const TextHistFn text_hist = text_hist_fn(npass);
+        if (!(ctx->text_hist_attr >> npass & 1)) {
+            GCZ_CUDA(cudaFuncSetAttribute(text_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ctx->text_hist_attr |= 1u << npass;
         }
         const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)220 << 10) / (smem + 1024)));
         const int grid = (int)std::min<int64_t>(ttiles, (int64_t)ctx->sm_count * per_sm);
         const char* fe = std::getenv("GCZ_TEXT_FLUSH_TILES");            // tests: the mid-run flush of the 16-bit counters
         const int flush_tiles = fe && std::atoi(fe) > 0 ? std::min(std::atoi(fe), kTextFlushTiles) : kTextFlushTiles;
-        GCZ_LAUNCH(ctx, text_hist_kernel, grid, kTextThreads, smem, st, *src, npass, hist, ttiles, flush_tiles);
+        GCZ_LAUNCH(ctx, text_hist, grid, kTextThreads, smem, st, *src, hist, ttiles, flush_tiles);
     } else {
         const int hist_grid = (int)std::min<int64_t>((n + kHistThreads * 8 - 1) / (kHistThreads * 8), (int64_t)ctx->sm_count * 4);
         GCZ_LAUNCH(ctx, radix_hist_kernel, hist_grid, kHistThreads, 0, st, b.keys[b.cur], n, begin_bit, npass, hist);
     }
     const bool force_wide = std::getenv("GCZ_SORT_WIDE_STATUS") != nullptr;    // tests: the 64-bit status words at any size
-    if (n < kNarrowStatusLimit && !force_wide) return digit_passes<uint32_t>(ctx, st, b, n, begin_bit, npass, hist, status_mem, stats, src);
-    return digit_passes<unsigned long long>(ctx, st, b, n, begin_bit, npass, hist, status_mem, stats, src);
+    if (n >= kNarrowStatusLimit || force_wide)
+        return digit_passes<unsigned long long, 512, 12, 2, 16, false>(ctx, st, b, n, begin_bit, npass, hist, status_mem, stats, src, 0);
+    // A/B switch (bit 0: look-back window 32, bit 1: values staged by a bulk copy, bit 2: 384 threads, three CTAs per SM)
+    const char* ve = std::getenv("GCZ_SORT_VARIANT");
+    switch (ve ? std::atoi(ve) : kDefaultSortVariant) {
+#define GCZ_V(id, T, M, L, A) case id: return digit_passes<uint32_t, T, 12, M, L, A>(ctx, st, b, n, begin_bit, npass, hist, status_mem, stats, src, 1 + id);
+        GCZ_V(0, 512, 2, 16, false) GCZ_V(1, 512, 2, 32, false) GCZ_V(2, 512, 2, 16, true) GCZ_V(3, 512, 2, 32, true)
+        GCZ_V(4, 384, 3, 16, false) GCZ_V(5, 384, 3, 32, false) GCZ_V(6, 384, 3, 16, true) GCZ_V(7, 384, 3, 32, true)
+#undef GCZ_V
+        default: return fail(GCZ_E_ARG, "GCZ_SORT_VARIANT");
+    }
 }
 
 void SortStats::resolve() {

@@ -26,5 +26,5 @@ for it in range(3):
     res.append((t.radix_ms, t.radix_launches))
 ok = bool((keys[1:] >= keys[:-1]).all())
 ms, passes = res[-1]
-print(f"persistent={os.environ.get('GCZ_SORT_PERSISTENT', '1')} n={n} bits={bits} passes={passes} ms={ms:.3f} "
+print(f"variant={os.environ.get('GCZ_SORT_VARIANT', 'default')} n={n} bits={bits} passes={passes} ms={ms:.3f} "
       f"per_pass={ms / passes:.3f} GB/s={24 * n * passes / ms / 1e6:.0f} sorted={ok}")
