@@ -43,7 +43,6 @@ template <> struct Status<unsigned long long> {
     static __device__ __forceinline__ unsigned long long ld(const unsigned long long* p) { return ld_relaxed_u64(p); }
     static __device__ __forceinline__ void st(unsigned long long* p, unsigned long long v) { st_relaxed_u64(p, v); }
 };
-constexpr int kDefaultSortVariant = 0;
 constexpr int64_t kNarrowStatusLimit = (int64_t)1 << 30;    // pairs a sort may have for 32-bit status words
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -365,7 +364,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
                 const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
                 int64_t n, int shift, const unsigned long long* __restrict__ digit_base,
-                S* __restrict__ status /* first real row (kPadRows pad rows in front) */, unsigned* __restrict__ ticket,
+                S* __restrict__ status /* row of tile 0, kPadRows "prefix 0" rows in front */, unsigned* __restrict__ ticket,
                 TextKeySource src) {
     constexpr int TILE = THREADS * ITEMS;
     constexpr int WARPS = THREADS / 32;
@@ -546,9 +545,9 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
         if (HAS_VALS) s_vals[pos] = val[i];
     }
 
-    // 6. decoupled look-back, LOOK predecessors per step: their status words are loaded together so the
-    //    walk back to the nearest inclusive prefix costs one memory latency per window, not one per tile.  The words are
-    //    summed with their flag bits on; the flags of `taken` aggregates and one prefix are subtracted at the end.
+    // 6. decoupled look-back, LOOK predecessors per step: their status words are loaded together so the walk back to the
+    //    nearest inclusive prefix costs one memory latency per window, not one per tile.  The words are summed with their flag
+    //    bits on; the flags of `taken - 1` aggregates and one prefix are subtracted at the end.
     if (threadIdx.x < kRadix) {
         S raw = 0;
         unsigned taken = 0;
@@ -597,11 +596,12 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
     }
 }
 
-// Shape of the pass: 512 threads x 12 elements, two CTAs per SM (what profiles/sort_variants_r01.md picked), or 384 x 12, three per SM.
+// Shape of the pass: 512 threads x 12 elements, two CTAs per SM (what profiles/sort_variants_r01.md picked; 384 x 12 with three CTAs
+// per SM was measured again in round 2 with the leaner kernel: 1.87 ms against 1.74).
 constexpr size_t onesweep_smem(int threads, int items, bool vals) {
     return (size_t)threads * items * (vals ? 12 : 8) + (size_t)(threads / 32) * kRadix * 4 + kRadix * 8 + kRadix * 4 + 64;
 }
-constexpr int kMinTile = 384 * 12;
+constexpr int kMinTile = 512 * 12;
 
 template <typename S, int THREADS, int ITEMS, int MINB, int LOOK, bool ASYNC>
 int digit_passes(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n, int begin_bit, int npass, unsigned long long* hist,
@@ -619,6 +619,7 @@ int digit_passes(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n, in
         ctx->sort_attr_mask |= 1u << attr_slot;
     }
     const int64_t tiles = (n + kTile - 1) / kTile;
+    // rows of 256 status words: kPadRows of "prefix 0", then one per tile
     S* pad = static_cast<S*>(status_mem);
     S* status = pad + (size_t)kPadRows * kRadix;
     auto* ticket = reinterpret_cast<unsigned*>(status + (size_t)tiles * kRadix);
@@ -697,16 +698,9 @@ int radix_sort_pairs(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n
     }
     const bool force_wide = std::getenv("GCZ_SORT_WIDE_STATUS") != nullptr;    // tests: the 64-bit status words at any size
     if (n >= kNarrowStatusLimit || force_wide)
-        return digit_passes<unsigned long long, 512, 12, 2, 16, false>(ctx, st, b, n, begin_bit, npass, hist, status_mem, stats, src, 0);
-    // A/B switch (bit 0: look-back window 32, bit 1: values staged by a bulk copy, bit 2: 384 threads, three CTAs per SM)
-    const char* ve = std::getenv("GCZ_SORT_VARIANT");
-    switch (ve ? std::atoi(ve) : kDefaultSortVariant) {
-#define GCZ_V(id, T, M, L, A) case id: return digit_passes<uint32_t, T, 12, M, L, A>(ctx, st, b, n, begin_bit, npass, hist, status_mem, stats, src, 1 + id);
-        GCZ_V(0, 512, 2, 16, false) GCZ_V(1, 512, 2, 32, false) GCZ_V(2, 512, 2, 16, true) GCZ_V(3, 512, 2, 32, true)
-        GCZ_V(4, 384, 3, 16, false) GCZ_V(5, 384, 3, 32, false) GCZ_V(6, 384, 3, 16, true) GCZ_V(7, 384, 3, 32, true)
-#undef GCZ_V
-        default: return fail(GCZ_E_ARG, "GCZ_SORT_VARIANT");
-    }
+        return digit_passes<unsigned long long, 512, 12, 2, 8, true>(ctx, st, b, n, begin_bit, npass, hist, status_mem, stats, src, 0);
+    // 32-bit status words, window of 8 rows, values staged by a bulk copy: profiles/onesweep_experiments_r02.md, second series
+    return digit_passes<uint32_t, 512, 12, 2, 8, true>(ctx, st, b, n, begin_bit, npass, hist, status_mem, stats, src, 1);
 }
 
 void SortStats::resolve() {

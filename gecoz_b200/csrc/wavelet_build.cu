@@ -9,6 +9,7 @@
 // The reference streams one symbol at a time into bit writers; here every structure is produced by
 // prefix sums over warp tiles (a bit's position in a node = number of earlier symbols routed to that node).
 #include "wavelet_build.cuh"
+#include "row_scan.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -691,7 +692,7 @@ size_t wavelet_workspace_bytes(int64_t n, int sampling_factor) {
     size_t raw_words = (size_t)superblocks(n) * 2048 * 15 + 256 * 2048;   // nodes: <= 15 levels of n bits + padding
     raw_words += (size_t)superblocks(n) * 2048;                   // marker
     raw_words += (size_t)superblocks(m) * 2048 * levels;          // IWT levels
-    return raw_words * 4 + tiles * 4 * 258 + (size_t)m * 8 + (size_t)((m + 31) / 32) * 4 + (4 << 20);
+    return raw_words * 4 + tiles * 4 * 258 + (size_t)m * 8 + (size_t)((m + 31) / 32) * 4 + row_scan_scratch_bytes(257, (int64_t)tiles) + (4 << 20);
 }
 
 int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, uint32_t* d_sa, int carry_shift, bool clean_sa,
@@ -773,7 +774,8 @@ int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_t
     uint32_t* d_zeros = arena.get<uint32_t>((size_t)((m + 31) >> 5) + 1);
     uint32_t* d_block_zeros = arena.get<uint32_t>((size_t)((m + 1023) >> 10) + 1);
     uint64_t* d_level_raw = arena.get<uint64_t>(64);
-    if (!d_block_zeros || !d_level_raw) return fail(GCZ_E_NOMEM, "wavelet workspace for n=%lld", (long long)n);
+    void* d_scan = arena.raw(row_scan_scratch_bytes(sigma + 1, tiles));
+    if (!d_block_zeros || !d_level_raw || !d_scan) return fail(GCZ_E_NOMEM, "wavelet workspace for n=%lld", (long long)n);
     if (!d_tab || !d_raw || !d_tile_counts || !d_node_raw || !d_vecs || !d_sb || !d_ssa[0] || !d_ssa[1] || !d_zeros)
         return fail(GCZ_E_NOMEM, "wavelet workspace for n=%lld", (long long)n);
 
@@ -832,7 +834,7 @@ int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_t
         GCZ_LAUNCH(ctx, bwt_count_kernel<false>, wt_grid, kWtThreads, 0, st, d_text, d_sa, n, d_tab, sample_mask, carry_shift,
                    (carry_shift && clean_sa) ? d_sa : (uint32_t*)nullptr, d_bwt, d_marker_raw, d_tile_counts, tiles);
     }
-    GCZ_LAUNCH(ctx, row_scan_kernel, (unsigned)(sigma + 1), 1024, 0, st, d_tile_counts, tiles, (uint32_t*)nullptr);
+    GCZ_TRY(row_scan(ctx, st, d_tile_counts, sigma + 1, tiles, false, d_scan, nullptr, nullptr));
     if (emit_lut) {
         const int entries = (int)h_lut.size();
         const size_t smem = sizeof(uint2) * (size_t)entries + (size_t)(kWtThreads / 32) * n_nodes * kLutStageWords * 4;
