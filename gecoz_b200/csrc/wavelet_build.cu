@@ -127,30 +127,6 @@ bwt_count_kernel(const uint8_t* __restrict__ text, const uint32_t* __restrict__ 
     for (int i = lane; i <= sigma; i += 32) tile_counts[(size_t)i * tiles + tile] = cnt[i];
 }
 
-// one CTA per row: exclusive scan of `len` u32 values in place; row total -> totals[row]
-__global__ void __launch_bounds__(1024)
-row_scan_kernel(uint32_t* __restrict__ rows, int64_t len, uint32_t* __restrict__ totals) {
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry;
-    uint32_t* row = rows + (size_t)blockIdx.x * len;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    for (int64_t base = 0; base < len; base += 1024) {
-        const int64_t i = base + threadIdx.x;
-        const uint32_t v = i < len ? row[i] : 0;
-        const uint32_t incl = warp_incl_sum(v);
-        if (lane_id() == 31) s_warp[threadIdx.x >> 5] = incl;
-        __syncthreads();
-        uint32_t b = s_carry;
-        for (unsigned w = 0; w < (threadIdx.x >> 5); w++) b += s_warp[w];
-        if (i < len) row[i] = b + incl - v;
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = b + incl;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0 && totals) totals[blockIdx.x] = s_carry;
-}
-
 // ---- node bit emission ------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kWtThreads)
 hswt_emit_kernel(const uint8_t* __restrict__ bwt, int64_t n, const SymbolTables* __restrict__ tab,
@@ -416,72 +392,163 @@ sample_kernel(const uint32_t* __restrict__ sa, int64_t n, uint32_t pos_mask, uin
 }
 
 // ---- IndexWaveletTree levels ---------------------------------------------------------------------------
-// level h, current order = values grouped (stably) by v >> (h + 1), group g at slot g << (h + 1).
-// One warp per 1024 positions: bit h of the values -> 32 raw words, zeros before each word inside the block,
-// zeros of the block.  A short scan over the block totals completes the two-level zero count.
-__global__ void __launch_bounds__(256)
-iwt_bits_kernel(const uint32_t* __restrict__ vals, int64_t m, int h, uint32_t* __restrict__ raw,
-                uint32_t* __restrict__ zeros_in_block /* per word, exclusive inside its 32-word block */,
-                uint32_t* __restrict__ block_zeros /* per block */) {
-    const int64_t blocks = (m + 1023) >> 10;
-    const int64_t words = (m + 31) >> 5;
-    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const unsigned lane = lane_id();
-    for (int64_t blk = gw; blk < blocks; blk += nwarps) {
-        unsigned my_word = 0, my_valid = 0;
-#pragma unroll 8
-        for (int w = 0; w < 32; w++) {
-            const int64_t p = (blk << 10) + w * 32 + lane;
-            const bool valid = p < m;
-            const unsigned bit = valid ? (vals[p] >> h) & 1u : 0u;
-            const unsigned word = __ballot_sync(0xffffffffu, bit);
-            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-            if ((int)lane == w) { my_word = word; my_valid = vmask; }
-        }
-        const unsigned z = __popc(~my_word & my_valid);
-        const unsigned incl = warp_incl_sum(z);
-        const int64_t wi = (blk << 5) + lane;
-        if (wi < words) { raw[wi] = my_word; zeros_in_block[wi] = incl - z; }
-        if (lane == 31) block_zeros[blk] = incl;
+// The values are a permutation of 0 .. m - 1 (sampled suffix array entries >> sampling factor).  Level h of the tree shows
+// bit h of the values in the order "grouped (stably) by v >> (h + 1)", group g at slot g << (h + 1).
+//
+// High levels (groups longer than a CTA's block): up to kTopBits levels per pass.  A pass over bits H .. H - L + 1 starts from
+// the order grouped by v >> (H + 1) and ends in the order grouped by v >> (H - L + 1):
+//   count   per block of kIwtBlock values, how many carry each value of the L-bit digit;
+//   scan    the counts over the blocks (row_scan.cuh); a block's parent group starts on a block boundary, so the number of
+//           earlier values of the same parent group with digit b is scanned[b][block] - scanned[b][first block of the parent];
+//   emit    the block runs the L levels in shared memory like the low-level kernel below: at sub-level l its values are
+//           grouped by the first l bits of the digit, group q's bits are consecutive in the block AND at their destination —
+//           after the values of q in earlier blocks, whose number the scan gives — so they go out as one bit run per group
+//           (whole words stored, edge words by atomicOr), then every group is split by the bit; after the last split the block
+//           is sorted by digit and each digit's run is copied to its place in the next order.
+// The first version ran three launches per level over global memory (74 us per level of 7.8 M values, ten levels per chr1 block).
+constexpr int kIwtLowBits = 13;
+constexpr int kIwtBlock = 1 << kIwtLowBits;              // values per CTA
+constexpr int kIwtThreads = 1024;
+constexpr int kIwtPer = kIwtBlock / kIwtThreads;         // consecutive values per thread
+static_assert(kIwtPer == 8, "one byte of level bits per thread");
+constexpr int kTopBits = 5;
+constexpr int kTopBins = 1 << kTopBits;
+
+__global__ void __launch_bounds__(kIwtThreads)
+iwt_top_count_kernel(const uint32_t* __restrict__ vals, int64_t m, int low_bit, int L, uint32_t* __restrict__ counts /* [1 << L][blocks] */,
+                     int64_t blocks) {
+    __shared__ unsigned s_c[kTopBins];
+    if (threadIdx.x < kTopBins) s_c[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t block_start = (int64_t)blockIdx.x * kIwtBlock;
+    const unsigned mask = (1u << L) - 1u;
+#pragma unroll
+    for (int i = 0; i < kIwtPer; i++) {
+        const int64_t p = block_start + i * kIwtThreads + threadIdx.x;
+        if (p < m) atomicAdd(&s_c[(vals[p] >> low_bit) & mask], 1u);
     }
+    __syncthreads();
+    if (threadIdx.x <= mask) counts[(size_t)threadIdx.x * blocks + blockIdx.x] = s_c[threadIdx.x];
 }
 
-__device__ __forceinline__ uint32_t zeros_before(const uint32_t* __restrict__ raw, const uint32_t* __restrict__ zeros_in_block,
-                                                 const uint32_t* __restrict__ block_excl, int64_t p) {
-    const unsigned r = (unsigned)(p & 31);
-    return block_excl[p >> 10] + zeros_in_block[p >> 5] + (r ? __popc(~raw[p >> 5] & ((1u << r) - 1u)) : 0);
-}
+constexpr size_t kIwtTopSmem = (size_t)(2 * kIwtBlock + kIwtThreads + 32 + kIwtBlock / 32 + 8 + kIwtThreads / 4) * 4;
 
-__global__ void iwt_scatter_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int64_t m, int h,
-                                   const uint32_t* __restrict__ raw, const uint32_t* __restrict__ zeros_in_block,
-                                   const uint32_t* __restrict__ block_excl) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < m; p += stride) {
-        const uint32_t v = in[p];
-        const int64_t bs = (int64_t)(v >> (h + 1)) << (h + 1);
-        const int64_t zp = zeros_before(raw, zeros_in_block, block_excl, p);
-        const int64_t zb = bs < m ? zeros_before(raw, zeros_in_block, block_excl, bs) : 0;
-        int64_t np;
-        if (((v >> h) & 1u) == 0) {
-            np = bs + (zp - zb);
-        } else {
-            const int64_t zeros_in_group = min((int64_t)1 << h, m - bs);
-            np = bs + zeros_in_group + ((p - zp) - (bs - zb));
+__global__ void __launch_bounds__(kIwtThreads, 2)
+iwt_top_emit_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int64_t m64, int H, int L, int levels,
+                    uint32_t* __restrict__ raw, const uint64_t* __restrict__ level_raw_word,
+                    const uint32_t* __restrict__ scanned /* [1 << L][blocks], exclusive over the blocks */, int64_t blocks) {
+    extern __shared__ __align__(16) uint32_t s_iwt[];
+    uint32_t* cur = s_iwt;
+    uint32_t* nxt = s_iwt + kIwtBlock;
+    uint32_t* s_zc = s_iwt + 2 * kIwtBlock;              // zeros before each thread's first value
+    uint32_t* s_wsum = s_zc + kIwtThreads;               // 32
+    uint32_t* s_bits = s_wsum + 32;                      // kIwtBlock / 32 words of level bits (+ 8 words of padding)
+    uint8_t* s_zm = reinterpret_cast<uint8_t*>(s_bits + kIwtBlock / 32 + 8);   // zero masks, one byte per thread
+    __shared__ unsigned s_c[kTopBins];                   // values of the block per digit
+    __shared__ unsigned s_pc[kTopBins + 1];              // ... with a smaller digit: where a digit's (or a group's) values start in the block
+    __shared__ unsigned s_pb[kTopBins + 1];              // values of the parent group with a smaller digit in earlier blocks
+
+    // slots and values are below m <= 2^31: 32-bit arithmetic throughout
+    const unsigned m = (unsigned)m64;
+    const unsigned block_start = blockIdx.x * (unsigned)kIwtBlock;
+    const int cnt = (int)min((unsigned)kIwtBlock, m - block_start);
+    const int t = threadIdx.x;
+    const int low_bit = H - L + 1;
+    const unsigned dmask = (1u << L) - 1u;
+    const unsigned parent = H + 1 >= 32 ? 0u : (block_start >> (H + 1)) << (H + 1);
+    const unsigned parent_len = H + 1 >= 31 ? m - parent : min(1u << (H + 1), m - parent);
+    if (t < kTopBins) s_c[t] = 0;
+    if (t < kIwtBlock / 32 + 8) s_bits[t] = 0;
+    __syncthreads();
+    for (int i = 0; i < kIwtPer; i++) {
+        const int e = i * kIwtThreads + t;
+        const uint32_t v = e < cnt ? in[block_start + e] : 0xFFFFFFFFu;
+        cur[e] = v;
+        if (e < cnt) atomicAdd(&s_c[(v >> low_bit) & dmask], 1u);
+    }
+    __syncthreads();
+    if (t < 32) {                                        // prefix sums over the digits (warp 0)
+        const unsigned c = t <= (int)dmask ? s_c[t] : 0u;
+        const unsigned before = t <= (int)dmask ? scanned[(size_t)t * blocks + blockIdx.x] - scanned[(size_t)t * blocks + (parent >> kIwtLowBits)] : 0u;
+        const unsigned ic = warp_incl_sum(c), ib = warp_incl_sum(before);
+        s_pc[t + 1] = ic; s_pb[t + 1] = ib;
+        if (t == 0) { s_pc[0] = 0; s_pb[0] = 0; }
+    }
+    __syncthreads();
+
+    const int e0 = t * kIwtPer;
+    const unsigned valid = e0 >= cnt ? 0u : (e0 + kIwtPer <= cnt ? 0xFFu : (1u << (cnt - e0)) - 1u);
+    for (int l = 0; l < L; l++) {
+        const int h = H - l;
+        const int groups = 1 << l, span_shift = L - l;                        // 1 << span_shift digits per group
+        const uint4 q0 = reinterpret_cast<const uint4*>(cur)[2 * t], q1 = reinterpret_cast<const uint4*>(cur)[2 * t + 1];
+        const uint32_t v[kIwtPer] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w };
+        unsigned bits = 0;
+#pragma unroll
+        for (int i = 0; i < kIwtPer; i++) bits |= ((v[i] >> h) & 1u) << i;
+        bits &= valid;
+        const unsigned zmask = ~bits & valid;
+        reinterpret_cast<uint8_t*>(s_bits)[t] = (uint8_t)bits;
+        s_zm[t] = (uint8_t)zmask;
+        const unsigned z = __popc(zmask);
+        const unsigned incl = warp_incl_sum(z);
+        if (lane_id() == 31) s_wsum[t >> 5] = incl;
+        __syncthreads();
+        const unsigned wincl = warp_incl_sum(s_wsum[lane_id()]);                         // every warp scans the warp totals
+        const unsigned wbase = __shfl_sync(0xffffffffu, wincl - s_wsum[lane_id()], t >> 5);
+        const unsigned zexcl = wbase + incl - z;
+        s_zc[t] = zexcl;
+        // the level's bits: one run per group (group q = digits q << span_shift .. : consecutive in the block and at the destination)
+        uint32_t* lraw = raw + level_raw_word[levels - 1 - h];
+        for (int q = 0; q < groups; q++) {
+            const unsigned A = s_pc[q << span_shift], C = s_pc[(q + 1) << span_shift] - A;
+            if (C == 0) continue;
+            const unsigned off = h + 1 >= 32 ? 0u : (unsigned)q << (h + 1);                      // the group's first slot inside the parent group
+            const unsigned D = parent + min(off, parent_len) + (s_pb[(q + 1) << span_shift] - s_pb[q << span_shift]);
+            const unsigned w0 = D >> 5;
+            const unsigned nwords = ((D & 31u) + C + 31u) >> 5;
+            for (unsigned k = t; k < nwords; k += kIwtThreads) {
+                const unsigned lo = max(D, (w0 + k) << 5), hi = min(D + C, (w0 + k + 1) << 5);
+                const unsigned src = A + (lo - D), len = hi - lo;
+                const unsigned long long x = (unsigned long long)s_bits[src >> 5] | (unsigned long long)s_bits[(src >> 5) + 1] << 32;
+                const unsigned val = (unsigned)(x >> (src & 31u)) & (len == 32u ? 0xFFFFFFFFu : (1u << len) - 1u);
+                if (len == 32u) lraw[w0 + k] = val; else atomicOr(&lraw[w0 + k], val << (lo & 31u));
+            }
         }
-        out[np] = v;
+        __syncthreads();                                                       // s_zc is complete
+        int q = -1;
+        unsigned A = 0, next_A = 0, zb = 0, zeros = 0;
+#pragma unroll
+        for (int i = 0; i < kIwtPer; i++) {
+            if (!((valid >> i) & 1u)) break;
+            const unsigned e = e0 + i;
+            if (q < 0 || e >= next_A) {                                            // first value, or the next group begins
+                do { q++; next_A = s_pc[(q + 1) << span_shift]; } while (e >= next_A);
+                A = s_pc[q << span_shift];
+                zeros = s_pc[(q << span_shift) + (1 << (span_shift - 1))] - A;       // values of the group whose bit h is 0
+                zb = s_zc[A >> 3] + __popc((unsigned)s_zm[A >> 3] & ((1u << (A & 7u)) - 1u));   // zeros before the group
+            }
+            const unsigned zp = zexcl + __popc(zmask & ((1u << i) - 1u));
+            const unsigned np = ((bits >> i) & 1u) ? A + zeros + ((e - zp) - (A - zb)) : A + (zp - zb);
+            nxt[np] = v[i];
+        }
+        __syncthreads();
+        uint32_t* tmp = cur; cur = nxt; nxt = tmp;
+    }
+    // the block is sorted by digit: every digit's run goes to its place among the values of the parent group with that digit
+    for (int i = 0; i < kIwtPer; i++) {
+        const int e = i * kIwtThreads + t;
+        if (e < cnt) {
+            const uint32_t v = cur[e];
+            const unsigned b = (v >> low_bit) & dmask;
+            out[parent + min(b << low_bit, parent_len) + (s_pb[b + 1] - s_pb[b]) + ((unsigned)e - s_pc[b])] = v;
+        }
     }
 }
 
 // The low levels: once a group (values sharing v >> (h + 1)) is no longer than kIwtBlock, one CTA keeps its
 // block of values in shared memory and runs every remaining level there — bit h of the values to the level's raw
 // vector, then the stable split inside each group — instead of three launches per level over global memory.
-constexpr int kIwtLowBits = 13;
-constexpr int kIwtBlock = 1 << kIwtLowBits;              // values per CTA
-constexpr int kIwtThreads = 1024;
-constexpr int kIwtPer = kIwtBlock / kIwtThreads;         // consecutive values per thread
-static_assert(kIwtPer == 8, "one byte of level bits per thread");
-
 __global__ void __launch_bounds__(kIwtThreads)
 iwt_low_levels_kernel(const uint32_t* __restrict__ vals, int64_t m, int top_h, int levels, uint32_t* __restrict__ raw,
                       const uint64_t* __restrict__ level_raw_word /* level vector (highest bit first) -> first raw word */) {
@@ -652,34 +719,39 @@ int layout_vectors(DeviceCtx* ctx, cudaStream_t st, const uint32_t* d_raw, const
     return GCZ_OK;
 }
 
-// All levels of an IndexWaveletTree over the m values in d_ssa[0] (d_ssa[1]: scratch of the same size): the high
-// levels with three launches each over global memory, the low ones in one launch (iwt_low_levels_kernel).
+// All levels of an IndexWaveletTree over the m values in d_ssa[0] (d_ssa[1]: scratch of the same size): the high levels in
+// passes of up to kTopBits levels (count, scan, emit), the low ones in one launch (iwt_low_levels_kernel).
+inline int64_t iwt_blocks(int64_t m) { return (m + kIwtBlock - 1) / kIwtBlock; }
+inline size_t iwt_scratch_bytes(int64_t m) {
+    return (size_t)kTopBins * (size_t)iwt_blocks(m) * 4 + 256 + row_scan_scratch_bytes(kTopBins, iwt_blocks(m)) + 256;
+}
+
 int iwt_levels(DeviceCtx* ctx, cudaStream_t st, uint32_t* const d_ssa[2], int64_t m, int levels, uint32_t* d_raw,
-               const std::vector<VectorDesc>& vecs, int level_vec0, uint32_t* d_zeros, uint32_t* d_block_zeros,
-               uint64_t* d_level_raw) {
+               const std::vector<VectorDesc>& vecs, int level_vec0, void* d_scratch, uint64_t* d_level_raw) {
     std::vector<uint64_t> h_level_raw((size_t)levels);
     for (int l = 0; l < levels; l++) h_level_raw[(size_t)l] = vecs[(size_t)(level_vec0 + l)].raw_word;
     GCZ_CUDA(cudaMemcpyAsync(d_level_raw, h_level_raw.data(), sizeof(uint64_t) * levels, cudaMemcpyHostToDevice, st));
     GCZ_CUDA(cudaStreamSynchronize(st));                 // h_level_raw goes out of scope
-    const int64_t mblocks = (m + 1023) >> 10;
-    const int lvl_grid = (int)std::min<int64_t>((m + 255) / 256, (int64_t)ctx->sm_count * 8);
-    const int bits_grid = (int)std::min<int64_t>((mblocks + 7) / 8, (int64_t)ctx->sm_count * 8);
-    int cur = 0;
-    int l = 0;
-    for (; l < levels && levels - 1 - l >= kIwtLowBits; l++) {
-        const int h = levels - 1 - l;
-        uint32_t* lraw = d_raw + vecs[(size_t)(level_vec0 + l)].raw_word;
-        GCZ_LAUNCH(ctx, iwt_bits_kernel, bits_grid, 256, 0, st, d_ssa[cur], m, h, lraw, d_zeros, d_block_zeros);
-        GCZ_LAUNCH(ctx, row_scan_kernel, 1, 1024, 0, st, d_block_zeros, mblocks, (uint32_t*)nullptr);
-        GCZ_LAUNCH(ctx, iwt_scatter_kernel, lvl_grid, 256, 0, st, d_ssa[cur], d_ssa[cur ^ 1], m, h, lraw, d_zeros, d_block_zeros);
-        cur ^= 1;
-    }
+    const int64_t blocks = iwt_blocks(m);
+    uint32_t* d_counts = static_cast<uint32_t*>(d_scratch);
+    void* d_scan = reinterpret_cast<char*>(d_scratch) + (((size_t)kTopBins * (size_t)blocks * 4 + 255) & ~(size_t)255);
     if (!ctx->iwt_attr) {
         GCZ_CUDA(cudaFuncSetAttribute(iwt_low_levels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kIwtLowSmem));
+        GCZ_CUDA(cudaFuncSetAttribute(iwt_top_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kIwtTopSmem));
         ctx->iwt_attr = true;
     }
-    GCZ_LAUNCH(ctx, iwt_low_levels_kernel, (unsigned)((m + kIwtBlock - 1) / kIwtBlock), kIwtThreads, kIwtLowSmem, st, d_ssa[cur], m,
-               levels - 1 - l, levels, d_raw, d_level_raw);
+    int cur = 0;
+    int H = levels - 1;                                  // highest bit not yet done
+    while (H >= kIwtLowBits) {
+        const int L = std::min(kTopBits, H - kIwtLowBits + 1);
+        GCZ_LAUNCH(ctx, iwt_top_count_kernel, (unsigned)blocks, kIwtThreads, 0, st, d_ssa[cur], m, H - L + 1, L, d_counts, blocks);
+        GCZ_TRY(row_scan(ctx, st, d_counts, 1 << L, blocks, false, d_scan, nullptr, nullptr));
+        GCZ_LAUNCH(ctx, iwt_top_emit_kernel, (unsigned)blocks, kIwtThreads, kIwtTopSmem, st, d_ssa[cur], d_ssa[cur ^ 1], m, H, L, levels,
+                   d_raw, d_level_raw, d_counts, blocks);
+        cur ^= 1;
+        H -= L;
+    }
+    GCZ_LAUNCH(ctx, iwt_low_levels_kernel, (unsigned)blocks, kIwtThreads, kIwtLowSmem, st, d_ssa[cur], m, H, levels, d_raw, d_level_raw);
     return GCZ_OK;
 }
 
@@ -771,12 +843,11 @@ int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_t
     VectorDesc* d_vecs = arena.get<VectorDesc>(vecs.size());
     uint32_t* d_sb = arena.get<uint32_t>((size_t)total_sb + 1);
     uint32_t* d_ssa[2] = { arena.get<uint32_t>((size_t)m), arena.get<uint32_t>((size_t)m) };
-    uint32_t* d_zeros = arena.get<uint32_t>((size_t)((m + 31) >> 5) + 1);
-    uint32_t* d_block_zeros = arena.get<uint32_t>((size_t)((m + 1023) >> 10) + 1);
+    void* d_iwt_scratch = arena.raw(iwt_scratch_bytes(m));
     uint64_t* d_level_raw = arena.get<uint64_t>(64);
     void* d_scan = arena.raw(row_scan_scratch_bytes(sigma + 1, tiles));
-    if (!d_block_zeros || !d_level_raw || !d_scan) return fail(GCZ_E_NOMEM, "wavelet workspace for n=%lld", (long long)n);
-    if (!d_tab || !d_raw || !d_tile_counts || !d_node_raw || !d_vecs || !d_sb || !d_ssa[0] || !d_ssa[1] || !d_zeros)
+    if (!d_iwt_scratch || !d_level_raw || !d_scan) return fail(GCZ_E_NOMEM, "wavelet workspace for n=%lld", (long long)n);
+    if (!d_tab || !d_raw || !d_tile_counts || !d_node_raw || !d_vecs || !d_sb || !d_ssa[0] || !d_ssa[1])
         return fail(GCZ_E_NOMEM, "wavelet workspace for n=%lld", (long long)n);
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -867,7 +938,7 @@ int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_t
     GCZ_LAUNCH(ctx, sample_kernel, wt_grid, kWtThreads, 0, st, d_sa, n,
                carry_shift ? (1u << carry_shift) - 1u : 0xFFFFFFFFu, sample_mask, sampling_factor,
                d_tile_counts + (size_t)sigma * tiles, tiles, d_ssa[0]);
-    GCZ_TRY(iwt_levels(ctx, st, d_ssa, m, levels, d_raw, vecs, level_vec0, d_zeros, d_block_zeros, d_level_raw));
+    GCZ_TRY(iwt_levels(ctx, st, d_ssa, m, levels, d_raw, vecs, level_vec0, d_iwt_scratch, d_level_raw));
 
     // ---- counters + final byte layout of every vector ---------------------------------------------------------
     GCZ_TRY(layout_vectors(ctx, st, d_raw, d_vecs, (int)vecs.size(), tail_vec0, (int)vecs.size(), tail_sb0, total_sb, d_sb));
@@ -934,15 +1005,14 @@ int index_wavelet_tree_from_values(DeviceCtx* ctx, cudaStream_t st, const uint32
     VectorDesc* d_vecs = arena.get<VectorDesc>(vecs.size());
     uint32_t* d_sb = arena.get<uint32_t>((size_t)total_sb + 1);
     uint32_t* d_ssa[2] = { arena.get<uint32_t>((size_t)m), arena.get<uint32_t>((size_t)m) };
-    uint32_t* d_zeros = arena.get<uint32_t>((size_t)((m + 31) >> 5) + 1);
-    uint32_t* d_block_zeros = arena.get<uint32_t>((size_t)((m + 1023) >> 10) + 1);
+    void* d_iwt_scratch = arena.raw(iwt_scratch_bytes(m));
     uint64_t* d_level_raw = arena.get<uint64_t>(64);
-    if (!d_raw || !d_vecs || !d_sb || !d_ssa[0] || !d_ssa[1] || !d_zeros || !d_block_zeros || !d_level_raw) return fail(GCZ_E_NOMEM, "IWT workspace");
+    if (!d_raw || !d_vecs || !d_sb || !d_ssa[0] || !d_ssa[1] || !d_iwt_scratch || !d_level_raw) return fail(GCZ_E_NOMEM, "IWT workspace");
     GCZ_CUDA(cudaMemsetAsync(d_raw, 0, ((size_t)raw_words + 16) * 4, st));
     GCZ_CUDA(cudaMemcpyAsync(d_vecs, vecs.data(), sizeof(VectorDesc) * vecs.size(), cudaMemcpyHostToDevice, st));
     GCZ_CUDA(cudaMemcpyAsync(d_ssa[0], d_vals, (size_t)m * 4, cudaMemcpyDeviceToDevice, st));
     GCZ_CUDA(cudaStreamSynchronize(st));
-    GCZ_TRY(iwt_levels(ctx, st, d_ssa, m, levels, d_raw, vecs, 0, d_zeros, d_block_zeros, d_level_raw));
+    GCZ_TRY(iwt_levels(ctx, st, d_ssa, m, levels, d_raw, vecs, 0, d_iwt_scratch, d_level_raw));
     GCZ_TRY(layout_vectors(ctx, st, d_raw, d_vecs, (int)vecs.size(), 0, (int)vecs.size(), 0, total_sb, d_sb));
     GCZ_CUDA(cudaStreamSynchronize(st));
     arena.release(mark0);
