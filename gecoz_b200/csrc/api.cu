@@ -72,8 +72,68 @@ int get_ctx(int device, DeviceCtx** out) {
     GCZ_CUDA(cudaStreamCreateWithFlags(&ctx->stage_stream, cudaStreamNonBlocking));
     GCZ_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->stage_counts), 256 * 8));
     GCZ_CUDA(cudaEventCreateWithFlags(&ctx->copy_event, cudaEventDisableTiming));
+    {
+        void* h = nullptr; void* d = nullptr;
+        const size_t bytes = (size_t)256 << 10;
+        if (cudaHostAlloc(&h, bytes, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess &&
+            cudaHostGetDevicePointer(&d, h, 0) == cudaSuccess) {
+            ctx->pinned = static_cast<uint8_t*>(h); ctx->pinned_dev = static_cast<uint8_t*>(d); ctx->pinned_bytes = bytes;
+        } else {
+            cudaGetLastError();                           // without it small transfers take the copy engines
+            if (h) cudaFreeHost(h);
+        }
+    }
     *out = ctx.get();
     g_ctx[device] = std::move(ctx);
+    return GCZ_OK;
+}
+
+__global__ void small_copy_kernel(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, size_t bytes) {
+    if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src) | bytes) & 3) == 0) {
+        for (size_t i = threadIdx.x; i < bytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(src)[i];
+    } else {
+        for (size_t i = threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
+    }
+}
+
+// a slot of the mapped buffer (16-byte aligned); when the buffer is full the stream is drained and it starts over
+static int small_slot(DeviceCtx* ctx, cudaStream_t st, size_t bytes, size_t* at) {
+    const size_t need = (bytes + 15) & ~(size_t)15;
+    if (ctx->pinned_top + need > ctx->pinned_bytes) {
+        GCZ_CUDA(cudaStreamSynchronize(st));
+        ctx->pinned_top = 0;
+    }
+    *at = ctx->pinned_top;
+    ctx->pinned_top += need;
+    return GCZ_OK;
+}
+
+int small_upload(DeviceCtx* ctx, cudaStream_t st, void* d_dst, const void* h_src, size_t bytes) {
+    if (bytes == 0) return GCZ_OK;
+    if (!ctx->pinned || bytes > ctx->pinned_bytes / 2) {
+        GCZ_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
+        GCZ_CUDA(cudaStreamSynchronize(st));              // the caller's buffer may go away
+        return GCZ_OK;
+    }
+    size_t at = 0;
+    GCZ_TRY(small_slot(ctx, st, bytes, &at));
+    std::memcpy(ctx->pinned + at, h_src, bytes);
+    GCZ_LAUNCH(ctx, small_copy_kernel, 1, 256, 0, st, static_cast<uint8_t*>(d_dst), ctx->pinned_dev + at, bytes);
+    return GCZ_OK;
+}
+
+int small_read(DeviceCtx* ctx, cudaStream_t st, void* h_dst, const void* d_src, size_t bytes) {
+    if (bytes == 0) return GCZ_OK;
+    if (!ctx->pinned || bytes > ctx->pinned_bytes / 2) {
+        GCZ_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, st));
+        GCZ_CUDA(cudaStreamSynchronize(st));
+        return GCZ_OK;
+    }
+    size_t at = 0;
+    GCZ_TRY(small_slot(ctx, st, bytes, &at));
+    GCZ_LAUNCH(ctx, small_copy_kernel, 1, 256, 0, st, ctx->pinned_dev + at, static_cast<const uint8_t*>(d_src), bytes);
+    GCZ_CUDA(cudaStreamSynchronize(st));
+    std::memcpy(h_dst, ctx->pinned + at, bytes);
     return GCZ_OK;
 }
 
@@ -92,6 +152,7 @@ void destroy_all_ctx() {
         if (kv.second->copy_event) cudaEventDestroy(kv.second->copy_event);
         if (kv.second->stage_stream) cudaStreamDestroy(kv.second->stage_stream);
         if (kv.second->stage_counts) cudaFree(kv.second->stage_counts);
+        if (kv.second->pinned) cudaFreeHost(kv.second->pinned);
         for (auto& slot : kv.second->staged) if (slot.dev) cudaFree(slot.dev);
         for (auto& slot : kv.second->out_slot) { if (slot.dev) cudaFree(slot.dev); if (slot.done) cudaEventDestroy(slot.done); }
     }

@@ -91,8 +91,14 @@ struct DeviceCtx {
     OutSlot                 out_slot[2];
     std::mutex   mu;                          // one build / query batch at a time per device (shared arena)
     Arena        arena;
-    void*        pinned = nullptr;            // small pinned scratch for read-backs
+    // Small transfers of a build (symbol tables, vector descriptors, the totals the host reads between refinement rounds) do
+    // not go through the copy engines: those are busy with the next block's text and the previous block's bodies, and a
+    // 256-byte copy queued behind a 77 MB one waits a millisecond.  They go through this mapped pinned buffer instead, moved
+    // by a one-CTA kernel on the build's stream (small_upload / small_read, api.cu).  Used under `mu` only.
+    uint8_t*     pinned = nullptr;             // host address
+    uint8_t*     pinned_dev = nullptr;         // the same memory as the device sees it
     size_t       pinned_bytes = 0;
+    size_t       pinned_top = 0;
     std::atomic<int64_t> launches{0};        // kernels launched by this library on this device
     bool         iwt_attr = false;             // dynamic-smem opt-in done for iwt_low_levels_kernel
     bool         sort_attr[3] = { false, false, false };   // dynamic-smem opt-in done for the onesweep kernels
@@ -103,6 +109,11 @@ struct DeviceCtx {
 int          get_ctx(int device, DeviceCtx** out);   // creates on first use; fails with GCZ_E_NODEVICE
 cudaStream_t stream_of(DeviceCtx* ctx);              // thread-local override from gcz_set_stream, else own
 void         destroy_all_ctx();
+
+// stream-ordered host -> device copy of a small object (the host bytes are taken before the call returns)
+int small_upload(DeviceCtx* ctx, cudaStream_t st, void* d_dst, const void* h_src, size_t bytes);
+// device -> host copy of a small object; returns after the stream has been synchronised
+int small_read(DeviceCtx* ctx, cudaStream_t st, void* h_dst, const void* d_src, size_t bytes);
 
 inline bool is_device_ptr(const void* p) {
     cudaPointerAttributes a;

@@ -524,8 +524,8 @@ int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t 
         GCZ_CUDA(cudaEventRecord(ev0, st));
     }
 
-    GCZ_CUDA(cudaMemcpyAsync(d_code, h_code, 256, cudaMemcpyHostToDevice, st));
-    GCZ_CUDA(cudaMemcpyAsync(d_allc, h_allc, sizeof(uint64_t) * sigma, cudaMemcpyHostToDevice, st));
+    GCZ_TRY(small_upload(ctx, st, d_code, h_code, 256));
+    GCZ_TRY(small_upload(ctx, st, d_allc, h_allc, sizeof(uint64_t) * sigma));
     GCZ_CUDA(cudaMemsetAsync(d_totals, 0, 8 * sizeof(long long), st));
     GCZ_CUDA(cudaMemsetAsync(d_rank, 0xFF, (size_t)n * 4, st));
 
@@ -577,8 +577,7 @@ int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t 
     ga.sample = six;
     GCZ_TRY(launch_group(true, ga));
     long long h_totals[5] = { 0, 0, 0, 0, 0 };
-    GCZ_CUDA(cudaMemcpyAsync(h_totals, d_totals, sizeof(h_totals), cudaMemcpyDeviceToHost, st));
-    GCZ_CUDA(cudaStreamSynchronize(st));
+    GCZ_TRY(small_read(ctx, st, h_totals, d_totals, sizeof(h_totals)));
     int64_t m = h_totals[0], groups = h_totals[1];
     const int64_t m_run = h_totals[2];
     const int64_t n_marks = (int64_t)(uint32_t)h_totals[4];
@@ -618,8 +617,7 @@ int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t 
         gr.keys = rb.keys[rb.cur]; gr.suf = rb.vals[rb.cur]; gr.pos = run_pos; gr.m = m_run;
         gr.pos_out = list_pos[0] + m; gr.suf_out = list_suf[0] + m; gr.gid_out = list_gid[0] + m; gr.gid_base = (uint32_t)groups;
         GCZ_TRY(launch_group(false, gr));
-        GCZ_CUDA(cudaMemcpyAsync(h_totals, d_totals, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
-        GCZ_CUDA(cudaStreamSynchronize(st));
+        GCZ_TRY(small_read(ctx, st, h_totals, d_totals, 2 * sizeof(long long)));
         m += h_totals[0]; groups += h_totals[1];
         rounds++;
     }
@@ -641,8 +639,7 @@ int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t 
         gr.keys = rb.keys[rb.cur]; gr.suf = rb.vals[rb.cur]; gr.pos = list_pos[cur]; gr.m = m;
         gr.pos_out = list_pos[cur ^ 1]; gr.suf_out = list_suf[cur ^ 1]; gr.gid_out = list_gid[cur ^ 1]; gr.gid_base = 0;
         GCZ_TRY(launch_group(false, gr));
-        GCZ_CUDA(cudaMemcpyAsync(h_totals, d_totals, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
-        GCZ_CUDA(cudaStreamSynchronize(st));
+        GCZ_TRY(small_read(ctx, st, h_totals, d_totals, 2 * sizeof(long long)));
         m = h_totals[0]; groups = h_totals[1];
         cur ^= 1;
         h *= 2;

@@ -730,8 +730,7 @@ int iwt_levels(DeviceCtx* ctx, cudaStream_t st, uint32_t* const d_ssa[2], int64_
                const std::vector<VectorDesc>& vecs, int level_vec0, void* d_scratch, uint64_t* d_level_raw) {
     std::vector<uint64_t> h_level_raw((size_t)levels);
     for (int l = 0; l < levels; l++) h_level_raw[(size_t)l] = vecs[(size_t)(level_vec0 + l)].raw_word;
-    GCZ_CUDA(cudaMemcpyAsync(d_level_raw, h_level_raw.data(), sizeof(uint64_t) * levels, cudaMemcpyHostToDevice, st));
-    GCZ_CUDA(cudaStreamSynchronize(st));                 // h_level_raw goes out of scope
+    GCZ_TRY(small_upload(ctx, st, d_level_raw, h_level_raw.data(), sizeof(uint64_t) * levels));
     const int64_t blocks = iwt_blocks(m);
     uint32_t* d_counts = static_cast<uint32_t*>(d_scratch);
     void* d_scan = reinterpret_cast<char*>(d_scratch) + (((size_t)kTopBins * (size_t)blocks * 4 + 255) & ~(size_t)255);
@@ -855,9 +854,9 @@ int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_t
         GCZ_CUDA(cudaEventCreate(&ev0)); GCZ_CUDA(cudaEventCreate(&ev1)); GCZ_CUDA(cudaEventCreate(&ev2));
         GCZ_CUDA(cudaEventRecord(ev0, st));
     }
-    GCZ_CUDA(cudaMemcpyAsync(d_tab, &h_tab, sizeof(h_tab), cudaMemcpyHostToDevice, st));
-    GCZ_CUDA(cudaMemcpyAsync(d_node_raw, h_node_raw.data(), sizeof(uint64_t) * n_nodes, cudaMemcpyHostToDevice, st));
-    GCZ_CUDA(cudaMemcpyAsync(d_vecs, vecs.data(), sizeof(VectorDesc) * vecs.size(), cudaMemcpyHostToDevice, st));
+    GCZ_TRY(small_upload(ctx, st, d_tab, &h_tab, sizeof(h_tab)));
+    GCZ_TRY(small_upload(ctx, st, d_node_raw, h_node_raw.data(), sizeof(uint64_t) * n_nodes));
+    GCZ_TRY(small_upload(ctx, st, d_vecs, vecs.data(), sizeof(VectorDesc) * vecs.size()));
     GCZ_CUDA(cudaMemsetAsync(d_raw, 0, ((size_t)raw_words + 16) * 4, st));
 
     // table-driven node emission for alphabets of up to 8 symbols (every DNA block): 1.6 ms -> 0.55 ms on the chr1-shaped block
@@ -882,7 +881,7 @@ int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_t
         }
         d_lut = arena.get<uint2>((size_t)entries);
         if (!d_lut) return fail(GCZ_E_NOMEM, "wavelet workspace for n=%lld", (long long)n);
-        GCZ_CUDA(cudaMemcpyAsync(d_lut, h_lut.data(), sizeof(uint2) * (size_t)entries, cudaMemcpyHostToDevice, st));   // synchronised below
+        GCZ_TRY(small_upload(ctx, st, d_lut, h_lut.data(), sizeof(uint2) * (size_t)entries));
     }
 
     // shape table at the head of the body
@@ -890,8 +889,7 @@ int build_wavelet_structures(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_t
         std::vector<uint8_t> tbl((size_t)shape->table_bytes + 8);
         const int64_t w = shape_write(shape, tbl.data(), (int64_t)tbl.size());
         if (w != shape->table_bytes) return w < 0 ? (int)w : fail(GCZ_E_INTERNAL, "shape table size changed");
-        GCZ_CUDA(cudaMemcpyAsync(d_gcz_body, tbl.data(), (size_t)w, cudaMemcpyHostToDevice, st));
-        GCZ_CUDA(cudaStreamSynchronize(st));             // tbl and the other host staging vectors go out of scope
+        GCZ_TRY(small_upload(ctx, st, d_gcz_body, tbl.data(), (size_t)w));     // (the host bytes are taken at once: no wait for the stream)
     }
 
     // ---- BWT, counts, marker bits ------------------------------------------------------------------------
