@@ -370,7 +370,7 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
     constexpr int WARPS = THREADS / 32;
     static_assert(THREADS >= kRadix, "one thread per digit is needed for the look-back");
     static_assert(!FROM_TEXT || HAS_VALS, "text input produces (key, position) pairs");
-    static_assert(TILE * 4 >= TILE + kMaxKeySymbols + 8 + 256, "the value staging area holds the tile's symbol codes");
+    static_assert(TILE * 4 >= 16 + TILE + kMaxKeySymbols + 16 + 256, "the value staging area holds the tile's symbol codes");
     static_assert((WARPS * kRadix) % (4 * THREADS) == 0, "the warp counters are cleared with 16-byte stores");
     static_assert(LOOK <= kPadRows, "pad rows cover the look-back window");
     static_assert(!ASYNC || (HAS_VALS && !FROM_TEXT), "only (key, value) array passes stage their values");
@@ -412,51 +412,57 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
     // 1. warp-striped load: item i of lane l in warp w is element w*ITEMS*32 + i*32 + l of the tile
     uint64_t key[ITEMS];
     const int warp_base = warp * ITEMS * 32;
-    uint8_t* s_codes = reinterpret_cast<uint8_t*>(s_vals);        // FROM_TEXT: code of position tile_base - 1 + i
+    uint8_t* s_codes = reinterpret_cast<uint8_t*>(s_vals);        // FROM_TEXT: s_codes[16 + e] = code of position tile_base + e
     if (FROM_TEXT) {
-        uint8_t* s_code_of = s_codes + TILE + kMaxKeySymbols + 8;
+        uint8_t* s_code_of = s_codes + 16 + TILE + kMaxKeySymbols + 16;
         if (threadIdx.x < 256) s_code_of[threadIdx.x] = src.code_of[threadIdx.x];
         __syncthreads();
         const int k = src.coder.k;
         const uint32_t radix = (uint32_t)src.coder.radix;
-        // codes of positions tile_base - 1 .. tile_base + TILE + k - 2 at s_codes[0 ..]; 16-byte loads where possible
+        // codes of positions tile_base - 1 .. tile_base + TILE + k - 2 at s_codes[15 ..]; 16-byte loads and stores where possible
         static_assert(TILE % 16 == 0, "tile starts stay 16-byte aligned");
         const bool aligned = (reinterpret_cast<uintptr_t>(src.text) & 15) == 0;
         for (int v = threadIdx.x; v < TILE / 16; v += THREADS) {
             const int64_t p0 = tile_base + (int64_t)v * 16;
             if (aligned && p0 + 16 <= n) {
                 const uint4 q = *reinterpret_cast<const uint4*>(src.text + p0);
-                const uint32_t w[4] = { q.x, q.y, q.z, q.w };
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    s_codes[1 + v * 16 + 4 * j] = s_code_of[w[j] & 255];
-                    s_codes[2 + v * 16 + 4 * j] = s_code_of[(w[j] >> 8) & 255];
-                    s_codes[3 + v * 16 + 4 * j] = s_code_of[(w[j] >> 16) & 255];
-                    s_codes[4 + v * 16 + 4 * j] = s_code_of[w[j] >> 24];
-                }
+                *reinterpret_cast<uint4*>(s_codes + 16 + v * 16) =
+                    make_uint4(translate4(s_code_of, q.x), translate4(s_code_of, q.y), translate4(s_code_of, q.z), translate4(s_code_of, q.w));
             } else {
-                for (int j = 0; j < 16; j++) s_codes[1 + v * 16 + j] = p0 + j < n ? s_code_of[src.text[p0 + j]] : 0;
+                for (int j = 0; j < 16; j++) s_codes[16 + v * 16 + j] = p0 + j < n ? s_code_of[src.text[p0 + j]] : 0;
             }
         }
         if (threadIdx.x < (unsigned)k) {
             const int64_t p = tile_base + TILE + threadIdx.x;
-            s_codes[1 + TILE + threadIdx.x] = p < n ? s_code_of[src.text[p]] : 0;
+            s_codes[16 + TILE + threadIdx.x] = p < n ? s_code_of[src.text[p]] : 0;
         }
-        if (threadIdx.x == THREADS - 1) s_codes[0] = s_code_of[src.text[tile_base > 0 ? tile_base - 1 : n - 1]];   // BWT symbol of the first suffix
+        if (threadIdx.x == THREADS - 1) s_codes[15] = s_code_of[src.text[tile_base > 0 ? tile_base - 1 : n - 1]];   // BWT symbol of the first suffix
         __syncthreads();
-        const int first = 1 + threadIdx.x * ITEMS;
+        // every thread slides the k-symbol window over ITEMS consecutive positions
+        const int first = 16 + threadIdx.x * ITEMS;
         uint64_t w = 0;
         for (int j = 0; j < k - 1; j++) w = w * radix + s_codes[first + j];
+        if (count == TILE) {
+            // A full tile keeps them: the first pass of an LSD sort need not be stable (its input has no order to keep), so
+            // the keys are ranked as (item, lane) although the thread's positions are consecutive — no trip through shared memory
 #pragma unroll
-        for (int i = 0; i < ITEMS; i++) {
-            w = slide_key(w, i > 0 ? s_codes[first + i - 1] : 0u, s_codes[first + i + k - 1], radix, src.coder.top);
-            s_keys[threadIdx.x * ITEMS + i] = w;
-        }
-        __syncthreads();
+            for (int i = 0; i < ITEMS; i++) {
+                w = slide_key(w, i > 0 ? s_codes[first + i - 1] : 0u, s_codes[first + i + k - 1], radix, src.coder.top);
+                key[i] = w;
+            }
+        } else {
+            // the last tile is transposed to the warp-striped order, in which the padding keys are the last elements
 #pragma unroll
-        for (int i = 0; i < ITEMS; i++) {
-            const int e = warp_base + i * 32 + lane;
-            key[i] = e < count ? s_keys[e] : ~0ull;
+            for (int i = 0; i < ITEMS; i++) {
+                w = slide_key(w, i > 0 ? s_codes[first + i - 1] : 0u, s_codes[first + i + k - 1], radix, src.coder.top);
+                s_keys[threadIdx.x * ITEMS + i] = w;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < ITEMS; i++) {
+                const int e = warp_base + i * 32 + lane;
+                key[i] = e < count ? s_keys[e] : ~0ull;
+            }
         }
     } else if (count == TILE) {               // all tiles but the last: no bounds predicates in the way of the loads
         const uint64_t* src_keys = keys_in + tile_base + warp_base + lane;
@@ -516,8 +522,8 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
     if (FROM_TEXT) {
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
-            const int e = warp_base + i * 32 + lane;
-            val[i] = (uint32_t)(tile_base + e) | (src.carry_shift ? (uint32_t)s_codes[e] << src.carry_shift : 0u);
+            const int e = count == TILE ? (int)threadIdx.x * ITEMS + i : warp_base + i * 32 + lane;     // the element key[i] belongs to
+            val[i] = (uint32_t)(tile_base + e) | (src.carry_shift ? (uint32_t)s_codes[15 + e] << src.carry_shift : 0u);
         }
         __syncthreads();                      // the symbol codes share their shared memory with the reordered values
     } else if (ASYNC && vals_aligned && count == TILE) {

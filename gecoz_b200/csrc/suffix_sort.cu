@@ -50,7 +50,7 @@ __global__ void pair_runs_kernel(const uint64_t* __restrict__ marks, int64_t n_r
 }
 
 // Copies of the first symbol left at suffix s if that is >= k (s is inside a long run), else 0.
-__device__ __forceinline__ uint32_t run_remaining(const Run* __restrict__ runs, int n_runs, uint32_t s, int k, bool* larger) {
+__device__ __forceinline__ uint32_t run_remaining(const Run* __restrict__ runs, int n_runs, uint32_t s, int k, bool* larger, int* index = nullptr) {
     int lo = 0, hi = n_runs;                    // first run with end > s
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
@@ -62,6 +62,7 @@ __device__ __forceinline__ uint32_t run_remaining(const Run* __restrict__ runs, 
     const uint32_t left = (r.end_side & 0x7FFFFFFFu) - s;
     if (left < (uint32_t)k) return 0;
     *larger = (r.end_side >> 31) != 0;
+    if (index) *index = lo;
     return left;
 }
 
@@ -69,7 +70,7 @@ __device__ __forceinline__ uint32_t run_remaining(const Run* __restrict__ runs, 
 constexpr int kGrpThreads = 256;
 constexpr int kGrpItems = 16;
 constexpr int kGrpTile = kGrpThreads * kGrpItems;
-constexpr int kSampleShift = 6;                 // every 64th sorted key is kept as an index for rank lookups (key_slot)
+constexpr int kSampleShift = 4;                 // every 16th sorted key is kept as an index for rank lookups (key_slot)
 constexpr int kSampleStep = 1 << kSampleShift;
 // ... and every 16th of those, and every 16th of those: five levels, a node of 16 keys (one 128-byte line) per level and lookup
 constexpr int kSampleLevels = 5;
@@ -392,14 +393,40 @@ __device__ __forceinline__ uint32_t key_slot(const uint64_t* __restrict__ sorted
     return (uint32_t)lo;
 }
 
+// rank[q] + 1 (0 past the end), looked up by its key when the suffix at q has been final since the first sort
+__device__ __forceinline__ uint32_t rank_plus_one(uint32_t* __restrict__ rank, int64_t n, int64_t q, const uint8_t* __restrict__ text,
+                                                  const uint8_t* __restrict__ code_of, const KeyCoder& kc,
+                                                  const uint64_t* __restrict__ sorted_keys, const SampleIndex& sample) {
+    if (q >= n) return 0;
+    uint32_t rk = rank[q];
+    if (rk == kNoRank) {
+        // final since the first sort: its key is unique, its slot is where the key sits
+        rk = key_slot(sorted_keys, n, sample, key_at(text, n, code_of, kc, q));
+        rank[q] = rk;                               // every writer stores the same value
+    }
+    return rk + 1;
+}
+
+// A suffix inside a long run of r >= k symbols looks r - k symbols further than the others (header, point 5): at
+// run end + h - k, the same place for every suffix of the run.  That rank is looked up ONCE per run and round here; in the
+// first version each of the 20 M run suffixes of a chr1-sized block read rank[] at one of 42 addresses, found it unset, and
+// thousands of them at a time repeated the same key search (2 GB of DRAM reads, 0.74 ms).
+__global__ void run_ranks_kernel(const Run* __restrict__ runs, int n_runs, int64_t h, uint32_t* __restrict__ rank, int64_t n,
+                                 const uint8_t* __restrict__ text, const uint8_t* __restrict__ code_of, KeyCoder kc,
+                                 const uint64_t* __restrict__ sorted_keys, SampleIndex sample, uint32_t* __restrict__ run_low) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_runs) return;
+    const int64_t q = (int64_t)(runs[j].end_side & 0x7FFFFFFFu) + h - kc.k;
+    run_low[j] = rank_plus_one(rank, n, q, text, code_of, kc, sorted_keys, sample);
+}
+
 // refinement key: (group ordinal, rank of the suffix `h` symbols further, 0 when that is past the end).
-// A suffix inside a long run of r >= k symbols looks r - k symbols further than the others (header, point 5).
 __global__ void __launch_bounds__(256)
 refine_keys_kernel(const uint32_t* __restrict__ suf, const uint32_t* __restrict__ gid, int64_t m,
                    uint32_t* __restrict__ rank, int64_t n, int64_t h, int low_bits, uint32_t pos_mask,
                    const Run* __restrict__ runs, int n_runs, const uint8_t* __restrict__ text,
                    const uint8_t* __restrict__ code_of, KeyCoder kc, const uint64_t* __restrict__ sorted_keys,
-                   SampleIndex sample,
+                   SampleIndex sample, const uint32_t* __restrict__ run_low,
                    uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     __shared__ uint8_t s_code_of[256];
     s_code_of[threadIdx.x] = code_of[threadIdx.x];
@@ -407,22 +434,14 @@ refine_keys_kernel(const uint32_t* __restrict__ suf, const uint32_t* __restrict_
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < m; u += stride) {
         const uint32_t sv = suf[u], s = sv & pos_mask;
-        int64_t q = (int64_t)s + h;
+        uint64_t low;
+        int run = -1;
         if (n_runs > 0) {
             bool larger;
-            const uint32_t r = run_remaining(runs, n_runs, s, kc.k, &larger);
-            if (r) q += (int64_t)r - kc.k;
+            if (run_remaining(runs, n_runs, s, kc.k, &larger, &run) == 0) run = -1;
         }
-        uint64_t low = 0;
-        if (q < n) {
-            uint32_t rk = rank[q];
-            if (rk == kNoRank) {
-                // final since the first sort: its key is unique, its slot is where the key sits
-                rk = key_slot(sorted_keys, n, sample, key_at(text, n, s_code_of, kc, q));
-                rank[q] = rk;                               // every writer stores the same value
-            }
-            low = (uint64_t)rk + 1;
-        }
+        if (run >= 0) low = run_low[run];
+        else low = rank_plus_one(rank, n, (int64_t)s + h, text, s_code_of, kc, sorted_keys, sample);
         keys[u] = ((uint64_t)gid[u] << low_bits) | low;
         vals[u] = sv;
     }
@@ -463,7 +482,7 @@ size_t suffix_sort_workspace_bytes(int64_t n) {
     const size_t tiles = (size_t)(n / kGrpTile + 2);
     // run marks: two arrays of n/8 + 1024 u64 (2 x n bytes) and the run list of half as many 8-byte entries (n/2 bytes);
     // every allocation below is rounded up to 256 bytes (the 8 MB at the end covers those)
-    const size_t marks = ((size_t)n / 8 + 1024) * 8 * 2 + ((size_t)n / 16 + 513) * sizeof(Run);
+    const size_t marks = ((size_t)n / 8 + 1024) * 8 * 2 + ((size_t)n / 16 + 513) * (sizeof(Run) + 4);
     return (size_t)n * (4 + 16 + 4 + 44) + marks + radix_sort_temp_bytes(n) + tiles * kAggs * 8 + row_scan_scratch_bytes(kAggs, (int64_t)tiles) + (size_t)n / 4 + sample_index_words(n) * 8 + (8 << 20);
 }
 
@@ -509,12 +528,13 @@ int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t 
     long long* d_totals = arena.get<long long>(8);                 // [0..3] group totals, [4] run marks (as unsigned)
     uint64_t* d_marks[2] = { arena.get<uint64_t>(mark_cap), arena.get<uint64_t>(mark_cap) };
     Run* d_runs = arena.get<Run>(mark_cap / 2 + 1);
+    uint32_t* d_run_low = arena.get<uint32_t>(mark_cap / 2 + 1);
     // first list and the long-run list: how many suffixes stay unresolved is only known after the grouping pass
     uint32_t* list0[3] = { arena.get<uint32_t>((size_t)n), arena.get<uint32_t>((size_t)n), arena.get<uint32_t>((size_t)n) };
     uint32_t* run_pos = arena.get<uint32_t>((size_t)n);
     uint32_t* run_suf = arena.get<uint32_t>((size_t)n);
     if (!d_code || !d_allc || !d_rank || !d_keys0 || !d_keys1 || !d_vals1 || !d_temp || !d_agg || !d_scan || !d_bits || !d_sample || !d_totals ||
-        !d_marks[0] || !d_marks[1] || !d_runs || !list0[0] || !list0[1] || !list0[2] || !run_pos || !run_suf)
+        !d_marks[0] || !d_marks[1] || !d_runs || !d_run_low || !list0[0] || !list0[1] || !list0[2] || !run_pos || !run_suf)
         return fail(GCZ_E_NOMEM, "suffix sort workspace for n=%lld", (long long)n);
     unsigned* d_mark_count = reinterpret_cast<unsigned*>(d_totals + 4);
 
@@ -631,8 +651,10 @@ int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t 
         rb.vals[0] = r_vals0; rb.vals[1] = r_vals1;
         rb.cur = 0;
         const int grid = (int)std::min<int64_t>((m + 255) / 256, (int64_t)ctx->sm_count * 16);
+        if (n_runs > 0) GCZ_LAUNCH(ctx, run_ranks_kernel, (unsigned)((n_runs + 127) / 128), 128, 0, st, d_runs, n_runs, h, d_rank, n, d_text, d_code, kc,
+                                   d_keys0, six, d_run_low);
         GCZ_LAUNCH(ctx, refine_keys_kernel, grid, 256, 0, st, list_suf[cur], list_gid[cur], m, d_rank, n, h, low_bits, pos_mask,
-                   d_runs, n_runs, d_text, d_code, kc, d_keys0, six, rb.keys[0], rb.vals[0]);
+                   d_runs, n_runs, d_text, d_code, kc, d_keys0, six, d_run_low, rb.keys[0], rb.vals[0]);
         const int gid_bits = bits_for((uint64_t)std::max<int64_t>(groups - 1, 0));
         GCZ_TRY(radix_sort_pairs(ctx, st, rb, m, 0, low_bits + gid_bits, d_temp, ssp));
         GroupArgs gr = ga;

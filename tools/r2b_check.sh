@@ -28,7 +28,7 @@ timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 6
 python tools/launch_shares.py gpurun_out/${T}_launches.csv 1
 if [ -n "$2" ]; then
 echo "== ncu --set full: digit passes + text histogram + grouping of a real build"
-timeout -k 10 600 ncu --set full --clock-control none --import-source on -k 'regex:onesweep_kernel|text_hist_kernel|group_flags_kernel|group_apply_kernel' -s 35 -c 9 -f -o gpurun_out/${T}_build python tools/build_once.py 2 > gpurun_out/${T}_ncu.log 2>&1; tail -2 gpurun_out/${T}_ncu.log
+timeout -k 10 600 ncu --set full --clock-control none --import-source on -k 'regex:onesweep_kernel|text_hist_kernel|group_flags_kernel|group_apply_kernel|refine_keys_kernel|iwt_top_emit_kernel' -s 39 -c 38 -f -o gpurun_out/${T}_build python tools/build_once.py 2 > gpurun_out/${T}_ncu.log 2>&1; tail -2 gpurun_out/${T}_ncu.log
 fi
 } > gpurun_out/${T}.log 2>&1
 tail -100 gpurun_out/${T}.log
