@@ -77,13 +77,13 @@ radix_hist_kernel(const uint64_t* __restrict__ keys, int64_t n, int begin_bit, i
 // Here counter (digit, bin) has 16 words, one per PAIR of lanes, and each lane of the pair owns a 16-bit half of the word:
 // word [digit][bin][lane / 2], bank (16 bin + lane / 2) % 32 — lanes of different pairs never meet in a bank, the two of a pair
 // do when their bins have the same parity (1.5 wavefronts on average), and the increment is a per-thread constant, so a count
-// is three instructions (byte of the key, address, reduction).  A half-word counts what the eight warps of the CTA add for one
-// lane: at most 128 per tile, so the table is summed into the global histogram every kTextFlushTiles tiles.  The text of the
+// is three instructions (byte of the key, address, reduction).  A half-word counts what the sixteen warps of the CTA add for one
+// lane: at most 256 per tile, so the table is summed into the global histogram every kTextFlushTiles tiles.  The text of the
 // next tile is requested before the current one is counted.
-constexpr int kTextThreads = 256;
+constexpr int kTextThreads = 512;
 constexpr int kTextItems = 16;
 constexpr int kTextTile = kTextThreads * kTextItems;
-constexpr int kTextFlushTiles = 500;                       // 500 x 128 < 2^16
+constexpr int kTextFlushTiles = 250;                       // 250 x 256 < 2^16
 constexpr int kTextCodes = 16 + kTextTile + kMaxKeySymbols + 16;
 constexpr int kTextDigitWords = kRadix * 16;               // words of one digit's table
 inline size_t text_hist_smem(int npass) { return (size_t)npass * kTextDigitWords * 4 + kTextCodes + 256; }
@@ -109,7 +109,7 @@ text_hist_kernel(TextKeySource src, unsigned long long* __restrict__ hist /* [NP
     uint8_t* s_code_of = s_codes + kTextCodes;
     constexpr int cnt_words = NPASS * kTextDigitWords;
     for (int i = threadIdx.x; i < cnt_words; i += kTextThreads) s_cnt[i] = 0;
-    s_code_of[threadIdx.x] = src.code_of[threadIdx.x];
+    if (threadIdx.x < 256) s_code_of[threadIdx.x] = src.code_of[threadIdx.x];
     const int k = src.coder.k;
     const uint32_t radix = (uint32_t)src.coder.radix;
     const uint64_t top = src.coder.top;
@@ -215,7 +215,7 @@ text_hist_kernel(TextKeySource src, unsigned long long* __restrict__ hist /* [NP
             since_flush = 0;
             __syncthreads();
 #pragma unroll 1
-            for (int d = 0; d < NPASS; d++) {              // thread b sums the 32 half-words of bin b (rotated: one bank per thread)
+            for (int d = 0; d < NPASS && threadIdx.x < kRadix; d++) {   // thread b sums the 32 half-words of bin b (rotated: one bank per thread)
                 const unsigned* row = s_cnt + d * kTextDigitWords + threadIdx.x * 16;
                 unsigned sum = 0;
 #pragma unroll

@@ -27,8 +27,11 @@ python tools/build_once.py 2
 timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${T}_launches.csv python tools/build_once.py 3 > gpurun_out/${T}_launches.log 2>&1; tail -2 gpurun_out/${T}_launches.log
 python tools/launch_shares.py gpurun_out/${T}_launches.csv 1
 if [ -n "$2" ]; then
-echo "== ncu --set full: digit passes + text histogram + grouping of a real build"
-timeout -k 10 600 ncu --set full --clock-control none --import-source on -k 'regex:onesweep_kernel|text_hist_kernel|group_flags_kernel|group_apply_kernel|refine_keys_kernel|iwt_top_emit_kernel' -s 39 -c 38 -f -o gpurun_out/${T}_build python tools/build_once.py 2 > gpurun_out/${T}_ncu.log 2>&1; tail -2 gpurun_out/${T}_ncu.log
+echo "== ncu --set full (second build of build_once.py): first two digit passes; text histogram + first grouping; refinement keys + IWT passes"
+NCU="ncu --set full --clock-control none --import-source on -f"
+timeout -k 10 300 $NCU -k regex:onesweep_kernel -s 26 -c 2 -o gpurun_out/${T}_passes python tools/build_once.py 2 2>&1 | tail -1
+timeout -k 10 300 $NCU -k 'regex:text_hist_kernel|group_flags_kernel<1>|group_apply_kernel<1>' -s 3 -c 3 -o gpurun_out/${T}_group python tools/build_once.py 2 2>&1 | tail -1
+timeout -k 10 300 $NCU -k 'regex:refine_keys_kernel|iwt_top_emit_kernel' -s 4 -c 4 -o gpurun_out/${T}_refine python tools/build_once.py 2 2>&1 | tail -1
 fi
 } > gpurun_out/${T}.log 2>&1
 tail -100 gpurun_out/${T}.log
