@@ -169,16 +169,6 @@ text_hist_kernel(TextKeySource src, unsigned long long* __restrict__ hist /* [NP
         }
         __syncthreads();
         fetch(tile + gridDim.x, q, edge);                  // in flight while this tile is counted
-        if (src.fill_ones) {                               // 16 words per thread, 16-byte stores when the array allows
-            const int64_t p0 = base + (int64_t)threadIdx.x * kTextItems;
-            if ((reinterpret_cast<uintptr_t>(src.fill_ones) & 15) == 0 && p0 + kTextItems <= n) {
-                uint4* dst = reinterpret_cast<uint4*>(src.fill_ones + p0);
-#pragma unroll
-                for (int j = 0; j < kTextItems / 4; j++) dst[j] = make_uint4(~0u, ~0u, ~0u, ~0u);
-            } else {
-                for (int j = 0; j < kTextItems; j++) if (p0 + j < n) src.fill_ones[p0 + j] = ~0u;
-            }
-        }
 
         uint32_t own[5], in[5];                            // own: codes of my positions; in: codes k - 1 positions further (17 of them)
         {

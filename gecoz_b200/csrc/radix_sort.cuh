@@ -34,8 +34,6 @@ struct TextKeySource {
     uint64_t*      run_marks = nullptr;         // device, run_mark_cap entries (optional)
     unsigned*      run_mark_count = nullptr;
     unsigned       run_mark_cap = 0;
-    uint32_t*      fill_ones = nullptr;         // optional: n words set to 0xFFFFFFFF by the histogram pass (it has DRAM bandwidth to spare;
-                                                // the suffix sorter's rank array would otherwise cost a 4 n byte memset of its own)
 };
 
 struct SortStats {

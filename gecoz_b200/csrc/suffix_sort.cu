@@ -547,6 +547,7 @@ int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t 
     GCZ_TRY(small_upload(ctx, st, d_code, h_code, 256));
     GCZ_TRY(small_upload(ctx, st, d_allc, h_allc, sizeof(uint64_t) * sigma));
     GCZ_CUDA(cudaMemsetAsync(d_totals, 0, 8 * sizeof(long long), st));
+    GCZ_CUDA(cudaMemsetAsync(d_rank, 0xFF, (size_t)n * 4, st));
 
     // full sort by the first k symbols; start in the buffer that makes the result land in d_sa
     const int npass = radix_sort_passes(key_bits);
@@ -558,7 +559,6 @@ int suffix_sort(DeviceCtx* ctx, cudaStream_t st, const uint8_t* d_text, int64_t 
     TextKeySource src;
     src.text = d_text; src.n = n; src.code_of = d_code; src.coder = kc; src.carry_shift = carry;
     src.run_marks = d_marks[0]; src.run_mark_count = d_mark_count; src.run_mark_cap = mark_cap;
-    src.fill_ones = d_rank;                               // rank[] = "no rank yet" everywhere, written by the histogram pass
     SortStats ss;
     SortStats* ssp = stats ? &ss : nullptr;
     GCZ_TRY(radix_sort_pairs(ctx, st, b, n, 0, key_bits, d_temp, ssp, &src));
