@@ -602,12 +602,14 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
     }
 }
 
-// Shape of the pass: 512 threads x 12 elements, two CTAs per SM (what profiles/sort_variants_r01.md picked; 384 x 12 with three CTAs
-// per SM was measured again in round 2 with the leaner kernel: 1.87 ms against 1.74).
+// Shape of the pass: 256 threads x 16 elements, three CTAs per SM (80 registers), look-back window of 8 rows.  Round 1's sweep had
+// picked 512 x 12 x 2; with the leaner kernel of round 2 fewer threads with more keys each and a third tile per SM win
+// (profiles/onesweep_experiments_r02.md, third series: 1.59 ms per pass against 1.69; 384 x 16 x 2: 1.63; 256 x 18 / 20 spill).
+constexpr int kThreads = 256, kItems = 16, kCtasPerSm = 3, kLook = 8;
 constexpr size_t onesweep_smem(int threads, int items, bool vals) {
     return (size_t)threads * items * (vals ? 12 : 8) + (size_t)(threads / 32) * kRadix * 4 + kRadix * 8 + kRadix * 4 + 64;
 }
-constexpr int kMinTile = 512 * 12;
+constexpr int kMinTile = kThreads * kItems;
 
 template <typename S, int THREADS, int ITEMS, int MINB, int LOOK, bool ASYNC>
 int digit_passes(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n, int begin_bit, int npass, unsigned long long* hist,
@@ -704,9 +706,9 @@ int radix_sort_pairs(DeviceCtx* ctx, cudaStream_t st, RadixBuffers& b, int64_t n
     }
     const bool force_wide = std::getenv("GCZ_SORT_WIDE_STATUS") != nullptr;    // tests: the 64-bit status words at any size
     if (n >= kNarrowStatusLimit || force_wide)
-        return digit_passes<unsigned long long, 512, 12, 2, 8, true>(ctx, st, b, n, begin_bit, npass, hist, status_mem, stats, src, 0);
+        return digit_passes<unsigned long long, kThreads, kItems, kCtasPerSm, kLook, true>(ctx, st, b, n, begin_bit, npass, hist, status_mem, stats, src, 0);
     // 32-bit status words, window of 8 rows, values staged by a bulk copy: profiles/onesweep_experiments_r02.md, second series
-    return digit_passes<uint32_t, 512, 12, 2, 8, true>(ctx, st, b, n, begin_bit, npass, hist, status_mem, stats, src, 1);
+    return digit_passes<uint32_t, kThreads, kItems, kCtasPerSm, kLook, true>(ctx, st, b, n, begin_bit, npass, hist, status_mem, stats, src, 1);
 }
 
 void SortStats::resolve() {

@@ -35,7 +35,7 @@ def _p(a):
 
 
 # ---- radix sort -------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n,bits", [(1, 64), (7, 64), (6143, 64), (6144, 64), (6145, 64), (100_000, 64),
+@pytest.mark.parametrize("n,bits", [(1, 64), (7, 64), (4095, 64), (4096, 64), (4097, 64), (6144, 64), (100_000, 64),
                                     (1_000_003, 64), (300_000, 41), (250_000, 8), (3_000_000, 63)])
 def test_sort_pairs(G, n, bits):
     rng = np.random.default_rng(n + bits)
@@ -64,7 +64,7 @@ def test_sort_skewed_digits(G):
     assert np.array_equal(k2, keys[order]) and np.array_equal(v2, vals[order])
 
 
-@pytest.mark.parametrize("n,bits", [(5, 64), (6145, 64), (1_000_003, 64), (3_000_000, 24)])
+@pytest.mark.parametrize("n,bits", [(5, 64), (4097, 64), (1_000_003, 64), (3_000_000, 24)])
 def test_sort_pairs_wide_status(G, monkeypatch, n, bits):
     """Sorts of 2^30 pairs and more use 64-bit status words in the look-back (radix_sort.cu: Status<unsigned long long>); the switch
     sends a small sort through that instantiation."""
