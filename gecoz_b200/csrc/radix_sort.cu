@@ -182,8 +182,10 @@ text_hist_kernel(TextKeySource src, unsigned long long* __restrict__ hist /* [NP
             for (int j = 0; j < 5; j++) in[j] = __byte_perm(raw[j], raw[j + 1], in_sel);
         }
         const uint32_t before = s_codes[first - 1];
-        uint64_t key = 0;
-        for (int j = 0; j < k - 1; j++) key = key * radix + s_codes[first + j];
+        uint64_t key = 0;                                  // the first k - 1 symbols: my own 16 from the registers, the rest byte by byte
+#pragma unroll
+        for (int j = 0; j < kTextItems; j++) if (j < k - 1) key = key * radix + byte_of(own, j);
+        for (int j = kTextItems; j < k - 1; j++) key = key * radix + s_codes[first + j];
         const int64_t p_first = base + first - 16;
         const bool whole = p_first + kTextItems <= n;
 #pragma unroll
@@ -441,16 +443,41 @@ onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ key
         // every thread slides the k-symbol window over ITEMS consecutive positions
         const int first = 16 + threadIdx.x * ITEMS;
         uint64_t w = 0;
-        for (int j = 0; j < k - 1; j++) w = w * radix + s_codes[first + j];
-        if (count == TILE) {
-            // A full tile keeps them: the first pass of an LSD sort need not be stable (its input has no order to keep), so
-            // the keys are ranked as (item, lane) although the thread's positions are consecutive — no trip through shared memory
+        if (ITEMS == 16 && count == TILE) {
+            // A full tile keeps its keys in registers: the first pass of an LSD sort need not be stable (its input has no order to
+            // keep), so the keys are ranked as (item, lane) although the thread's positions are consecutive — no trip through
+            // shared memory.  The codes come as words (a thread's 16 bytes are 16 apart from its neighbour's: byte loads would
+            // meet four to a bank): one 16-byte load of my own positions, six words around the window's leading edge.
+            uint32_t own[5], in[5];
+            {
+                const uint4 o = *reinterpret_cast<const uint4*>(s_codes + first);
+                own[0] = o.x; own[1] = o.y; own[2] = o.z; own[3] = o.w; own[4] = 0;
+                const int in_at = first + k - 1;
+                const uint32_t in_sel = 0x3210u + 0x1111u * (uint32_t)(in_at & 3);
+                const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_codes + (in_at & ~3));
+                uint32_t raw[6];
+#pragma unroll
+                for (int j = 0; j < 6; j++) raw[j] = wp[j];
+#pragma unroll
+                for (int j = 0; j < 5; j++) in[j] = __byte_perm(raw[j], raw[j + 1], in_sel);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j++) if (j < k - 1) w = w * radix + byte_of(own, j);
+            for (int j = 16; j < k - 1; j++) w = w * radix + s_codes[first + j];
+#pragma unroll
+            for (int i = 0; i < ITEMS; i++) {
+                w = slide_key(w, i > 0 ? byte_of(own, i - 1) : 0u, byte_of(in, i), radix, src.coder.top);
+                key[i] = w;
+            }
+        } else if (count == TILE) {
+            for (int j = 0; j < k - 1; j++) w = w * radix + s_codes[first + j];
 #pragma unroll
             for (int i = 0; i < ITEMS; i++) {
                 w = slide_key(w, i > 0 ? s_codes[first + i - 1] : 0u, s_codes[first + i + k - 1], radix, src.coder.top);
                 key[i] = w;
             }
         } else {
+            for (int j = 0; j < k - 1; j++) w = w * radix + s_codes[first + j];
             // the last tile is transposed to the warp-striped order, in which the padding keys are the last elements
 #pragma unroll
             for (int i = 0; i < ITEMS; i++) {
