@@ -142,6 +142,12 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned l
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// 32 bytes per thread and instruction (sm_100: LDG.E.256): a thread that owns consecutive elements fetches whole 32-byte sectors,
+// where two 16-byte loads ask for each sector twice.  The address is 32-byte aligned; the data is not written by the kernel.
+__device__ __forceinline__ void ld_nc_256(const void* p, unsigned long long (&v)[4]) {
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
+}
+
 // warp inclusive scans
 __device__ __forceinline__ unsigned warp_incl_sum(unsigned v) {
 #pragma unroll

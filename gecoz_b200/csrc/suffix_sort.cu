@@ -143,23 +143,28 @@ group_flags_kernel(GroupArgs a) {
     static_assert(kGrpItems == 16, "two threads fill one 32-bit word of the bit arrays");
     __shared__ uint64_t s_allc[256];
     __shared__ unsigned s_agg[kAggs][kGrpThreads / 32];
+    const int64_t tile_base = (int64_t)blockIdx.x * kGrpTile;
+    const int64_t t0 = tile_base + (int64_t)threadIdx.x * kGrpItems;
+    const int cnt = (int)max((int64_t)0, min((int64_t)kGrpItems, a.m - t0));
+    uint64_t key[kGrpItems];
+    if (cnt == kGrpItems && (reinterpret_cast<uintptr_t>(a.keys) & 31) == 0) {
+#pragma unroll
+        for (int i = 0; i < kGrpItems / 4; i++) {
+            unsigned long long q[4];
+            ld_nc_256(a.keys + t0 + 4 * i, q);
+            key[4 * i] = q[0]; key[4 * i + 1] = q[1]; key[4 * i + 2] = q[2]; key[4 * i + 3] = q[3];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kGrpItems; i++) key[i] = i < cnt ? a.keys[t0 + i] : 0;
+    }
+    // the small table is fetched while the keys are on their way (a CTA lives for a few microseconds: a dependent global load
+    // and a barrier in front of the key loads cost a sixth of it)
     int sigma = 0;
     if (INITIAL) {
         sigma = (a.sigma > 0 && *a.run_mark_count <= a.run_mark_cap) ? a.sigma : 0;
         if ((int)threadIdx.x < sigma) s_allc[threadIdx.x] = a.allc[threadIdx.x];
         __syncthreads();
-    }
-    const int64_t tile_base = (int64_t)blockIdx.x * kGrpTile;
-    const int64_t t0 = tile_base + (int64_t)threadIdx.x * kGrpItems;
-    const int cnt = (int)max((int64_t)0, min((int64_t)kGrpItems, a.m - t0));
-    uint64_t key[kGrpItems];
-    if (cnt == kGrpItems && (reinterpret_cast<uintptr_t>(a.keys) & 15) == 0) {
-        const ulonglong2* src = reinterpret_cast<const ulonglong2*>(a.keys + t0);
-#pragma unroll
-        for (int i = 0; i < kGrpItems / 2; i++) { const ulonglong2 q = src[i]; key[2 * i] = q.x; key[2 * i + 1] = q.y; }
-    } else {
-#pragma unroll
-        for (int i = 0; i < kGrpItems; i++) key[i] = i < cnt ? a.keys[t0 + i] : 0;
     }
     // the key before my first slot and the key after my last one
     uint64_t prev = __shfl_up_sync(0xffffffffu, key[kGrpItems - 1], 1);
@@ -264,11 +269,11 @@ group_apply_kernel(GroupArgs a) {
 #pragma unroll
         for (int q = 0; q < 4; q++) s_w[1 + q][threadIdx.x >> 5] = inc[q];
     }
-    __syncthreads();
-    unsigned last1 = a.agg[blockIdx.x];
+    unsigned last1 = a.agg[blockIdx.x];                       // (requested before the barrier: five independent loads)
     unsigned cnt[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) cnt[q] = a.agg[(size_t)(1 + q) * gridDim.x + blockIdx.x];
+    __syncthreads();
     for (unsigned w = 0; w < (threadIdx.x >> 5); w++) {
         last1 = max(last1, s_w[0][w]);
 #pragma unroll
@@ -284,10 +289,14 @@ group_apply_kernel(GroupArgs a) {
 
     // the suffixes of my slots, requested together (unresolved slots come in long stretches: the members of a big group)
     uint32_t sv[kGrpItems];
-    if (valid == (1u << kGrpItems) - 1u && (reinterpret_cast<uintptr_t>(a.suf) & 15) == 0) {
-        const uint4* src = reinterpret_cast<const uint4*>(a.suf + t0);
+    if (valid == (1u << kGrpItems) - 1u && (reinterpret_cast<uintptr_t>(a.suf) & 31) == 0) {
 #pragma unroll
-        for (int i = 0; i < kGrpItems / 4; i++) { const uint4 q = src[i]; sv[4 * i] = q.x; sv[4 * i + 1] = q.y; sv[4 * i + 2] = q.z; sv[4 * i + 3] = q.w; }
+        for (int i = 0; i < kGrpItems / 8; i++) {
+            unsigned long long q[4];
+            ld_nc_256(a.suf + t0 + 8 * i, q);
+#pragma unroll
+            for (int j = 0; j < 4; j++) { sv[8 * i + 2 * j] = (uint32_t)q[j]; sv[8 * i + 2 * j + 1] = (uint32_t)(q[j] >> 32); }
+        }
     } else {
 #pragma unroll
         for (int i = 0; i < kGrpItems; i++) sv[i] = ((valid & ~single) >> i) & 1 ? a.suf[t0 + i] : 0u;
