@@ -7,8 +7,8 @@
 //             one tiny scan launch (digit bases),
 // per digit:  one "onesweep" launch: every CTA takes tiles by ticket, ranks their keys with warp ballots into
 //             per-warp digit counters, learns a tile's global offsets through a decoupled look-back over
-//             64-bit status words (aggregate | inclusive-prefix flags), reorders the tile in shared memory
-//             and writes digit runs out coalesced.
+//             status words (count + aggregate / inclusive-prefix flags; 32 bits wide below 2^30 pairs), reorders the tile
+//             in shared memory and writes digit runs out coalesced.
 // Algorithmic traffic per digit pass: read 12 B + write 12 B per pair (8 + 8 for keys only).
 #include "radix_sort.cuh"
 
@@ -340,27 +340,29 @@ __device__ __forceinline__ void rank_in_warp(const uint64_t (&key)[ITEMS], int s
 
 // ---- one digit pass ---------------------------------------------------------------------------------------------
 // One CTA per tile of THREADS x ITEMS elements (tiles are taken by ticket: forward progress for the look-back):
+//   0 the thread that takes the ticket starts a bulk copy (TMA) of the tile's values into shared memory (ASYNC)
 //   1 load keys, warp-striped (FROM_TEXT: the tile's keys are computed from the text instead — codes to shared memory,
-//     a k-symbol window slid over ITEMS consecutive positions per thread, transposed through shared memory)
+//     a k-symbol window slid over ITEMS consecutive positions per thread; full tiles keep those keys in registers, because
+//     a first pass need not be stable, the last one is transposed through shared memory)
 //   2 digit counts of every warp: one shared-memory reduction per key                                      | barrier
 //   3 threads 0..255: counts -> the tile's histogram, PUBLISHED NOW as the aggregate the tiles behind this one will
 //     look back at; scan -> digit starts; per-warp starting positions (digit start + keys of the digit in earlier
 //     warps)                                                                                               | barrier x2
 //   4 rank keys inside each warp: peers with the same digit (8 ballots) get consecutive positions in element order,
 //     counted up from the warp's starting position — the rank IS the position in the reordered tile
-//   5 values are requested from global memory only now (they are not live during the ranking); reorder in shared memory
-//   6 threads 0..255: decoupled look-back over windows of 16 predecessor tiles                             | barrier
+//   5 values picked up (from the staged copy, or requested from global memory only now: they are not live during the
+//     ranking); reorder in shared memory
+//   6 threads 0..255: decoupled look-back over windows of LOOK predecessor tiles                           | barrier
 //   7 write digit runs out, coalesced
 //
-// Why the histogram comes before the ranking: at 25 tiles per microsecond (249 M pairs in 1.6 ms) all of a tile's near
-// predecessors are in flight at once, and a dependent round trip through the loaded L2 takes 2 - 3 us.  With the
-// aggregate published after the ranking (round 1) the look-back found the nearest tiles unpublished and polled: 2.7
-// round trips per tile, 10 % of all warp samples parked at the barrier behind it.  Published before the ranking, an
-// aggregate is ~5 us old when it is looked at (1.9 round trips; what remains is the distance to the nearest PREFIX).
-// Two designs that remove the chain from the tile CTAs and one that hides the tile's DRAM latency were built, measured
-// and dropped — profiles/onesweep_experiments_r02.md has their kernels' numbers: persistent CTAs fed by TMA bulk copies
-// (cp.async.bulk + mbarrier; 1.86 ms per pass against 1.69), and a scan-ahead CTA that turns aggregates into prefixes
-// (2.99 ms: one chain of dependent L2 round trips cannot follow 25 tiles per microsecond).
+// What bounds it (profiles/onesweep_experiments_r02.md, three series of measured variants): not issue slots (a third fewer
+// instructions changed nothing), not the look-back (half its traffic or a variant that always ends in one round trip changed
+// nothing; a wider window is slower), not DRAM (half of its cycles active) — seven barrier-separated phases per tile, each
+// saturating a different unit, and only as many tiles per SM to overlap them as registers and shared memory allow.  The
+// histogram comes before the ranking so that the aggregate is published early (round 1 published it after: 2.7 look-back round
+// trips per tile).  Built, verified, measured and dropped: persistent CTAs fed by TMA bulk copies of keys and values (1.86 ms per
+// pass against 1.69), a scan-ahead CTA that turns aggregates into prefixes (2.99 ms), 9-bit digits (+47 % per pass), a
+// grouped look-back, windows of 16 / 32 rows, 512 x 12 x 2, 384 x 12 x 3, 384 x 16 x 2, 256 x 12 x 4, 256 x 18 / 20 x 3.
 template <int THREADS, int ITEMS, bool HAS_VALS, int MIN_BLOCKS, bool FROM_TEXT, typename S, int LOOK, bool ASYNC>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 onesweep_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
