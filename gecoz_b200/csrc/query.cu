@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(256, 5)      // 48 registers: 5 CTAs per SM me
 count_kernel(const QueryTables* __restrict__ tables, const uint32_t* __restrict__ sectors,
              const uint8_t* __restrict__ pats, const int64_t* __restrict__ pat_off, int64_t n_pats,
              int64_t* __restrict__ sp_out, int64_t* __restrict__ ep_out, unsigned long long* __restrict__ next_pattern,
-             unsigned long long* __restrict__ stats_out) {
+             unsigned long long* __restrict__ stats_out, int use_table) {
     __shared__ QueryTables t;
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
@@ -230,6 +230,22 @@ count_kernel(const QueryTables* __restrict__ tables, const uint32_t* __restrict_
                         ep = (ch < 255 ? t.c[ch + 1] : t.n) - 1;
                         i = e - 2;
                     }
+                    // the last kmer_k symbols at once, when the table has a non-empty interval for them (an empty one means
+                    // the search fails inside them: it is then made step by step, to report what the reference reports)
+                    const int K = use_table ? t.kmer_k : 0;
+                    if (K > 0 && e - b >= K) {
+                        unsigned at = 0, bad = 0;
+                        for (int j = K; j >= 1; j--) {
+                            const unsigned c2 = t.code2[pats[e - j]];
+                            bad |= c2;
+                            at = at << 2 | (c2 & 3u);
+                        }
+                        if (bad < 4u) {
+                            const uint2 iv = __ldg(&t.kmer[at]);
+                            if (MODE == 2) stats.sectors++;
+                            if (iv.x <= iv.y) { sp = iv.x; ep = iv.y; i = e - K - 1; }
+                        }
+                    }
                 }
             }
             wnext = min(wend, wnext + (long long)__popc(idle));
@@ -261,13 +277,40 @@ count_kernel(const QueryTables* __restrict__ tables, const uint32_t* __restrict_
         }
     }
     if (MODE == 2) {
-        unsigned long long v[3] = { stats.sectors, stats.ref_calls, stats.steps };
+        // with the table: the sectors this kernel loads; without: the rank calls and steps of the reference's loop
+        unsigned long long v[3] = { use_table ? stats.sectors : 0ull, use_table ? 0ull : stats.ref_calls, use_table ? 0ull : stats.steps };
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
             if (lane == 0 && v[k]) atomicAdd(&stats_out[k], v[k]);
         }
     }
+}
+
+// (sp, ep) of every string of K symbols out of A, C, G, T: thread `at` searches the string whose 2-bit codes are the digits of
+// `at` (first symbol highest) exactly as count_kernel would, last symbol first
+__global__ void __launch_bounds__(256)
+kmer_table_kernel(const QueryTables* __restrict__ tables, const uint32_t* __restrict__ sectors, int K, uint2* __restrict__ out) {
+    __shared__ QueryTables t;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&t);
+        for (int i = threadIdx.x; i < (int)(sizeof(QueryTables) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const unsigned at = blockIdx.x * blockDim.x + threadIdx.x;
+    if (at >= 1u << (2 * K)) return;
+    const int sym[4] = { 'A', 'C', 'G', 'T' };
+    int ch = sym[at & 3u];
+    long long sp = t.c[ch], ep = t.c[ch + 1] - 1;
+    for (int j = 1; j < K && sp <= ep; j++) {
+        ch = sym[(at >> (2 * j)) & 3u];
+        long long o1 = sp - 1, o2 = ep;
+        hswt_occ2<false>(&t, sectors, ch, o1, o2, nullptr);
+        sp = t.c[ch] + o1 + 1;
+        ep = t.c[ch] + o2;
+    }
+    out[at] = sp <= ep ? make_uint2((unsigned)sp, (unsigned)ep) : make_uint2(1u, 0u);
 }
 
 // ---- locate ------------------------------------------------------------------------------------------------------
@@ -635,6 +678,24 @@ int open_block(DeviceCtx* ctx, const uint8_t* gcz_body, int64_t body_len, int64_
     GCZ_CUDA(cudaMemcpyAsync(idx->d_tables, &qt, sizeof(qt), cudaMemcpyHostToDevice, st));
     GCZ_CUDA(cudaStreamSynchronize(st));
 
+    // interval table of the K-symbol strings over A, C, G, T (K such that a string occurs a few dozen times on average)
+    for (int c = 0; c < 256; c++) qt.code2[c] = 0xFF;
+    qt.code2['A'] = 0; qt.code2['C'] = 1; qt.code2['G'] = 2; qt.code2['T'] = 3;
+    {
+        int K = 0;
+        while (K < 10 && ((int64_t)64 << (2 * (K + 1))) <= text_len) K++;
+        const bool dna = qt.len['A'] && qt.len['C'] && qt.len['G'] && qt.len['T'];
+        if (dna && K >= 4 && !std::getenv("GCZ_NO_KMER_TABLE")) {
+            const size_t entries = (size_t)1 << (2 * K);
+            GCZ_CUDA(cudaMalloc(&idx->d_kmer, entries * sizeof(uint2)));
+            GCZ_LAUNCH(ctx, kmer_table_kernel, (unsigned)((entries + 255) / 256), 256, 0, st, idx->d_tables, idx->d_sectors, K, idx->d_kmer);
+            qt.kmer = idx->d_kmer;
+            qt.kmer_k = K;
+        }
+        GCZ_CUDA(cudaMemcpyAsync(idx->d_tables, &qt, sizeof(qt), cudaMemcpyHostToDevice, st));
+        GCZ_CUDA(cudaStreamSynchronize(st));
+    }
+
     // e[]: text positions of the separators = locate(i) for i < C[1], sorted  algo/ssa/GSSA.java:232-238
     const int64_t ns = qt.c[1];
     idx->e.resize((size_t)ns);
@@ -658,6 +719,7 @@ void close_block(gcz_index* idx) {
     cudaSetDevice(idx->ctx->device);
     if (idx->d_sectors) cudaFree(idx->d_sectors);
     if (idx->d_tables) cudaFree(idx->d_tables);
+    if (idx->d_kmer) cudaFree(idx->d_kmer);
     delete idx;
 }
 
@@ -856,7 +918,7 @@ int find_block(gcz_index* idx, cudaStream_t st, const DeviceBatch& batch, BlockH
     GCZ_CUDA(cudaMemsetAsync(d_next, 0, 32, st));
     if (ns > 0) GCZ_CUDA(cudaMemcpyAsync(d_e, idx->e.data(), (size_t)ns * 8, cudaMemcpyHostToDevice, st));
     GCZ_LAUNCH(ctx, count_kernel<0>, count_grid(ctx, n_pats), 256, 0, st, idx->d_tables, idx->d_sectors, batch.pats, batch.off, n_pats,
-               d_sp, d_ep, d_next, (unsigned long long*)nullptr);
+               d_sp, d_ep, d_next, (unsigned long long*)nullptr, 1);
     int64_t* d_total = reinterpret_cast<int64_t*>(d_next + 1);
     GCZ_LAUNCH(ctx, occ_chunk_sums_kernel, (unsigned)chunks, kScanThreads, 0, st, d_sp, d_ep, n_pats, d_chunk);
     GCZ_LAUNCH(ctx, scan_chunk_sums_kernel, 1, 1024, 0, st, d_chunk, chunks, d_total);
@@ -992,7 +1054,7 @@ int count_batch(gcz_index* idx, const uint8_t* pats, const int64_t* pat_off, int
     if (!d_sp || !d_ep || !d_next) return fail(GCZ_E_NOMEM, "query staging");
     GCZ_CUDA(cudaMemsetAsync(d_next, 0, 8, st));
     GCZ_LAUNCH(ctx, count_kernel<0>, count_grid(ctx, n_pats), 256, 0, st, idx->d_tables, idx->d_sectors, batch.pats, batch.off, n_pats,
-               d_sp, d_ep, d_next, (unsigned long long*)nullptr);
+               d_sp, d_ep, d_next, (unsigned long long*)nullptr, 1);
     if (!out_dev) {
         GCZ_CUDA(cudaMemcpyAsync(sp, d_sp, (size_t)n_pats * 8, cudaMemcpyDeviceToHost, st));
         GCZ_CUDA(cudaMemcpyAsync(ep, d_ep, (size_t)n_pats * 8, cudaMemcpyDeviceToHost, st));
@@ -1027,7 +1089,7 @@ int count_multi(gcz_index* const* blocks, int32_t n_blocks, const uint8_t* pats,
     GCZ_CUDA(cudaEventRecord(e0, st));
     for (int32_t b = 0; b < n_blocks; b++) {
         GCZ_LAUNCH(ctx, count_kernel<1>, count_grid(ctx, n_pats), 256, 0, st, blocks[b]->d_tables, blocks[b]->d_sectors, batch.pats, batch.off,
-                   n_pats, d_tot, (int64_t*)nullptr, d_next + b, (unsigned long long*)nullptr);
+                   n_pats, d_tot, (int64_t*)nullptr, d_next + b, (unsigned long long*)nullptr, 1);
     }
     GCZ_CUDA(cudaEventRecord(e1, st));
     if (!out_dev) GCZ_CUDA(cudaMemcpyAsync(totals, d_tot, (size_t)n_pats * 8, cudaMemcpyDeviceToHost, st));
@@ -1056,16 +1118,22 @@ int count_stats(gcz_index* const* blocks, int32_t n_blocks, const uint8_t* pats,
     GCZ_TRY(stage_batch(st, ctx->arena, pats, pat_off, n_pats, &batch));
     int64_t* d_sp = ctx->arena.get<int64_t>((size_t)n_pats + 1);
     int64_t* d_ep = ctx->arena.get<int64_t>((size_t)n_pats + 1);
-    unsigned long long* d_next = ctx->arena.get<unsigned long long>((size_t)n_blocks + 4);
+    unsigned long long* d_next = ctx->arena.get<unsigned long long>((size_t)2 * n_blocks + 4);
     if (!d_sp || !d_ep || !d_next) return fail(GCZ_E_NOMEM, "query staging");
-    GCZ_CUDA(cudaMemsetAsync(d_next, 0, ((size_t)n_blocks + 4) * 8, st));
-    unsigned long long* d_stats = d_next + n_blocks;
+    GCZ_CUDA(cudaMemsetAsync(d_next, 0, ((size_t)2 * n_blocks + 4) * 8, st));
+    unsigned long long* d_stats = d_next + 2 * n_blocks;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     GCZ_CUDA(cudaEventCreate(&e0)); GCZ_CUDA(cudaEventCreate(&e1));
+    // first the search the way the reference makes it, symbol by symbol (its rank calls and steps), then the way this library
+    // makes it, with the interval table for the last symbols of a pattern (the sectors it loads, and its time)
+    for (int32_t b = 0; b < n_blocks && n_pats > 0; b++) {
+        GCZ_LAUNCH(ctx, count_kernel<2>, count_grid(ctx, n_pats), 256, 0, st, blocks[b]->d_tables, blocks[b]->d_sectors, batch.pats, batch.off,
+                   n_pats, d_sp, d_ep, d_next + b, d_stats, 0);
+    }
     GCZ_CUDA(cudaEventRecord(e0, st));
     for (int32_t b = 0; b < n_blocks && n_pats > 0; b++) {
         GCZ_LAUNCH(ctx, count_kernel<2>, count_grid(ctx, n_pats), 256, 0, st, blocks[b]->d_tables, blocks[b]->d_sectors, batch.pats, batch.off,
-                   n_pats, d_sp, d_ep, d_next + b, d_stats);
+                   n_pats, d_sp, d_ep, d_next + n_blocks + b, d_stats, 1);
     }
     GCZ_CUDA(cudaEventRecord(e1, st));
     unsigned long long h[3] = { 0, 0, 0 };

@@ -24,6 +24,12 @@ struct QueryTables {
     uint16_t code[256];             // byte -> code bits
     uint8_t  len[256];              // byte -> code length (0 = absent)
     uint8_t  node_of[256][16];      // byte, depth -> node on the symbol's path
+    // (sp, ep) of every string of kmer_k symbols out of A, C, G, T, as the backward search leaves them (x > y: the search of
+    // that string fails on the way): built at open by that very search, looked up for the last kmer_k symbols of a pattern
+    const uint2* kmer;              // 4^kmer_k entries, index = the symbols' 2-bit codes, first symbol highest; null: no table
+    int32_t  kmer_k;
+    int32_t  pad2_;
+    uint8_t  code2[256];            // byte -> 0..3 for A, C, G, T, 0xFF otherwise
 };
 
 }  // namespace gcz
@@ -36,6 +42,7 @@ struct gcz_index {
     uint32_t*         d_sectors = nullptr;
     size_t            sector_bytes = 0;
     gcz::QueryTables* d_tables = nullptr;
+    uint2*            d_kmer = nullptr;
     int64_t           c[256];
     std::vector<int64_t> e;          // sorted separator positions
 };

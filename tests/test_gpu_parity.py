@@ -272,11 +272,17 @@ def test_open_and_tables(G, O, block_1m):
     g.close()
 
 
-def test_count_batch(G, O, block_1m):
+@pytest.mark.parametrize("table", [True, False], ids=["kmer_table", "step_by_step"])
+def test_count_batch(G, O, block_1m, monkeypatch, table):
+    """(sp, ep) of every pattern as GSSA.search leaves them, found or not — with the interval table of the block's 6-symbol strings
+    (the last symbols of a pattern in one lookup; a search that fails inside them is redone step by step) and without it."""
     from gecoz_b200 import synth
     text, ref = block_1m
     og = O.GSSA(ref["gcz_body"], len(text), ref["gcx_body"])
+    if not table:
+        monkeypatch.setenv("GCZ_NO_KMER_TABLE", "1")
     g = G.GSSA.open(0, ref["gcz_body"], len(text), ref["gcx_body"])
+    monkeypatch.delenv("GCZ_NO_KMER_TABLE", raising=False)
     data, off = synth.patterns(text, 20_000, 1, 60, seed=2)
     # edge cases appended: poly-N (huge interval), absent symbol, separator, byte >= 0x80
     extra = [b"N" * 30, b"NNNNA", b"Z", b"AC\0", b"\0", bytes([200, 65]), b"A"]
