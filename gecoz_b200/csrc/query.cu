@@ -678,12 +678,16 @@ int open_block(DeviceCtx* ctx, const uint8_t* gcz_body, int64_t body_len, int64_
     GCZ_CUDA(cudaMemcpyAsync(idx->d_tables, &qt, sizeof(qt), cudaMemcpyHostToDevice, st));
     GCZ_CUDA(cudaStreamSynchronize(st));
 
-    // interval table of the K-symbol strings over A, C, G, T (K such that a string occurs a few dozen times on average)
+    // interval table of the K-symbol strings over A, C, G, T: the largest K <= 12 whose table is no larger than the block's rank
+    // sectors (it at most doubles the device footprint of a block: 134 MB for a chr1-sized one) and whose strings still occur
+    // 16 times on average.  Measured on six 200 Mbp blocks, 2 M patterns of 15..100 symbols: no table 6.41 ms, K = 8 / 9 / 10 /
+    // 11 / 12: 4.55 / 4.31 / 3.91 / 3.44 / 3.02 ms.
     for (int c = 0; c < 256; c++) qt.code2[c] = 0xFF;
     qt.code2['A'] = 0; qt.code2['C'] = 1; qt.code2['G'] = 2; qt.code2['T'] = 3;
     {
         int K = 0;
-        while (K < 10 && ((int64_t)64 << (2 * (K + 1))) <= text_len) K++;
+        while (K < 12 && ((int64_t)16 << (2 * (K + 1))) <= text_len && ((size_t)8 << (2 * (K + 1))) <= idx->sector_bytes) K++;
+        if (const char* ke = std::getenv("GCZ_KMER_K")) K = std::max(0, std::min(13, std::atoi(ke)));      // tuning aid
         const bool dna = qt.len['A'] && qt.len['C'] && qt.len['G'] && qt.len['T'];
         if (dna && K >= 4 && !std::getenv("GCZ_NO_KMER_TABLE")) {
             const size_t entries = (size_t)1 << (2 * K);
