@@ -721,7 +721,11 @@ class Bench:
                                       "what": "SURVEY.md 8(d) B_count: 74 B per RankedWTNode.count call of the reference's loop (64 B chunk + uint16 + uint64 "
                                               "counters); the re-laid-out index serves bit + rank from one 32 B sector and both ends of an interval from one load "
                                               "when they share it"},
-                 "index_bytes": st["index_bytes"], "l2": "random 32 B sector reads; the index of one block (0.1-0.15 GB) is about the size of the 126 MB L2"}
+                 "index_bytes": st["index_bytes"], "l2": "random 32 B sector reads; the index of one block (0.1-0.15 GB) is about the size of the 126 MB L2",
+                 "interval_table": "the last K <= 12 symbols of a pattern are one lookup in a table of the block's K-symbol strings (built at open by "
+                                   "the search itself; a lookup counts as one sector): rank_sectors / steps-with-table shrink ~3x against the "
+                                   "reference's loop (reference_rank_calls, steps: counted without the table), so the kernel is latency- rather than "
+                                   "bandwidth-bound and frac is lower than the 0.61 it had when every step loaded its sectors"}
         out = {"metric": "count queries/s against the hg38-shaped index (every pattern x every block, backward-search intervals summed)",
                "value": npat / (cms / 1e3), "unit": "queries/s", "patterns": npat, "blocks": len(self.gssas),
                "pattern_length": "uniform 15..100, 50% text-sampled (N-free windows of the rank's largest block) / 50% random",
