@@ -116,7 +116,10 @@ typedef struct gcz_index gcz_index;
 /* GecozFileReader.read(header)  fmt/GecozFileReader.java:115-177: gcz_body starts at the shape table
  * (just after the block header), gcx_body just after the 25-byte GecozSSA header.  The sampling factor is
  * recovered from gcx_len like GSSAIndex(ByteBuffer,long)  algo/ssa/GSSAIndex.java:57-71.  The .gcx is
- * mandatory (the reference cannot locate without it): NULL fails fast with GCZ_E_ARG. */
+ * mandatory (the reference cannot locate without it): NULL fails fast with GCZ_E_ARG.
+ * Device memory of an open block: the two bodies re-laid out as 32-byte rank sectors (1.14 x their size) and, for DNA
+ * blocks, a table of the backward-search intervals of all strings of K <= 12 symbols over A, C, G, T (never larger than
+ * the sectors), which the searches use for the last K symbols of a pattern; results are those of GSSA.search. */
 int  gcz_open_block(int device, const uint8_t* gcz_body, int64_t body_len, int64_t text_len,
                     const uint8_t* gcx_body, int64_t gcx_len, gcz_index** out);
 void gcz_close_block(gcz_index* idx);
@@ -178,10 +181,12 @@ int  gcz_find_multi(gcz_index* const* blocks, int32_t n_blocks, const uint8_t* p
                     gcz_hits* out);
 void gcz_hits_free(gcz_hits* hits);
 
-/* What a batch of backward searches reads (measurement, not a timed path): rank sectors of 32 bytes loaded by the
- * kernel, its backward-search steps, and the RankedWTNode.count calls (algo/tree/RankedWTNode.java:98-122) the
- * reference's own loop makes for the same patterns — 2 per character and code bit while the position is >= 0
- * (algo/tree/HuffmanShapedWaveletTree.java:247-267), 74 bytes each in the file layout. */
+/* What a batch of backward searches reads (measurement, not a timed path).  rank_sectors: 32-byte sectors the search kernel
+ * loads (a lookup in the interval table counts as one); kernel_ms: its device time.  steps, reference_rank_calls: the
+ * backward-search steps and the RankedWTNode.count calls (algo/tree/RankedWTNode.java:98-122) of the reference's own loop
+ * for the same patterns — 2 per character and code bit while the position is >= 0
+ * (algo/tree/HuffmanShapedWaveletTree.java:247-267), 74 bytes each in the file layout — counted by running
+ * the search once more symbol by symbol, without the table. */
 typedef struct gcz_query_stats {
     int64_t patterns, blocks, steps, rank_sectors, reference_rank_calls, index_bytes;
     float   kernel_ms;       /* device time of the search kernels of the call */
