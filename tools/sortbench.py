@@ -1,5 +1,4 @@
-"""Tuning aid: device time of the onesweep digit passes over (u64, u32) pairs.  GCZ_SORT_PERSISTENT=0 sends pairs through the
-one-tile-per-CTA kernel instead of the persistent TMA one (A/B):  python tools/sortbench.py [n] [bits]"""
+"""Tuning aid: device time of the onesweep digit passes over (u64, u32) pairs with random keys:  python tools/sortbench.py [n] [bits]"""
 import ctypes as C
 import os
 import sys
@@ -26,5 +25,5 @@ for it in range(3):
     res.append((t.radix_ms, t.radix_launches))
 ok = bool((keys[1:] >= keys[:-1]).all())
 ms, passes = res[-1]
-print(f"variant={os.environ.get('GCZ_SORT_VARIANT', 'default')} n={n} bits={bits} passes={passes} ms={ms:.3f} "
+print(f"n={n} bits={bits} passes={passes} ms={ms:.3f} "
       f"per_pass={ms / passes:.3f} GB/s={24 * n * passes / ms / 1e6:.0f} sorted={ok}")
