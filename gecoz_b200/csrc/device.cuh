@@ -101,8 +101,7 @@ struct DeviceCtx {
     size_t       pinned_top = 0;
     std::atomic<int64_t> launches{0};        // kernels launched by this library on this device
     bool         iwt_attr = false;             // dynamic-smem opt-in done for iwt_low_levels_kernel
-    bool         sort_attr[3] = { false, false, false };   // dynamic-smem opt-in done for the onesweep kernels
-    unsigned     sort_attr_mask = 0;           // bit v: the same, per variant of the digit pass
+    unsigned     sort_attr_mask = 0;           // bit 0 / 1: dynamic-smem opt-in done for the onesweep kernels with 64- / 32-bit status words
     unsigned     text_hist_attr = 0;           // bit p: the same for text_hist_kernel<p>
 };
 

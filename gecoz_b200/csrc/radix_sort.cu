@@ -26,7 +26,7 @@ constexpr int kPadRows = 32;                // "prefix 0" rows in front of the s
 
 // Status word of (tile, digit): count in the low bits, two flag bits on top (aggregate = this tile's count, prefix = the
 // count of this and all earlier tiles).  32-bit words whenever a prefix fits 30 bits (any block below 2^30 pairs): half
-// the L2 traffic of the look-back and a third of its instructions.  The array starts with kLookWindow rows of "prefix 0"
+// the L2 traffic of the look-back and a third of its instructions.  The array starts with kPadRows rows of "prefix 0"
 // (written once per sort by radix_scan_kernel), so a window of predecessors never needs a bounds test.
 template <typename S> struct Status;
 template <> struct Status<uint32_t> {
